@@ -1,0 +1,176 @@
+/* se_b200.h -- C ABI of libse_b200.so: the B200 (sm_100a) enhancement signal path.
+ *
+ * Drop-in boundary for the hot path of leo19941227/Speech-Enhancement-by-S3PRL
+ * (SURVEY.md section 8b).  The reference is pure Python: what it "binds" for this
+ * path are PyTorch library calls made from the call sites cited on each entry
+ * point below; a maintainer swaps those call sites for the ctypes stubs shown in
+ * INTEGRATION.md (or simply imports the drop-in Python classes of
+ * speech_enhancement_by_s3prl_b200, which wrap exactly these functions).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     parameter name starts with h_ (host); all tensors are dense fp32 unless noted
+ *   - the caller owns every buffer; the library allocates only its private
+ *     twiddle tables (once per device and n_fft, see se_prepare) and keeps no
+ *     reference to caller memory after return
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*)
+ *   - return value: SE_OK or a negative SE_ERR_*; se_last_error() gives the text
+ *     of the last failure on the calling thread.  No C++ exception crosses the ABI.
+ *   - spectra are TIME-MAJOR (n_utt, n_frames, K), K = n_fft/2 + 1,
+ *     n_frames = T / hop + 1  (runner.py:455: stft_lengths = lengths // hop + 1)
+ *   - supported n_fft: 256, 400, 512, 1024, 2048; window length n_fft (a shorter
+ *     analysis window is passed already centred and zero-padded, as torch.stft does)
+ */
+#ifndef SE_B200_H
+#define SE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE_OK 0
+#define SE_ERR_BAD_ARG (-1)        /* null pointer, non-positive size, T <= n_fft/2 (reflect padding undefined) */
+#define SE_ERR_UNSUPPORTED (-2)    /* n_fft / hop combination without a kernel */
+#define SE_ERR_CUDA (-3)           /* a CUDA runtime call failed; text in se_last_error */
+#define SE_ERR_NO_DEVICE (-4)      /* no sm_100 device: there is NO CPU fallback */
+
+#define SE_NSUMS 6                 /* doubles per utterance written by se_mask_istft */
+#define SE_SUM_YC 0                /* sum_t y*c  (t < length)   y = enhanced, c = clean */
+#define SE_SUM_CC 1                /* sum_t c*c                                        */
+#define SE_SUM_YY 2                /* sum_t y*y                                        */
+#define SE_SUM_SPEC_ST 3           /* sum_{f,k} sqrt(relu(pred))*sqrt(tar)  (f < length/hop+1) */
+#define SE_SUM_SPEC_TT 4           /* sum_{f,k} tar                                    */
+#define SE_SUM_SPEC_SS 5           /* sum_{f,k} relu(pred)                             */
+
+#define SE_ACT_IDENTITY 0
+#define SE_ACT_RELU 1
+#define SE_ACT_SIGMOID 2
+
+int se_version(void);
+int se_last_error(char* h_buf, int n);
+
+/* Create the per-device twiddle tables for n_fft and opt the kernels into their
+ * shared-memory size.  Idempotent.  Call once before capturing a CUDA graph. */
+int se_prepare(int n_fft);
+
+/* ---- K1: STFT + magphase (+log) ----------------------------------------------
+ * Replaces OnlinePreprocessor.forward's torch.stft -> magphase(power=2) -> log ->
+ * transpose chain (S3PRL utility/preprocessor.py; call sites runner.py:433,558,297,
+ * sampler.py:60; the same primitives are used directly at sampler.py:226-229).
+ * Row u of the input starts at wav + u*utt_stride (so one channel of a (B,3,T)
+ * batch is wav + c*T with utt_stride 3*T).  center=True, reflect padding,
+ * one-sided, not normalised.  Any of power / phase / logpower may be NULL.
+ *   power    = re^2 + im^2            ("linear" feature)
+ *   phase    = atan2(im, re)
+ *   logpower = log(power + log_eps)   (feature config log: True) */
+int se_stft(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop,
+            const float* window, float log_eps, float* power, float* phase, float* logpower, void* stream);
+
+/* ---- iSTFT from (power, phase) --------------------------------------------------
+ * Replaces OnlinePreprocessor.istft(linears, phases) (call site runner.py:267):
+ * polar(power^(1/2), phase) -> irfft -> window -> overlap-add -> / sum w^2 -> trim.
+ * Writes hop*(n_frames-1) samples per row and zero-fills up to pad_to (runner.py:268). */
+int se_istft(const float* power, const float* phase, int64_t n_utt, int64_t n_frames, int n_fft, int hop,
+             const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, void* stream);
+
+/* ---- K3: fused mask multiply + iSTFT + overlap-add (+ metric sums) ---------------
+ * wav_out = istft(linear_inp * mask, phase_inp) computed as iSTFT(sqrt(mask) * STFT(noisy))
+ * without materialising the spectrum, `predicted` or the phase
+ * (model.py:33 `predicted = linears * offset`; runner.py:569-570 `_decode_wav`).
+ * If sums != NULL (n_utt x SE_NSUMS doubles, overwritten) it accumulates the
+ * reductions that masked_normalize_decibel (utils.py:31-46), sisdr_eval
+ * (evaluation.py:5-10) and, with want_spec, objective.SISDR (objective.py:86-100)
+ * need; `clean` may be NULL (only SE_SUM_YY is produced then).  lengths may be NULL (= T). */
+int se_mask_istft(const float* noisy, const float* clean, int64_t utt_stride, const float* mask,
+                  const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
+                  float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int want_spec, void* stream);
+
+/* ---- K3 epilogue: level normalisation + metrics from the sums --------------------
+ * Per utterance: gain so that the masked mean-square of wav matches the clean
+ * reference's (target_db_or_nan = NaN; runner.py:570 + utils.py:38-40) or a fixed level
+ * in dB (runner.py:266 default -25); wav *= gain in place over [0, width);
+ * sisdr_wave[u] = evaluation.sisdr_eval(gain*y[:len], c[:len]);
+ * loss_spec[u]  = per-utterance term of objective.SISDR (its batch mean is the loss).
+ * Any of gain / sisdr_wave / loss_spec may be NULL; wav may be NULL (no scaling). */
+int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_utt, int64_t T,
+                        float target_db_or_nan, float* wav, int64_t wav_stride, int64_t width,
+                        float* gain, float* sisdr_wave, float* loss_spec, void* stream);
+
+/* ---- K4a: spectral SI-SDR objective (objective.py:86-100) -------------------------
+ * fwd: per-utterance sums (n_utt x 3 doubles: st, tt, ss; overwritten) over frames
+ *      f < stft_len[u] of src = sqrt(relu(predicted)), tar = sqrt(relu(linear_tar));
+ *      loss_per_utt[u] = -10 log10(|a t|^2 / (|a t - s|^2 + eps) + eps), a = st/(tt+eps).
+ * bwd: grad_predicted[u] = grad_out[u] * d loss_u / d predicted[u] (grad_out: (n_utt,), 1/B each
+ *      for loss.mean(); 0 where predicted <= 0 or the frame is masked), from the saved sums. */
+int se_sisdr_spec_fwd(const float* predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+                      int64_t n_frames, int64_t K, float eps, double* sums3, float* loss_per_utt, void* stream);
+int se_sisdr_spec_bwd(const float* predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+                      int64_t n_frames, int64_t K, float eps, const double* sums3, const float* grad_out,
+                      float* grad_predicted, void* stream);
+
+/* ---- K4b: log-spectral L1 objective (objective.py:109-117) ------------------------
+ * fwd: acc2[0] = sum |log_predicted - log(linear_tar + eps)| over valid frames,
+ *      acc2[1] = number of valid elements (2 doubles, overwritten); loss = acc2[0]/acc2[1]
+ *      (the global element mean: under data parallelism all-reduce both before dividing).
+ * bwd: grad = sign(log_predicted - log(tar+eps)) * grad_out / count on valid frames, else 0. */
+int se_l1_logspec_fwd(const float* log_predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+                      int64_t n_frames, int64_t K, float eps, double* acc2, void* stream);
+int se_l1_logspec_bwd(const float* log_predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+                      int64_t n_frames, int64_t K, float eps, double count, const float* grad_out,
+                      float* grad_log_predicted, void* stream);
+
+/* ---- K4c: batched waveform SI-SDR (evaluation.py:5-10 over runner.py:587-602) -----
+ * sisdr[u] = sisdr_eval(src[u, :len[u]], tar[u, :len[u]]).  ws_sums3: caller workspace of
+ * n_utt x 3 doubles (overwritten: <s,t>, <t,t>, <s,s>). */
+int se_sisdr_wave(const float* src, int64_t src_stride, const float* tar, int64_t tar_stride, const int64_t* lengths,
+                  int64_t n_utt, int64_t T, float eps, double* ws_sums3, float* sisdr, void* stream);
+
+/* ---- a11: masked_normalize_decibel (utils.py:31-46) -------------------------------
+ * out = audio * sqrt(10^(target/10) / (masked_mean(audio^2) + eps)); target per row is
+ * target_db[u] if target_db != NULL, else the masked level of ref[u] (utils.py:38-40).
+ * ws_sums3: caller workspace of n_utt x 3 doubles.  out may alias audio. */
+int se_masked_normalize_db(const float* audio, int64_t stride, const int64_t* lengths, int64_t n_utt, int64_t width,
+                           const float* target_db, const float* ref, int64_t ref_stride, float eps,
+                           double* ws_sums3, float* out, int64_t out_stride, void* stream);
+
+/* ---- a4: length masks (runner.py:216-220) ------------------------------------------
+ * masks[u, i] = i < lengths[u] ? 1 : 0, int64, shape (n_utt, width). */
+int se_length_masks(const int64_t* lengths, int64_t n_utt, int64_t width, int64_t* masks, void* stream);
+
+/* ---- K2: mask head (model.py:14-17 Linear, model.py:28-34 LinearResidual) ---------
+ * se_cmvn_stats: per (utterance, feature) mean and unbiased std over ALL n_frames
+ *   (padding included, as model.py:30 does).  mean/std: (n_utt, D).
+ * se_linear_head_fwd: act((x - mean)/(std + cmvn_eps)) W^T + b) [* linears]
+ *   x (n_utt*n_frames, D_in), W (D_out, D_in) row-major (nn.Linear layout), b (D_out) or NULL;
+ *   mean/std NULL = no CMVN; offset_out and/or predicted_out (= linears * offset) may be NULL.
+ *   precision: 0 = fp32 SIMT (bit-comparable with torch fp32), 1 = TF32 tcgen05 tensor cores.
+ * se_linear_head_bwd: given grad_offset (dL/d offset after activation) computes grad_W, grad_b
+ *   (overwritten).  grad_x is not produced: the head's input features come from the
+ *   preprocessor and never require a gradient in the reference (runner.py:433-453). */
+int se_cmvn_stats(const float* x, int64_t n_utt, int64_t n_frames, int64_t D, float* mean, float* std, void* stream);
+int se_linear_head_fwd(const float* x, const float* mean, const float* std, float cmvn_eps, const float* W,
+                       const float* b, int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int act,
+                       const float* linears, float* offset_out, float* predicted_out, int precision, void* stream);
+int se_linear_head_bwd(const float* x, const float* mean, const float* std, float cmvn_eps, const float* W,
+                       const float* offset, const float* grad_offset, int64_t n_utt, int64_t n_frames,
+                       int64_t D_in, int64_t D_out, int act, float* grad_W, float* grad_b, void* stream);
+
+/* ---- K1b: feature post-processing (S3PRL OnlinePreprocessor feature configs:
+ * config/pretrain_sample.yaml:54-65, config/pseudo_noise.yaml:10-15) ------------------
+ * se_mel: out[u,f,m] = log?(sum_k power[u,f,k] * fb[k,m] (+eps)), fb (K, n_mels) row-major
+ * se_delta: 5-tap regression deltas with replicate padding along time, order-times
+ *           recursive, reading columns [0, D) of x and writing columns [D, (order+1)*D)
+ *           of the same (n_utt, n_frames, (order+1)*D) buffer
+ * se_cmvn_apply: x = (x - mean) / (std + eps) per (utterance, feature) in place */
+int se_mel(const float* power, int64_t n_rows, int64_t K, const float* fb, int64_t n_mels, int take_log, float eps,
+           float* out, int64_t out_row_stride, void* stream);
+int se_delta(float* x, int64_t n_utt, int64_t n_frames, int64_t D, int order, void* stream);
+int se_cmvn_apply(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const float* mean, const float* std,
+                  float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE_B200_H */

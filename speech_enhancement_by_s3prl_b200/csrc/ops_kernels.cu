@@ -1,0 +1,620 @@
+// libse_b200.so -- objectives, metrics, level normalisation, length masks, feature
+// post-processing and the fp32 (SIMT) mask head.  Entry points: include/se_b200.h.
+// All of these are streaming / reduction kernels bounded by HBM bandwidth except the
+// head GEMM, whose tensor-core (tcgen05) variant lives in head_tc.cu.
+#include <algorithm>
+#include <cmath>
+#include "se_common.cuh"
+
+using secommon::fail;
+using secommon::block_accumulate_to;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float relu(float x) { return x > 0.0f ? x : 0.0f; }
+
+// SI-SDR in dB from the three sums st = <s,t>, tt = <t,t>, ss = <s,s>  (evaluation.py:5-10,
+// objective.py:94-97): a = st/(tt+eps); 10 log10(|a t|^2 / (|a t - s|^2 + eps) + eps)
+__device__ __forceinline__ double sisdr_from_sums(double st, double tt, double ss, double eps) {
+    const double a = st / (tt + eps);
+    const double num = a * a * tt;
+    double den = a * a * tt - 2.0 * a * st + ss;
+    if (den < 0.0) den = 0.0;                      // rounding when s is (numerically) a multiple of t
+    return 10.0 * log10(num / (den + eps) + eps);
+}
+
+// ------------------------------------------------------------------ finalize (gain + metrics)
+__global__ void finalize_metrics_kernel(const double* __restrict__ sums, const long long* __restrict__ lengths,
+                                        int T, float target_db, float* __restrict__ wav, long long wav_stride,
+                                        int width, float* __restrict__ gain_out, float* __restrict__ sisdr_wave,
+                                        float* __restrict__ loss_spec, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const double* s = sums + (long long)u * SE_NSUMS;
+    const double len = lengths ? (double)lengths[u] : (double)T;
+    const double eps_mean = 1e-8;                                   // utils.py:26, utils.py:31
+    const double mean_yy = s[SE_SUM_YY] / (len + eps_mean);
+    double level;                                                   // 10^(target/10)
+    if (isnan(target_db)) level = pow(10.0, (10.0 * log10(s[SE_SUM_CC] / (len + eps_mean))) / 10.0);
+    else level = pow(10.0, (double)target_db / 10.0);
+    const double gain = sqrt(level / (mean_yy + eps_mean));
+    if (chunk == 0 && threadIdx.x == 0) {
+        if (gain_out) gain_out[u] = (float)gain;
+        if (sisdr_wave) sisdr_wave[u] = (float)sisdr_from_sums(gain * s[SE_SUM_YC], s[SE_SUM_CC], gain * gain * s[SE_SUM_YY], 1e-10);
+        if (loss_spec) loss_spec[u] = (float)(-sisdr_from_sums(s[SE_SUM_SPEC_ST], s[SE_SUM_SPEC_TT], s[SE_SUM_SPEC_SS], 1e-10));
+    }
+    if (wav) {
+        const float g = (float)gain;
+        float* row = wav + (long long)u * wav_stride;
+        const int per = (width + chunks - 1) / chunks;
+        const int lo = chunk * per, hi = min(width, lo + per);
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) row[i] *= g;
+    }
+}
+
+// ------------------------------------------------------------------ spectral SI-SDR objective
+__global__ void sisdr_spec_sums_kernel(const float* __restrict__ pred, const float* __restrict__ tar,
+                                       const long long* __restrict__ stft_len, int n_frames, int K,
+                                       double* __restrict__ sums3, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const long long valid = (long long)min((long long)n_frames, stft_len ? stft_len[u] : (long long)n_frames) * K;
+    const long long per = (valid + chunks - 1) / chunks;
+    const long long lo = chunk * per, hi = min(valid, lo + per);
+    const float* p = pred + (long long)u * n_frames * K;
+    const float* t = tar + (long long)u * n_frames * K;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float rp = relu(p[i]), rt = relu(t[i]);
+        acc[0] += sqrtf(rp) * sqrtf(rt);
+        acc[1] += rt;
+        acc[2] += rp;
+    }
+    block_accumulate_to<3, float>(acc, sums3 + (long long)u * 3);
+}
+
+__global__ void sisdr_spec_finish_kernel(const double* __restrict__ sums3, int n_utt, float eps, float* __restrict__ loss) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n_utt) loss[u] = (float)(-sisdr_from_sums(sums3[3 * u], sums3[3 * u + 1], sums3[3 * u + 2], (double)eps));
+}
+
+__global__ void sisdr_spec_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar,
+                                      const long long* __restrict__ stft_len, int n_utt, int n_frames, int K, float eps_f,
+                                      const double* __restrict__ sums3, const float* __restrict__ grad_out,
+                                      float* __restrict__ grad_pred, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const long long total = (long long)n_frames * K;
+    const long long valid = (long long)min((long long)n_frames, stft_len ? stft_len[u] : (long long)n_frames) * K;
+    const long long per = (total + chunks - 1) / chunks;
+    const long long lo = chunk * per, hi = min(total, lo + per);
+    const double eps = eps_f;
+    const double st = sums3[3 * u], tt = sums3[3 * u + 1], ss = sums3[3 * u + 2];
+    const double a = st / (tt + eps);
+    const double A = a * a * tt;
+    const double D = a * a * tt - 2.0 * a * st + ss + eps;
+    const double R = A / D;
+    // loss_u = -10 log10(R + eps);  d loss_u / d s_i = kappa * ((ca*D - A*cd) t_i - 2 A s_i)
+    const double kappa = -10.0 / (log(10.0) * (R + eps) * D * D);
+    const double ca = 2.0 * a * tt / (tt + eps);
+    const double cd = 2.0 * (a * tt - st) / (tt + eps) - 2.0 * a;
+    const double go = (double)grad_out[u];                                 // d L / d loss_u (1/B for loss.mean())
+    const float c_t = (float)(go * kappa * (ca * D - A * cd));
+    const float c_s = (float)(go * kappa * (-2.0 * A));
+    const float* p = pred + (long long)u * total;
+    const float* t = tar + (long long)u * total;
+    float* g = grad_pred + (long long)u * total;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        float out = 0.0f;
+        const float pi = p[i];
+        if (i < valid && pi > 0.0f) {
+            const float s = sqrtf(pi), ti = sqrtf(relu(t[i]));
+            out = (c_t * ti + c_s * s) * (0.5f / s);                    // ds/dp = 1/(2 sqrt(p)), 0 where p <= 0
+        }
+        g[i] = out;
+    }
+}
+
+// ------------------------------------------------------------------ log-spectral L1 objective
+__global__ void l1_logspec_fwd_kernel(const float* __restrict__ logp, const float* __restrict__ tar,
+                                      const long long* __restrict__ stft_len, int n_frames, int K, float eps,
+                                      double* __restrict__ acc2, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const long long valid = (long long)min((long long)n_frames, stft_len ? stft_len[u] : (long long)n_frames) * K;
+    const long long per = (valid + chunks - 1) / chunks;
+    const long long lo = chunk * per, hi = min(valid, lo + per);
+    const float* p = logp + (long long)u * n_frames * K;
+    const float* t = tar + (long long)u * n_frames * K;
+    float acc[2] = {0.f, 0.f};
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) acc[0] += fabsf(p[i] - logf(t[i] + eps));
+    if (threadIdx.x == 0 && hi > lo) acc[1] = (float)(hi - lo);         // exact for < 2^24 elements per chunk
+    block_accumulate_to<2, float>(acc, acc2);
+}
+
+__global__ void l1_logspec_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ tar,
+                                      const long long* __restrict__ stft_len, int n_frames, int K, float eps,
+                                      double count, const float* __restrict__ grad_out, float* __restrict__ grad, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const long long total = (long long)n_frames * K;
+    const long long valid = (long long)min((long long)n_frames, stft_len ? stft_len[u] : (long long)n_frames) * K;
+    const long long per = (total + chunks - 1) / chunks;
+    const long long lo = chunk * per, hi = min(total, lo + per);
+    const float scale = (float)((double)grad_out[0] / count);
+    const float* p = logp + (long long)u * total;
+    const float* t = tar + (long long)u * total;
+    float* g = grad + (long long)u * total;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        float out = 0.0f;
+        if (i < valid) {
+            const float d = p[i] - logf(t[i] + eps);
+            out = d > 0.0f ? scale : (d < 0.0f ? -scale : 0.0f);
+        }
+        g[i] = out;
+    }
+}
+
+// ------------------------------------------------------------------ waveform-level reductions
+// sums3[u] += (<s,t>, <t,t>, <s,s>) over t < len[u]
+__global__ void wave_sums_kernel(const float* __restrict__ src, long long src_stride, const float* __restrict__ tar,
+                                 long long tar_stride, const long long* __restrict__ lengths, int T,
+                                 double* __restrict__ sums3, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const int len = lengths ? (int)min((long long)T, lengths[u]) : T;
+    const int per = (len + chunks - 1) / chunks;
+    const int lo = chunk * per, hi = min(len, lo + per);
+    const float* s = src + (long long)u * src_stride;
+    const float* t = tar ? tar + (long long)u * tar_stride : nullptr;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float a = s[i];
+        acc[2] += a * a;
+        if (t) { const float b = t[i]; acc[0] += a * b; acc[1] += b * b; }
+    }
+    block_accumulate_to<3, float>(acc, sums3 + (long long)u * 3);
+}
+
+__global__ void sisdr_wave_finish_kernel(const double* __restrict__ sums3, int n_utt, float eps, float* __restrict__ out) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n_utt) out[u] = (float)sisdr_from_sums(sums3[3 * u], sums3[3 * u + 1], sums3[3 * u + 2], (double)eps);
+}
+
+// out = audio * sqrt(10^(target/10) / (mean(audio^2) + eps)); sums3[u] = (<a,r>, <r,r>, <a,a>) with r = ref
+__global__ void normalize_db_kernel(const float* __restrict__ audio, long long stride, const long long* __restrict__ lengths,
+                                    int width, const float* __restrict__ target_db, int have_ref, float eps,
+                                    const double* __restrict__ sums3, float* __restrict__ out, long long out_stride, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const double len = lengths ? (double)min((long long)width, lengths[u]) : (double)width;
+    const double mean_aa = sums3[3 * u + 2] / (len + (double)eps);
+    double tdb;
+    if (target_db) tdb = (double)target_db[u];
+    else tdb = have_ref ? 10.0 * log10(sums3[3 * u + 1] / (len + (double)eps)) : -25.0;
+    const float g = (float)sqrt(pow(10.0, tdb / 10.0) / (mean_aa + (double)eps));
+    const int per = (width + chunks - 1) / chunks;
+    const int lo = chunk * per, hi = min(width, lo + per);
+    const float* a = audio + (long long)u * stride;
+    float* o = out + (long long)u * out_stride;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) o[i] = a[i] * g;
+}
+
+__global__ void length_masks_kernel(const long long* __restrict__ lengths, long long n_utt, long long width,
+                                    long long* __restrict__ masks) {
+    const long long total = n_utt * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long u = i / width, t = i - u * width;
+        masks[i] = t < lengths[u] ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------ CMVN statistics over time
+// x (n_utt, F, D): mean / unbiased std per (u, d).  block = 32 features x 8 frame lanes.
+__global__ void cmvn_stats_kernel(const float* __restrict__ x, int n_frames, int D, float* __restrict__ mean,
+                                  float* __restrict__ stdv) {
+    const int dchunks = (D + 31) / 32;
+    const int u = blockIdx.x / dchunks, dc = blockIdx.x - u * dchunks;
+    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, nrows = blockDim.x >> 5;
+    const int d = dc * 32 + lane;
+    const float* base = x + (long long)u * n_frames * D;
+    __shared__ double red[8][33];
+    double s = 0.0;
+    if (d < D) for (int f = row; f < n_frames; f += nrows) s += (double)base[(long long)f * D + d];
+    red[row][lane] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int r = 0; r < nrows; ++r) tot += red[r][lane];
+    const double mu = tot / (double)n_frames;
+    __syncthreads();
+    double q = 0.0;
+    if (d < D) for (int f = row; f < n_frames; f += nrows) { const double v = (double)base[(long long)f * D + d] - mu; q += v * v; }
+    red[row][lane] = q;
+    __syncthreads();
+    if (row == 0 && d < D) {
+        double qt = 0.0;
+        for (int r = 0; r < nrows; ++r) qt += red[r][lane];
+        mean[(long long)u * D + d] = (float)mu;
+        stdv[(long long)u * D + d] = (float)sqrt(qt / (double)(n_frames - 1));      // unbiased (model.py:30)
+    }
+}
+
+__global__ void cmvn_apply_kernel(float* __restrict__ x, long long n_frames, int D, const float* __restrict__ mean,
+                                  const float* __restrict__ stdv, float eps, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / D;
+        const int d = (int)(i - row * D);
+        const long long u = row / n_frames;
+        x[i] = (x[i] - mean[u * D + d]) / (stdv[u * D + d] + eps);
+    }
+}
+
+// ------------------------------------------------------------------ mel filterbank / deltas
+// one warp per spectrogram row: out[row, m] = log?(sum_k power[row,k] fb[k,m] + eps)
+__global__ void mel_kernel(const float* __restrict__ power, long long n_rows, int K, const float* __restrict__ fb,
+                           int n_mels, int take_log, float eps, float* __restrict__ out, long long out_stride) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float* p = power + row * K;
+    for (int m0 = 0; m0 < n_mels; m0 += 64) {
+        const int ma = m0 + lane, mb = m0 + 32 + lane;
+        float acc_a = 0.f, acc_b = 0.f;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const float pv = (k0 + lane < K) ? p[k0 + lane] : 0.f;
+            const int kn = min(32, K - k0);
+            for (int j = 0; j < kn; ++j) {
+                const float pk = __shfl_sync(0xffffffffu, pv, j);
+                const float* f = fb + (long long)(k0 + j) * n_mels;
+                if (ma < n_mels) acc_a = fmaf(pk, f[ma], acc_a);
+                if (mb < n_mels) acc_b = fmaf(pk, f[mb], acc_b);
+            }
+        }
+        if (ma < n_mels) out[row * out_stride + ma] = take_log ? logf(acc_a + eps) : acc_a;
+        if (mb < n_mels) out[row * out_stride + mb] = take_log ? logf(acc_b + eps) : acc_b;
+    }
+}
+
+// columns [dst_col, dst_col+D) <- 5-tap regression delta over time of columns [src_col, src_col+D)
+__global__ void delta_kernel(float* __restrict__ x, int n_frames, int D, int row_stride, int src_col, int dst_col, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / D;
+        const int d = (int)(i - row * D);
+        const long long u = row / n_frames;
+        const int f = (int)(row - u * n_frames);
+        const float* base = x + u * n_frames * (long long)row_stride + src_col + d;
+        auto at = [&](int t) { t = t < 0 ? 0 : (t >= n_frames ? n_frames - 1 : t); return base[(long long)t * row_stride]; };
+        const float v = (-2.0f * at(f - 2) - at(f - 1) + at(f + 1) + 2.0f * at(f + 2)) / 10.0f;
+        x[row * row_stride + dst_col + d] = v;
+    }
+}
+
+// ------------------------------------------------------------------ fp32 mask head (SIMT GEMM)
+// offset = act( cmvn(x) W^T + b ),  predicted = linears * offset
+// x (R, Din) with R = n_utt*n_frames, W (Dout, Din); 64x64 tile, 16-deep k-slab, 4x4 micro-tile.
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__device__ __forceinline__ float activate(float z, int act) {
+    if (act == SE_ACT_RELU) return z > 0.f ? z : 0.f;
+    if (act == SE_ACT_SIGMOID) return 1.0f / (1.0f + expf(-z));
+    return z;
+}
+
+__global__ void __launch_bounds__(256) linear_head_fwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv, float cmvn_eps,
+    const float* __restrict__ W, const float* __restrict__ bias, long long R, int n_frames, int Din, int Dout, int act,
+    const float* __restrict__ linears, float* __restrict__ offset_out, float* __restrict__ pred_out) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const long long r0 = (long long)blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads, 4x4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // loader mapping: 256 threads fetch a 64 x 16 slab: thread -> (row = tid/4, 4 consecutive k)
+    const int lrow = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
+    for (int k0 = 0; k0 < Din; k0 += BK) {
+        {
+            const long long r = r0 + lrow;
+            const long long u = r / n_frames;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + lk + j;
+                float v = 0.f;
+                if (r < R && k < Din) {
+                    v = x[r * Din + k];
+                    if (mean) v = (v - mean[u * Din + k]) / (stdv[u * Din + k] + cmvn_eps);
+                }
+                As[lk + j][lrow] = v;
+            }
+            const int n = n0 + lrow;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + lk + j;
+                Bs[lk + j][lrow] = (n < Dout && k < Din) ? W[(long long)n * Din + k] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + ty * 4 + i;
+        if (r >= R) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= Dout) continue;
+            const float o = activate(acc[i][j] + (bias ? bias[n] : 0.f), act);
+            if (offset_out) offset_out[r * Dout + n] = o;
+            if (pred_out) pred_out[r * Dout + n] = linears[r * Dout + n] * o;
+        }
+    }
+}
+
+// grad_W[n,k] += sum_r gz[r,n] * xn[r,k],  grad_b[n] += sum_r gz[r,n],  gz = grad_offset * act'(offset)
+__global__ void __launch_bounds__(256) linear_head_bwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv, float cmvn_eps,
+    const float* __restrict__ offset, const float* __restrict__ grad_offset, long long R, int n_frames, int Din, int Dout,
+    int act, float* __restrict__ grad_W, float* __restrict__ grad_b, long long rows_per_split) {
+    __shared__ float Gs[BK][BM + 4];      // [r][n]
+    __shared__ float Xs[BK][BN + 4];      // [r][k]
+    const int n0 = blockIdx.y * BM, k0 = blockIdx.x * BN;
+    const long long ra = (long long)blockIdx.z * rows_per_split, rb = min(R, ra + rows_per_split);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // loader: thread -> (r = tid/16 in [0,16), 4 consecutive columns starting at (tid%16)*4)
+    const int lr = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;
+    for (long long rr = ra; rr < rb; rr += BK) {
+        const long long r = rr + lr;
+        const long long u = r / n_frames;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + lc + j;
+            float g = 0.f;
+            if (r < rb && n < Dout) {
+                const float o = offset[r * Dout + n];
+                g = grad_offset[r * Dout + n];
+                if (act == SE_ACT_SIGMOID) g *= o * (1.0f - o);
+                else if (act == SE_ACT_RELU) g = o > 0.f ? g : 0.f;
+            }
+            Gs[lr][lc + j] = g;
+            const int k = k0 + lc + j;
+            float v = 0.f;
+            if (r < rb && k < Din) {
+                v = x[r * Din + k];
+                if (mean) v = (v - mean[u * Din + k]) / (stdv[u * Din + k] + cmvn_eps);
+            }
+            Xs[lr][lc + j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Gs[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Xs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bsum[i] += a[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= Dout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < Din) atomicAdd(grad_W + (long long)n * Din + k, acc[i][j]);
+        }
+        if (grad_b && blockIdx.x == 0 && tx == 0) atomicAdd(grad_b + n, bsum[i]);
+    }
+}
+
+int pick_chunks(long long n_utt, long long work_per_utt, long long min_per_chunk) {
+    // enough CTAs to fill 148 SMs a few times over without making chunks tiny
+    long long want = (148LL * 8 + n_utt - 1) / n_utt;
+    long long cap = work_per_utt / min_per_chunk;
+    if (cap < 1) cap = 1;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+}  // namespace
+
+extern "C" {
+
+int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_utt, int64_t T, float target_db_or_nan,
+                        float* wav, int64_t wav_stride, int64_t width, float* gain, float* sisdr_wave, float* loss_spec,
+                        void* stream) {
+    SE_REQUIRE(sums && n_utt > 0, "sums must not be null");
+    const int chunks = wav ? pick_chunks(n_utt, width, 4096) : 1;
+    finalize_metrics_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
+        sums, (const long long*)lengths, (int)T, target_db_or_nan, wav, wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks);
+    return secommon::check_launch("finalize_metrics_kernel");
+}
+
+int se_sisdr_spec_fwd(const float* predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+                      int64_t n_frames, int64_t K, float eps, double* sums3, float* loss_per_utt, void* stream) {
+    SE_REQUIRE(predicted && linear_tar && sums3 && n_utt > 0 && n_frames > 0 && K > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemsetAsync(sums3, 0, sizeof(double) * 3 * n_utt, st));
+    const int chunks = pick_chunks(n_utt, n_frames * K, 8192);
+    sisdr_spec_sums_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, st>>>(predicted, linear_tar, (const long long*)stft_len,
+                                                                            (int)n_frames, (int)K, sums3, chunks);
+    int rc = secommon::check_launch("sisdr_spec_sums_kernel");
+    if (rc != SE_OK || !loss_per_utt) return rc;
+    sisdr_spec_finish_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, st>>>(sums3, (int)n_utt, eps, loss_per_utt);
+    return secommon::check_launch("sisdr_spec_finish_kernel");
+}
+
+int se_sisdr_spec_bwd(const float* predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+                      int64_t n_frames, int64_t K, float eps, const double* sums3, const float* grad_out,
+                      float* grad_predicted, void* stream) {
+    SE_REQUIRE(predicted && linear_tar && sums3 && grad_out && grad_predicted && n_utt > 0, "bad argument");
+    const int chunks = pick_chunks(n_utt, n_frames * K, 8192);
+    sisdr_spec_bwd_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
+        predicted, linear_tar, (const long long*)stft_len, (int)n_utt, (int)n_frames, (int)K, eps, sums3, grad_out, grad_predicted, chunks);
+    return secommon::check_launch("sisdr_spec_bwd_kernel");
+}
+
+int se_l1_logspec_fwd(const float* log_predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+                      int64_t n_frames, int64_t K, float eps, double* acc2, void* stream) {
+    SE_REQUIRE(log_predicted && linear_tar && acc2 && n_utt > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemsetAsync(acc2, 0, sizeof(double) * 2, st));
+    int chunks = pick_chunks(n_utt, n_frames * K, 8192);
+    const long long per = (n_frames * K + chunks - 1) / chunks;
+    if (per > (1LL << 24)) chunks = (int)((n_frames * K + (1LL << 24) - 1) >> 24);
+    l1_logspec_fwd_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, st>>>(log_predicted, linear_tar, (const long long*)stft_len,
+                                                                           (int)n_frames, (int)K, eps, acc2, chunks);
+    return secommon::check_launch("l1_logspec_fwd_kernel");
+}
+
+int se_l1_logspec_bwd(const float* log_predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+                      int64_t n_frames, int64_t K, float eps, double count, const float* grad_out,
+                      float* grad_log_predicted, void* stream) {
+    SE_REQUIRE(log_predicted && linear_tar && grad_out && grad_log_predicted && n_utt > 0 && count > 0, "bad argument");
+    const int chunks = pick_chunks(n_utt, n_frames * K, 8192);
+    l1_logspec_bwd_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
+        log_predicted, linear_tar, (const long long*)stft_len, (int)n_frames, (int)K, eps, count, grad_out, grad_log_predicted, chunks);
+    return secommon::check_launch("l1_logspec_bwd_kernel");
+}
+
+int se_sisdr_wave(const float* src, int64_t src_stride, const float* tar, int64_t tar_stride, const int64_t* lengths,
+                  int64_t n_utt, int64_t T, float eps, double* ws_sums3, float* sisdr, void* stream) {
+    SE_REQUIRE(src && tar && ws_sums3 && sisdr && n_utt > 0 && T > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemsetAsync(ws_sums3, 0, sizeof(double) * 3 * n_utt, st));
+    const int chunks = pick_chunks(n_utt, T, 8192);
+    wave_sums_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, st>>>(src, src_stride, tar, tar_stride, (const long long*)lengths,
+                                                                      (int)T, ws_sums3, chunks);
+    int rc = secommon::check_launch("wave_sums_kernel");
+    if (rc != SE_OK) return rc;
+    sisdr_wave_finish_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, st>>>(ws_sums3, (int)n_utt, eps, sisdr);
+    return secommon::check_launch("sisdr_wave_finish_kernel");
+}
+
+int se_masked_normalize_db(const float* audio, int64_t stride, const int64_t* lengths, int64_t n_utt, int64_t width,
+                           const float* target_db, const float* ref, int64_t ref_stride, float eps, double* ws_sums3,
+                           float* out, int64_t out_stride, void* stream) {
+    SE_REQUIRE(audio && out && ws_sums3 && n_utt > 0 && width > 0, "bad argument");
+    SE_REQUIRE(target_db || ref, "either target_db or ref must be given");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemsetAsync(ws_sums3, 0, sizeof(double) * 3 * n_utt, st));
+    const int chunks = pick_chunks(n_utt, width, 8192);
+    wave_sums_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, st>>>(audio, stride, target_db ? nullptr : ref, ref_stride,
+                                                                      (const long long*)lengths, (int)width, ws_sums3, chunks);
+    int rc = secommon::check_launch("wave_sums_kernel");
+    if (rc != SE_OK) return rc;
+    normalize_db_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, st>>>(audio, stride, (const long long*)lengths, (int)width,
+                                                                         target_db, ref ? 1 : 0, eps, ws_sums3, out, out_stride, chunks);
+    return secommon::check_launch("normalize_db_kernel");
+}
+
+int se_length_masks(const int64_t* lengths, int64_t n_utt, int64_t width, int64_t* masks, void* stream) {
+    SE_REQUIRE(lengths && masks && n_utt > 0 && width > 0, "bad argument");
+    const long long total = n_utt * width;
+    const unsigned blocks = (unsigned)std::min<long long>((total + kThreads - 1) / kThreads, 148LL * 16);
+    length_masks_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>((const long long*)lengths, n_utt, width, (long long*)masks);
+    return secommon::check_launch("length_masks_kernel");
+}
+
+int se_cmvn_stats(const float* x, int64_t n_utt, int64_t n_frames, int64_t D, float* mean, float* std, void* stream) {
+    SE_REQUIRE(x && mean && std && n_utt > 0 && n_frames > 0 && D > 0, "bad argument");
+    const long long blocks = n_utt * ((D + 31) / 32);
+    cmvn_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, (int)n_frames, (int)D, mean, std);
+    return secommon::check_launch("cmvn_stats_kernel");
+}
+
+int se_cmvn_apply(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const float* mean, const float* std, float eps,
+                  void* stream) {
+    SE_REQUIRE(x && mean && std && n_utt > 0, "bad argument");
+    const long long total = n_utt * n_frames * D;
+    const unsigned blocks = (unsigned)std::min<long long>((total + kThreads - 1) / kThreads, 148LL * 16);
+    cmvn_apply_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(x, n_frames, (int)D, mean, std, eps, total);
+    return secommon::check_launch("cmvn_apply_kernel");
+}
+
+int se_mel(const float* power, int64_t n_rows, int64_t K, const float* fb, int64_t n_mels, int take_log, float eps,
+           float* out, int64_t out_row_stride, void* stream) {
+    SE_REQUIRE(power && fb && out && n_rows > 0 && K > 0 && n_mels > 0 && out_row_stride >= n_mels, "bad argument");
+    const int warps = 8;
+    mel_kernel<<<(unsigned)((n_rows + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
+        power, n_rows, (int)K, fb, (int)n_mels, take_log, eps, out, out_row_stride);
+    return secommon::check_launch("mel_kernel");
+}
+
+int se_delta(float* x, int64_t n_utt, int64_t n_frames, int64_t D, int order, void* stream) {
+    SE_REQUIRE(x && n_utt > 0 && n_frames > 0 && D > 0 && order >= 0 && order <= 4, "bad argument");
+    const long long total = n_utt * n_frames * D;
+    const unsigned blocks = (unsigned)std::min<long long>((total + kThreads - 1) / kThreads, 148LL * 16);
+    const int stride = (int)((order + 1) * D);
+    for (int o = 1; o <= order; ++o) {
+        delta_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(x, (int)n_frames, (int)D, stride, (int)((o - 1) * D), (int)(o * D), total);
+        int rc = secommon::check_launch("delta_kernel");
+        if (rc != SE_OK) return rc;
+    }
+    return SE_OK;
+}
+
+int se_linear_head_fwd(const float* x, const float* mean, const float* std, float cmvn_eps, const float* W,
+                       const float* b, int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int act,
+                       const float* linears, float* offset_out, float* predicted_out, int precision, void* stream) {
+    SE_REQUIRE(x && W && n_utt > 0 && n_frames > 0 && D_in > 0 && D_out > 0, "bad argument");
+    SE_REQUIRE((mean == nullptr) == (std == nullptr), "mean and std go together");
+    SE_REQUIRE(offset_out || predicted_out, "no output requested");
+    SE_REQUIRE(!predicted_out || linears, "predicted_out needs linears");
+    SE_REQUIRE(act >= SE_ACT_IDENTITY && act <= SE_ACT_SIGMOID, "unknown activation %d", act);
+    if (precision != 0) return fail(SE_ERR_UNSUPPORTED, "precision=%d: only the fp32 SIMT head is built", precision);
+    const long long R = n_utt * n_frames;
+    dim3 grid((unsigned)((D_out + BN - 1) / BN), (unsigned)((R + BM - 1) / BM));
+    linear_head_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mean, std, cmvn_eps, W, b, R, (int)n_frames, (int)D_in,
+                                                                   (int)D_out, act, linears, offset_out, predicted_out);
+    return secommon::check_launch("linear_head_fwd_kernel");
+}
+
+int se_linear_head_bwd(const float* x, const float* mean, const float* std, float cmvn_eps, const float* W,
+                       const float* offset, const float* grad_offset, int64_t n_utt, int64_t n_frames, int64_t D_in,
+                       int64_t D_out, int act, float* grad_W, float* grad_b, void* stream) {
+    (void)W;
+    SE_REQUIRE(x && offset && grad_offset && grad_W && n_utt > 0 && n_frames > 0, "bad argument");
+    SE_REQUIRE((mean == nullptr) == (std == nullptr), "mean and std go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemsetAsync(grad_W, 0, sizeof(float) * D_in * D_out, st));
+    if (grad_b) SE_CUDA_CHECK(cudaMemsetAsync(grad_b, 0, sizeof(float) * D_out, st));
+    const long long R = n_utt * n_frames;
+    const int tiles = (int)(((D_out + BM - 1) / BM) * ((D_in + BN - 1) / BN));
+    long long splits = std::max<long long>(1, (148LL * 4) / tiles);
+    long long rows_per_split = (R + splits - 1) / splits;
+    rows_per_split = ((rows_per_split + BK - 1) / BK) * BK;
+    splits = (R + rows_per_split - 1) / rows_per_split;
+    dim3 grid((unsigned)((D_in + BN - 1) / BN), (unsigned)((D_out + BM - 1) / BM), (unsigned)splits);
+    linear_head_bwd_kernel<<<grid, 256, 0, st>>>(x, mean, std, cmvn_eps, offset, grad_offset, R, (int)n_frames, (int)D_in,
+                                                 (int)D_out, act, grad_W, grad_b, rows_per_split);
+    return secommon::check_launch("linear_head_bwd_kernel");
+}
+
+}  // extern "C"

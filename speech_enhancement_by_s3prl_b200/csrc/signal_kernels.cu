@@ -1,0 +1,214 @@
+// libse_b200.so -- STFT / iSTFT / fused mask->iSTFT entry points (generic tile path).
+// The per-CTA bodies live in tile_kernels.cuh (shared with the CPU test harness); this file
+// supplies the CTA executor, the __global__ wrappers, the per-device twiddle tables and the
+// extern "C" functions declared in include/se_b200.h.
+#include <map>
+#include <mutex>
+#include <vector>
+#include "se_common.cuh"
+#include "tile_kernels.cuh"
+#include "host_plan.h"
+
+using namespace sekern;
+using secommon::fail;
+
+namespace {
+
+struct BlockExec {
+    template <class F> __device__ __forceinline__ void foreach(int n, F f) {
+        for (int w = threadIdx.x; w < n; w += blockDim.x) f(w);
+    }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    template <int NS> __device__ __forceinline__ void block_accumulate(const float* acc, double* dst) {
+        secommon::block_accumulate_to<NS, float>(acc, dst);
+    }
+};
+
+template <int N> __global__ void __launch_bounds__(Cfg<N>::THREADS) stft_kernel(StftArgs a, int tiles) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    BlockExec ex;
+    const int utt = blockIdx.x / tiles, tile = blockIdx.x - utt * tiles;
+    stft_tile<N>(ex, a, utt, tile, smem);
+}
+template <int N> __global__ void __launch_bounds__(Cfg<N>::THREADS) istft_kernel(IstftArgs a, int tiles) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    BlockExec ex;
+    const int utt = blockIdx.x / tiles, tile = blockIdx.x - utt * tiles;
+    istft_tile<N>(ex, a, utt, tile, smem);
+}
+template <int N> __global__ void __launch_bounds__(Cfg<N>::THREADS) mask_istft_kernel(MaskIstftArgs a, int tiles) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    BlockExec ex;
+    const int utt = blockIdx.x / tiles, tile = blockIdx.x - utt * tiles;
+    mask_istft_tile<N>(ex, a, utt, tile, smem);
+}
+
+// ------------------------------------------------------------------ per-device tables
+struct DeviceTables { float2* twM = nullptr; float2* twN = nullptr; };
+std::mutex g_mu;
+std::map<std::pair<int, int>, DeviceTables> g_tables;      // (device, n_fft)
+constexpr size_t kMaxSmem = 200 * 1024;
+
+template <int N> int opt_in_smem() {
+    SE_CUDA_CHECK(cudaFuncSetAttribute(stft_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    SE_CUDA_CHECK(cudaFuncSetAttribute(istft_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    SE_CUDA_CHECK(cudaFuncSetAttribute(mask_istft_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    return SE_OK;
+}
+
+int get_tables(int n_fft, DeviceTables* out) {
+    if (!seplan::supported_nfft(n_fft)) return fail(SE_ERR_UNSUPPORTED, "n_fft=%d has no kernel (supported: 256, 400, 512, 1024, 2048)", n_fft);
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(SE_ERR_NO_DEVICE, "no CUDA device: %s (libse_b200 has no CPU fallback)", cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto key = std::make_pair(dev, n_fft);
+    auto it = g_tables.find(key);
+    if (it == g_tables.end()) {
+        std::vector<float> twM, twN;
+        seplan::make_twiddles(n_fft, twM, twN);
+        DeviceTables t;
+        SE_CUDA_CHECK(cudaMalloc(&t.twM, twM.size() * sizeof(float)));
+        SE_CUDA_CHECK(cudaMalloc(&t.twN, twN.size() * sizeof(float)));
+        SE_CUDA_CHECK(cudaMemcpy(t.twM, twM.data(), twM.size() * sizeof(float), cudaMemcpyHostToDevice));
+        SE_CUDA_CHECK(cudaMemcpy(t.twN, twN.data(), twN.size() * sizeof(float), cudaMemcpyHostToDevice));
+        int rc = SE_OK;
+        switch (n_fft) {
+            case 256: rc = opt_in_smem<256>(); break;
+            case 400: rc = opt_in_smem<400>(); break;
+            case 512: rc = opt_in_smem<512>(); break;
+            case 1024: rc = opt_in_smem<1024>(); break;
+            case 2048: rc = opt_in_smem<2048>(); break;
+        }
+        if (rc != SE_OK) return rc;
+        it = g_tables.emplace(key, t).first;
+    }
+    *out = it->second;
+    return SE_OK;
+}
+
+template <int N> int launch_stft(StftArgs a, cudaStream_t st) {
+    constexpr int G = Cfg<N>::G;
+    const int tiles = (a.n_frames + G - 1) / G;
+    const size_t smem = Smem<N>::bytes((G - 1) * a.hop + N, 0);
+    if (smem > kMaxSmem) return fail(SE_ERR_UNSUPPORTED, "hop=%d needs %zu B of shared memory", a.hop, smem);
+    const long long blocks = (long long)a.n_utt * tiles;
+    if (blocks > 0x7fffffffLL) return fail(SE_ERR_BAD_ARG, "grid too large");
+    stft_kernel<N><<<(unsigned)blocks, Cfg<N>::THREADS, smem, st>>>(a, tiles);
+    return secommon::check_launch("stft_kernel");
+}
+template <int N> int launch_istft(IstftArgs a, cudaStream_t st) {
+    constexpr int G = Cfg<N>::G;
+    a.tile_len = seplan::inverse_tile_len(N, a.hop, G);
+    if (a.tile_len <= 0) return fail(SE_ERR_UNSUPPORTED, "hop=%d too small for n_fft=%d", a.hop, N);
+    const int tiles = seplan::inverse_num_tiles(a.out_len, a.pad_to, a.tile_len);
+    const size_t smem = Smem<N>::bytes(0, 0);
+    const long long blocks = (long long)a.n_utt * tiles;
+    if (blocks > 0x7fffffffLL) return fail(SE_ERR_BAD_ARG, "grid too large");
+    istft_kernel<N><<<(unsigned)blocks, Cfg<N>::THREADS, smem, st>>>(a, tiles);
+    return secommon::check_launch("istft_kernel");
+}
+template <int N> int launch_mask_istft(MaskIstftArgs a, cudaStream_t st) {
+    constexpr int G = Cfg<N>::G;
+    a.tile_len = seplan::inverse_tile_len(N, a.hop, G);
+    if (a.tile_len <= 0) return fail(SE_ERR_UNSUPPORTED, "hop=%d too small for n_fft=%d", a.hop, N);
+    const int tiles = seplan::inverse_num_tiles(a.out_len, a.pad_to, a.tile_len);
+    const size_t smem = Smem<N>::bytes((G - 1) * a.hop + N, a.want_spec ? G * (N / 2 + 1) : 0);
+    if (smem > kMaxSmem) return fail(SE_ERR_UNSUPPORTED, "hop=%d needs %zu B of shared memory", a.hop, smem);
+    const long long blocks = (long long)a.n_utt * tiles;
+    if (blocks > 0x7fffffffLL) return fail(SE_ERR_BAD_ARG, "grid too large");
+    mask_istft_kernel<N><<<(unsigned)blocks, Cfg<N>::THREADS, smem, st>>>(a, tiles);
+    return secommon::check_launch("mask_istft_kernel");
+}
+
+#define SE_DISPATCH_NFFT(n_fft, FN, ...)                 \
+    switch (n_fft) {                                     \
+        case 256: return FN<256>(__VA_ARGS__);           \
+        case 400: return FN<400>(__VA_ARGS__);           \
+        case 512: return FN<512>(__VA_ARGS__);           \
+        case 1024: return FN<1024>(__VA_ARGS__);         \
+        case 2048: return FN<2048>(__VA_ARGS__);         \
+        default: return fail(SE_ERR_UNSUPPORTED, "n_fft=%d has no kernel", n_fft); \
+    }
+
+int check_geometry(int64_t n_utt, int64_t T, int n_fft, int hop) {
+    SE_REQUIRE(n_utt > 0 && T > 0, "n_utt=%lld and T=%lld must be positive", (long long)n_utt, (long long)T);
+    SE_REQUIRE(hop > 0 && hop <= n_fft, "hop=%d must be in [1, n_fft=%d]", hop, n_fft);
+    SE_REQUIRE(T > n_fft / 2, "T=%lld must exceed n_fft/2=%d (reflect padding, as torch.stft requires)", (long long)T, n_fft / 2);
+    SE_REQUIRE(T < (1LL << 30), "T=%lld too long", (long long)T);
+    return SE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int se_version(void) { return 100; }
+
+int se_last_error(char* h_buf, int n) {
+    if (!h_buf || n <= 0) return SE_ERR_BAD_ARG;
+    strncpy(h_buf, secommon::last_error_buf(), (size_t)n);
+    h_buf[n - 1] = 0;
+    return SE_OK;
+}
+
+int se_prepare(int n_fft) {
+    DeviceTables t;
+    return get_tables(n_fft, &t);
+}
+
+int se_stft(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
+            float log_eps, float* power, float* phase, float* logpower, void* stream) {
+    SE_REQUIRE(wav && window, "wav and window must not be null");
+    int rc = check_geometry(n_utt, T, n_fft, hop);
+    if (rc != SE_OK) return rc;
+    DeviceTables t;
+    if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
+    StftArgs a{};
+    a.wav = wav; a.utt_stride = utt_stride; a.n_utt = (int)n_utt; a.T = (int)T; a.hop = hop;
+    a.n_frames = (int)(T / hop) + 1;
+    a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
+    a.power = power; a.phase = phase; a.logp = logpower; a.log_eps = log_eps;
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_DISPATCH_NFFT(n_fft, launch_stft, a, st)
+}
+
+int se_istft(const float* power, const float* phase, int64_t n_utt, int64_t n_frames, int n_fft, int hop,
+             const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, void* stream) {
+    SE_REQUIRE(power && phase && window && wav_out, "null pointer");
+    SE_REQUIRE(n_utt > 0 && n_frames > 1, "n_utt=%lld, n_frames=%lld", (long long)n_utt, (long long)n_frames);
+    SE_REQUIRE(hop > 0 && hop <= n_fft, "hop=%d must be in [1, n_fft=%d]", hop, n_fft);
+    DeviceTables t;
+    int rc = get_tables(n_fft, &t);
+    if (rc != SE_OK) return rc;
+    IstftArgs a{};
+    a.power = power; a.phase = phase; a.n_utt = (int)n_utt; a.n_frames = (int)n_frames; a.hop = hop;
+    a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
+    a.wav_out = wav_out; a.out_stride = out_stride; a.out_len = hop * ((int)n_frames - 1); a.pad_to = (int)pad_to;
+    SE_REQUIRE(out_stride >= a.out_len && out_stride >= pad_to, "out_stride=%lld too small", (long long)out_stride);
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_DISPATCH_NFFT(n_fft, launch_istft, a, st)
+}
+
+int se_mask_istft(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, const int64_t* lengths,
+                  int64_t n_utt, int64_t T, int n_fft, int hop, const float* window, float* wav_out, int64_t out_stride,
+                  int64_t pad_to, double* sums, int want_spec, void* stream) {
+    SE_REQUIRE(noisy && mask && window && wav_out, "null pointer");
+    int rc = check_geometry(n_utt, T, n_fft, hop);
+    if (rc != SE_OK) return rc;
+    DeviceTables t;
+    if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
+    MaskIstftArgs a{};
+    a.noisy = noisy; a.clean = clean; a.utt_stride = utt_stride; a.mask = mask;
+    a.lengths = reinterpret_cast<const long long*>(lengths);
+    a.n_utt = (int)n_utt; a.T = (int)T; a.hop = hop; a.n_frames = (int)(T / hop) + 1;
+    a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
+    a.wav_out = wav_out; a.out_stride = out_stride; a.out_len = hop * (a.n_frames - 1); a.pad_to = (int)pad_to;
+    a.sums = sums; a.want_spec = (want_spec && clean && sums) ? 1 : 0;
+    SE_REQUIRE(out_stride >= a.out_len && out_stride >= pad_to, "out_stride=%lld too small", (long long)out_stride);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sums) SE_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * SE_NSUMS * n_utt, st));
+    SE_DISPATCH_NFFT(n_fft, launch_mask_istft, a, st)
+}
+
+}  // extern "C"

@@ -1,0 +1,427 @@
+"""Torch-facing operator layer over the C ABI of ``libse_b200.so``.
+
+Every function takes CUDA fp32 tensors, allocates its outputs with torch (the
+library itself never allocates user-visible memory) and launches on torch's
+current stream.  The differentiable operators are registered with
+``torch.library.custom_op`` (+ fake + autograd) so that they compose with
+autograd, ``torch.no_grad`` and graph capture.  There is NO CPU implementation:
+CPU tensors raise, as does a missing library.
+"""
+import math
+
+import torch
+
+from . import _lib
+
+ACT = {"Identity": 0, "ReLU": 1, "Sigmoid": 2}
+NSUMS = 6
+SUPPORTED_NFFT = (256, 400, 512, 1024, 2048)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, name, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"se_b200: {name} must be a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"se_b200: {name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _c(t, name, dtype=torch.float32):
+    t = _chk(t, name, dtype)
+    return None if t is None else t.contiguous()
+
+
+def prepare(n_fft):
+    """Create the device tables for n_fft (call before CUDA-graph capture)."""
+    _lib.check(_lib.load().se_prepare(int(n_fft)), "se_prepare")
+
+
+def centered_window(window, n_fft):
+    """torch.stft centres a window shorter than n_fft in the frame."""
+    win = window.shape[0]
+    if win == n_fft:
+        return window.contiguous()
+    left = (n_fft - win) // 2
+    return torch.nn.functional.pad(window, (left, n_fft - win - left)).contiguous()
+
+
+# --------------------------------------------------------------------------- STFT / iSTFT
+def stft(wavs, channel, n_fft, hop, window, power=True, phase=False, logpower=False, log_eps=1e-10):
+    """wavs (B, C, T) contiguous -> dict of (B, F, K) tensors for channel ``channel``."""
+    wavs = _chk(wavs, "wavs")
+    assert wavs.dim() == 3 and wavs.is_contiguous()
+    B, C, T = wavs.shape
+    F, K = T // hop + 1, n_fft // 2 + 1
+    window = _c(window, "window")
+    assert window.numel() == n_fft
+    out = {}
+    with torch.cuda.device(wavs.device):
+        mk = lambda want: torch.empty(B, F, K, device=wavs.device, dtype=torch.float32) if want else None
+        pw, ph, lg = mk(power), mk(phase), mk(logpower)
+        rc = _lib.load().se_stft(wavs.data_ptr() + 4 * int(channel) * T, B, C * T, T, n_fft, hop, window.data_ptr(),
+                                 float(log_eps), _p(pw), _p(ph), _p(lg), _stream())
+        _lib.check(rc, "se_stft")
+    if power:
+        out["power"] = pw
+    if phase:
+        out["phase"] = ph
+    if logpower:
+        out["logpower"] = lg
+    return out
+
+
+def istft(power, phase, n_fft, hop, window, pad_to=0):
+    """(B, F, K) power + phase -> (B, max(hop*(F-1), pad_to)); reference OnlinePreprocessor.istft."""
+    power, phase, window = _c(power, "linears"), _c(phase, "phases"), _c(window, "window")
+    B, F, K = power.shape
+    assert K == n_fft // 2 + 1 and phase.shape == power.shape
+    out_len = hop * (F - 1)
+    width = max(out_len, int(pad_to))
+    with torch.cuda.device(power.device):
+        wav = torch.empty(B, width, device=power.device, dtype=torch.float32)
+        rc = _lib.load().se_istft(power.data_ptr(), phase.data_ptr(), B, F, n_fft, hop, window.data_ptr(),
+                                  wav.data_ptr(), width, int(pad_to), _stream())
+        _lib.check(rc, "se_istft")
+    return wav
+
+
+def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, want_sums=True, want_spec=True,
+               out=None, sums=None):
+    """Fused ``istft(linear_inp * mask, phase_inp)`` straight from the noisy waveform.
+
+    wavs (B, C, T); mask (B, F, K); lengths (B,) int64 or None.  Returns (wav (B, width), sums (B, 6) float64|None)."""
+    wavs, mask, window = _chk(wavs, "wavs"), _c(mask, "mask"), _c(window, "window")
+    assert wavs.dim() == 3 and wavs.is_contiguous()
+    B, C, T = wavs.shape
+    F, K = T // hop + 1, n_fft // 2 + 1
+    assert mask.shape == (B, F, K), f"mask {tuple(mask.shape)} != {(B, F, K)}"
+    lengths = _c(lengths, "lengths", torch.int64)
+    out_len = hop * (F - 1)
+    width = max(out_len, int(pad_to))
+    with torch.cuda.device(wavs.device):
+        if out is None:
+            out = torch.empty(B, width, device=wavs.device, dtype=torch.float32)
+        if want_sums and sums is None:
+            sums = torch.empty(B, NSUMS, device=wavs.device, dtype=torch.float64)
+        clean = None if ch_tar is None else wavs.data_ptr() + 4 * int(ch_tar) * T
+        rc = _lib.load().se_mask_istft(wavs.data_ptr() + 4 * int(ch_inp) * T, clean, C * T, mask.data_ptr(), _p(lengths),
+                                       B, T, n_fft, hop, window.data_ptr(), out.data_ptr(), out.stride(0), int(pad_to),
+                                       _p(sums) if want_sums else None, int(bool(want_spec)), _stream())
+        _lib.check(rc, "se_mask_istft")
+    return out, (sums if want_sums else None)
+
+
+def finalize_metrics(sums, lengths, T, wav=None, target_db=None, want_gain=True, want_sisdr=True, want_loss=True):
+    """Gain / waveform SI-SDR / spectral-SISDR terms from the sums of mask_istft; scales wav in place."""
+    B = sums.shape[0]
+    dev = sums.device
+    with torch.cuda.device(dev):
+        gain = torch.empty(B, device=dev) if want_gain else None
+        sisdr = torch.empty(B, device=dev) if want_sisdr else None
+        loss = torch.empty(B, device=dev) if want_loss else None
+        tdb = float("nan") if target_db is None else float(target_db)
+        rc = _lib.load().se_finalize_metrics(sums.data_ptr(), _p(lengths), B, int(T), tdb, _p(wav),
+                                             0 if wav is None else wav.stride(0), 0 if wav is None else wav.shape[1],
+                                             _p(gain), _p(sisdr), _p(loss), _stream())
+        _lib.check(rc, "se_finalize_metrics")
+    return gain, sisdr, loss
+
+
+# --------------------------------------------------------------------------- waveform-level helpers
+def sisdr_wave(src, tar, lengths=None, eps=1e-10):
+    """Batched evaluation.sisdr_eval: src, tar (B, T) -> (B,) dB."""
+    src, tar = _chk(src, "src"), _chk(tar, "tar")
+    assert src.dim() == 2 and src.shape == tar.shape and src.stride(1) == 1 and tar.stride(1) == 1
+    B, T = src.shape
+    lengths = _c(lengths, "lengths", torch.int64)
+    with torch.cuda.device(src.device):
+        ws = torch.empty(B, 3, device=src.device, dtype=torch.float64)
+        out = torch.empty(B, device=src.device)
+        rc = _lib.load().se_sisdr_wave(src.data_ptr(), src.stride(0), tar.data_ptr(), tar.stride(0), _p(lengths), B, T,
+                                       float(eps), ws.data_ptr(), out.data_ptr(), _stream())
+        _lib.check(rc, "se_sisdr_wave")
+    return out
+
+
+def masked_normalize_db(audio, lengths, target_db=None, ref=None, eps=1e-8):
+    """utils.masked_normalize_decibel on lengths instead of (B, T) int64 masks."""
+    audio = _chk(audio, "audio")
+    assert audio.dim() == 2 and audio.stride(1) == 1
+    B, W = audio.shape
+    lengths = _c(lengths, "lengths", torch.int64)
+    target_db = _c(target_db, "target_db")
+    if ref is not None:
+        ref = _chk(ref, "ref")
+        assert ref.shape[0] == B and ref.shape[1] >= W and ref.stride(1) == 1
+    with torch.cuda.device(audio.device):
+        ws = torch.empty(B, 3, device=audio.device, dtype=torch.float64)
+        out = torch.empty(B, W, device=audio.device)
+        rc = _lib.load().se_masked_normalize_db(audio.data_ptr(), audio.stride(0), _p(lengths), B, W, _p(target_db),
+                                                _p(ref), 0 if ref is None else ref.stride(0), float(eps), ws.data_ptr(),
+                                                out.data_ptr(), W, _stream())
+        _lib.check(rc, "se_masked_normalize_db")
+    return out
+
+
+def length_masks(lengths, width=None):
+    """runner._get_length_masks: (B,) int64 -> (B, width or max(lengths)) int64 0/1."""
+    lengths = _c(lengths, "lengths", torch.int64)
+    if width is None:
+        width = int(lengths.max().item())          # the reference syncs here too (runner.py:218)
+    B = lengths.shape[0]
+    with torch.cuda.device(lengths.device):
+        out = torch.empty(B, width, device=lengths.device, dtype=torch.int64)
+        _lib.check(_lib.load().se_length_masks(lengths.data_ptr(), B, width, out.data_ptr(), _stream()), "se_length_masks")
+    return out
+
+
+# --------------------------------------------------------------------------- features
+def cmvn_stats(x):
+    """x (B, F, D) -> mean, unbiased std over time, each (B, D)."""
+    x = _c(x, "x")
+    B, F, D = x.shape
+    with torch.cuda.device(x.device):
+        mean = torch.empty(B, D, device=x.device)
+        std = torch.empty(B, D, device=x.device)
+        _lib.check(_lib.load().se_cmvn_stats(x.data_ptr(), B, F, D, mean.data_ptr(), std.data_ptr(), _stream()), "se_cmvn_stats")
+    return mean, std
+
+
+def cmvn_apply_(x, mean, std, eps):
+    B, F, D = x.shape
+    assert x.is_contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().se_cmvn_apply(x.data_ptr(), B, F, D, mean.data_ptr(), std.data_ptr(), float(eps), _stream()),
+                   "se_cmvn_apply")
+    return x
+
+
+def mel(power, fb, take_log, eps, out=None, out_cols=None):
+    """power (B, F, K) x fb (K, n_mels) -> (B, F, out_cols or n_mels) with the mel part in the first columns."""
+    power, fb = _c(power, "power"), _c(fb, "fb")
+    B, F, K = power.shape
+    n_mels = fb.shape[1]
+    cols = n_mels if out_cols is None else int(out_cols)
+    with torch.cuda.device(power.device):
+        if out is None:
+            out = torch.empty(B, F, cols, device=power.device)
+        rc = _lib.load().se_mel(power.data_ptr(), B * F, K, fb.data_ptr(), n_mels, int(bool(take_log)), float(eps),
+                                out.data_ptr(), cols, _stream())
+        _lib.check(rc, "se_mel")
+    return out
+
+
+def delta_(x, D, order):
+    """x (B, F, (order+1)*D): fill column blocks 1..order with recursive regression deltas of block 0."""
+    B, F, W = x.shape
+    assert W == (order + 1) * D and x.is_contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().se_delta(x.data_ptr(), B, F, D, int(order), _stream()), "se_delta")
+    return x
+
+
+# --------------------------------------------------------------------------- objectives (custom ops + autograd)
+def _stft_len_or_none(t):
+    return None if t is None else t.contiguous()
+
+
+@torch.library.custom_op("se_b200::sisdr_spec", mutates_args=())
+def _sisdr_spec(predicted: torch.Tensor, linear_tar: torch.Tensor, stft_len: torch.Tensor, eps: float) -> tuple[torch.Tensor, torch.Tensor]:
+    predicted, linear_tar = _c(predicted, "predicted"), _c(linear_tar, "linear_tar")
+    B, F, K = predicted.shape
+    with torch.cuda.device(predicted.device):
+        sums = torch.empty(B, 3, device=predicted.device, dtype=torch.float64)
+        loss = torch.empty(B, device=predicted.device)
+        rc = _lib.load().se_sisdr_spec_fwd(predicted.data_ptr(), linear_tar.data_ptr(), stft_len.data_ptr(), B, F, K, eps,
+                                           sums.data_ptr(), loss.data_ptr(), _stream())
+        _lib.check(rc, "se_sisdr_spec_fwd")
+    return loss, sums
+
+
+@_sisdr_spec.register_fake
+def _(predicted, linear_tar, stft_len, eps):
+    B = predicted.shape[0]
+    return predicted.new_empty(B), predicted.new_empty(B, 3, dtype=torch.float64)
+
+
+@torch.library.custom_op("se_b200::sisdr_spec_bwd", mutates_args=())
+def _sisdr_spec_bwd(predicted: torch.Tensor, linear_tar: torch.Tensor, stft_len: torch.Tensor, eps: float,
+                    sums: torch.Tensor, grad_mean: torch.Tensor) -> torch.Tensor:
+    predicted, linear_tar = _c(predicted, "predicted"), _c(linear_tar, "linear_tar")
+    B, F, K = predicted.shape
+    with torch.cuda.device(predicted.device):
+        grad = torch.empty_like(predicted)
+        g = grad_mean.reshape(B).to(torch.float32).contiguous()
+        rc = _lib.load().se_sisdr_spec_bwd(predicted.data_ptr(), linear_tar.data_ptr(), stft_len.data_ptr(), B, F, K, eps,
+                                           sums.data_ptr(), g.data_ptr(), grad.data_ptr(), _stream())
+        _lib.check(rc, "se_sisdr_spec_bwd")
+    return grad
+
+
+@_sisdr_spec_bwd.register_fake
+def _(predicted, linear_tar, stft_len, eps, sums, grad_mean):
+    return torch.empty_like(predicted)
+
+
+def _sisdr_setup(ctx, inputs, output):
+    predicted, linear_tar, stft_len, eps = inputs
+    ctx.save_for_backward(predicted, linear_tar, stft_len, output[1])
+    ctx.eps = eps
+
+
+def _sisdr_backward(ctx, grad_loss, grad_sums):
+    predicted, linear_tar, stft_len, sums = ctx.saved_tensors
+    grad = torch.ops.se_b200.sisdr_spec_bwd(predicted, linear_tar, stft_len, ctx.eps, sums, grad_loss)
+    return grad, None, None, None
+
+
+_sisdr_spec.register_autograd(_sisdr_backward, setup_context=_sisdr_setup)
+
+
+def sisdr_spec(predicted, linear_tar, stft_len, eps=1e-10):
+    """Per-utterance terms of objective.SISDR (their mean is the loss); differentiable in ``predicted``."""
+    loss, _ = torch.ops.se_b200.sisdr_spec(predicted, linear_tar, stft_len.contiguous(), float(eps))
+    return loss
+
+
+@torch.library.custom_op("se_b200::l1_logspec", mutates_args=())
+def _l1_logspec(log_predicted: torch.Tensor, linear_tar: torch.Tensor, stft_len: torch.Tensor, eps: float) -> torch.Tensor:
+    log_predicted, linear_tar = _c(log_predicted, "log_predicted"), _c(linear_tar, "linear_tar")
+    B, F, K = log_predicted.shape
+    with torch.cuda.device(log_predicted.device):
+        acc = torch.empty(2, device=log_predicted.device, dtype=torch.float64)
+        rc = _lib.load().se_l1_logspec_fwd(log_predicted.data_ptr(), linear_tar.data_ptr(), stft_len.data_ptr(), B, F, K, eps,
+                                           acc.data_ptr(), _stream())
+        _lib.check(rc, "se_l1_logspec_fwd")
+    return acc
+
+
+@_l1_logspec.register_fake
+def _(log_predicted, linear_tar, stft_len, eps):
+    return log_predicted.new_empty(2, dtype=torch.float64)
+
+
+@torch.library.custom_op("se_b200::l1_logspec_bwd", mutates_args=())
+def _l1_logspec_bwd(log_predicted: torch.Tensor, linear_tar: torch.Tensor, stft_len: torch.Tensor, eps: float,
+                    count: float, grad_sum: torch.Tensor) -> torch.Tensor:
+    log_predicted, linear_tar = _c(log_predicted, "log_predicted"), _c(linear_tar, "linear_tar")
+    B, F, K = log_predicted.shape
+    with torch.cuda.device(log_predicted.device):
+        grad = torch.empty_like(log_predicted)
+        g = grad_sum.reshape(1).to(torch.float32).contiguous()
+        rc = _lib.load().se_l1_logspec_bwd(log_predicted.data_ptr(), linear_tar.data_ptr(), stft_len.data_ptr(), B, F, K, eps,
+                                           float(count), g.data_ptr(), grad.data_ptr(), _stream())
+        _lib.check(rc, "se_l1_logspec_bwd")
+    return grad
+
+
+@_l1_logspec_bwd.register_fake
+def _(log_predicted, linear_tar, stft_len, eps, count, grad_sum):
+    return torch.empty_like(log_predicted)
+
+
+def _l1_setup(ctx, inputs, output):
+    log_predicted, linear_tar, stft_len, eps = inputs
+    ctx.save_for_backward(log_predicted, linear_tar, stft_len)
+    ctx.eps = eps
+
+
+def _l1_backward(ctx, grad_acc):
+    log_predicted, linear_tar, stft_len = ctx.saved_tensors
+    # acc[0] = sum |d|: gradient of the SUM with count = 1; the caller divides by the count
+    grad = torch.ops.se_b200.l1_logspec_bwd(log_predicted, linear_tar, stft_len, ctx.eps, 1.0, grad_acc[0])
+    return grad, None, None, None
+
+
+_l1_logspec.register_autograd(_l1_backward, setup_context=_l1_setup)
+
+
+def l1_logspec_sums(log_predicted, linear_tar, stft_len, eps=1e-10):
+    """(sum |log_pred - log(tar+eps)|, number of valid elements) as a float64 (2,) tensor; differentiable."""
+    return torch.ops.se_b200.l1_logspec(log_predicted, linear_tar, stft_len.contiguous(), float(eps))
+
+
+# --------------------------------------------------------------------------- mask head
+@torch.library.custom_op("se_b200::linear_head", mutates_args=())
+def _linear_head(x: torch.Tensor, mean: torch.Tensor | None, std: torch.Tensor | None, cmvn_eps: float,
+                 weight: torch.Tensor, bias: torch.Tensor | None, act: int, precision: int) -> torch.Tensor:
+    x, weight, bias = _c(x, "features"), _c(weight, "weight"), _c(bias, "bias")
+    B, F, Din = x.shape
+    Dout = weight.shape[0]
+    assert weight.shape[1] == Din
+    with torch.cuda.device(x.device):
+        out = torch.empty(B, F, Dout, device=x.device)
+        rc = _lib.load().se_linear_head_fwd(x.data_ptr(), _p(mean), _p(std), cmvn_eps, weight.data_ptr(), _p(bias), B, F, Din,
+                                            Dout, act, None, out.data_ptr(), None, precision, _stream())
+        _lib.check(rc, "se_linear_head_fwd")
+    return out
+
+
+@_linear_head.register_fake
+def _(x, mean, std, cmvn_eps, weight, bias, act, precision):
+    return x.new_empty(x.shape[0], x.shape[1], weight.shape[0])
+
+
+@torch.library.custom_op("se_b200::linear_head_bwd", mutates_args=())
+def _linear_head_bwd(x: torch.Tensor, mean: torch.Tensor | None, std: torch.Tensor | None, cmvn_eps: float,
+                     weight: torch.Tensor, offset: torch.Tensor, grad_offset: torch.Tensor, act: int) -> tuple[torch.Tensor, torch.Tensor]:
+    x, offset, grad_offset = _c(x, "features"), _c(offset, "offset"), _c(grad_offset, "grad_offset")
+    B, F, Din = x.shape
+    Dout = weight.shape[0]
+    with torch.cuda.device(x.device):
+        gw = torch.empty(Dout, Din, device=x.device)
+        gb = torch.empty(Dout, device=x.device)
+        rc = _lib.load().se_linear_head_bwd(x.data_ptr(), _p(mean), _p(std), cmvn_eps, weight.data_ptr(), offset.data_ptr(),
+                                            grad_offset.data_ptr(), B, F, Din, Dout, act, gw.data_ptr(), gb.data_ptr(), _stream())
+        _lib.check(rc, "se_linear_head_bwd")
+    return gw, gb
+
+
+@_linear_head_bwd.register_fake
+def _(x, mean, std, cmvn_eps, weight, offset, grad_offset, act):
+    return torch.empty_like(weight), weight.new_empty(weight.shape[0])
+
+
+def _head_setup(ctx, inputs, output):
+    x, mean, std, cmvn_eps, weight, bias, act, precision = inputs
+    ctx.save_for_backward(x, mean, std, weight, output)
+    ctx.cmvn_eps, ctx.act, ctx.has_bias = cmvn_eps, act, bias is not None
+
+
+def _head_backward(ctx, grad_out):
+    x, mean, std, weight, offset = ctx.saved_tensors
+    gw, gb = torch.ops.se_b200.linear_head_bwd(x, mean, std, ctx.cmvn_eps, weight, offset, grad_out, ctx.act)
+    return None, None, None, None, gw, (gb if ctx.has_bias else None), None, None
+
+
+_linear_head.register_autograd(_head_backward, setup_context=_head_setup)
+
+
+def linear_head(x, weight, bias, activation="Sigmoid", mean=None, std=None, cmvn_eps=1e-6, precision=0):
+    """act(cmvn(x) W^T + b): x (B, F, Din) -> (B, F, Dout); gradients flow to weight and bias."""
+    return torch.ops.se_b200.linear_head(x, mean, std, float(cmvn_eps), weight, bias, ACT[activation], int(precision))
+
+
+def linear_head_fused(x, weight, bias, activation, mean, std, cmvn_eps, linears=None, want_offset=True, precision=0):
+    """Inference-only variant that can also emit predicted = linears * offset from the GEMM epilogue."""
+    x, weight, bias = _c(x, "features"), _c(weight, "weight"), _c(bias, "bias")
+    B, F, Din = x.shape
+    Dout = weight.shape[0]
+    linears = _c(linears, "linears")
+    with torch.cuda.device(x.device):
+        off = torch.empty(B, F, Dout, device=x.device) if want_offset else None
+        pred = torch.empty(B, F, Dout, device=x.device) if linears is not None else None
+        rc = _lib.load().se_linear_head_fwd(x.data_ptr(), _p(mean), _p(std), float(cmvn_eps), weight.data_ptr(), _p(bias), B, F,
+                                            Din, Dout, ACT[activation], _p(linears), _p(off), _p(pred), int(precision), _stream())
+        _lib.check(rc, "se_linear_head_fwd")
+    return off, pred

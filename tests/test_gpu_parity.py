@@ -1,0 +1,410 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes) and through the drop-in
+classes, against the CPU oracle on the same seeded inputs and against the golden fixtures.
+
+Tolerances (BASELINE.json north_star): spectra within 1e-4 relative in fp32; reconstructed
+waveforms within 0.01 dB SI-SDR.  "Relative" for a power spectrum is taken against the
+largest bin of the utterance (bins 120 dB below it hold rounding noise in the oracle too).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import signal_path as sp
+from oracle.preprocessor import OnlinePreprocessor as OraclePre
+
+pytestmark = pytest.mark.gpu
+
+SPEC_RTOL = 1e-4
+SISDR_TOL_DB = 0.01
+CFGS = {256: (129, 16, 8), 400: (201, 25, 10), 512: (257, 32, 16), 1024: (513, 64, 16), 2048: (1025, 128, 32)}
+
+
+@pytest.fixture(scope="module")
+def se():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import speech_enhancement_by_s3prl_b200 as pkg
+    return pkg
+
+
+def make_pair(se, n_fft):
+    n_freq, win_ms, hop_ms = CFGS[n_fft]
+    ora = OraclePre(win_ms=win_ms, hop_ms=hop_ms, n_freq=n_freq)
+    mine = se.OnlinePreprocessor(win_ms=win_ms, hop_ms=hop_ms, n_freq=n_freq).cuda()
+    for p in (ora, mine):
+        p.channel_inp, p.channel_tar = 0, 1
+    return ora, mine
+
+
+def synth(B, T, seed, lengths=None):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(T) / 16000.0
+    clean = torch.zeros(B, T)
+    for b in range(B):
+        f0 = 100 + 40 * b
+        for h in range(1, 6):
+            clean[b] += torch.sin(2 * np.pi * f0 * h * t + h) / h
+        clean[b] *= 0.02 * (1 + 0.5 * torch.sin(2 * np.pi * 2.5 * t))
+    noise = torch.randn(B, T, generator=g) * 0.01
+    wavs = torch.stack([clean + noise, clean, noise], 1).contiguous()
+    if lengths is None:
+        lengths = torch.full((B,), T, dtype=torch.int64)
+    for b, n in enumerate(lengths.tolist()):
+        wavs[b, :, n:] = 0                                   # collate_fn zero-pads (dataset.py:175)
+    return lengths, wavs
+
+
+def rel_to_max(a, b):
+    a, b = a.double(), b.double()
+    scale = b.abs().amax(dim=(-1, -2), keepdim=True)
+    return ((a - b).abs() / scale).max().item()
+
+
+def sisdr_db(a, b):
+    return sp.sisdr_eval(a, b)
+
+
+# ------------------------------------------------------------------------------ STFT
+@pytest.mark.parametrize("n_fft,T", [(512, 16000), (512, 16001), (512, 300), (512, 4096), (400, 16000), (400, 7777),
+                                     (1024, 20000), (256, 3000), (2048, 30000)])
+def test_stft_matches_oracle(se, n_fft, T):
+    ora, mine = make_pair(se, n_fft)
+    _, wavs = synth(3, T, seed=T)
+    c = ora.get_feat_config
+    cfgs = [c("linear", 0), c("phase", 0), c("linear", 1, log=True), c("linear", 2)]
+    ref = ora(wavs, cfgs)
+    got = [g.cpu() for g in mine(wavs.cuda(), cfgs)]
+    hop = ora._win_args["hop_length"]
+    assert got[0].shape == ref[0].shape == (3, T // hop + 1, n_fft // 2 + 1)
+    assert rel_to_max(got[0], ref[0]) < SPEC_RTOL
+    assert rel_to_max(got[3], ref[3]) < SPEC_RTOL
+    strong = ref[0] > 1e-5 * ref[0].amax()
+    dphi = torch.angle(torch.polar(torch.ones_like(ref[1]), got[1] - ref[1]))
+    assert dphi[strong].abs().max() < 2e-3
+    big = ref[2] > np.log(1e-9)
+    assert (got[2] - ref[2])[big].abs().max() < 1e-2
+    assert torch.isfinite(got[2]).all()
+
+
+def test_stft_through_raw_c_abi(se):
+    """ctypes straight into libse_b200.so, no Python wrapper classes in between."""
+    from speech_enhancement_by_s3prl_b200 import _lib
+    lib = _lib.load()
+    ora, _ = make_pair(se, 512)
+    _, wavs = synth(2, 5000, seed=9)
+    d = wavs.cuda()
+    win = torch.hann_window(512).cuda()
+    power = torch.empty(2, 5000 // 256 + 1, 257, device="cuda")
+    rc = lib.se_stft(d.data_ptr() + 4 * 5000, 2, 3 * 5000, 5000, 512, 256, win.data_ptr(), 1e-10, power.data_ptr(), None, None,
+                     torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    ref = ora(wavs, [ora.get_feat_config("linear", 1)])[0]
+    assert rel_to_max(power.cpu(), ref) < SPEC_RTOL
+
+
+def test_abi_error_codes_on_device(se):
+    from speech_enhancement_by_s3prl_b200 import _lib, ops
+    x = torch.zeros(1, 1, 200, device="cuda")
+    with pytest.raises(RuntimeError, match="reflect"):
+        ops.stft(x, 0, 512, 256, torch.hann_window(512).cuda())         # T <= n_fft/2, as torch.stft refuses
+    with pytest.raises(RuntimeError, match="n_fft"):
+        ops.stft(torch.zeros(1, 1, 2000, device="cuda"), 0, 384, 128, torch.hann_window(384).cuda())
+
+
+# ------------------------------------------------------------------------------ iSTFT
+@pytest.mark.parametrize("n_fft,T", [(512, 16000), (512, 16100), (400, 16000), (400, 7777), (1024, 20000)])
+def test_istft_matches_oracle(se, n_fft, T):
+    ora, mine = make_pair(se, n_fft)
+    _, wavs = synth(2, T, seed=T + 1)
+    c = ora.get_feat_config
+    lin, ph = ora(wavs, [c("linear", 0), c("phase", 0)])
+    g = torch.Generator().manual_seed(1)
+    lin = lin * torch.rand(lin.shape, generator=g)
+    ref = ora.istft(lin, ph)
+    got = mine.istft(lin.cuda(), ph.cuda()).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() < 5e-6 * max(1.0, ref.abs().max().item() / 0.05)
+    for b in range(2):
+        assert sisdr_db(got[b], ref[b]) > 90.0
+
+
+def test_stft_istft_round_trip_full_size(se):
+    """Config-2 size (64 x 4 s): size-independent property, no oracle needed."""
+    _, mine = make_pair(se, 512)
+    _, wavs = synth(64, 64000, seed=5)
+    d = wavs.cuda()
+    c = mine.get_feat_config
+    lin, ph = mine(d, [c("linear", 0), c("phase", 0)])
+    back = mine.istft(lin, ph)
+    assert back.shape == (64, 64000)
+    assert (back - d[:, 0, :64000]).abs().max().item() < 5e-6
+    # linearity of the analysis: STFT power of 2x is 4x
+    lin2 = mine(d * 2, [c("linear", 0)])[0]
+    assert rel_to_max(lin2.cpu(), 4 * lin.cpu()) < 1e-6
+
+
+# ------------------------------------------------------------------------------ fused mask -> iSTFT
+@pytest.mark.parametrize("n_fft,T", [(512, 16000), (512, 9999), (400, 16000), (1024, 20000)])
+def test_mask_istft_matches_unfused_oracle(se, n_fft, T):
+    from speech_enhancement_by_s3prl_b200 import ops
+    ora, mine = make_pair(se, n_fft)
+    B = 4
+    lengths = torch.LongTensor([T, T - 1234, T // 2 + 7, T // 3])
+    lengths, wavs = synth(B, T, seed=T + 2, lengths=lengths)
+    hop = ora._win_args["hop_length"]
+    K, F = n_fft // 2 + 1, T // hop + 1
+    g = torch.Generator().manual_seed(3)
+    mask = torch.rand(B, F, K, generator=g)
+    c = ora.get_feat_config
+    lin, ph, lin_t = ora(wavs, [c("linear", 0), c("phase", 0), c("linear", 1)])
+    ref = ora.istft(lin * mask, ph)
+    ref = torch.cat([ref, ref.new_zeros(B, T - ref.shape[1])], 1)
+    wav, sums = ops.mask_istft(wavs.cuda(), 0, 1, mask.cuda(), lengths.cuda(), n_fft, hop, mine._frame_window, pad_to=T)
+    wav, sums = wav.cpu(), sums.cpu()
+    assert (wav - ref).abs().max() < 5e-6
+    masks = sp.length_masks(sp.stft_lengths(lengths, hop))
+    _, per_utt = sp.sisdr_spectral(lin * mask, lin_t, masks)
+    gain, sisdr, loss = ops.finalize_metrics(sums.cuda(), lengths.cuda(), T, wav=None)
+    np.testing.assert_allclose(loss.cpu().numpy(), per_utt.numpy(), atol=2e-3)
+    for b in range(B):
+        n = int(lengths[b])
+        assert sisdr[b].item() == pytest.approx(sisdr_db(ref[b, :n], wavs[b, 1, :n]), abs=SISDR_TOL_DB)
+
+
+# ------------------------------------------------------------------------------ objectives
+def test_objectives_match_reference_golden(se, golden_dir):
+    g = np.load(os.path.join(golden_dir, "signal_path_ref.npz"))
+    T_ = lambda k: torch.from_numpy(g[k]).cuda()
+    masks = T_("masks")
+    pred = T_("predicted").requires_grad_(True)
+    loss, _ = se.SISDR()(predicted=pred, linear_tar=T_("linear_tar"), stft_length_masks=masks, junk=1)
+    assert loss.item() == pytest.approx(float(g["SISDR"]), abs=1e-4)
+    loss.backward()
+    np.testing.assert_allclose(pred.grad.cpu().numpy(), g["SISDR_grad"], rtol=2e-4, atol=1e-7)
+    lp = T_("log_predicted").requires_grad_(True)
+    l1, _ = se.L1()(log_predicted=lp, linear_tar=T_("linear_tar"), stft_length_masks=masks, loss=None)
+    assert l1.item() == pytest.approx(float(g["L1"]), rel=1e-5)
+    l1.backward()
+    np.testing.assert_allclose(lp.grad.cpu().numpy(), g["L1_grad"], rtol=1e-5, atol=1e-9)
+    w, _ = se.WSD(alpha=0.3, db_interval=50)(T_("linear_inp"), T_("offset"), T_("linear_tar"), masks)
+    assert w.item() == pytest.approx(float(g["WSD"]), rel=1e-5)
+
+
+def test_objectives_match_oracle_at_scale(se):
+    g = torch.Generator().manual_seed(11)
+    B, F, K = 6, 251, 257
+    pred = (torch.randn(B, F, K, generator=g) + 0.3).abs() * torch.rand(B, F, K, generator=g)
+    pred[0, :5] = -1.0                                     # relu branch
+    tar = torch.rand(B, F, K, generator=g) * 2
+    frames = torch.LongTensor([251, 200, 1, 77, 251, 130])
+    masks = sp.length_masks(frames)
+    masks = torch.cat([masks, masks.new_zeros(B, F - masks.shape[1])], 1)
+    p_ref = pred.clone().requires_grad_(True)
+    ref, _ = sp.sisdr_spectral(p_ref, tar, masks)
+    ref.backward()
+    p = pred.cuda().requires_grad_(True)
+    loss, _ = se.SISDR()(predicted=p, linear_tar=tar.cuda(), stft_lengths=frames.cuda())
+    loss.backward()
+    assert loss.item() == pytest.approx(ref.item(), abs=1e-4)
+    np.testing.assert_allclose(p.grad.cpu().numpy(), p_ref.grad.numpy(), rtol=1e-3, atol=1e-8)
+    assert (p.grad[0, :5] == 0).all() and torch.isfinite(p.grad).all()
+    lp_ref = torch.randn(B, F, K, generator=g).requires_grad_(True)
+    r1 = sp.l1_logspectral(lp_ref, tar, masks)
+    r1.backward()
+    lp = lp_ref.detach().cuda().requires_grad_(True)
+    l1, _ = se.L1()(log_predicted=lp, linear_tar=tar.cuda(), stft_length_masks=masks.cuda())
+    l1.backward()
+    assert l1.item() == pytest.approx(r1.item(), rel=1e-5)
+    np.testing.assert_allclose(lp.grad.cpu().numpy(), lp_ref.grad.numpy(), rtol=1e-5, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------ waveform helpers
+def test_waveform_helpers_match_reference_golden(se, golden_dir):
+    g = np.load(os.path.join(golden_dir, "signal_path_ref.npz"))
+    T_ = lambda k: torch.from_numpy(g[k])
+    assert se.sisdr_eval(T_("ev_src"), T_("ev_tar")) == pytest.approx(float(g["sisdr_eval"]), abs=1e-3)
+    assert se.sisdr_eval(T_("ev_src").cuda(), T_("ev_src").cuda()) == pytest.approx(float(g["sisdr_eval_self"]), abs=0.5)
+    lengths = T_("nd_len").cuda()
+    masks = se.get_length_masks(lengths)
+    assert masks.dtype == torch.int64 and masks.shape == (3, 50)
+    np.testing.assert_array_equal(masks.cpu().numpy(), sp.length_masks(T_("nd_len")).numpy())
+    a, r = T_("nd_audio").cuda(), T_("nd_ref").cuda()
+    np.testing.assert_allclose(se.masked_normalize_decibel(a, -25, masks).cpu().numpy(), g["nd_scalar"], rtol=2e-5)
+    np.testing.assert_allclose(se.masked_normalize_decibel(a, r, masks).cpu().numpy(), g["nd_tensor"], rtol=2e-5)
+    np.testing.assert_allclose(se.masked_normalize_decibel(a, r, lengths).cpu().numpy(), g["nd_tensor"], rtol=2e-5)
+    np.testing.assert_array_equal(se.get_length_masks(T_("stft_len").cuda()).cpu().numpy(), g["masks"])
+
+
+# ------------------------------------------------------------------------------ heads
+def test_heads_match_reference_golden(se, golden_dir):
+    g = np.load(os.path.join(golden_dir, "signal_path_ref.npz"))
+    T_ = lambda k: torch.from_numpy(g[k]).cuda()
+    head = se.LinearResidual(input_size=9, output_size=9).cuda()
+    head.load_state_dict({"linear.weight": T_("lr_weight"), "linear.bias": T_("lr_bias")})
+    pred, res = head(features=T_("lr_feats"), linears=T_("lr_linears"))
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), g["lr_predicted"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(res["offset"].detach().cpu().numpy(), g["lr_offset"], rtol=1e-4, atol=1e-6)
+    lin = se.Linear(9, 9, activation="ReLU").cuda()
+    lin.load_state_dict({"linear.weight": T_("li_weight"), "linear.bias": T_("li_bias")})
+    np.testing.assert_allclose(lin(features=T_("lr_feats"))[0].detach().cpu().numpy(), g["li_predicted"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("D,act,cmvn", [(257, "Sigmoid", True), (201, "ReLU", False), (513, "Sigmoid", True), (120, "Identity", True)])
+def test_head_forward_backward_match_torch_fp32(se, D, act, cmvn):
+    g = torch.Generator().manual_seed(D)
+    B, F, K = 3, 101, (D if D != 120 else 201)
+    feats = torch.randn(B, F, D, generator=g) * 2 - 3
+    linears = torch.rand(B, F, K, generator=g)
+    torch.manual_seed(1)
+    head = se.LinearResidual(input_size=D, output_size=K, activation=act, cmvn=cmvn).cuda()
+    w = head.linear.weight.detach().cpu().clone().requires_grad_(True)
+    b = head.linear.bias.detach().cpu().clone().requires_grad_(True)
+    ref_pred, ref_off = sp.linear_residual_head(feats, linears, w, b, activation=act, cmvn=cmvn)
+    upstream = torch.randn(B, F, K, generator=g)
+    (ref_pred * upstream).sum().backward()
+    pred, res = head(features=feats.cuda(), linears=linears.cuda())
+    (pred * upstream.cuda()).sum().backward()
+    np.testing.assert_allclose(res["offset"].detach().cpu().numpy(), ref_off.detach().numpy(), rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), ref_pred.detach().numpy(), rtol=1e-4, atol=2e-6)
+    scale = w.grad.abs().max().item()
+    np.testing.assert_allclose(head.linear.weight.grad.cpu().numpy(), w.grad.numpy(), rtol=1e-3, atol=1e-4 * scale)
+    np.testing.assert_allclose(head.linear.bias.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-4 * b.grad.abs().max().item())
+
+
+# ------------------------------------------------------------------------------ features (K1b)
+@pytest.mark.parametrize("n_fft", [400, 512])
+def test_mel_delta_cmvn_features_match_oracle(se, n_fft):
+    ora, mine = make_pair(se, n_fft)
+    _, wavs = synth(2, 12000, seed=21)
+    c = ora.get_feat_config
+    cfgs = [c("mel", 0, log=True, delta=2), c("mel", 1, log=True, delta=1, cmvn=True), c("linear", 0, log=True, delta=1),
+            c("linear", 1, log=True, cmvn=True), c("mel", 0)]
+    ref = ora(wavs, cfgs)
+    got = [g.cpu() for g in mine(wavs.cuda(), cfgs)]
+    assert got[0].shape[-1] == 120 and got[1].shape[-1] == 80
+    for r, g_, tol in zip(ref, got, (2e-3, 5e-3, 2e-2, 2e-2, None)):
+        assert r.shape == g_.shape
+        if tol is None:
+            assert rel_to_max(g_, r) < SPEC_RTOL
+        else:
+            # log features: compare where the bin is not 90 dB below the peak (log amplifies rounding noise there)
+            assert (g_ - r).abs().median() < 1e-4
+            assert torch.quantile((g_ - r).abs().flatten()[:1000000], 0.999) < tol
+
+
+def test_no_wav_call_and_cpu_inputs(se):
+    """run_downstream.py:163 (no-argument call) and runner.py:50-51 (CPU copy fed CPU audio)."""
+    _, mine = make_pair(se, 400)
+    c = mine.get_feat_config
+    outs = mine(feat_list=[c("mel", 0, log=True, delta=1, cmvn=True), c("linear", 1)])
+    assert outs[0].shape == (1, 101, 80) and outs[1].shape == (1, 101, 201)
+    import copy
+    cpu_pre = copy.deepcopy(mine).cpu()
+    out = cpu_pre(torch.randn(1, 1, 4000) * 0.1, [c("linear", 0, log=True)])[0]
+    assert out.device.type == "cpu" and out.shape == (1, 26, 201)
+
+
+# ------------------------------------------------------------------------------ whole step
+def _load_runner_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "runner_evaluate_ref.npz"))
+    items = [torch.from_numpy(g[f"item{i}"]) for i in range(len(g["lengths"]))]
+    return g, items
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_eval_step_matches_reference_runner_evaluate(se, golden_dir, use_graph):
+    """Fused engine vs the loss / SI-SDR the reference's own Runner.evaluate() produced."""
+    g, items = _load_runner_golden(golden_dir)
+    _, mine = make_pair(se, 512)
+    head = se.LinearResidual(input_size=257, output_size=257).cuda()
+    head.load_state_dict({"linear.weight": torch.from_numpy(g["weight"]), "linear.bias": torch.from_numpy(g["bias"])})
+    eng = se.EnhancementEngine(mine, head, log_features=True)
+    losses, scores = [], []
+    for i in range(0, len(items), 2):
+        lengths, wavs = sp.collate(items[i:i + 2])
+        if use_graph:
+            out = eng.eval_step_graph(lengths.cuda(), wavs.cuda())
+        else:
+            out = eng.eval_step(lengths.cuda(), wavs.cuda())
+        losses.append(out["loss_per_utt"].mean().item())
+        scores.append(out["sisdr"].mean().item())
+        if i == 0:
+            enh = out["wav_predicted"][0].cpu()
+            ref = torch.from_numpy(g["enhanced0"])
+            assert sisdr_db(enh[:len(ref)], ref) > 60.0
+            np.testing.assert_allclose(enh[:len(ref)].numpy(), g["enhanced0"], atol=2e-5)
+    assert np.mean(losses) == pytest.approx(float(g["loss"]), abs=2e-3)
+    assert np.mean(scores) == pytest.approx(float(g["scores"][0]), abs=SISDR_TOL_DB)
+
+
+def test_eval_step_matches_oracle_ragged_batch(se):
+    ora, mine = make_pair(se, 512)
+    B, T = 5, 24000
+    lengths = torch.LongTensor([24000, 20011, 16000, 9000, 5120])
+    lengths, wavs = synth(B, T, seed=77, lengths=lengths)
+    torch.manual_seed(1337)
+    head = se.LinearResidual(input_size=257, output_size=257).cuda()
+    c = ora.get_feat_config
+    ora.feat_list = [c("linear", 0, log=True), c("linear", 0, log=True), c("linear", 0), c("phase", 0), c("linear", 1), c("phase", 1)]
+    ref = sp.eval_step(ora, dict(weight=head.linear.weight.detach().cpu(), bias=head.linear.bias.detach().cpu()), lengths, wavs)
+    out = se.EnhancementEngine(mine, head).eval_step(lengths.cuda(), wavs.cuda())
+    np.testing.assert_allclose(out["sisdr"].cpu().numpy(), ref["sisdr"].numpy(), atol=SISDR_TOL_DB)
+    assert out["loss_per_utt"].mean().item() == pytest.approx(ref["loss"].item(), abs=2e-3)
+    for b in range(B):
+        n = int(lengths[b])
+        assert sisdr_db(out["wav_predicted"][b, :n].cpu(), ref["wav_predicted"][b, :n]) > 50.0
+
+
+def test_dropin_call_sequence_matches_oracle(se):
+    """The reference's own call sequence (runner.py:556-575) on the drop-in classes."""
+    ora, mine = make_pair(se, 400)
+    B, T = 3, 16000
+    lengths = torch.LongTensor([16000, 12345, 8000])
+    lengths, wavs = synth(B, T, seed=5, lengths=lengths)
+    c = ora.get_feat_config
+    fl = [c("mel", 0, log=True, delta=1, cmvn=True), c("linear", 0, log=True), c("linear", 0), c("phase", 0), c("linear", 1), c("phase", 1)]
+    ora.feat_list = fl
+    mine.feat_list = fl
+    torch.manual_seed(3)
+    head = se.LinearResidual(input_size=201, output_size=201).cuda()
+    hw = dict(weight=head.linear.weight.detach().cpu(), bias=head.linear.bias.detach().cpu())
+    ref = sp.eval_step(ora, hw, lengths, wavs)
+    d_wavs, d_len = wavs.cuda(), lengths.cuda()
+    with torch.no_grad():
+        feats_up, feats_down, linear_inp, phase_inp, linear_tar, phase_tar = mine(d_wavs)
+        predicted, model_results = head(features=feats_down, linears=linear_inp)
+        wav_predicted = se.decode_wav(mine, predicted, phase_inp, d_len, d_wavs[:, mine.channel_tar, :])
+        stft_len = d_len // mine._win_args["hop_length"] + 1
+        masks = se.get_length_masks(stft_len)
+        loss, _ = se.SISDR()(**dict(predicted=predicted, linear_tar=linear_tar, stft_length_masks=masks, wavs=d_wavs), **model_results)
+    assert loss.item() == pytest.approx(ref["loss"].item(), abs=2e-3)
+    for b in range(B):
+        n = int(lengths[b])
+        mine_db = se.sisdr_eval(wav_predicted[b, :n].cpu(), wavs[b, 1, :n])
+        assert mine_db == pytest.approx(ref["sisdr"][b].item(), abs=SISDR_TOL_DB)
+
+
+def test_train_step_gradients_match_oracle(se):
+    ora, mine = make_pair(se, 400)
+    B, T = 4, 8000
+    lengths = torch.LongTensor([8000, 6000, 4000, 7999])
+    lengths, wavs = synth(B, T, seed=8, lengths=lengths)
+    torch.manual_seed(5)
+    head = se.LinearResidual(input_size=201, output_size=201).cuda()
+    w = head.linear.weight.detach().cpu().clone().requires_grad_(True)
+    b = head.linear.bias.detach().cpu().clone().requires_grad_(True)
+    c = ora.get_feat_config
+    feats, lin_i, lin_t = ora(wavs, [c("linear", 0, log=True), c("linear", 0), c("linear", 1)])
+    pred, _ = sp.linear_residual_head(feats, lin_i, w, b)
+    masks = sp.length_masks(sp.stft_lengths(lengths, 160))
+    ref_loss, _ = sp.sisdr_spectral(pred, lin_t, masks)
+    ref_loss.backward()
+    eng = se.EnhancementEngine(mine, head)
+    loss = eng.train_step(lengths.cuda(), wavs.cuda(), se.SISDR())
+    loss.backward()
+    assert loss.item() == pytest.approx(ref_loss.item(), abs=2e-3)
+    gw = head.linear.weight.grad.cpu()
+    assert torch.nn.functional.cosine_similarity(gw.flatten(), w.grad.flatten(), dim=0).item() > 0.9999
+    np.testing.assert_allclose(gw.numpy(), w.grad.numpy(), rtol=5e-2, atol=2e-3 * w.grad.abs().max().item())
