@@ -170,6 +170,12 @@ int se_delta(float* x, int64_t n_utt, int64_t n_frames, int64_t D, int order, vo
 int se_cmvn_apply(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const float* mean, const float* std,
                   float eps, void* stream);
 
+/* ---- a1: host batch -> device (dataset.py:169-179 collate_fn output; runner.py:431, 556) ----
+ * Copies channels [0, n_ch) of a pinned HOST batch h_wavs (B, C, T) into a compact device batch
+ * d_wavs (B, n_ch, T) with one strided async copy (the path consumes the noisy and clean channels
+ * only; the scaled-noise channel never crosses PCIe). */
+int se_h2d_channels(const float* h_wavs, int64_t B, int64_t C, int64_t T, int64_t n_ch, float* d_wavs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

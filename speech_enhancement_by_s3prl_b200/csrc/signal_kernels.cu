@@ -211,4 +211,11 @@ int se_mask_istft(const float* noisy, const float* clean, int64_t utt_stride, co
     SE_DISPATCH_NFFT(n_fft, launch_mask_istft, a, st)
 }
 
+int se_h2d_channels(const float* h_wavs, int64_t B, int64_t C, int64_t T, int64_t n_ch, float* d_wavs, void* stream) {
+    SE_REQUIRE(h_wavs && d_wavs && B > 0 && T > 0 && n_ch > 0 && n_ch <= C, "bad argument");
+    SE_CUDA_CHECK(cudaMemcpy2DAsync(d_wavs, (size_t)(n_ch * T) * sizeof(float), h_wavs, (size_t)(C * T) * sizeof(float),
+                                    (size_t)(n_ch * T) * sizeof(float), (size_t)B, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return SE_OK;
+}
+
 }  // extern "C"
