@@ -48,8 +48,11 @@ extern "C" {
 #define SE_ACT_RELU 1
 #define SE_ACT_SIGMOID 2
 
+#define SE_OPT_FORCE_GENERIC 0     /* 1: use the generic tile kernels even where a fast path exists (tests) */
+
 int se_version(void);
 int se_last_error(char* h_buf, int n);
+int se_set_option(int key, int value);
 
 /* Create the per-device twiddle tables for n_fft and opt the kernels into their
  * shared-memory size.  Idempotent.  Call once before capturing a CUDA graph. */

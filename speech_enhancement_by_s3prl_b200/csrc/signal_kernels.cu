@@ -12,6 +12,11 @@
 using namespace sekern;
 using secommon::fail;
 
+namespace sefast {
+int launch_stft512(const StftArgs& a, cudaStream_t st);
+int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st);
+}
+
 namespace {
 
 struct BlockExec {
@@ -141,9 +146,16 @@ int check_geometry(int64_t n_utt, int64_t T, int n_fft, int hop) {
 
 }  // namespace
 
+static int g_force_generic = 0;
+
 extern "C" {
 
 int se_version(void) { return 100; }
+
+int se_set_option(int key, int value) {
+    if (key == SE_OPT_FORCE_GENERIC) { g_force_generic = value; return SE_OK; }
+    return fail(SE_ERR_BAD_ARG, "unknown option %d", key);
+}
 
 int se_last_error(char* h_buf, int n) {
     if (!h_buf || n <= 0) return SE_ERR_BAD_ARG;
@@ -170,6 +182,7 @@ int se_stft(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int 
     a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
     a.power = power; a.phase = phase; a.logp = logpower; a.log_eps = log_eps;
     cudaStream_t st = (cudaStream_t)stream;
+    if (n_fft == 512 && !g_force_generic) return sefast::launch_stft512(a, st);
     SE_DISPATCH_NFFT(n_fft, launch_stft, a, st)
 }
 
@@ -208,6 +221,7 @@ int se_mask_istft(const float* noisy, const float* clean, int64_t utt_stride, co
     SE_REQUIRE(out_stride >= a.out_len && out_stride >= pad_to, "out_stride=%lld too small", (long long)out_stride);
     cudaStream_t st = (cudaStream_t)stream;
     if (sums) SE_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * SE_NSUMS * n_utt, st));
+    if (n_fft == 512 && hop == 256 && a.n_frames >= 2 && !g_force_generic) return sefast::launch_mask_istft512(a, st);
     SE_DISPATCH_NFFT(n_fft, launch_mask_istft, a, st)
 }
 

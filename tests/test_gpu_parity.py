@@ -410,3 +410,50 @@ def test_train_step_gradients_match_oracle(se):
     gw = head.linear.weight.grad.cpu()
     assert torch.nn.functional.cosine_similarity(gw.flatten(), w.grad.flatten(), dim=0).item() > 0.9999
     np.testing.assert_allclose(gw.numpy(), w.grad.numpy(), rtol=5e-2, atol=2e-3 * w.grad.abs().max().item())
+
+
+# ------------------------------------------------------------------------------ fast paths vs generic tile kernels
+@pytest.mark.parametrize("T,hop_ms", [(16000, 16), (16001, 16), (12345, 16), (700, 16), (16000, 10), (9999, 8)])
+def test_fast512_stft_equals_generic_path(se, T, hop_ms):
+    from speech_enhancement_by_s3prl_b200 import _lib
+    mine = se.OnlinePreprocessor(win_ms=32, hop_ms=hop_ms, n_freq=257).cuda()
+    ora = OraclePre(win_ms=32, hop_ms=hop_ms, n_freq=257)
+    _, wavs = synth(3, T, seed=T)
+    c = mine.get_feat_config
+    cfgs = [c("linear", 0), c("phase", 0), c("linear", 1, log=True), c("linear", 2)]
+    lib = _lib.load()
+    fast = [t.cpu() for t in mine(wavs.cuda(), cfgs)]
+    try:
+        lib.se_set_option(0, 1)
+        slow = [t.cpu() for t in mine(wavs.cuda(), cfgs)]
+    finally:
+        lib.se_set_option(0, 0)
+    ref = ora(wavs, cfgs)
+    assert rel_to_max(fast[0], slow[0]) < 2e-6 and rel_to_max(fast[3], slow[3]) < 2e-6
+    assert rel_to_max(fast[0], ref[0]) < SPEC_RTOL
+    strong = ref[0] > 1e-5 * ref[0].amax()
+    dphi = torch.angle(torch.polar(torch.ones_like(ref[1]), fast[1] - ref[1]))
+    assert dphi[strong].abs().max() < 2e-3
+
+
+@pytest.mark.parametrize("T,B", [(16000, 3), (16001, 2), (9999, 3), (1100, 2), (64000, 5)])
+def test_fast512_mask_istft_equals_generic_path(se, T, B):
+    from speech_enhancement_by_s3prl_b200 import _lib, ops
+    mine = se.OnlinePreprocessor(win_ms=32, hop_ms=16, n_freq=257).cuda()
+    lengths = torch.LongTensor([T, max(300, T - 777), T // 2 + 3, T, T // 3 + 1][:B])
+    lengths, wavs = synth(B, T, seed=T + 5, lengths=lengths)
+    g = torch.Generator().manual_seed(4)
+    mask = torch.rand(B, T // 256 + 1, 257, generator=g).cuda()
+    lib = _lib.load()
+    args = (wavs.cuda(), 0, 1, mask, lengths.cuda(), 512, 256, mine._frame_window)
+    wav_f, sums_f = ops.mask_istft(*args, pad_to=T)
+    try:
+        lib.se_set_option(0, 1)
+        wav_s, sums_s = ops.mask_istft(*args, pad_to=T)
+    finally:
+        lib.se_set_option(0, 0)
+    assert (wav_f - wav_s).abs().max().item() < 2e-6
+    np.testing.assert_allclose(sums_f.cpu().numpy(), sums_s.cpu().numpy(), rtol=2e-5, atol=1e-9)
+    # without clean / sums / lengths
+    wav_n, none = ops.mask_istft(wavs.cuda(), 0, None, mask, None, 512, 256, mine._frame_window, pad_to=T, want_sums=False)
+    assert none is None and (wav_n - wav_s).abs().max().item() < 2e-6
