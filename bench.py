@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU oracle timing for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--head-precision", type=int, default=1, help="0 = fp32 SIMT head, 1 = TF32 tcgen05 head")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -205,7 +206,7 @@ def main():
     pre.channel_inp, pre.channel_tar = 0, 1
     torch.manual_seed(1337)
     head = se.LinearResidual(input_size=257, output_size=257).to(dev)
-    engine = se.EnhancementEngine(pre, head, log_features=True)
+    engine = se.EnhancementEngine(pre, head, log_features=True, precision=args.head_precision)
     T = int(SECONDS * SR)
     ring_host = [synth.batch(N_UTT, SECONDS, first_index=(rank * args.ring + r) * N_UTT) for r in range(min(args.ring, 4))]
     # device ring: the first few slots come from the host batches, the rest are level-preserving
@@ -332,7 +333,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "utterances_per_gpu": N_UTT, "seconds": SECONDS, "n_fft": N_FFT, "hop": HOP,
+                "config": {"workload": WORKLOAD, "head": "tf32 tcgen05 (fp32 accumulate)" if args.head_precision == 1 else "fp32 SIMT", "utterances_per_gpu": N_UTT, "seconds": SECONDS, "n_fft": N_FFT, "hop": HOP,
                            "launch": "eager" if args.eager else "cuda-graph replay",
                            "l2": f"inputs rotate over {args.ring} distinct device batches ({args.ring * N_UTT * 3 * T * 4 / 1e6:.0f} MB > 126 MB L2); no explicit flush",
                            "parallelism": f"dp{world} (utterance-sharded, no data-path collective)"},

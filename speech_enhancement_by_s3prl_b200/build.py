@@ -14,6 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libse_b200.so")
+HASH_PATH = LIB_PATH + ".sha256"
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -28,12 +29,23 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def source_hash():
+    """sha256 over csrc/ and include/ (file names + contents): mtimes do not survive the copy to the GPU box."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        if os.path.isfile(path):
+            h.update(os.path.basename(path).encode())
+            with open(path, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
-    return any(os.path.getmtime(d) > built for d in deps)
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build_library(force=False, verbose=False):
@@ -61,6 +73,8 @@ def build_library(force=False, verbose=False):
     tmp = LIB_PATH + ".tmp"
     subprocess.check_call([nvcc, *ARCH_FLAGS, "-shared", "-o", tmp, *objs, "-lcudart"])
     os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash())
     return LIB_PATH
 
 

@@ -1,0 +1,266 @@
+// libse_b200.so -- tensor-core mask head (precision = 1):  offset = act(cmvn(x) W^T + b)  [* linears]
+//
+// tcgen05 (5th-gen tensor core) TF32 GEMM with the accumulator in tensor memory:
+//   * CTA tile: 128 rows (frames) x BN columns (BN <= 512, all of Dout when it fits) x 32-deep k-blocks
+//   * warps 0-3  producers: read x / W rows with coalesced 128-byte loads, apply the per-utterance CMVN
+//                (model.py:30) on the fly, round to TF32 (cvt.rna) and store into the K-major
+//                SWIZZLE_128B shared-memory layout the MMA descriptors expect; later the same four
+//                warps run the epilogue (tcgen05.ld -> +bias -> activation -> coalesced stores)
+//   * warp 4     allocates TMEM and issues tcgen05.mma (one elected lane), committing each stage to
+//                its "empty" mbarrier and the finished accumulator to the epilogue barrier
+// Operands go through registers instead of TMA on purpose: the rows of the (B, F, K) feature tensor are
+// K*4 = 1028 bytes apart (not 16-byte aligned, so no tensor map can describe them), and the CMVN has to
+// be applied between the load and the MMA anyway.
+#include "se_common.cuh"
+
+using secommon::fail;
+
+namespace {
+
+constexpr int BM = 128, BK = 32, kStagesMax = 4;
+constexpr int kProducerThreads = 128, kThreads = 160;            // 4 producer/epilogue warps + 1 MMA warp
+constexpr unsigned kSpinLimit = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > kSpinLimit) __trap();                          // never hang the GPU on a protocol bug
+    }
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// rows are 128 B apart, 8-row groups 1024 B apart (SBO), 16-byte chunks XOR-swizzled with (row & 7).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                                       // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                             // SBO
+    d |= (uint64_t)1 << 46;                                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                                       // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {           // kind::tf32, fp32 accumulate, A/B K-major, M = 128
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float activate(float z, int act) {
+    if (act == SE_ACT_RELU) return z > 0.f ? z : 0.f;
+    if (act == SE_ACT_SIGMOID) return 1.0f / (1.0f + __expf(-z));
+    return z;
+}
+
+struct HeadArgs {
+    const float* x; const float* mean; const float* stdv; float cmvn_eps;
+    const float* W; const float* bias;
+    long long R; int n_frames, Din, Dout, act;
+    const float* linears; float* offset_out; float* pred_out;
+    int bn;          // columns per CTA (multiple of 16, <= 512)
+    int tmem_cols;   // power of two >= bn
+    int stages, kblocks;
+};
+
+// element (row, kk) of a [rows][32 fp32] K-major SWIZZLE_128B tile
+__device__ __forceinline__ int sw128(int row, int kk) { return row * 32 + ((((kk >> 2) ^ (row & 7)) << 2) | (kk & 3)); }
+
+__global__ void __launch_bounds__(kThreads, 1) linear_head_tc_kernel(HeadArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: [stages][A 128x32 | B bn x 32] fp32, then barriers, tmem slot, epilogue staging
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int stage_floats = (BM + a.bn) * BK;
+    float* tiles = reinterpret_cast<float*>(base);
+    float* stage_out = tiles + (size_t)a.stages * stage_floats;                  // 4 warps x 32 x 33 floats
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + 4 * 32 * 33);
+    uint64_t* empty = full + kStagesMax;
+    uint64_t* accum_full = empty + kStagesMax;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * a.bn;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===================== producers =====================
+        // each warp fills rows [32*warp, 32*warp+32) of A and rows warp, warp+4, ... of B; lane = k within the block
+        const long long u_first = r0 / a.n_frames;                        // a 128-row tile spans at most ... utterances; handled per row
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+            const int s = kb % a.stages;
+            if (kb >= a.stages) mbar_wait(&empty[s], ((kb / a.stages) - 1) & 1);
+            float* As = tiles + (size_t)s * stage_floats;
+            float* Bs = As + BM * BK;
+            const int k = kb * BK + lane;
+            const bool kin = k < a.Din;
+            // per-utterance CMVN constants for this column (reloaded when the utterance changes)
+            long long u_cur = -1;
+            float mu = 0.f, inv = 1.f;
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const int row = warp * 32 + i;
+                const long long r = r0 + row;
+                float v = 0.f;
+                if (kin && r < a.R) {
+                    v = __ldg(a.x + r * a.Din + k);
+                    if (a.mean) {
+                        const long long u = r / a.n_frames;
+                        if (u != u_cur) { u_cur = u; mu = __ldg(a.mean + u * a.Din + k); inv = 1.0f / (__ldg(a.stdv + u * a.Din + k) + a.cmvn_eps); }
+                        v = (v - mu) * inv;
+                    }
+                }
+                As[sw128(row, lane)] = to_tf32(v);
+            }
+            for (int row = warp; row < a.bn; row += 4) {
+                const int n = n0 + row;
+                const float w = (kin && n < a.Dout) ? __ldg(a.W + (long long)n * a.Din + k) : 0.f;
+                Bs[sw128(row, lane)] = to_tf32(w);
+            }
+            (void)u_first;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+        // ===================== epilogue =====================
+        mbar_wait(accum_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* st = stage_out + warp * 32 * 33;
+        for (int c0 = 0; c0 < a.bn; c0 += 32) {
+            if (n0 + c0 >= a.Dout) break;
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) st[lane * 33 + c] = __uint_as_float(acc[c]);
+            __syncwarp();
+            const int n = n0 + c0 + lane;
+            const bool nin = n < a.Dout && (c0 + lane) < a.bn;
+            const float bz = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
+            for (int rr = 0; rr < 32; ++rr) {
+                const long long r = r0 + warp * 32 + rr;
+                if (r >= a.R) break;
+                if (nin) {
+                    const float o = activate(st[rr * 33 + lane] + bz, a.act);
+                    if (a.offset_out) a.offset_out[r * a.Dout + n] = o;
+                    if (a.pred_out) a.pred_out[r * a.Dout + n] = __ldg(a.linears + r * a.Dout + n) * o;
+                }
+            }
+            __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===================== MMA issuer =====================
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+            const int s = kb % a.stages;
+            mbar_wait(&full[s], (kb / a.stages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_floats);
+                const uint32_t b_addr = a_addr + BM * BK * 4;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint64_t adesc = make_desc(a_addr + kk * 32);
+                    for (int nn = 0; nn < a.bn; nn += 256) {
+                        const int nw = min(256, a.bn - nn);
+                        const uint64_t bdesc = make_desc(b_addr + nn * 128 + kk * 32);
+                        umma_tf32(tmem_base + nn, adesc, bdesc, make_idesc(nw), (kb | kk) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);                                   // stage reusable once these MMAs have read it
+                if (kb == a.kblocks - 1) umma_commit(accum_full);         // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace
+
+namespace sehead {
+
+int launch_linear_head_tc(const float* x, const float* mean, const float* stdv, float cmvn_eps, const float* W, const float* b,
+                          long long R, int n_frames, int Din, int Dout, int act, const float* linears, float* offset_out,
+                          float* pred_out, cudaStream_t st) {
+    HeadArgs a{};
+    a.x = x; a.mean = mean; a.stdv = stdv; a.cmvn_eps = cmvn_eps; a.W = W; a.bias = b;
+    a.R = R; a.n_frames = n_frames; a.Din = Din; a.Dout = Dout; a.act = act;
+    a.linears = linears; a.offset_out = offset_out; a.pred_out = pred_out;
+    const int chunks = (Dout + 511) / 512;
+    a.bn = ((((Dout + chunks - 1) / chunks) + 15) / 16) * 16;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < a.bn) a.tmem_cols *= 2;
+    a.kblocks = (Din + BK - 1) / BK;
+    const size_t stage_bytes = (size_t)(BM + a.bn) * BK * 4;
+    int stages = (int)((200 * 1024 - 4 * 32 * 33 * 4 - 256 - 1024) / stage_bytes);
+    a.stages = stages > kStagesMax ? kStagesMax : stages;
+    if (a.stages > a.kblocks) a.stages = a.kblocks;
+    if (a.stages < 1) return fail(SE_ERR_UNSUPPORTED, "head tile does not fit in shared memory (Dout=%d)", Dout);
+    const size_t smem = 1024 + (size_t)a.stages * stage_bytes + 4 * 32 * 33 * 4 + 256;
+    static bool opted = false;
+    if (!opted) {
+        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        opted = true;
+    }
+    dim3 grid((unsigned)((R + BM - 1) / BM), (unsigned)chunks);
+    linear_head_tc_kernel<<<grid, kThreads, smem, st>>>(a);
+    return secommon::check_launch("linear_head_tc_kernel");
+}
+
+}  // namespace sehead

@@ -9,6 +9,12 @@
 using secommon::fail;
 using secommon::block_accumulate_to;
 
+namespace sehead {
+int launch_linear_head_tc(const float* x, const float* mean, const float* stdv, float cmvn_eps, const float* W, const float* b,
+                          long long R, int n_frames, int Din, int Dout, int act, const float* linears, float* offset_out,
+                          float* pred_out, cudaStream_t st);
+}
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -588,8 +594,11 @@ int se_linear_head_fwd(const float* x, const float* mean, const float* std, floa
     SE_REQUIRE(offset_out || predicted_out, "no output requested");
     SE_REQUIRE(!predicted_out || linears, "predicted_out needs linears");
     SE_REQUIRE(act >= SE_ACT_IDENTITY && act <= SE_ACT_SIGMOID, "unknown activation %d", act);
-    if (precision != 0) return fail(SE_ERR_UNSUPPORTED, "precision=%d: only the fp32 SIMT head is built", precision);
     const long long R = n_utt * n_frames;
+    if (precision == 1)
+        return sehead::launch_linear_head_tc(x, mean, std, cmvn_eps, W, b, R, (int)n_frames, (int)D_in, (int)D_out, act, linears,
+                                             offset_out, predicted_out, (cudaStream_t)stream);
+    if (precision != 0) return fail(SE_ERR_BAD_ARG, "precision=%d (0 = fp32 SIMT, 1 = TF32 tcgen05)", precision);
     dim3 grid((unsigned)((D_out + BN - 1) / BN), (unsigned)((R + BM - 1) / BM));
     linear_head_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mean, std, cmvn_eps, W, b, R, (int)n_frames, (int)D_in,
                                                                    (int)D_out, act, linears, offset_out, predicted_out);

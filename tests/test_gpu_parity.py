@@ -457,3 +457,43 @@ def test_fast512_mask_istft_equals_generic_path(se, T, B):
     # without clean / sums / lengths
     wav_n, none = ops.mask_istft(wavs.cuda(), 0, None, mask, None, 512, 256, mine._frame_window, pad_to=T, want_sums=False)
     assert none is None and (wav_n - wav_s).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------------------ tensor-core head (tcgen05, TF32)
+@pytest.mark.parametrize("B,F,Din,Dout,act,cmvn", [(3, 101, 257, 257, "Sigmoid", True), (2, 300, 201, 201, "ReLU", False),
+                                                   (1, 77, 513, 513, "Sigmoid", True), (2, 128, 120, 201, "Identity", True),
+                                                   (64, 251, 257, 257, "Sigmoid", True)])
+def test_tensor_core_head_matches_fp32_head(se, B, F, Din, Dout, act, cmvn):
+    from speech_enhancement_by_s3prl_b200 import ops
+    g = torch.Generator().manual_seed(Din + F)
+    feats = (torch.randn(B, F, Din, generator=g) * 2 - 3).cuda()
+    linears = torch.rand(B, F, Dout, generator=g).cuda()
+    torch.manual_seed(2)
+    lin = torch.nn.Linear(Din, Dout).cuda()
+    mean = std = None
+    if cmvn:
+        mean, std = ops.cmvn_stats(feats)
+    off0, pred0 = ops.linear_head_fused(feats, lin.weight, lin.bias, act, mean, std, 1e-6, linears=linears, precision=0)
+    off1, pred1 = ops.linear_head_fused(feats, lin.weight, lin.bias, act, mean, std, 1e-6, linears=linears, precision=1)
+    torch.cuda.synchronize()
+    # TF32 operands (10-bit mantissa, round-to-nearest), fp32 accumulation
+    scale = max(1.0, feats.abs().max().item() * 0.1)              # error scales with |x| |w| sqrt(Din)
+    assert (off1 - off0).abs().max().item() < 3e-3 * scale
+    assert (pred1 - pred0).abs().max().item() < 3e-3 * scale
+    assert (off1 - off0).abs().mean().item() < 3e-4 * scale
+
+
+def test_eval_step_with_tensor_core_head_keeps_sisdr_parity(se, golden_dir):
+    g, items = _load_runner_golden(golden_dir)
+    _, mine = make_pair(se, 512)
+    head = se.LinearResidual(input_size=257, output_size=257).cuda()
+    head.load_state_dict({"linear.weight": torch.from_numpy(g["weight"]), "linear.bias": torch.from_numpy(g["bias"])})
+    eng = se.EnhancementEngine(mine, head, log_features=True, precision=1)
+    losses, scores = [], []
+    for i in range(0, len(items), 2):
+        lengths, wavs = sp.collate(items[i:i + 2])
+        out = eng.eval_step(lengths.cuda(), wavs.cuda())
+        losses.append(out["loss_per_utt"].mean().item())
+        scores.append(out["sisdr"].mean().item())
+    assert np.mean(losses) == pytest.approx(float(g["loss"]), abs=5e-3)
+    assert np.mean(scores) == pytest.approx(float(g["scores"][0]), abs=SISDR_TOL_DB)
