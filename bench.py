@@ -273,11 +273,13 @@ def main():
             if i == 3:
                 for v in ev.values():
                     v.clear()
-            feats = timed("stft", lambda: ops.stft(wavs, 0, N_FFT, HOP, window, power=False, logpower=True)["logpower"])
-            mean, std = timed("cmvn_stats", lambda: ops.cmvn_stats(feats))
-            mask, _ = timed("head", lambda: ops.linear_head_fused(feats, head.linear.weight, head.linear.bias, head.activation,
-                                                                  mean, std, head.eps, precision=engine.precision))
-            wav, sums = timed("mask_istft", lambda: ops.mask_istft(wavs, 0, 1, mask, lengths, N_FFT, HOP, window, pad_to=T))
+            feats = timed("stft", lambda: ops.stft_padded(wavs, 0, N_FFT, HOP, window, logpower=True))
+            mean, std = timed("cmvn_stats", lambda: ops.cmvn_stats_padded(feats, K))
+            wpad = engine._padded_weight()
+            mask = timed("head", lambda: ops.linear_head_padded(feats, K, wpad, head.linear.bias, head.activation, mean, std,
+                                                                head.eps, precision=engine.precision))
+            wav, sums = timed("mask_istft", lambda: ops.mask_istft(wavs, 0, 1, mask, lengths, N_FFT, HOP, window, pad_to=T,
+                                                                   mask_padded=True))
             timed("finalize", lambda: ops.finalize_metrics(sums, lengths, T, wav=wav))
     torch.cuda.synchronize()
     kernel_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in ev.items()}

@@ -70,6 +70,11 @@ int se_prepare(int n_fft);
  *   logpower = log(power + log_eps)   (feature config log: True) */
 int se_stft(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop,
             const float* window, float log_eps, float* power, float* phase, float* logpower, void* stream);
+/* same, with spec_stride floats between consecutive frames of every output (>= K).  A stride that is a
+ * multiple of 4 floats makes the rows 16-byte aligned for the tensor-core head's vector loads. */
+int se_stft_strided(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop,
+                    const float* window, float log_eps, float* power, float* phase, float* logpower,
+                    int64_t spec_stride, void* stream);
 
 /* ---- iSTFT from (power, phase) --------------------------------------------------
  * Replaces OnlinePreprocessor.istft(linears, phases) (call site runner.py:267):
@@ -89,6 +94,10 @@ int se_istft(const float* power, const float* phase, int64_t n_utt, int64_t n_fr
 int se_mask_istft(const float* noisy, const float* clean, int64_t utt_stride, const float* mask,
                   const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
                   float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int want_spec, void* stream);
+int se_mask_istft_strided(const float* noisy, const float* clean, int64_t utt_stride, const float* mask,
+                          int64_t mask_stride, const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop,
+                          const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, double* sums,
+                          int want_spec, void* stream);
 
 /* ---- K3 epilogue: level normalisation + metrics from the sums --------------------
  * Per utterance: gain so that the masked mean-square of wav matches the clean
@@ -156,6 +165,15 @@ int se_cmvn_stats(const float* x, int64_t n_utt, int64_t n_frames, int64_t D, fl
 int se_linear_head_fwd(const float* x, const float* mean, const float* std, float cmvn_eps, const float* W,
                        const float* b, int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int act,
                        const float* linears, float* offset_out, float* predicted_out, int precision, void* stream);
+/* strided forms used by the fused evaluation step: ldx = floats between rows of x, ld_stats between rows of
+ * mean / std, ldw between rows of W, ld_out between rows of linears / offset_out / predicted_out.  With
+ * precision 1 and every stride a multiple of 4 floats (16-byte aligned rows) the producers use 128-bit loads. */
+int se_cmvn_stats_strided(const float* x, int64_t ldx, int64_t n_utt, int64_t n_frames, int64_t D, float* mean,
+                          float* std, int64_t ld_stats, void* stream);
+int se_linear_head_fwd_strided(const float* x, int64_t ldx, const float* mean, const float* std, int64_t ld_stats,
+                               float cmvn_eps, const float* W, int64_t ldw, const float* b, int64_t n_utt,
+                               int64_t n_frames, int64_t D_in, int64_t D_out, int act, const float* linears,
+                               float* offset_out, float* predicted_out, int64_t ld_out, int precision, void* stream);
 int se_linear_head_bwd(const float* x, const float* mean, const float* std, float cmvn_eps, const float* W,
                        const float* offset, const float* grad_offset, int64_t n_utt, int64_t n_frames,
                        int64_t D_in, int64_t D_out, int act, float* grad_W, float* grad_b, void* stream);

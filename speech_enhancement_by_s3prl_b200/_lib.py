@@ -25,8 +25,10 @@ _SIGNATURES = {
     "se_prepare": [c_int],
     "se_set_option": [c_int, c_int],
     "se_stft": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_f, c_f, c_f, c_f],
+    "se_stft_strided": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_f, c_f, c_f, i64, c_f],
     "se_istft": [c_f, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f],
     "se_mask_istft": [c_f, c_f, i64, c_f, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
+    "se_mask_istft_strided": [c_f, c_f, i64, c_f, i64, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
     "se_finalize_metrics": [c_f, c_f, i64, i64, c_float, c_f, i64, i64, c_f, c_f, c_f, c_f],
     "se_sisdr_spec_fwd": [c_f, c_f, c_f, i64, i64, i64, c_float, c_f, c_f, c_f],
     "se_sisdr_spec_bwd": [c_f, c_f, c_f, i64, i64, i64, c_float, c_f, c_f, c_f, c_f],
@@ -37,6 +39,8 @@ _SIGNATURES = {
     "se_length_masks": [c_f, i64, i64, c_f, c_f],
     "se_cmvn_stats": [c_f, i64, i64, i64, c_f, c_f, c_f],
     "se_linear_head_fwd": [c_f, c_f, c_f, c_float, c_f, c_f, i64, i64, i64, i64, c_int, c_f, c_f, c_f, c_int, c_f],
+    "se_cmvn_stats_strided": [c_f, i64, i64, i64, i64, c_f, c_f, i64, c_f],
+    "se_linear_head_fwd_strided": [c_f, i64, c_f, c_f, i64, c_float, c_f, i64, c_f, i64, i64, i64, i64, c_int, c_f, c_f, c_f, i64, c_int, c_f],
     "se_linear_head_bwd": [c_f, c_f, c_f, c_float, c_f, c_f, c_f, i64, i64, i64, i64, c_int, c_f, c_f, c_f],
     "se_mel": [c_f, i64, i64, c_f, i64, c_int, c_float, c_f, i64, c_f],
     "se_delta": [c_f, i64, i64, i64, c_int, c_f],

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft512_kernel(StftArgs a, long l
         fft256<-1>(v, xbuf, j, tw, hmask);
         float2 zm[8];
         fetch_mirror(v, lane, zm);
-        const long long o = gg * K;
+        const long long o = gg * a.spec_stride;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int k = j + 16 * q;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads3, 3) mask_istft512_kernel(MaskIstftAr
     for (int f = b0 - 1; f <= b1; ++f) {
         const bool halo = (f == b0 - 1);
         const bool own = spec && (!halo || f == 0) && f < valid_frames;
-        const float* mk = a.mask + ((long long)u * F + f) * K;
+        const float* mk = a.mask + ((long long)u * F + f) * a.mask_stride;
         float pta[8], ptb[8], pt128 = 0.0f;
         if (own) {                                                  // |STFT(clean)|^2 for the spectral SI-SDR sums
             float2 c[16];

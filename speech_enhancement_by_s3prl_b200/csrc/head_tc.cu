@@ -18,7 +18,8 @@ using secommon::fail;
 namespace {
 
 constexpr int BM = 128, BK = 32, kStagesMax = 4;
-constexpr int kProducerThreads = 128, kThreads = 160;            // 4 producer/epilogue warps + 1 MMA warp
+constexpr int kProducerWarps = 8, kProducerThreads = kProducerWarps * 32, kThreads = kProducerThreads + 32;   // + 1 MMA warp
+constexpr int kMaxWRows = 8;                                      // W rows per producer thread: bn <= 256 -> 8
 constexpr unsigned kSpinLimit = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,7 +89,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 __device__ __forceinline__ float activate(float z, int act) {
     if (act == SE_ACT_RELU) return z > 0.f ? z : 0.f;
-    if (act == SE_ACT_SIGMOID) return 1.0f / (1.0f + __expf(-z));
+    if (act == SE_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-z));
     return z;
 }
 
@@ -97,7 +98,9 @@ struct HeadArgs {
     const float* W; const float* bias;
     long long R; int n_frames, Din, Dout, act;
     const float* linears; float* offset_out; float* pred_out;
-    int bn;          // columns per CTA (multiple of 16, <= 512)
+    long long ldx, ld_stats, ldw, ld_out;   // row strides (floats)
+    int vec;         // 1: every stride and base pointer allows 128-bit loads
+    int bn;          // columns per CTA (multiple of 16, <= 256)
     int tmem_cols;   // power of two >= bn
     int stages, kblocks;
 };
@@ -105,14 +108,14 @@ struct HeadArgs {
 // element (row, kk) of a [rows][32 fp32] K-major SWIZZLE_128B tile
 __device__ __forceinline__ int sw128(int row, int kk) { return row * 32 + ((((kk >> 2) ^ (row & 7)) << 2) | (kk & 3)); }
 
-__global__ void __launch_bounds__(kThreads, 1) linear_head_tc_kernel(HeadArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve: [stages][A 128x32 | B bn x 32] fp32, then barriers, tmem slot, epilogue staging
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+__global__ void __launch_bounds__(kThreads, 2) linear_head_tc_kernel(HeadArgs a) {
+    // [stages][A 128x32 | B bn x 32] fp32 (1024-byte aligned: SWIZZLE_128B atoms), epilogue staging, barriers, TMEM slot
+    extern __shared__ __align__(1024) float tiles[];
     const int stage_floats = (BM + a.bn) * BK;
-    float* tiles = reinterpret_cast<float*>(base);
-    float* stage_out = tiles + (size_t)a.stages * stage_floats;                  // 4 warps x 32 x 33 floats
-    uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + 4 * 32 * 33);
+    float* stage_out = tiles;                                 // epilogue staging (8 warps x 32 x 33 floats) reuses the operand
+                                                              // ring: every MMA has finished reading it by then
+    const int ring_floats = max(a.stages * stage_floats, kProducerWarps * 32 * 33);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + ring_floats);
     uint64_t* empty = full + kStagesMax;
     uint64_t* accum_full = empty + kStagesMax;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
@@ -122,11 +125,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_tc_kernel(HeadArgs a)
     const int n0 = blockIdx.y * a.bn;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
+        if (smem_u32(tiles) & 1023) __trap();                                    // swizzle atoms need the alignment
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], kProducerWarps); mbar_init(&empty[s], 1); }
         mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == kProducerWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -135,66 +139,144 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_tc_kernel(HeadArgs a)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < kProducerWarps) {
         // ===================== producers =====================
-        // each warp fills rows [32*warp, 32*warp+32) of A and rows warp, warp+4, ... of B; lane = k within the block
-        const long long u_first = r0 / a.n_frames;                        // a 128-row tile spans at most ... utterances; handled per row
-        for (int kb = 0; kb < a.kblocks; ++kb) {
-            const int s = kb % a.stages;
-            if (kb >= a.stages) mbar_wait(&empty[s], ((kb / a.stages) - 1) & 1);
-            float* As = tiles + (size_t)s * stage_floats;
-            float* Bs = As + BM * BK;
-            const int k = kb * BK + lane;
-            const bool kin = k < a.Din;
-            // per-utterance CMVN constants for this column (reloaded when the utterance changes)
-            long long u_cur = -1;
-            float mu = 0.f, inv = 1.f;
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                const int row = warp * 32 + i;
-                const long long r = r0 + row;
-                float v = 0.f;
-                if (kin && r < a.R) {
-                    v = __ldg(a.x + r * a.Din + k);
-                    if (a.mean) {
-                        const long long u = r / a.n_frames;
-                        if (u != u_cur) { u_cur = u; mu = __ldg(a.mean + u * a.Din + k); inv = 1.0f / (__ldg(a.stdv + u * a.Din + k) + a.cmvn_eps); }
-                        v = (v - mu) * inv;
+        const int t = threadIdx.x;
+        if (a.vec) {
+            // 128-bit path: thread -> 16-byte chunk c of the k-block, rows rbase + 32 i.  Each quarter-warp reads one
+            // row's 128 B; every load of the k-block is issued before the first one is consumed.
+            const int c = t & 7, rbase = t >> 3;
+            // per-row constants, independent of the k-block: source pointers and the utterance of each A row
+            const float* xrow[4];
+            int urow[4];
+            {
+                const long long u0 = r0 / a.n_frames;
+                const int rem0 = (int)(r0 - u0 * a.n_frames);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = rbase + 32 * i;
+                    xrow[i] = (r0 + row < a.R) ? a.x + (r0 + row) * a.ldx : nullptr;
+                    urow[i] = (int)u0 + (rem0 + row) / a.n_frames;
+                }
+            }
+            const float* wrow[kMaxWRows];
+#pragma unroll
+            for (int i = 0; i < kMaxWRows; ++i) {
+                const int row = rbase + 32 * i;
+                wrow[i] = (row < a.bn && n0 + row < a.Dout) ? a.W + (long long)(n0 + row) * a.ldw : nullptr;
+            }
+            for (int kb = 0; kb < a.kblocks; ++kb) {
+                const int s = kb % a.stages;
+                if (kb >= a.stages) mbar_wait(&empty[s], ((kb / a.stages) - 1) & 1);
+                float* As = tiles + s * stage_floats;
+                float* Bs = As + BM * BK;
+                const int k = kb * BK + 4 * c;
+                const bool kin = k < a.Din;
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 xa[4], wb[kMaxWRows];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xa[i] = (kin && xrow[i]) ? __ldg(reinterpret_cast<const float4*>(xrow[i] + k)) : zero4;
+#pragma unroll
+                for (int i = 0; i < kMaxWRows; ++i) wb[i] = (kin && wrow[i]) ? __ldg(reinterpret_cast<const float4*>(wrow[i] + k)) : zero4;
+                const bool k1 = k + 1 < a.Din, k2 = k + 2 < a.Din, k3 = k + 3 < a.Din;
+                int u_cur = -1;
+                float4 mu = zero4, inv = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = rbase + 32 * i;
+                    float4 v = xa[i];
+                    if (a.mean && kin && xrow[i]) {
+                        if (urow[i] != u_cur) {
+                            u_cur = urow[i];
+                            mu = __ldg(reinterpret_cast<const float4*>(a.mean + (long long)u_cur * a.ld_stats + k));
+                            const float4 sd = __ldg(reinterpret_cast<const float4*>(a.stdv + (long long)u_cur * a.ld_stats + k));
+                            inv = make_float4(__fdividef(1.0f, sd.x + a.cmvn_eps), __fdividef(1.0f, sd.y + a.cmvn_eps),
+                                              __fdividef(1.0f, sd.z + a.cmvn_eps), __fdividef(1.0f, sd.w + a.cmvn_eps));
+                        }
+                        v = make_float4((v.x - mu.x) * inv.x, (v.y - mu.y) * inv.y, (v.z - mu.z) * inv.z, (v.w - mu.w) * inv.w);
+                    }
+                    v = make_float4(to_tf32(v.x), k1 ? to_tf32(v.y) : 0.f, k2 ? to_tf32(v.z) : 0.f, k3 ? to_tf32(v.w) : 0.f);
+                    *reinterpret_cast<float4*>(As + row * 32 + ((c ^ (row & 7)) << 2)) = v;
+                }
+#pragma unroll
+                for (int i = 0; i < kMaxWRows; ++i) {
+                    const int row = rbase + 32 * i;
+                    if (row < a.bn) {
+                        float4 v = wb[i];
+                        v = make_float4(to_tf32(v.x), k1 ? to_tf32(v.y) : 0.f, k2 ? to_tf32(v.z) : 0.f, k3 ? to_tf32(v.w) : 0.f);
+                        *reinterpret_cast<float4*>(Bs + row * 32 + ((c ^ (row & 7)) << 2)) = v;
                     }
                 }
-                As[sw128(row, lane)] = to_tf32(v);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
             }
-            for (int row = warp; row < a.bn; row += 4) {
-                const int n = n0 + row;
-                const float w = (kin && n < a.Dout) ? __ldg(a.W + (long long)n * a.Din + k) : 0.f;
-                Bs[sw128(row, lane)] = to_tf32(w);
+        } else {
+            // scalar path (dense rows that are only 4-byte aligned): warp -> rows, lane = k within the block
+            for (int kb = 0; kb < a.kblocks; ++kb) {
+                const int s = kb % a.stages;
+                if (kb >= a.stages) mbar_wait(&empty[s], ((kb / a.stages) - 1) & 1);
+                float* As = tiles + s * stage_floats;
+                float* Bs = As + BM * BK;
+                const int k = kb * BK + lane;
+                const bool kin = k < a.Din;
+                const long long u0 = r0 / a.n_frames;
+                const int rem0 = (int)(r0 - u0 * a.n_frames);
+                int u_cur = -1;
+                float mu = 0.f, inv = 1.f;
+#pragma unroll 4
+                for (int i = 0; i < BM / kProducerWarps; ++i) {
+                    const int row = warp * (BM / kProducerWarps) + i;
+                    const long long r = r0 + row;
+                    float v = 0.f;
+                    if (kin && r < a.R) {
+                        v = __ldg(a.x + r * a.ldx + k);
+                        if (a.mean) {
+                            const int u = (int)u0 + (rem0 + row) / a.n_frames;
+                            if (u != u_cur) { u_cur = u; mu = __ldg(a.mean + (long long)u * a.ld_stats + k); inv = __fdividef(1.0f, __ldg(a.stdv + (long long)u * a.ld_stats + k) + a.cmvn_eps); }
+                            v = (v - mu) * inv;
+                        }
+                    }
+                    As[sw128(row, lane)] = to_tf32(v);
+                }
+#pragma unroll 4
+                for (int row = warp; row < a.bn; row += kProducerWarps) {
+                    const int n = n0 + row;
+                    const float w = (kin && n < a.Dout) ? __ldg(a.W + (long long)n * a.ldw + k) : 0.f;
+                    Bs[sw128(row, lane)] = to_tf32(w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
             }
-            (void)u_first;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
         }
         // ===================== epilogue =====================
+        // warp w reads TMEM lanes 32 (w & 3) .. +31 (its quadrant) and every second 32-column chunk
         mbar_wait(accum_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* st = stage_out + warp * 32 * 33;
-        for (int c0 = 0; c0 < a.bn; c0 += 32) {
+        const int quad = warp & 3;
+        for (int c0 = 32 * (warp >> 2); c0 < a.bn; c0 += 64) {
             if (n0 + c0 >= a.Dout) break;
             uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
 #pragma unroll
             for (int c = 0; c < 32; ++c) st[lane * 33 + c] = __uint_as_float(acc[c]);
             __syncwarp();
             const int n = n0 + c0 + lane;
             const bool nin = n < a.Dout && (c0 + lane) < a.bn;
             const float bz = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
-            for (int rr = 0; rr < 32; ++rr) {
-                const long long r = r0 + warp * 32 + rr;
-                if (r >= a.R) break;
-                if (nin) {
+            const long long rq = r0 + quad * 32;
+            const int rows = (int)(a.R - rq < 32 ? a.R - rq : 32);
+            if (nin) {
+                float* optr = a.offset_out ? a.offset_out + rq * a.ld_out + n : nullptr;
+                float* pptr = a.pred_out ? a.pred_out + rq * a.ld_out + n : nullptr;
+                const float* lptr = a.pred_out ? a.linears + rq * a.ld_out + n : nullptr;
+#pragma unroll 4
+                for (int rr = 0; rr < rows; ++rr) {
                     const float o = activate(st[rr * 33 + lane] + bz, a.act);
-                    if (a.offset_out) a.offset_out[r * a.Dout + n] = o;
-                    if (a.pred_out) a.pred_out[r * a.Dout + n] = __ldg(a.linears + r * a.Dout + n) * o;
+                    if (optr) optr[(long long)rr * a.ld_out] = o;
+                    if (pptr) pptr[(long long)rr * a.ld_out] = __ldg(lptr + (long long)rr * a.ld_out) * o;
                 }
             }
             __syncwarp();
@@ -202,22 +284,17 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_tc_kernel(HeadArgs a)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
         // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc(a.bn);
         for (int kb = 0; kb < a.kblocks; ++kb) {
             const int s = kb % a.stages;
             mbar_wait(&full[s], (kb / a.stages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_floats);
+                const uint32_t a_addr = smem_u32(tiles + s * stage_floats);
                 const uint32_t b_addr = a_addr + BM * BK * 4;
 #pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {
-                    const uint64_t adesc = make_desc(a_addr + kk * 32);
-                    for (int nn = 0; nn < a.bn; nn += 256) {
-                        const int nw = min(256, a.bn - nn);
-                        const uint64_t bdesc = make_desc(b_addr + nn * 128 + kk * 32);
-                        umma_tf32(tmem_base + nn, adesc, bdesc, make_idesc(nw), (kb | kk) ? 1u : 0u);
-                    }
-                }
+                for (int kk = 0; kk < BK / 8; ++kk)
+                    umma_tf32(tmem_base, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), idesc, (kb | kk) ? 1u : 0u);
                 umma_commit(&empty[s]);                                   // stage reusable once these MMAs have read it
                 if (kb == a.kblocks - 1) umma_commit(accum_full);         // accumulator complete
             }
@@ -225,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_tc_kernel(HeadArgs a)
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kProducerWarps) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
     }
@@ -235,27 +312,32 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_tc_kernel(HeadArgs a)
 
 namespace sehead {
 
-int launch_linear_head_tc(const float* x, const float* mean, const float* stdv, float cmvn_eps, const float* W, const float* b,
-                          long long R, int n_frames, int Din, int Dout, int act, const float* linears, float* offset_out,
-                          float* pred_out, cudaStream_t st) {
+int launch_linear_head_tc(const float* x, long long ldx, const float* mean, const float* stdv, long long ld_stats, float cmvn_eps,
+                          const float* W, long long ldw, const float* b, long long R, int n_frames, int Din, int Dout, int act,
+                          const float* linears, float* offset_out, float* pred_out, long long ld_out, cudaStream_t st) {
     HeadArgs a{};
+    a.ldx = ldx; a.ld_stats = ld_stats; a.ldw = ldw; a.ld_out = ld_out;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    a.vec = (ldx % 4 == 0 && ldw % 4 == 0 && al16(x) && al16(W) && (!mean || (ld_stats % 4 == 0 && al16(mean) && al16(stdv)))) ? 1 : 0;
     a.x = x; a.mean = mean; a.stdv = stdv; a.cmvn_eps = cmvn_eps; a.W = W; a.bias = b;
     a.R = R; a.n_frames = n_frames; a.Din = Din; a.Dout = Dout; a.act = act;
     a.linears = linears; a.offset_out = offset_out; a.pred_out = pred_out;
-    const int chunks = (Dout + 511) / 512;
+    const int chunks = (Dout + 255) / 256;                       // <= 256 accumulator columns per CTA: two CTAs share an SM's TMEM
     a.bn = ((((Dout + chunks - 1) / chunks) + 15) / 16) * 16;
     a.tmem_cols = 32;
     while (a.tmem_cols < a.bn) a.tmem_cols *= 2;
     a.kblocks = (Din + BK - 1) / BK;
     const size_t stage_bytes = (size_t)(BM + a.bn) * BK * 4;
-    int stages = (int)((200 * 1024 - 4 * 32 * 33 * 4 - 256 - 1024) / stage_bytes);
+    const size_t fixed = 256, staging = (size_t)kProducerWarps * 32 * 33 * 4;
+    int stages = (int)((110 * 1024 - fixed) / stage_bytes);        // <= ~110 KB so that two CTAs fit per SM
     a.stages = stages > kStagesMax ? kStagesMax : stages;
     if (a.stages > a.kblocks) a.stages = a.kblocks;
     if (a.stages < 1) return fail(SE_ERR_UNSUPPORTED, "head tile does not fit in shared memory (Dout=%d)", Dout);
-    const size_t smem = 1024 + (size_t)a.stages * stage_bytes + 4 * 32 * 33 * 4 + 256;
+    const size_t ring = (size_t)a.stages * stage_bytes;
+    const size_t smem = (ring > staging ? ring : staging) + fixed;
     static bool opted = false;
     if (!opted) {
-        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         opted = true;
     }
     dim3 grid((unsigned)((R + BM - 1) / BM), (unsigned)chunks);

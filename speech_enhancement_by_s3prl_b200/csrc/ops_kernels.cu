@@ -10,9 +10,9 @@ using secommon::fail;
 using secommon::block_accumulate_to;
 
 namespace sehead {
-int launch_linear_head_tc(const float* x, const float* mean, const float* stdv, float cmvn_eps, const float* W, const float* b,
-                          long long R, int n_frames, int Din, int Dout, int act, const float* linears, float* offset_out,
-                          float* pred_out, cudaStream_t st);
+int launch_linear_head_tc(const float* x, long long ldx, const float* mean, const float* stdv, long long ld_stats, float cmvn_eps,
+                          const float* W, long long ldw, const float* b, long long R, int n_frames, int Din, int Dout, int act,
+                          const float* linears, float* offset_out, float* pred_out, long long ld_out, cudaStream_t st);
 }
 
 namespace {
@@ -212,16 +212,16 @@ __global__ void length_masks_kernel(const long long* __restrict__ lengths, long 
 
 // ------------------------------------------------------------------ CMVN statistics over time
 // x (n_utt, F, D): mean / unbiased std per (u, d).  block = 32 features x 8 frame lanes.
-__global__ void cmvn_stats_kernel(const float* __restrict__ x, int n_frames, int D, float* __restrict__ mean,
-                                  float* __restrict__ stdv) {
+__global__ void cmvn_stats_kernel(const float* __restrict__ x, long long ldx, int n_frames, int D, float* __restrict__ mean,
+                                  float* __restrict__ stdv, long long ld_stats) {
     const int dchunks = (D + 31) / 32;
     const int u = blockIdx.x / dchunks, dc = blockIdx.x - u * dchunks;
     const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, nrows = blockDim.x >> 5;
     const int d = dc * 32 + lane;
-    const float* base = x + (long long)u * n_frames * D;
+    const float* base = x + (long long)u * n_frames * ldx;
     __shared__ double red[8][33];
     double s = 0.0;
-    if (d < D) for (int f = row; f < n_frames; f += nrows) s += (double)base[(long long)f * D + d];
+    if (d < D) for (int f = row; f < n_frames; f += nrows) s += (double)base[(long long)f * ldx + d];
     red[row][lane] = s;
     __syncthreads();
     double tot = 0.0;
@@ -229,14 +229,14 @@ __global__ void cmvn_stats_kernel(const float* __restrict__ x, int n_frames, int
     const double mu = tot / (double)n_frames;
     __syncthreads();
     double q = 0.0;
-    if (d < D) for (int f = row; f < n_frames; f += nrows) { const double v = (double)base[(long long)f * D + d] - mu; q += v * v; }
+    if (d < D) for (int f = row; f < n_frames; f += nrows) { const double v = (double)base[(long long)f * ldx + d] - mu; q += v * v; }
     red[row][lane] = q;
     __syncthreads();
     if (row == 0 && d < D) {
         double qt = 0.0;
         for (int r = 0; r < nrows; ++r) qt += red[r][lane];
-        mean[(long long)u * D + d] = (float)mu;
-        stdv[(long long)u * D + d] = (float)sqrt(qt / (double)(n_frames - 1));      // unbiased (model.py:30)
+        mean[(long long)u * ld_stats + d] = (float)mu;
+        stdv[(long long)u * ld_stats + d] = (float)sqrt(qt / (double)(n_frames - 1));      // unbiased (model.py:30)
     }
 }
 
@@ -304,7 +304,8 @@ __device__ __forceinline__ float activate(float z, int act) {
 __global__ void __launch_bounds__(256) linear_head_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv, float cmvn_eps,
     const float* __restrict__ W, const float* __restrict__ bias, long long R, int n_frames, int Din, int Dout, int act,
-    const float* __restrict__ linears, float* __restrict__ offset_out, float* __restrict__ pred_out) {
+    const float* __restrict__ linears, float* __restrict__ offset_out, float* __restrict__ pred_out,
+    long long ldx, long long ld_stats, long long ldw, long long ld_out) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const long long r0 = (long long)blockIdx.y * BM;
@@ -326,8 +327,8 @@ __global__ void __launch_bounds__(256) linear_head_fwd_kernel(
                 const int k = k0 + lk + j;
                 float v = 0.f;
                 if (r < R && k < Din) {
-                    v = x[r * Din + k];
-                    if (mean) v = (v - mean[u * Din + k]) / (stdv[u * Din + k] + cmvn_eps);
+                    v = x[r * ldx + k];
+                    if (mean) v = (v - mean[u * ld_stats + k]) / (stdv[u * ld_stats + k] + cmvn_eps);
                 }
                 As[lk + j][lrow] = v;
             }
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(256) linear_head_fwd_kernel(
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = k0 + lk + j;
-                Bs[lk + j][lrow] = (n < Dout && k < Din) ? W[(long long)n * Din + k] : 0.f;
+                Bs[lk + j][lrow] = (n < Dout && k < Din) ? W[(long long)n * ldw + k] : 0.f;
             }
         }
         __syncthreads();
@@ -362,8 +363,8 @@ __global__ void __launch_bounds__(256) linear_head_fwd_kernel(
             const int n = n0 + tx * 4 + j;
             if (n >= Dout) continue;
             const float o = activate(acc[i][j] + (bias ? bias[n] : 0.f), act);
-            if (offset_out) offset_out[r * Dout + n] = o;
-            if (pred_out) pred_out[r * Dout + n] = linears[r * Dout + n] * o;
+            if (offset_out) offset_out[r * ld_out + n] = o;
+            if (pred_out) pred_out[r * ld_out + n] = linears[r * ld_out + n] * o;
         }
     }
 }
@@ -549,9 +550,14 @@ int se_length_masks(const int64_t* lengths, int64_t n_utt, int64_t width, int64_
 }
 
 int se_cmvn_stats(const float* x, int64_t n_utt, int64_t n_frames, int64_t D, float* mean, float* std, void* stream) {
-    SE_REQUIRE(x && mean && std && n_utt > 0 && n_frames > 0 && D > 0, "bad argument");
+    return se_cmvn_stats_strided(x, D, n_utt, n_frames, D, mean, std, D, stream);
+}
+
+int se_cmvn_stats_strided(const float* x, int64_t ldx, int64_t n_utt, int64_t n_frames, int64_t D, float* mean, float* std,
+                          int64_t ld_stats, void* stream) {
+    SE_REQUIRE(x && mean && std && n_utt > 0 && n_frames > 0 && D > 0 && ldx >= D && ld_stats >= D, "bad argument");
     const long long blocks = n_utt * ((D + 31) / 32);
-    cmvn_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, (int)n_frames, (int)D, mean, std);
+    cmvn_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, (int)n_frames, (int)D, mean, std, ld_stats);
     return secommon::check_launch("cmvn_stats_kernel");
 }
 
@@ -589,19 +595,29 @@ int se_delta(float* x, int64_t n_utt, int64_t n_frames, int64_t D, int order, vo
 int se_linear_head_fwd(const float* x, const float* mean, const float* std, float cmvn_eps, const float* W,
                        const float* b, int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int act,
                        const float* linears, float* offset_out, float* predicted_out, int precision, void* stream) {
+    return se_linear_head_fwd_strided(x, D_in, mean, std, D_in, cmvn_eps, W, D_in, b, n_utt, n_frames, D_in, D_out, act, linears,
+                                      offset_out, predicted_out, D_out, precision, stream);
+}
+
+int se_linear_head_fwd_strided(const float* x, int64_t ldx, const float* mean, const float* std, int64_t ld_stats,
+                               float cmvn_eps, const float* W, int64_t ldw, const float* b, int64_t n_utt,
+                               int64_t n_frames, int64_t D_in, int64_t D_out, int act, const float* linears,
+                               float* offset_out, float* predicted_out, int64_t ld_out, int precision, void* stream) {
     SE_REQUIRE(x && W && n_utt > 0 && n_frames > 0 && D_in > 0 && D_out > 0, "bad argument");
+    SE_REQUIRE(ldx >= D_in && ldw >= D_in && ld_out >= D_out && (!mean || ld_stats >= D_in), "row stride smaller than the row");
     SE_REQUIRE((mean == nullptr) == (std == nullptr), "mean and std go together");
     SE_REQUIRE(offset_out || predicted_out, "no output requested");
     SE_REQUIRE(!predicted_out || linears, "predicted_out needs linears");
     SE_REQUIRE(act >= SE_ACT_IDENTITY && act <= SE_ACT_SIGMOID, "unknown activation %d", act);
     const long long R = n_utt * n_frames;
     if (precision == 1)
-        return sehead::launch_linear_head_tc(x, mean, std, cmvn_eps, W, b, R, (int)n_frames, (int)D_in, (int)D_out, act, linears,
-                                             offset_out, predicted_out, (cudaStream_t)stream);
+        return sehead::launch_linear_head_tc(x, ldx, mean, std, ld_stats, cmvn_eps, W, ldw, b, R, (int)n_frames, (int)D_in, (int)D_out,
+                                             act, linears, offset_out, predicted_out, ld_out, (cudaStream_t)stream);
     if (precision != 0) return fail(SE_ERR_BAD_ARG, "precision=%d (0 = fp32 SIMT, 1 = TF32 tcgen05)", precision);
     dim3 grid((unsigned)((D_out + BN - 1) / BN), (unsigned)((R + BM - 1) / BM));
     linear_head_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mean, std, cmvn_eps, W, b, R, (int)n_frames, (int)D_in,
-                                                                   (int)D_out, act, linears, offset_out, predicted_out);
+                                                                   (int)D_out, act, linears, offset_out, predicted_out,
+                                                                   ldx, ld_stats, ldw, ld_out);
     return secommon::check_launch("linear_head_fwd_kernel");
 }
 

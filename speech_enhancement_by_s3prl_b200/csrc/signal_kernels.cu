@@ -171,7 +171,13 @@ int se_prepare(int n_fft) {
 
 int se_stft(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
             float log_eps, float* power, float* phase, float* logpower, void* stream) {
+    return se_stft_strided(wav, n_utt, utt_stride, T, n_fft, hop, window, log_eps, power, phase, logpower, n_fft / 2 + 1, stream);
+}
+
+int se_stft_strided(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
+                    float log_eps, float* power, float* phase, float* logpower, int64_t spec_stride, void* stream) {
     SE_REQUIRE(wav && window, "wav and window must not be null");
+    SE_REQUIRE(spec_stride >= n_fft / 2 + 1, "spec_stride=%lld smaller than K", (long long)spec_stride);
     int rc = check_geometry(n_utt, T, n_fft, hop);
     if (rc != SE_OK) return rc;
     DeviceTables t;
@@ -180,7 +186,7 @@ int se_stft(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int 
     a.wav = wav; a.utt_stride = utt_stride; a.n_utt = (int)n_utt; a.T = (int)T; a.hop = hop;
     a.n_frames = (int)(T / hop) + 1;
     a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
-    a.power = power; a.phase = phase; a.logp = logpower; a.log_eps = log_eps;
+    a.power = power; a.phase = phase; a.logp = logpower; a.log_eps = log_eps; a.spec_stride = spec_stride;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_fft == 512 && !g_force_generic) return sefast::launch_stft512(a, st);
     SE_DISPATCH_NFFT(n_fft, launch_stft, a, st)
@@ -206,7 +212,15 @@ int se_istft(const float* power, const float* phase, int64_t n_utt, int64_t n_fr
 int se_mask_istft(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, const int64_t* lengths,
                   int64_t n_utt, int64_t T, int n_fft, int hop, const float* window, float* wav_out, int64_t out_stride,
                   int64_t pad_to, double* sums, int want_spec, void* stream) {
+    return se_mask_istft_strided(noisy, clean, utt_stride, mask, n_fft / 2 + 1, lengths, n_utt, T, n_fft, hop, window, wav_out,
+                                 out_stride, pad_to, sums, want_spec, stream);
+}
+
+int se_mask_istft_strided(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
+                          const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
+                          float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int want_spec, void* stream) {
     SE_REQUIRE(noisy && mask && window && wav_out, "null pointer");
+    SE_REQUIRE(mask_stride >= n_fft / 2 + 1, "mask_stride=%lld smaller than K", (long long)mask_stride);
     int rc = check_geometry(n_utt, T, n_fft, hop);
     if (rc != SE_OK) return rc;
     DeviceTables t;
@@ -217,7 +231,7 @@ int se_mask_istft(const float* noisy, const float* clean, int64_t utt_stride, co
     a.n_utt = (int)n_utt; a.T = (int)T; a.hop = hop; a.n_frames = (int)(T / hop) + 1;
     a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
     a.wav_out = wav_out; a.out_stride = out_stride; a.out_len = hop * (a.n_frames - 1); a.pad_to = (int)pad_to;
-    a.sums = sums; a.want_spec = (want_spec && clean && sums) ? 1 : 0;
+    a.sums = sums; a.want_spec = (want_spec && clean && sums) ? 1 : 0; a.mask_stride = mask_stride;
     SE_REQUIRE(out_stride >= a.out_len && out_stride >= pad_to, "out_stride=%lld too small", (long long)out_stride);
     cudaStream_t st = (cudaStream_t)stream;
     if (sums) SE_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * SE_NSUMS * n_utt, st));

@@ -40,6 +40,7 @@ struct StftArgs {
     float* phase;              // idem or null
     float* logp;               // log(power + log_eps), idem or null
     float log_eps;
+    long long spec_stride;     // floats between consecutive frames of an output (>= K; K = dense)
 };
 
 struct IstftArgs {
@@ -70,6 +71,7 @@ struct MaskIstftArgs {
     int out_len, pad_to, tile_len;
     double* sums;              // (n_utt, NSUMS) or null
     int want_spec;             // also accumulate the spectral SI-SDR sums (needs clean)
+    long long mask_stride;     // floats between consecutive frames of mask (>= K)
 };
 
 SE_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -184,10 +186,11 @@ SE_HD void stft_tile(Exec& ex, const StftArgs& a, int utt, int tile, unsigned ch
         return make_float2(fr[2 * i] * win[2 * i], fr[2 * i + 1] * win[2 * i + 1]);
     };
     const float2* Z = fft_run<P, -1>(ex, nf, load0, s.bx, s.by, s.twM);
-    const long long out0 = ((long long)utt * a.n_frames + f0) * K;
-    ex.foreach(nf * K, [&](int w) {
-        const int g = w / K;
-        const int k = w - g * K;
+    const long long out0 = ((long long)utt * a.n_frames + f0) * a.spec_stride;
+    ex.foreach(nf * K, [&](int w0) {
+        const int g = w0 / K;
+        const int k = w0 - g * K;
+        const long long w = (long long)g * a.spec_stride + k;
         const float2* z = Z + g * PAD;
         const float2 zk = z[phys(k == M ? 0 : k)];
         const float2 zmk = z[phys(k == 0 ? 0 : M - k)];
@@ -335,14 +338,14 @@ SE_HD void mask_istft_tile(Exec& ex, const MaskIstftArgs& a, int utt, int tile, 
         ex.sync();
         float2* Zn = fft_run<P, -1>(ex, nf, load0, s.bx, s.by, s.twM);
         float2* other = (Zn == s.bx) ? s.by : s.bx;
-        const long long m0 = ((long long)utt * a.n_frames + f_lo) * K;
+        const long long m0 = ((long long)utt * a.n_frames + f_lo) * a.mask_stride;
         // split -> mask -> merge, pairwise in place
         ex.foreach(nf * (M / 2 + 1), [&](int w) {
             const int g = w / (M / 2 + 1);
             const int k = w - g * (M / 2 + 1);
             const int k2 = M - k;
             float2* z = Zn + g * PAD;
-            const float* mk = a.mask + m0 + (long long)g * K;
+            const float* mk = a.mask + m0 + (long long)g * a.mask_stride;
             const float2 za = z[phys(k)], zb = z[phys(k2 == M ? 0 : k2)];
             float2 xa = rfft_split(za, zb, s.twN[k]);
             float2 xb = rfft_split(zb, za, s.twN[k2]);

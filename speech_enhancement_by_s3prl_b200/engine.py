@@ -44,19 +44,30 @@ class EnhancementEngine:
             self.pre.to(dev)
             window = self.pre._frame_window
         head = self.head
+        K = self.n_fft // 2 + 1
         with torch.no_grad():
-            spec = ops.stft(wavs, self.ch_inp, self.n_fft, self.hop, window, power=not self.log_features,
-                            logpower=self.log_features, log_eps=self.pre.eps)
-            feats = spec["logpower"] if self.log_features else spec["power"]
+            # internal tensors use rows padded to 16 bytes (K = 257 -> 260 floats) so that the tensor-core head can
+            # read them with 128-bit loads; nothing outside this function sees the padding
+            feats = ops.stft_padded(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=self.log_features, log_eps=self.pre.eps)
             mean = std = None
             if head.cmvn:
-                mean, std = ops.cmvn_stats(feats)
-            mask, _ = ops.linear_head_fused(feats, head.linear.weight, head.linear.bias, head.activation, mean, std,
-                                            head.eps, precision=self.precision)
+                mean, std = ops.cmvn_stats_padded(feats, K)
+            mask = ops.linear_head_padded(feats, K, self._padded_weight(), head.linear.bias, head.activation, mean, std,
+                                          head.eps, precision=self.precision)
             wav, sums = ops.mask_istft(wavs, self.ch_inp, self.ch_tar, mask, lengths, self.n_fft, self.hop, window,
-                                       pad_to=T, want_sums=True, want_spec=want_spec_loss)
+                                       pad_to=T, want_sums=True, want_spec=want_spec_loss, mask_padded=True)
             gain, sisdr, loss = ops.finalize_metrics(sums, lengths, T, wav=wav, target_db=None)
-        return {"loss_per_utt": loss, "sisdr": sisdr, "wav_predicted": wav, "gain": gain, "mask": mask}
+        return {"loss_per_utt": loss, "sisdr": sisdr, "wav_predicted": wav, "gain": gain, "mask": mask[..., :K]}
+
+    def _padded_weight(self):
+        """16-byte-row copy of the head weight, refreshed when the parameter changes (optimizer step / load_state_dict)."""
+        w = self.head.linear.weight
+        key = (w.data_ptr(), w._version, str(w.device))
+        if getattr(self, "_wpad_key", None) != key:
+            with torch.no_grad():
+                self._wpad = ops.pad_weight(w.detach())
+            self._wpad_key = key
+        return self._wpad
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def capture_bound(self, lengths, wavs):

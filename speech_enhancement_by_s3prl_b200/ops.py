@@ -80,6 +80,62 @@ def stft(wavs, channel, n_fft, hop, window, power=True, phase=False, logpower=Fa
     return out
 
 
+def round4(n):
+    return (int(n) + 3) // 4 * 4
+
+
+def stft_padded(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10):
+    """Fused-path variant of stft: ONE output (log-power or power) with rows padded to a multiple of
+    4 floats (16-byte aligned rows for the tensor-core head).  Returns a (B, F, LD) tensor whose
+    columns [K, LD) are unspecified."""
+    wavs = _chk(wavs, "wavs")
+    B, C, T = wavs.shape
+    F, K = T // hop + 1, n_fft // 2 + 1
+    LD = round4(K)
+    window = _c(window, "window")
+    with torch.cuda.device(wavs.device):
+        out = torch.empty(B, F, LD, device=wavs.device, dtype=torch.float32)
+        rc = _lib.load().se_stft_strided(wavs.data_ptr() + 4 * int(channel) * T, B, C * T, T, n_fft, hop, window.data_ptr(),
+                                         float(log_eps), None if logpower else out.data_ptr(), None,
+                                         out.data_ptr() if logpower else None, LD, _stream())
+        _lib.check(rc, "se_stft_strided")
+    return out
+
+
+def cmvn_stats_padded(x, D):
+    """x (B, F, LD) with D valid columns -> mean, std (B, LD) (valid columns [0, D))."""
+    B, F, LD = x.shape
+    with torch.cuda.device(x.device):
+        mean = torch.empty(B, LD, device=x.device)
+        std = torch.empty(B, LD, device=x.device)
+        rc = _lib.load().se_cmvn_stats_strided(x.data_ptr(), LD, B, F, D, mean.data_ptr(), std.data_ptr(), LD, _stream())
+        _lib.check(rc, "se_cmvn_stats_strided")
+    return mean, std
+
+
+def pad_weight(weight):
+    """(Dout, Din) -> contiguous (Dout, round4(Din)) zero-padded copy (16-byte aligned rows)."""
+    Dout, Din = weight.shape
+    LD = round4(Din)
+    if LD == Din:
+        return weight.contiguous()
+    return torch.nn.functional.pad(weight, (0, LD - Din)).contiguous()
+
+
+def linear_head_padded(x, D_in, weight_padded, bias, activation, mean, std, cmvn_eps, precision=1):
+    """x (B, F, LDx), weight_padded (Dout, LDw) -> mask (B, F, round4(Dout)) (valid columns [0, Dout))."""
+    B, F, LDx = x.shape
+    Dout, LDw = weight_padded.shape
+    LDo = round4(Dout)
+    with torch.cuda.device(x.device):
+        out = torch.empty(B, F, LDo, device=x.device)
+        rc = _lib.load().se_linear_head_fwd_strided(x.data_ptr(), LDx, _p(mean), _p(std), 0 if mean is None else mean.shape[1],
+                                                    float(cmvn_eps), weight_padded.data_ptr(), LDw, _p(bias), B, F, int(D_in), Dout,
+                                                    ACT[activation], None, out.data_ptr(), None, LDo, int(precision), _stream())
+        _lib.check(rc, "se_linear_head_fwd_strided")
+    return out
+
+
 def istft(power, phase, n_fft, hop, window, pad_to=0):
     """(B, F, K) power + phase -> (B, max(hop*(F-1), pad_to)); reference OnlinePreprocessor.istft."""
     power, phase, window = _c(power, "linears"), _c(phase, "phases"), _c(window, "window")
@@ -96,7 +152,7 @@ def istft(power, phase, n_fft, hop, window, pad_to=0):
 
 
 def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, want_sums=True, want_spec=True,
-               out=None, sums=None):
+               out=None, sums=None, mask_padded=False):
     """Fused ``istft(linear_inp * mask, phase_inp)`` straight from the noisy waveform.
 
     wavs (B, C, T); mask (B, F, K); lengths (B,) int64 or None.  Returns (wav (B, width), sums (B, 6) float64|None)."""
@@ -104,7 +160,8 @@ def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, 
     assert wavs.dim() == 3 and wavs.is_contiguous()
     B, C, T = wavs.shape
     F, K = T // hop + 1, n_fft // 2 + 1
-    assert mask.shape == (B, F, K), f"mask {tuple(mask.shape)} != {(B, F, K)}"
+    mask_stride = mask.shape[2] if mask_padded else K
+    assert mask.shape == (B, F, mask_stride) and mask_stride >= K, f"mask {tuple(mask.shape)} != {(B, F, mask_stride)}"
     lengths = _c(lengths, "lengths", torch.int64)
     out_len = hop * (F - 1)
     width = max(out_len, int(pad_to))
@@ -114,10 +171,10 @@ def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, 
         if want_sums and sums is None:
             sums = torch.empty(B, NSUMS, device=wavs.device, dtype=torch.float64)
         clean = None if ch_tar is None else wavs.data_ptr() + 4 * int(ch_tar) * T
-        rc = _lib.load().se_mask_istft(wavs.data_ptr() + 4 * int(ch_inp) * T, clean, C * T, mask.data_ptr(), _p(lengths),
-                                       B, T, n_fft, hop, window.data_ptr(), out.data_ptr(), out.stride(0), int(pad_to),
-                                       _p(sums) if want_sums else None, int(bool(want_spec)), _stream())
-        _lib.check(rc, "se_mask_istft")
+        rc = _lib.load().se_mask_istft_strided(wavs.data_ptr() + 4 * int(ch_inp) * T, clean, C * T, mask.data_ptr(), mask_stride,
+                                               _p(lengths), B, T, n_fft, hop, window.data_ptr(), out.data_ptr(), out.stride(0),
+                                               int(pad_to), _p(sums) if want_sums else None, int(bool(want_spec)), _stream())
+        _lib.check(rc, "se_mask_istft_strided")
     return out, (sums if want_sums else None)
 
 

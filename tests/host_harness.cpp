@@ -97,7 +97,7 @@ int h_stft(int n_fft, const float* wav, int n_utt, long long utt_stride, int T, 
            float* power, float* phase, float* logp, float log_eps) {
     StftArgs a{};
     a.wav = wav; a.utt_stride = utt_stride; a.n_utt = n_utt; a.T = T; a.hop = hop; a.n_frames = T / hop + 1;
-    a.tab.window = window; a.power = power; a.phase = phase; a.logp = logp; a.log_eps = log_eps;
+    a.tab.window = window; a.power = power; a.phase = phase; a.logp = logp; a.log_eps = log_eps; a.spec_stride = n_fft / 2 + 1;
 #define CALL(NN) run_stft<NN>(a)
     DISPATCH(n_fft, CALL)
 #undef CALL
@@ -120,7 +120,7 @@ int h_mask_istft(int n_fft, const float* noisy, const float* clean, long long ut
     a.noisy = noisy; a.clean = clean; a.utt_stride = utt_stride; a.mask = mask; a.lengths = lengths;
     a.n_utt = n_utt; a.T = T; a.hop = hop; a.n_frames = T / hop + 1; a.tab.window = window;
     a.wav_out = wav_out; a.out_stride = out_stride; a.out_len = hop * (a.n_frames - 1); a.pad_to = pad_to;
-    a.sums = sums; a.want_spec = want_spec;
+    a.sums = sums; a.want_spec = want_spec; a.mask_stride = n_fft / 2 + 1;
 #define CALL(NN) run_mask_istft<NN>(a)
     DISPATCH(n_fft, CALL)
 #undef CALL
