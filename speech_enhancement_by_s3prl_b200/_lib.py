@@ -62,8 +62,8 @@ def load():
         return _lib
     with _lock:
         if _lib is None:
-            path = _build.LIB_PATH
-            if _build.is_stale():
+            path = os.environ.get("SE_B200_LIB") or _build.LIB_PATH      # override: experiment builds
+            if path == _build.LIB_PATH and _build.is_stale():
                 try:
                     path = _build.build_library()
                 except Exception as exc:           # no nvcc and no prebuilt library

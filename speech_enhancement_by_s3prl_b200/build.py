@@ -48,8 +48,9 @@ def is_stale():
         return f.read().strip() != source_hash()
 
 
-def build_library(force=False, verbose=False):
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, extra_flags=(), out_path=None):
+    """extra_flags / out_path: experiment builds (e.g. -DSE_K3_MIN_BLOCKS=4 into another file, loaded via SE_B200_LIB)."""
+    if out_path is None and not force and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
     objs = []
@@ -58,7 +59,9 @@ def build_library(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *ARCH_FLAGS, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+        if out_path is not None:
+            obj = obj[:-2] + ".exp.o"
+        cmd = [nvcc, *ARCH_FLAGS, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", *extra_flags,
                "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -70,12 +73,14 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    tmp = LIB_PATH + ".tmp"
+    target = out_path or LIB_PATH
+    tmp = target + ".tmp"
     subprocess.check_call([nvcc, *ARCH_FLAGS, "-shared", "-o", tmp, *objs, "-lcudart"])
-    os.replace(tmp, LIB_PATH)
-    with open(HASH_PATH, "w") as f:
-        f.write(source_hash())
-    return LIB_PATH
+    os.replace(tmp, target)
+    if out_path is None:
+        with open(HASH_PATH, "w") as f:
+            f.write(source_hash())
+    return target
 
 
 if __name__ == "__main__":

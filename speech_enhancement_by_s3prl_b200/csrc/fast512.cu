@@ -1,13 +1,23 @@
 // libse_b200.so -- n_fft = 512 fast paths: one frame per half-warp, FFT values in registers
 // (fft256_warp.cuh), frames gathered straight from global memory with coalesced 8-byte loads
 // (each half-warp reads the 2 KB of its frame as 16 x 128 B), spectra written straight from
-// registers.  No block-level barrier anywhere: warps run independently and the kernels are
-// persistent (grid sized from the SM count).
+// registers.  No block-level barrier in the main loops: half-warps run independently.
 //
 //   stft512_kernel        K1: frame -> window -> rFFT -> power / phase / log-power
 //   mask_istft512_kernel  K3: frame -> rFFT -> x sqrt(mask) -> irFFT -> window -> overlap-add in
 //                             registers along a run of consecutive frames -> / envelope -> wav,
 //                             plus the per-utterance metric sums
+//
+// Both kernels are bound by instruction issue, not by HBM, so the code is organised
+// to keep the instruction count and the instruction footprint down:
+//   * the analysis window is pre-scaled by 1/2, which removes the 1/2 of the real-FFT split;
+//     X[k] = E + T and X[M-k] = conj(E - T) share one complex multiply (T = W^k * (-i)(Z[k] - conj Z[M-k]))
+//   * the inverse transform reuses the forward FFT code: IFFT(Z) = conj(FFT(conj Z)), with the
+//     conjugations, the 1/M, the synthesis window and the 1/envelope folded into one table
+//   * in K3 the three transforms of a frame (clean, noisy, inverse) run through ONE copy of the FFT
+//     code inside a non-unrolled pass loop, so the kernel fits the instruction cache
+//   * rarely taken paths (reflect padding at utterance edges, unaligned rows) go through a small
+//     rolled loop into the half-warp's shared-memory buffer instead of being unrolled in registers
 #include <cstdlib>
 #include "se_common.cuh"
 #include "fft256_warp.cuh"
@@ -19,26 +29,37 @@ using sekern::MaskIstftArgs;
 
 namespace {
 
-constexpr int N = 512, K = 257, kWarps = 8, kThreads = kWarps * 32;
+constexpr int N = 512, H = 256;
 
-// gather z[m] = (x[2m], x[2m+1]) * (w[2m], w[2m+1]) for m = j + 16 r of the frame starting at original
-// coordinate t0 (may run over either end of the row -> reflect, torch.stft pad_mode='reflect')
+// sqrt.approx: no denormal / special-value fix-up path (2 ulp), keeps the kernels free of slow-path calls
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// v[r] = (x[2m], x[2m+1]) * win2[m], m = j + 16 r, for the frame whose first sample is row[t0]
+// (t0 may run over either end of the row -> reflect, as torch.stft pad_mode='reflect')
 __device__ __forceinline__ void load_frame(const float* __restrict__ row, int T, int t0, int j, const float2* __restrict__ win2,
-                                           float2 (&v)[16]) {
-    const bool interior = (t0 >= 0) && (t0 + N <= T);
+                                           float2* __restrict__ xbuf, unsigned hmask, float2 (&v)[16]) {
     const float* src = row + t0;
-    if (interior && ((reinterpret_cast<uintptr_t>(src) & 7) == 0)) {
+    if ((t0 >= 0) && (t0 + N <= T) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0)) {
         const float2* s2 = reinterpret_cast<const float2*>(src);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = __ldg(s2 + j + 16 * r);
-    } else {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            int ta = t0 + 2 * (j + 16 * r), tb = ta + 1;
-            ta = ta < 0 ? -ta : ta; ta = ta >= T ? 2 * (T - 1) - ta : ta;
-            tb = tb < 0 ? -tb : tb; tb = tb >= T ? 2 * (T - 1) - tb : tb;
-            v[r] = make_float2(__ldg(row + ta), __ldg(row + tb));
+    } else {                                           // rare: rolled loop through the half-warp's buffer
+        float* xf = reinterpret_cast<float*>(xbuf);
+#pragma unroll 1
+        for (int i = j; i < N; i += 16) {
+            int t = t0 + i;
+            t = t < 0 ? -t : t;
+            t = t >= T ? 2 * (T - 1) - t : t;
+            xf[i] = __ldg(row + t);
         }
+        __syncwarp(hmask);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = xbuf[j + 16 * r];
+        __syncwarp(hmask);
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -48,72 +69,101 @@ __device__ __forceinline__ void load_frame(const float* __restrict__ row, int T,
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) stft512_kernel(StftArgs a, long long total_frames) {
-    __shared__ __align__(16) float2 s_x[kWarps * 2][M];       // transpose buffers, one per half-warp
-    __shared__ __align__(16) float2 s_win2[M];                 // window as (w[2m], w[2m+1])
-    for (int i = threadIdx.x; i < M; i += kThreads) s_win2[i] = make_float2(a.tab.window[2 * i], a.tab.window[2 * i + 1]);
+// One pair of bins (k, M-k) of the real-input split.  zk = Z[k], zm = Z[M-k] (of the 1/2-scaled frame),
+// w = exp(-2*pi*i*k/N).  xa = X[k], xb = X[M-k].
+__device__ __forceinline__ void split_pair(float2 zk, float2 zm, float2 w, float2& xa, float2& xb) {
+    const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
+    const float2 o = make_float2(zk.y + zm.y, zm.x - zk.x);                 // -i * (Z[k] - conj Z[M-k])
+    const float2 t = cmul(o, w);
+    xa = make_float2(e.x + t.x, e.y + t.y);
+    xb = make_float2(e.x - t.x, t.y - e.y);
+}
+// Inverse of split_pair up to a factor 2: from Y[k], Y[M-k] the values conj(Zinv[k]), conj(Zinv[M-k])
+// that feed the forward FFT used as an inverse.
+__device__ __forceinline__ void merge_pair_conj(float2 ya, float2 yb, float2 w, float2& ca, float2& cb) {
+    const float2 e = make_float2(ya.x + yb.x, ya.y - yb.y);
+    const float2 d = make_float2(ya.x - yb.x, ya.y + yb.y);
+    const float2 o = cmul(d, make_float2(w.x, -w.y));
+    const float2 u = make_float2(-o.y, o.x);                                  // i * o
+    ca = make_float2(e.x + u.x, -(e.y + u.y));                                // conj(Zinv[k])   = conj(e + u)
+    cb = make_float2(e.x - u.x, e.y - u.y);                                   // conj(Zinv[M-k]) = e - u
+}
+
+// ------------------------------------------------------------------ K1
+constexpr int kWarps1 = 8, kThreads1 = kWarps1 * 32;
+
+template <bool POWER, bool PHASE, bool LOGP>
+__global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long long total_frames) {
+    __shared__ __align__(16) float2 s_x[kWarps1 * 2][M];       // transpose buffers, one per half-warp
+    __shared__ __align__(16) float2 s_win2[M];                  // 0.5 * window as (w[2m], w[2m+1])
+    for (int i = threadIdx.x; i < M; i += kThreads1) s_win2[i] = make_float2(0.5f * a.tab.window[2 * i], 0.5f * a.tab.window[2 * i + 1]);
     const int lane = threadIdx.x & 31, j = lane & 15;
-    const int hw = (threadIdx.x >> 4);                          // half-warp in CTA
+    const int hw = (threadIdx.x >> 4);
     float2 tw[15], twn[8];
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     __syncthreads();
     float2* xbuf = s_x[hw];
-    const long long n_hw = (long long)gridDim.x * (kThreads / 16);
-    const long long first = (long long)blockIdx.x * (kThreads / 16) + hw;
-    const unsigned hmask = half_mask(lane);                     // half-warps are independent of each other
+    const long long n_hw = (long long)gridDim.x * (kThreads1 / 16);
+    const long long first = (long long)blockIdx.x * (kThreads1 / 16) + hw;
+    const unsigned hmask = half_mask(lane);
+#pragma unroll 1
     for (long long gg = first; gg < total_frames; gg += n_hw) {
         const int u = (int)(gg / a.n_frames), f = (int)(gg - (long long)u * a.n_frames);
         float2 v[16];
-        load_frame(a.wav + (long long)u * a.utt_stride, a.T, f * a.hop - N / 2, j, s_win2, v);
+        load_frame(a.wav + (long long)u * a.utt_stride, a.T, f * a.hop - N / 2, j, s_win2, xbuf, hmask, v);
         fft256<-1>(v, xbuf, j, tw, hmask);
         float2 zm[8];
         fetch_mirror(v, lane, zm);
         const long long o = gg * a.spec_stride;
+        float* pw = POWER ? a.power + o : nullptr;
+        float* lg = LOGP ? a.logp + o : nullptr;
+        float* ph = PHASE ? a.phase + o : nullptr;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int k = j + 16 * q;
-            float2 xa = rfft_split(v[q], zm[q], twn[q]);
-            float2 xb = rfft_split(zm[q], v[q], make_float2(-twn[q].x, twn[q].y));     // W_N^(M-k) = -conj(W_N^k)
-            if (k == 0) { xa.y = 0.0f; xb.y = 0.0f; }
+            float2 xa, xb;
+            split_pair(v[q], zm[q], twn[q], xa, xb);
             const float pa = xa.x * xa.x + xa.y * xa.y, pb = xb.x * xb.x + xb.y * xb.y;
-            if (a.power) { a.power[o + k] = pa; a.power[o + M - k] = pb; }
-            if (a.logp) { a.logp[o + k] = logf(pa + a.log_eps); a.logp[o + M - k] = logf(pb + a.log_eps); }
-            if (a.phase) { a.phase[o + k] = atan2f(xa.y, xa.x); a.phase[o + M - k] = atan2f(xb.y, xb.x); }
+            if (POWER) { pw[k] = pa; pw[M - k] = pb; }
+            if (LOGP) { lg[k] = __logf(pa + a.log_eps); lg[M - k] = __logf(pb + a.log_eps); }
+            if (PHASE) { ph[k] = atan2f(k == 0 ? 0.0f : xa.y, xa.x); ph[M - k] = atan2f(k == 0 ? 0.0f : xb.y, xb.x); }
         }
-        if (j == 0) {                                               // k = 128 pairs with itself
-            const float2 x = rfft_split(v[8], v[8], make_float2(0.0f, -1.0f));
+        if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
+            const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
             const float p = x.x * x.x + x.y * x.y;
-            if (a.power) a.power[o + 128] = p;
-            if (a.logp) a.logp[o + 128] = logf(p + a.log_eps);
-            if (a.phase) a.phase[o + 128] = atan2f(x.y, x.x);
+            if (POWER) pw[128] = p;
+            if (LOGP) lg[128] = __logf(p + a.log_eps);
+            if (PHASE) ph[128] = atan2f(x.y, x.x);
         }
     }
 }
-
 
 // ------------------------------------------------------------------ K3: fused mask -> iSTFT, hop = 256
 // One half-warp owns a RUN of consecutive output blocks b = b0 .. b1 of one utterance (block b = output
 // samples [(b-1)*256, b*256), the sum of the second half of frame b-1 and the first half of frame b).
 // It walks frames b0-1 .. b1; the second half of each inverse transform stays in registers ("carry")
 // and is added to the first half of the next one, so the overlap-add needs neither shared memory nor
-// atomics.  Frame b0-1 is a halo frame (recomputed by the neighbouring run).  The synthesis window, the
-// 1/M of the inverse transform and the division by the overlap-added squared window are folded into
-// one table:  bw[n] = w[n] / (M * (w[n mod H]^2 + w[n mod H + H]^2)).
-constexpr int H = 256, kWarps3 = 4, kThreads3 = kWarps3 * 32;
+// atomics.  Frame b0-1 is a halo frame (recomputed by the neighbouring run).
+// Synthesis table: bw[n] = s(n) * w[n] / (2 M (w[n mod H]^2 + w[n mod H + H]^2)) with s = +1 for even n
+// and -1 for odd n (the conjugation of the forward-as-inverse FFT); the 2 undoes merge_pair_conj's factor.
+constexpr int kWarps3 = 4, kThreads3 = kWarps3 * 32;
 
 struct RunPlan { int run_len; int runs_per_utt; long long total_runs; };
 
-__global__ void __launch_bounds__(kThreads3, 3) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
+#ifndef SE_K3_MIN_BLOCKS
+#define SE_K3_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
     __shared__ __align__(16) float2 s_x[kWarps3 * 2][M];
-    __shared__ __align__(16) float2 s_win2[M];        // analysis window pairs
-    __shared__ __align__(16) float2 s_bw2[M];         // synthesis table pairs (see above)
+    __shared__ __align__(16) float2 s_win2[M];
+    __shared__ __align__(16) float2 s_bw2[M];
     for (int i = threadIdx.x; i < M; i += kThreads3) {
         const float w0 = a.tab.window[2 * i], w1 = a.tab.window[2 * i + 1];
-        s_win2[i] = make_float2(w0, w1);
+        s_win2[i] = make_float2(0.5f * w0, 0.5f * w1);
         const int n0 = (2 * i) & (H - 1), n1 = (2 * i + 1) & (H - 1);
         const float e0 = a.tab.window[n0] * a.tab.window[n0] + a.tab.window[n0 + H] * a.tab.window[n0 + H];
         const float e1 = a.tab.window[n1] * a.tab.window[n1] + a.tab.window[n1 + H] * a.tab.window[n1 + H];
-        s_bw2[i] = make_float2(w0 / (M * e0), w1 / (M * e1));
+        s_bw2[i] = make_float2(w0 / (2.0f * M * e0), -w1 / (2.0f * M * e1));
     }
     const int lane = threadIdx.x & 31, j = lane & 15, hw = threadIdx.x >> 4;
     const unsigned hmask = half_mask(lane);
@@ -142,69 +192,62 @@ __global__ void __launch_bounds__(kThreads3, 3) mask_istft512_kernel(MaskIstftAr
 #pragma unroll
     for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.0f, 0.0f);
 
+#pragma unroll 1
     for (int f = b0 - 1; f <= b1; ++f) {
         const bool halo = (f == b0 - 1);
         const bool own = spec && (!halo || f == 0) && f < valid_frames;
         const float* mk = a.mask + ((long long)u * F + f) * a.mask_stride;
         float pta[8], ptb[8], pt128 = 0.0f;
-        if (own) {                                                  // |STFT(clean)|^2 for the spectral SI-SDR sums
-            float2 c[16];
-            load_frame(crow, a.T, f * H - N / 2, j, s_win2, c);
-            fft256<-1>(c, xbuf, j, tw, hmask);
-            float2 cm[8];
-            fetch_mirror(c, lane, cm);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float2 xa = rfft_split(c[q], cm[q], twn[q]);
-                float2 xb = rfft_split(cm[q], c[q], make_float2(-twn[q].x, twn[q].y));
-                if (j == 0 && q == 0) { xa.y = 0.0f; xb.y = 0.0f; }
-                pta[q] = xa.x * xa.x + xa.y * xa.y;
-                ptb[q] = xb.x * xb.x + xb.y * xb.y;
-            }
-            const float2 x = rfft_split(c[8], c[8], make_float2(0.0f, -1.0f));
-            pt128 = x.x * x.x + x.y * x.y;
-        }
+        for (int q = 0; q < 8; ++q) { pta[q] = 0.0f; ptb[q] = 0.0f; }
         float2 v[16];
-        load_frame(nrow, a.T, f * H - N / 2, j, s_win2, v);
-        float ga[8], gb[8];
+        // pass 0: clean frame (spectral sums only), pass 1: noisy frame -> masked spectrum, pass 2: inverse
+#pragma unroll 1
+        for (int pass = own ? 0 : 1; pass < 3; ++pass) {
+            if (pass < 2) load_frame(pass == 0 ? crow : nrow, a.T, f * H - N / 2, j, s_win2, xbuf, hmask, v);
+            fft256<-1>(v, xbuf, j, tw, hmask);
+            if (pass == 2) break;
+            float2 zm[8];
+            fetch_mirror(v, lane, zm);
+            if (pass == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { ga[q] = __ldg(mk + j + 16 * q); gb[q] = __ldg(mk + M - j - 16 * q); }
-        const float g128 = __ldg(mk + 128);
-        fft256<-1>(v, xbuf, j, tw, hmask);
-        float2 zm[8];
-        fetch_mirror(v, lane, zm);
-        float2 za[8], zb[8];
+                for (int q = 0; q < 8; ++q) {
+                    float2 xa, xb;
+                    split_pair(v[q], zm[q], twn[q], xa, xb);
+                    pta[q] = xa.x * xa.x + xa.y * xa.y;
+                    ptb[q] = xb.x * xb.x + xb.y * xb.y;
+                }
+                pt128 = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
+            } else {
+                float2 ca[8], cb[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float2 wk = twn[q], wmk = make_float2(-twn[q].x, twn[q].y);
-            float2 xa = rfft_split(v[q], zm[q], wk);
-            float2 xb = rfft_split(zm[q], v[q], wmk);
-            if (j == 0 && q == 0) { xa.y = 0.0f; xb.y = 0.0f; }
-            if (own) {
-                const float ra = fmaxf(ga[q] * (xa.x * xa.x + xa.y * xa.y), 0.0f);      // relu(predicted), objective.py:89
-                const float rb = fmaxf(gb[q] * (xb.x * xb.x + xb.y * xb.y), 0.0f);
-                acc[sekern::SUM_SPEC_ST] += sqrtf(ra * pta[q]) + sqrtf(rb * ptb[q]);
-                acc[sekern::SUM_SPEC_TT] += pta[q] + ptb[q];
-                acc[sekern::SUM_SPEC_SS] += ra + rb;
+                for (int q = 0; q < 8; ++q) {
+                    const float ga = __ldg(mk + j + 16 * q), gb = __ldg(mk + M - j - 16 * q);
+                    float2 xa, xb;
+                    split_pair(v[q], zm[q], twn[q], xa, xb);
+                    if (own) {
+                        const float ra = fmaxf(ga * (xa.x * xa.x + xa.y * xa.y), 0.0f);      // relu(predicted), objective.py:89
+                        const float rb = fmaxf(gb * (xb.x * xb.x + xb.y * xb.y), 0.0f);
+                        acc[sekern::SUM_SPEC_ST] += fast_sqrt(ra * pta[q]) + fast_sqrt(rb * ptb[q]);
+                        acc[sekern::SUM_SPEC_TT] += pta[q] + ptb[q];
+                        acc[sekern::SUM_SPEC_SS] += ra + rb;
+                    }
+                    merge_pair_conj(cscale(xa, fast_sqrt(ga)), cscale(xb, fast_sqrt(gb)), twn[q], ca[q], cb[q]);
+                }
+                const float g128 = __ldg(mk + 128);
+                const float2 x128 = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
+                if (own && j == 0) {
+                    const float r = fmaxf(g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
+                    acc[sekern::SUM_SPEC_ST] += fast_sqrt(r * pt128);
+                    acc[sekern::SUM_SPEC_TT] += pt128;
+                    acc[sekern::SUM_SPEC_SS] += r;
+                }
+                // Zinv[128] = 2 conj(Y[128]) (same factor 2 as merge_pair_conj); its conjugate feeds the FFT
+                const float s128 = 2.0f * fast_sqrt(g128);
+                scatter_mirror(ca, cb, make_float2(s128 * x128.x, s128 * x128.y), lane, v);
             }
-            const float2 ya = cscale(xa, sqrtf(ga[q])), yb = cscale(xb, sqrtf(gb[q]));
-            za[q] = irfft_merge(ya, yb, wk);
-            zb[q] = irfft_merge(yb, ya, wmk);
         }
-        float2 z128;
-        {
-            const float2 x = rfft_split(v[8], v[8], make_float2(0.0f, -1.0f));
-            if (own && j == 0) {
-                const float r = fmaxf(g128 * (x.x * x.x + x.y * x.y), 0.0f);
-                acc[sekern::SUM_SPEC_ST] += sqrtf(r * pt128);
-                acc[sekern::SUM_SPEC_TT] += pt128;
-                acc[sekern::SUM_SPEC_SS] += r;
-            }
-            const float2 y = cscale(x, sqrtf(g128));
-            z128 = irfft_merge(y, y, make_float2(0.0f, -1.0f));
-        }
-        scatter_mirror(za, zb, z128, lane, v);
-        fft256<+1>(v, xbuf, j, tw, hmask);                          // v[q] = (x[2m], x[2m+1]), m = j + 16 q
+        // v[q] = conj(z[m]), z[m] = (x[2m], x[2m+1]) unnormalised, m = j + 16 q; signs and scales are in s_bw2
         if (!halo) {
             const int t0 = (f - 1) * H;
 #pragma unroll
@@ -264,17 +307,27 @@ int num_sms() {
 
 int launch_stft512(const StftArgs& a, cudaStream_t st) {
     const long long total = (long long)a.n_utt * a.n_frames;
-    const long long want = (total + (kThreads / 16) - 1) / (kThreads / 16);
+    const long long want = (total + (kThreads1 / 16) - 1) / (kThreads1 / 16);
     const long long cap = 2LL * num_sms();
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    stft512_kernel<<<grid, kThreads, 0, st>>>(a, total);
+    const int sel = (a.power ? 1 : 0) | (a.phase ? 2 : 0) | (a.logp ? 4 : 0);
+    switch (sel) {
+        case 1: stft512_kernel<true, false, false><<<grid, kThreads1, 0, st>>>(a, total); break;
+        case 2: stft512_kernel<false, true, false><<<grid, kThreads1, 0, st>>>(a, total); break;
+        case 3: stft512_kernel<true, true, false><<<grid, kThreads1, 0, st>>>(a, total); break;
+        case 4: stft512_kernel<false, false, true><<<grid, kThreads1, 0, st>>>(a, total); break;
+        case 5: stft512_kernel<true, false, true><<<grid, kThreads1, 0, st>>>(a, total); break;
+        case 6: stft512_kernel<false, true, true><<<grid, kThreads1, 0, st>>>(a, total); break;
+        case 7: stft512_kernel<true, true, true><<<grid, kThreads1, 0, st>>>(a, total); break;
+        default: return SE_OK;                                   // nothing requested
+    }
     return secommon::check_launch("stft512_kernel");
 }
 
 int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     // run length: long enough that the halo frame is a small overhead, short enough to fill the GPU
     const long long blocks_total = (long long)a.n_utt * (a.n_frames - 1);
-    const long long slots = 3LL * num_sms() * (kThreads3 / 16);           // resident half-warps
+    const long long slots = (long long)SE_K3_MIN_BLOCKS * num_sms() * (kThreads3 / 16);           // resident half-warps
     long long rl = (blocks_total + slots - 1) / slots;
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("SE_B200_RUN_LEN"); forced = e ? atoi(e) : 0; }

@@ -37,24 +37,39 @@ __global__ void finalize_metrics_kernel(const double* __restrict__ sums, const l
                                         int width, float* __restrict__ gain_out, float* __restrict__ sisdr_wave,
                                         float* __restrict__ loss_spec, int chunks) {
     const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
-    const double* s = sums + (long long)u * SE_NSUMS;
-    const double len = lengths ? (double)lengths[u] : (double)T;
-    const double eps_mean = 1e-8;                                   // utils.py:26, utils.py:31
-    const double mean_yy = s[SE_SUM_YY] / (len + eps_mean);
-    double level;                                                   // 10^(target/10)
-    if (isnan(target_db)) level = pow(10.0, (10.0 * log10(s[SE_SUM_CC] / (len + eps_mean))) / 10.0);
-    else level = pow(10.0, (double)target_db / 10.0);
-    const double gain = sqrt(level / (mean_yy + eps_mean));
-    if (chunk == 0 && threadIdx.x == 0) {
-        if (gain_out) gain_out[u] = (float)gain;
-        if (sisdr_wave) sisdr_wave[u] = (float)sisdr_from_sums(gain * s[SE_SUM_YC], s[SE_SUM_CC], gain * gain * s[SE_SUM_YY], 1e-10);
-        if (loss_spec) loss_spec[u] = (float)(-sisdr_from_sums(s[SE_SUM_SPEC_ST], s[SE_SUM_SPEC_TT], s[SE_SUM_SPEC_SS], 1e-10));
+    __shared__ float s_gain;
+    if (threadIdx.x == 0) {                                             // double-precision scalars: once per CTA
+        const double* s = sums + (long long)u * SE_NSUMS;
+        const double len = lengths ? (double)lengths[u] : (double)T;
+        const double eps_mean = 1e-8;                                   // utils.py:26, utils.py:31
+        const double mean_yy = s[SE_SUM_YY] / (len + eps_mean);
+        double level;                                                   // 10^(target/10)
+        if (isnan(target_db)) level = pow(10.0, (10.0 * log10(s[SE_SUM_CC] / (len + eps_mean))) / 10.0);
+        else level = pow(10.0, (double)target_db / 10.0);
+        const double gain = sqrt(level / (mean_yy + eps_mean));
+        s_gain = (float)gain;
+        if (chunk == 0) {
+            if (gain_out) gain_out[u] = (float)gain;
+            if (sisdr_wave) sisdr_wave[u] = (float)sisdr_from_sums(gain * s[SE_SUM_YC], s[SE_SUM_CC], gain * gain * s[SE_SUM_YY], 1e-10);
+            if (loss_spec) loss_spec[u] = (float)(-sisdr_from_sums(s[SE_SUM_SPEC_ST], s[SE_SUM_SPEC_TT], s[SE_SUM_SPEC_SS], 1e-10));
+        }
     }
-    if (wav) {
-        const float g = (float)gain;
-        float* row = wav + (long long)u * wav_stride;
-        const int per = (width + chunks - 1) / chunks;
-        const int lo = chunk * per, hi = min(width, lo + per);
+    if (!wav) return;
+    __syncthreads();
+    const float g = s_gain;
+    float* row = wav + (long long)u * wav_stride;
+    const int per = (((width + chunks - 1) / chunks) + 3) & ~3;
+    const int lo = chunk * per, hi = min(width, lo + per);
+    if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+        float4* r4 = reinterpret_cast<float4*>(row);
+        const int hi4 = hi & ~3;
+        for (int i = lo / 4 + threadIdx.x; i < hi4 / 4; i += blockDim.x) {
+            float4 v = r4[i];
+            v.x *= g; v.y *= g; v.z *= g; v.w *= g;
+            r4[i] = v;
+        }
+        for (int i = hi4 + threadIdx.x; i < hi; i += blockDim.x) row[i] *= g;
+    } else {
         for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) row[i] *= g;
     }
 }
@@ -218,19 +233,37 @@ __global__ void cmvn_stats_kernel(const float* __restrict__ x, long long ldx, in
     const int u = blockIdx.x / dchunks, dc = blockIdx.x - u * dchunks;
     const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, nrows = blockDim.x >> 5;
     const int d = dc * 32 + lane;
-    const float* base = x + (long long)u * n_frames * ldx;
+    const float* base = x + (long long)u * n_frames * ldx + d;
     __shared__ double red[8][33];
-    double s = 0.0;
-    if (d < D) for (int f = row; f < n_frames; f += nrows) s += (double)base[(long long)f * ldx + d];
-    red[row][lane] = s;
+    // pass 1: mean.  Four independent accumulators keep four loads in flight per thread.
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (d < D) {
+        int f = row;
+        for (; f + 3 * nrows < n_frames; f += 4 * nrows) {
+            const float a0 = base[(long long)f * ldx], a1 = base[(long long)(f + nrows) * ldx];
+            const float a2 = base[(long long)(f + 2 * nrows) * ldx], a3 = base[(long long)(f + 3 * nrows) * ldx];
+            s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+        }
+        for (; f < n_frames; f += nrows) s0 += base[(long long)f * ldx];
+    }
+    red[row][lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     double tot = 0.0;
     for (int r = 0; r < nrows; ++r) tot += red[r][lane];
     const double mu = tot / (double)n_frames;
     __syncthreads();
-    double q = 0.0;
-    if (d < D) for (int f = row; f < n_frames; f += nrows) { const double v = (double)base[(long long)f * ldx + d] - mu; q += v * v; }
-    red[row][lane] = q;
+    // pass 2: centred sum of squares (the data is L1/L2 resident now)
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+    if (d < D) {
+        int f = row;
+        for (; f + 3 * nrows < n_frames; f += 4 * nrows) {
+            const double v0 = (double)base[(long long)f * ldx] - mu, v1 = (double)base[(long long)(f + nrows) * ldx] - mu;
+            const double v2 = (double)base[(long long)(f + 2 * nrows) * ldx] - mu, v3 = (double)base[(long long)(f + 3 * nrows) * ldx] - mu;
+            q0 += v0 * v0; q1 += v1 * v1; q2 += v2 * v2; q3 += v3 * v3;
+        }
+        for (; f < n_frames; f += nrows) { const double v = (double)base[(long long)f * ldx] - mu; q0 += v * v; }
+    }
+    red[row][lane] = (q0 + q1) + (q2 + q3);
     __syncthreads();
     if (row == 0 && d < D) {
         double qt = 0.0;
@@ -457,7 +490,7 @@ int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_ut
                         float* wav, int64_t wav_stride, int64_t width, float* gain, float* sisdr_wave, float* loss_spec,
                         void* stream) {
     SE_REQUIRE(sums && n_utt > 0, "sums must not be null");
-    const int chunks = wav ? pick_chunks(n_utt, width, 4096) : 1;
+    const int chunks = wav ? pick_chunks(n_utt, width, 8192) : 1;
     finalize_metrics_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
         sums, (const long long*)lengths, (int)T, target_db_or_nan, wav, wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks);
     return secommon::check_launch("finalize_metrics_kernel");
