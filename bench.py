@@ -254,35 +254,52 @@ def main():
     ms_total = t.item()
     value = world * audio_s_per_step * args.steps / (ms_total * 1e-3)
 
-    # ---------------------------------------------------------------- per-kernel events (eager), roofline of the dominant kernel
+    # ---------------------------------------------------------------- per-kernel timing, roofline of the dominant kernel
+    # Each kernel is captured alone in a CUDA graph that launches it once per ring slot (distinct, HBM-cold
+    # inputs; no CPU launch gaps between the launches) and timed with CUDA events around the replays.
     window = pre._frame_window
-    ev = {k: [] for k in ("stft", "cmvn_stats", "head", "mask_istft", "finalize")}
-
-    def timed(name, fn):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = fn()
-        b.record()
-        ev[name].append((a, b))
-        return r
-
-    n_prof = min(args.steps, 64)
+    wpad = engine._padded_weight()
+    slots = []
     with torch.no_grad():
-        for i in range(3 + n_prof):
-            lengths, wavs = ring[i % len(ring)]
-            if i == 3:
-                for v in ev.values():
-                    v.clear()
-            feats = timed("stft", lambda: ops.stft_padded(wavs, 0, N_FFT, HOP, window, logpower=True))
-            mean, std = timed("cmvn_stats", lambda: ops.cmvn_stats_padded(feats, K))
-            wpad = engine._padded_weight()
-            mask = timed("head", lambda: ops.linear_head_padded(feats, K, wpad, head.linear.bias, head.activation, mean, std,
-                                                                head.eps, precision=engine.precision))
-            wav, sums = timed("mask_istft", lambda: ops.mask_istft(wavs, 0, 1, mask, lengths, N_FFT, HOP, window, pad_to=T,
-                                                                   mask_padded=True))
-            timed("finalize", lambda: ops.finalize_metrics(sums, lengths, T, wav=wav))
+        for lengths, wavs in ring:
+            feats = ops.stft_padded(wavs, 0, N_FFT, HOP, window, logpower=True)
+            mean, std = ops.cmvn_stats_padded(feats, K)
+            mask = ops.linear_head_padded(feats, K, wpad, head.linear.bias, head.activation, mean, std, head.eps, precision=engine.precision)
+            wav, sums = ops.mask_istft(wavs, 0, 1, mask, lengths, N_FFT, HOP, window, pad_to=T, mask_padded=True)
+            slots.append(dict(lengths=lengths, wavs=wavs, feats=feats, mean=mean, std=std, mask=mask, wav=wav, sums=sums))
     torch.cuda.synchronize()
-    kernel_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in ev.items()}
+    launchers = {
+        "stft": lambda s: ops.stft_padded(s["wavs"], 0, N_FFT, HOP, window, logpower=True),
+        "cmvn_stats": lambda s: ops.cmvn_stats_padded(s["feats"], K),
+        "head": lambda s: ops.linear_head_padded(s["feats"], K, wpad, head.linear.bias, head.activation, s["mean"], s["std"], head.eps,
+                                                 precision=engine.precision),
+        "mask_istft": lambda s: ops.mask_istft(s["wavs"], 0, 1, s["mask"], s["lengths"], N_FFT, HOP, window, pad_to=T, mask_padded=True,
+                                               out=s["wav"], sums=s["sums"]),
+        "finalize": lambda s: ops.finalize_metrics(s["sums"], s["lengths"], T, wav=s["wav"]),
+    }
+    kernel_ms = {}
+    reps = max(3, min(20, args.steps // len(slots)))
+    for name, fn in launchers.items():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for sl in slots[:2]:
+                fn(sl)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), torch.no_grad():
+            for sl in slots:
+                fn(sl)
+        g.replay()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            g.replay()
+        a1.record()
+        torch.cuda.synchronize()
+        kernel_ms[name] = a0.elapsed_time(a1) / (reps * len(slots))
     # algorithmic bytes per launch (DESIGN.md "kernels"): K3 reads noisy + clean (2 x 4T), the mask (4FK), writes 4T per utterance
     alg_bytes = {"stft": N_UTT * (4 * T + 4 * F * K), "cmvn_stats": N_UTT * 4 * F * K, "head": N_UTT * 8 * F * K,
                  "mask_istft": N_UTT * (12 * T + 4 * F * K), "finalize": N_UTT * 8 * T}

@@ -38,6 +38,54 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
+// ---- asynchronous staging (cp.async): the global loads of frame i+1 are in flight while frame i is
+// transformed, so no half-warp ever waits on a DRAM round trip between its transforms.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_PENDING> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
+}
+
+// stage `count` floats (multiple of 4) of a waveform row starting at original coordinate t0 into dst (16-byte
+// aligned shared memory): 16-byte cp.async when the span is interior and aligned, else a rolled reflect loop
+__device__ __forceinline__ void stage_wave(float* __restrict__ dst, const float* __restrict__ row, int T, int t0, int count, int j) {
+    const float* src = row + t0;
+    if ((t0 >= 0) && (t0 + count <= T) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        for (int c = j; c < count / 4; c += 16) cp_async16(dst + 4 * c, src + 4 * c);
+    } else {
+#pragma unroll 1
+        for (int i = j; i < count; i += 16) {
+            int t = t0 + i;
+            t = t < 0 ? -t : t;
+            t = t >= T ? 2 * (T - 1) - t : t;
+            dst[i] = __ldg(row + t);
+        }
+    }
+}
+// stage a row of `count` floats (any alignment) that needs no reflection
+__device__ __forceinline__ void stage_row(float* __restrict__ dst, const float* __restrict__ src, int count, int j, bool padded) {
+    if (padded && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {                              // padded: row stride >= round4(count)
+        for (int c = j; c < (count + 3) / 4; c += 16) cp_async16(dst + 4 * c, src + 4 * c);
+    } else {
+#pragma unroll 1
+        for (int i = j; i < count; i += 16) dst[i] = __ldg(src + i);
+    }
+}
+
+// v[r] = (x[2m], x[2m+1]) * win2[m], m = j + 16 r, from a staged frame
+__device__ __forceinline__ void frame_from_stage(const float* __restrict__ st, int j, const float2* __restrict__ win2, float2 (&v)[16]) {
+    const float2* s2 = reinterpret_cast<const float2*>(st);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const float2 x = s2[j + 16 * r];
+        const float2 w = win2[j + 16 * r];
+        v[r] = make_float2(x.x * w.x, x.y * w.y);
+    }
+}
+
 // v[r] = (x[2m], x[2m+1]) * win2[m], m = j + 16 r, for the frame whose first sample is row[t0]
 // (t0 may run over either end of the row -> reflect, as torch.stft pad_mode='reflect')
 __device__ __forceinline__ void load_frame(const float* __restrict__ row, int T, int t0, int j, const float2* __restrict__ win2,
@@ -92,25 +140,38 @@ __device__ __forceinline__ void merge_pair_conj(float2 ya, float2 yb, float2 w, 
 // ------------------------------------------------------------------ K1
 constexpr int kWarps1 = 8, kThreads1 = kWarps1 * 32;
 
+// dynamic shared memory of K1: transpose buffers [16][256] float2, frame staging [16][2][512] float, window pairs
+constexpr size_t kSmem1 = (size_t)(kWarps1 * 2) * (M * 8 + 2 * N * 4) + M * 8;
+
 template <bool POWER, bool PHASE, bool LOGP>
 __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long long total_frames) {
-    __shared__ __align__(16) float2 s_x[kWarps1 * 2][M];       // transpose buffers, one per half-warp
-    __shared__ __align__(16) float2 s_win2[M];                  // 0.5 * window as (w[2m], w[2m+1])
-    for (int i = threadIdx.x; i < M; i += kThreads1) s_win2[i] = make_float2(0.5f * a.tab.window[2 * i], 0.5f * a.tab.window[2 * i + 1]);
+    extern __shared__ __align__(16) unsigned char smem1[];
     const int lane = threadIdx.x & 31, j = lane & 15;
     const int hw = (threadIdx.x >> 4);
+    float2* xbuf = reinterpret_cast<float2*>(smem1) + hw * M;
+    float* stage = reinterpret_cast<float*>(smem1 + (size_t)(kWarps1 * 2) * M * 8) + hw * 2 * N;
+    float2* s_win2 = reinterpret_cast<float2*>(smem1 + (size_t)(kWarps1 * 2) * (M * 8 + 2 * N * 4));
+    for (int i = threadIdx.x; i < M; i += kThreads1) s_win2[i] = make_float2(0.5f * a.tab.window[2 * i], 0.5f * a.tab.window[2 * i + 1]);
     float2 tw[15], twn[8];
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     __syncthreads();
-    float2* xbuf = s_x[hw];
     const long long n_hw = (long long)gridDim.x * (kThreads1 / 16);
     const long long first = (long long)blockIdx.x * (kThreads1 / 16) + hw;
     const unsigned hmask = half_mask(lane);
-#pragma unroll 1
-    for (long long gg = first; gg < total_frames; gg += n_hw) {
+    auto prefetch = [&](long long gg, int buf) {
         const int u = (int)(gg / a.n_frames), f = (int)(gg - (long long)u * a.n_frames);
+        stage_wave(stage + buf * N, a.wav + (long long)u * a.utt_stride, a.T, f * a.hop - N / 2, N, j);
+        cp_async_commit();
+    };
+    if (first < total_frames) prefetch(first, 0);
+    int buf = 0;
+#pragma unroll 1
+    for (long long gg = first; gg < total_frames; gg += n_hw, buf ^= 1) {
+        if (gg + n_hw < total_frames) { prefetch(gg + n_hw, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp(hmask);
         float2 v[16];
-        load_frame(a.wav + (long long)u * a.utt_stride, a.T, f * a.hop - N / 2, j, s_win2, xbuf, hmask, v);
+        frame_from_stage(stage + buf * N, j, s_win2, v);
         fft256<-1>(v, xbuf, j, tw, hmask);
         float2 zm[8];
         fetch_mirror(v, lane, zm);
@@ -135,6 +196,7 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
             if (LOGP) lg[128] = __logf(p + a.log_eps);
             if (PHASE) ph[128] = atan2f(x.y, x.x);
         }
+        __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
     }
 }
 
@@ -153,10 +215,14 @@ struct RunPlan { int run_len; int runs_per_utt; long long total_runs; };
 #ifndef SE_K3_MIN_BLOCKS
 #define SE_K3_MIN_BLOCKS 3
 #endif
+// per half-warp, per stage: noisy frame (512) | clean frame (512) | mask row (272) floats
+constexpr int kStageFloats3 = N + N + 272;
+constexpr size_t kSmem3 = (size_t)(kWarps3 * 2) * (M * 8 + 2 * kStageFloats3 * 4) + 2 * M * 8;
+
 __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
-    __shared__ __align__(16) float2 s_x[kWarps3 * 2][M];
-    __shared__ __align__(16) float2 s_win2[M];
-    __shared__ __align__(16) float2 s_bw2[M];
+    extern __shared__ __align__(16) unsigned char smem3[];
+    float2* s_win2 = reinterpret_cast<float2*>(smem3 + (size_t)(kWarps3 * 2) * (M * 8 + 2 * kStageFloats3 * 4));
+    float2* s_bw2 = s_win2 + M;
     for (int i = threadIdx.x; i < M; i += kThreads3) {
         const float w0 = a.tab.window[2 * i], w1 = a.tab.window[2 * i + 1];
         s_win2[i] = make_float2(0.5f * w0, 0.5f * w1);
@@ -170,7 +236,8 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     float2 tw[15], twn[8];
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     __syncthreads();
-    float2* xbuf = s_x[hw];
+    float2* xbuf = reinterpret_cast<float2*>(smem3) + hw * M;
+    float* stage = reinterpret_cast<float*>(smem3 + (size_t)(kWarps3 * 2) * M * 8) + hw * 2 * kStageFloats3;
     const long long unit = (long long)blockIdx.x * (kThreads3 / 16) + hw;
     if (unit >= plan.total_runs) return;                          // no block-level barrier below
     const int u = (int)(unit / plan.runs_per_utt), ri = (int)(unit - (long long)u * plan.runs_per_utt);
@@ -184,7 +251,6 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     const int valid_frames = min(F, len / H + 1);                  // runner.py:455
     const bool spec = a.want_spec && crow && a.sums;
     const bool out_aligned = (reinterpret_cast<uintptr_t>(orow) & 7) == 0;
-    const bool clean_aligned = crow && (reinterpret_cast<uintptr_t>(crow) & 7) == 0;
     float acc[sekern::NSUMS];
 #pragma unroll
     for (int i = 0; i < sekern::NSUMS; ++i) acc[i] = 0.0f;
@@ -192,11 +258,27 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
 #pragma unroll
     for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.0f, 0.0f);
 
+    const bool mask_padded = a.mask_stride >= 260;
+    // stage frame f: noisy samples, clean samples (when they are needed: spectral sums or waveform sums) and the mask row
+    auto prefetch = [&](int f, int buf) {
+        float* st = stage + buf * kStageFloats3;
+        stage_wave(st, nrow, a.T, f * H - N / 2, N, j);
+        const bool halo_f = (f == b0 - 1);
+        if (crow && a.sums && (!halo_f || (spec && f == 0))) stage_wave(st + N, crow, a.T, f * H - N / 2, N, j);
+        stage_row(st + 2 * N, a.mask + ((long long)u * F + f) * a.mask_stride, M + 1, j, mask_padded);
+        cp_async_commit();
+    };
+    prefetch(b0 - 1, 0);
+    int buf = 0;
 #pragma unroll 1
-    for (int f = b0 - 1; f <= b1; ++f) {
+    for (int f = b0 - 1; f <= b1; ++f, buf ^= 1) {
         const bool halo = (f == b0 - 1);
         const bool own = spec && (!halo || f == 0) && f < valid_frames;
-        const float* mk = a.mask + ((long long)u * F + f) * a.mask_stride;
+        if (f < b1) { prefetch(f + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp(hmask);
+        const float* st = stage + buf * kStageFloats3;
+        const float* mk = st + 2 * N;
         float pta[8], ptb[8], pt128 = 0.0f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) { pta[q] = 0.0f; ptb[q] = 0.0f; }
@@ -204,7 +286,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
         // pass 0: clean frame (spectral sums only), pass 1: noisy frame -> masked spectrum, pass 2: inverse
 #pragma unroll 1
         for (int pass = own ? 0 : 1; pass < 3; ++pass) {
-            if (pass < 2) load_frame(pass == 0 ? crow : nrow, a.T, f * H - N / 2, j, s_win2, xbuf, hmask, v);
+            if (pass < 2) frame_from_stage(pass == 0 ? st + N : st, j, s_win2, v);
             fft256<-1>(v, xbuf, j, tw, hmask);
             if (pass == 2) break;
             float2 zm[8];
@@ -222,7 +304,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 float2 ca[8], cb[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float ga = __ldg(mk + j + 16 * q), gb = __ldg(mk + M - j - 16 * q);
+                    const float ga = mk[j + 16 * q], gb = mk[M - j - 16 * q];
                     float2 xa, xb;
                     split_pair(v[q], zm[q], twn[q], xa, xb);
                     if (own) {
@@ -234,7 +316,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                     }
                     merge_pair_conj(cscale(xa, fast_sqrt(ga)), cscale(xb, fast_sqrt(gb)), twn[q], ca[q], cb[q]);
                 }
-                const float g128 = __ldg(mk + 128);
+                const float g128 = mk[128];
                 const float2 x128 = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
                 if (own && j == 0) {
                     const float r = fmaxf(g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
@@ -260,7 +342,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 else { orow[t] = y.x; orow[t + 1] = y.y; }
                 if (a.sums) {
                     float2 c = make_float2(0.0f, 0.0f);
-                    if (crow) c = clean_aligned ? __ldg(reinterpret_cast<const float2*>(crow + t)) : make_float2(__ldg(crow + t), __ldg(crow + t + 1));
+                    if (crow) c = *reinterpret_cast<const float2*>(st + N + 2 * m);           // first half of the clean frame = this block
                     if (t < len) { acc[sekern::SUM_YY] += y.x * y.x; acc[sekern::SUM_YC] += y.x * c.x; acc[sekern::SUM_CC] += c.x * c.x; }
                     if (t + 1 < len) { acc[sekern::SUM_YY] += y.y * y.y; acc[sekern::SUM_YC] += y.y * c.y; acc[sekern::SUM_CC] += c.y * c.y; }
                 }
@@ -271,6 +353,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
             const float2 bw = s_bw2[j + 16 * q + 128];
             carry[q] = make_float2(bw.x * v[q + 8].x, bw.y * v[q + 8].y);
         }
+        __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
     }
     // the last run of an utterance also zero-fills [out_len, pad_to) and finishes sum c^2 over [out_len, len)
     if (b1 == F - 1) {
@@ -305,6 +388,21 @@ int num_sms() {
     return sms;
 }
 
+// opt the kernels into their dynamic shared-memory sizes (called once per device from se_prepare / first use)
+int prepare512() {
+#define SE_OPT(K, BYTES) SE_CUDA_CHECK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)))
+    SE_OPT((stft512_kernel<true, false, false>), kSmem1);
+    SE_OPT((stft512_kernel<false, true, false>), kSmem1);
+    SE_OPT((stft512_kernel<true, true, false>), kSmem1);
+    SE_OPT((stft512_kernel<false, false, true>), kSmem1);
+    SE_OPT((stft512_kernel<true, false, true>), kSmem1);
+    SE_OPT((stft512_kernel<false, true, true>), kSmem1);
+    SE_OPT((stft512_kernel<true, true, true>), kSmem1);
+    SE_OPT(mask_istft512_kernel, kSmem3);
+#undef SE_OPT
+    return SE_OK;
+}
+
 int launch_stft512(const StftArgs& a, cudaStream_t st) {
     const long long total = (long long)a.n_utt * a.n_frames;
     const long long want = (total + (kThreads1 / 16) - 1) / (kThreads1 / 16);
@@ -312,13 +410,13 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     const int sel = (a.power ? 1 : 0) | (a.phase ? 2 : 0) | (a.logp ? 4 : 0);
     switch (sel) {
-        case 1: stft512_kernel<true, false, false><<<grid, kThreads1, 0, st>>>(a, total); break;
-        case 2: stft512_kernel<false, true, false><<<grid, kThreads1, 0, st>>>(a, total); break;
-        case 3: stft512_kernel<true, true, false><<<grid, kThreads1, 0, st>>>(a, total); break;
-        case 4: stft512_kernel<false, false, true><<<grid, kThreads1, 0, st>>>(a, total); break;
-        case 5: stft512_kernel<true, false, true><<<grid, kThreads1, 0, st>>>(a, total); break;
-        case 6: stft512_kernel<false, true, true><<<grid, kThreads1, 0, st>>>(a, total); break;
-        case 7: stft512_kernel<true, true, true><<<grid, kThreads1, 0, st>>>(a, total); break;
+        case 1: stft512_kernel<true, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
+        case 2: stft512_kernel<false, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
+        case 3: stft512_kernel<true, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
+        case 4: stft512_kernel<false, false, true><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
+        case 5: stft512_kernel<true, false, true><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
+        case 6: stft512_kernel<false, true, true><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
+        case 7: stft512_kernel<true, true, true><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
         default: return SE_OK;                                   // nothing requested
     }
     return secommon::check_launch("stft512_kernel");
@@ -339,7 +437,7 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     plan.total_runs = (long long)a.n_utt * plan.runs_per_utt;
     const long long grid = (plan.total_runs + (kThreads3 / 16) - 1) / (kThreads3 / 16);
     if (grid > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "grid too large");
-    mask_istft512_kernel<<<(unsigned)grid, kThreads3, 0, st>>>(a, plan);
+    mask_istft512_kernel<<<(unsigned)grid, kThreads3, kSmem3, st>>>(a, plan);
     return secommon::check_launch("mask_istft512_kernel");
 }
 

@@ -13,6 +13,7 @@ using namespace sekern;
 using secommon::fail;
 
 namespace sefast {
+int prepare512();
 int launch_stft512(const StftArgs& a, cudaStream_t st);
 int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st);
 }
@@ -81,7 +82,7 @@ int get_tables(int n_fft, DeviceTables* out) {
         switch (n_fft) {
             case 256: rc = opt_in_smem<256>(); break;
             case 400: rc = opt_in_smem<400>(); break;
-            case 512: rc = opt_in_smem<512>(); break;
+            case 512: rc = opt_in_smem<512>(); if (rc == SE_OK) rc = sefast::prepare512(); break;
             case 1024: rc = opt_in_smem<1024>(); break;
             case 2048: rc = opt_in_smem<2048>(); break;
         }
