@@ -423,17 +423,34 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
 }
 
 int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
-    // run length: long enough that the halo frame is a small overhead, short enough to fill the GPU
-    const long long blocks_total = (long long)a.n_utt * (a.n_frames - 1);
-    const long long slots = (long long)SE_K3_MIN_BLOCKS * num_sms() * (kThreads3 / 16);           // resident half-warps
-    long long rl = (blocks_total + slots - 1) / slots;
+    // Run length: long enough that the halo frame is a small overhead, short enough to fill the GPU, and chosen so
+    // that the number of CTAs is (just under) a whole number of waves -- with ~2 CTAs per SM a ragged last wave
+    // leaves a third of the SMs idle for half of the kernel.
+    const int blocks_per_utt = a.n_frames - 1;
+    const long long hw_per_wave = 2LL * num_sms() * (kThreads3 / 16);          // 2 CTAs/SM resident (shared memory)
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("SE_B200_RUN_LEN"); forced = e ? atoi(e) : 0; }
-    if (forced > 0) rl = forced;
-    else rl = rl < 8 ? 8 : (rl > 64 ? 64 : rl);
     RunPlan plan;
-    plan.runs_per_utt = (int)((a.n_frames - 1 + rl - 1) / rl);
-    plan.run_len = (int)((a.n_frames - 1 + plan.runs_per_utt - 1) / plan.runs_per_utt);     // balanced runs
+    if (forced > 0) {
+        plan.runs_per_utt = (blocks_per_utt + forced - 1) / forced;
+    } else {
+        // candidates: runs_per_utt such that n_utt * runs_per_utt fills w waves, w = 1, 2, ...; take the first whose
+        // run length is <= 64 blocks, but never go below 6 blocks per run (halo overhead 1/6)
+        int best = 0;
+        for (int w = 1; w <= 4096; ++w) {
+            const int rpu = (int)((w * hw_per_wave) / a.n_utt);
+            if (rpu < 1) continue;
+            const int rl = (blocks_per_utt + rpu - 1) / rpu;
+            if (rl < 6) break;
+            best = rpu;
+            if (rl <= 64) break;
+        }
+        if (best == 0) best = (blocks_per_utt + 5) / 6 > 0 ? (blocks_per_utt + 5) / 6 : 1;
+        plan.runs_per_utt = best;
+    }
+    if (plan.runs_per_utt > blocks_per_utt) plan.runs_per_utt = blocks_per_utt;
+    plan.run_len = (blocks_per_utt + plan.runs_per_utt - 1) / plan.runs_per_utt;
+    plan.runs_per_utt = (blocks_per_utt + plan.run_len - 1) / plan.run_len;
     plan.total_runs = (long long)a.n_utt * plan.runs_per_utt;
     const long long grid = (plan.total_runs + (kThreads3 / 16) - 1) / (kThreads3 / 16);
     if (grid > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "grid too large");

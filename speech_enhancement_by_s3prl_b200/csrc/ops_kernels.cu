@@ -32,45 +32,47 @@ __device__ __forceinline__ double sisdr_from_sums(double st, double tt, double s
 }
 
 // ------------------------------------------------------------------ finalize (gain + metrics)
+// level_or_neg: 10^(target_dB/10) computed on the host, or < 0 to match the clean reference's own level.
+// 10^(10 log10(x) / 10) == x, so the reference's dB round trip (utils.py:38-42) needs no pow/log here.
 __global__ void finalize_metrics_kernel(const double* __restrict__ sums, const long long* __restrict__ lengths,
-                                        int T, float target_db, float* __restrict__ wav, long long wav_stride,
+                                        int T, double level_or_neg, float* __restrict__ wav, long long wav_stride,
                                         int width, float* __restrict__ gain_out, float* __restrict__ sisdr_wave,
                                         float* __restrict__ loss_spec, int chunks) {
     const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
-    __shared__ float s_gain;
-    if (threadIdx.x == 0) {                                             // double-precision scalars: once per CTA
-        const double* s = sums + (long long)u * SE_NSUMS;
-        const double len = lengths ? (double)lengths[u] : (double)T;
-        const double eps_mean = 1e-8;                                   // utils.py:26, utils.py:31
-        const double mean_yy = s[SE_SUM_YY] / (len + eps_mean);
-        double level;                                                   // 10^(target/10)
-        if (isnan(target_db)) level = pow(10.0, (10.0 * log10(s[SE_SUM_CC] / (len + eps_mean))) / 10.0);
-        else level = pow(10.0, (double)target_db / 10.0);
-        const double gain = sqrt(level / (mean_yy + eps_mean));
-        s_gain = (float)gain;
-        if (chunk == 0) {
-            if (gain_out) gain_out[u] = (float)gain;
-            if (sisdr_wave) sisdr_wave[u] = (float)sisdr_from_sums(gain * s[SE_SUM_YC], s[SE_SUM_CC], gain * gain * s[SE_SUM_YY], 1e-10);
-            if (loss_spec) loss_spec[u] = (float)(-sisdr_from_sums(s[SE_SUM_SPEC_ST], s[SE_SUM_SPEC_TT], s[SE_SUM_SPEC_SS], 1e-10));
-        }
+    const double* s = sums + (long long)u * SE_NSUMS;
+    const double len = lengths ? (double)lengths[u] : (double)T;
+    const double eps_mean = 1e-8;                                       // utils.py:26, utils.py:31
+    const double mean_yy = s[SE_SUM_YY] / (len + eps_mean);
+    const double level = level_or_neg < 0.0 ? s[SE_SUM_CC] / (len + eps_mean) : level_or_neg;
+    const double gain = sqrt(level / (mean_yy + eps_mean));
+    if (chunk == 0 && threadIdx.x == 0) {
+        if (gain_out) gain_out[u] = (float)gain;
+        if (sisdr_wave) sisdr_wave[u] = (float)sisdr_from_sums(gain * s[SE_SUM_YC], s[SE_SUM_CC], gain * gain * s[SE_SUM_YY], 1e-10);
+        if (loss_spec) loss_spec[u] = (float)(-sisdr_from_sums(s[SE_SUM_SPEC_ST], s[SE_SUM_SPEC_TT], s[SE_SUM_SPEC_SS], 1e-10));
     }
     if (!wav) return;
-    __syncthreads();
-    const float g = s_gain;
+    const float g = (float)gain;
     float* row = wav + (long long)u * wav_stride;
     const int per = (((width + chunks - 1) / chunks) + 3) & ~3;
     const int lo = chunk * per, hi = min(width, lo + per);
     if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
         float4* r4 = reinterpret_cast<float4*>(row);
         const int hi4 = hi & ~3;
-        for (int i = lo / 4 + threadIdx.x; i < hi4 / 4; i += blockDim.x) {
+        int i = lo / 4 + threadIdx.x;
+        for (; i + 3 * (int)blockDim.x < hi4 / 4; i += 4 * blockDim.x) {       // four loads in flight per thread
+            float4 v0 = r4[i], v1 = r4[i + blockDim.x], v2 = r4[i + 2 * blockDim.x], v3 = r4[i + 3 * blockDim.x];
+            v0.x *= g; v0.y *= g; v0.z *= g; v0.w *= g;  v1.x *= g; v1.y *= g; v1.z *= g; v1.w *= g;
+            v2.x *= g; v2.y *= g; v2.z *= g; v2.w *= g;  v3.x *= g; v3.y *= g; v3.z *= g; v3.w *= g;
+            r4[i] = v0; r4[i + blockDim.x] = v1; r4[i + 2 * blockDim.x] = v2; r4[i + 3 * blockDim.x] = v3;
+        }
+        for (; i < hi4 / 4; i += blockDim.x) {
             float4 v = r4[i];
             v.x *= g; v.y *= g; v.z *= g; v.w *= g;
             r4[i] = v;
         }
-        for (int i = hi4 + threadIdx.x; i < hi; i += blockDim.x) row[i] *= g;
+        for (int k = hi4 + threadIdx.x; k < hi; k += blockDim.x) row[k] *= g;
     } else {
-        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) row[i] *= g;
+        for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) row[k] *= g;
     }
 }
 
@@ -227,6 +229,8 @@ __global__ void length_masks_kernel(const long long* __restrict__ lengths, long 
 
 // ------------------------------------------------------------------ CMVN statistics over time
 // x (n_utt, F, D): mean / unbiased std per (u, d).  block = 32 features x 8 frame lanes.
+// One pass: sums of (x - x0) and (x - x0)^2 with x0 = the utterance's first frame (a shift that removes the
+// cancellation of the one-pass variance), eight independent loads in flight per thread, double accumulators.
 __global__ void cmvn_stats_kernel(const float* __restrict__ x, long long ldx, int n_frames, int D, float* __restrict__ mean,
                                   float* __restrict__ stdv, long long ld_stats) {
     const int dchunks = (D + 31) / 32;
@@ -234,42 +238,33 @@ __global__ void cmvn_stats_kernel(const float* __restrict__ x, long long ldx, in
     const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, nrows = blockDim.x >> 5;
     const int d = dc * 32 + lane;
     const float* base = x + (long long)u * n_frames * ldx + d;
-    __shared__ double red[8][33];
-    // pass 1: mean.  Four independent accumulators keep four loads in flight per thread.
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    __shared__ double red1[8][33], red2[8][33];
+    double s = 0.0, q = 0.0;
+    float x0 = 0.0f;
     if (d < D) {
+        x0 = base[0];
         int f = row;
-        for (; f + 3 * nrows < n_frames; f += 4 * nrows) {
-            const float a0 = base[(long long)f * ldx], a1 = base[(long long)(f + nrows) * ldx];
-            const float a2 = base[(long long)(f + 2 * nrows) * ldx], a3 = base[(long long)(f + 3 * nrows) * ldx];
-            s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+        for (; f + 7 * nrows < n_frames; f += 8 * nrows) {
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = base[(long long)(f + i * nrows) * ldx];
+            float ps = 0.0f, pq = 0.0f;                                   // eight terms: fp32 partials are exact enough
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float v = a[i] - x0; ps += v; pq += v * v; }
+            s += (double)ps; q += (double)pq;
         }
-        for (; f < n_frames; f += nrows) s0 += base[(long long)f * ldx];
+        for (; f < n_frames; f += nrows) { const float v = base[(long long)f * ldx] - x0; s += (double)v; q += (double)v * v; }
     }
-    red[row][lane] = (s0 + s1) + (s2 + s3);
-    __syncthreads();
-    double tot = 0.0;
-    for (int r = 0; r < nrows; ++r) tot += red[r][lane];
-    const double mu = tot / (double)n_frames;
-    __syncthreads();
-    // pass 2: centred sum of squares (the data is L1/L2 resident now)
-    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-    if (d < D) {
-        int f = row;
-        for (; f + 3 * nrows < n_frames; f += 4 * nrows) {
-            const double v0 = (double)base[(long long)f * ldx] - mu, v1 = (double)base[(long long)(f + nrows) * ldx] - mu;
-            const double v2 = (double)base[(long long)(f + 2 * nrows) * ldx] - mu, v3 = (double)base[(long long)(f + 3 * nrows) * ldx] - mu;
-            q0 += v0 * v0; q1 += v1 * v1; q2 += v2 * v2; q3 += v3 * v3;
-        }
-        for (; f < n_frames; f += nrows) { const double v = (double)base[(long long)f * ldx] - mu; q0 += v * v; }
-    }
-    red[row][lane] = (q0 + q1) + (q2 + q3);
+    red1[row][lane] = s;
+    red2[row][lane] = q;
     __syncthreads();
     if (row == 0 && d < D) {
-        double qt = 0.0;
-        for (int r = 0; r < nrows; ++r) qt += red[r][lane];
-        mean[(long long)u * ld_stats + d] = (float)mu;
-        stdv[(long long)u * ld_stats + d] = (float)sqrt(qt / (double)(n_frames - 1));      // unbiased (model.py:30)
+        double st = 0.0, qt = 0.0;
+        for (int r = 0; r < nrows; ++r) { st += red1[r][lane]; qt += red2[r][lane]; }
+        const double n = (double)n_frames;
+        const double var = (qt - st * st / n) / (n - 1.0);                  // unbiased (model.py:30)
+        mean[(long long)u * ld_stats + d] = (float)((double)x0 + st / n);
+        stdv[(long long)u * ld_stats + d] = (float)sqrt(var > 0.0 ? var : 0.0);
     }
 }
 
@@ -490,9 +485,10 @@ int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_ut
                         float* wav, int64_t wav_stride, int64_t width, float* gain, float* sisdr_wave, float* loss_spec,
                         void* stream) {
     SE_REQUIRE(sums && n_utt > 0, "sums must not be null");
-    const int chunks = wav ? pick_chunks(n_utt, width, 8192) : 1;
+    const int chunks = wav ? pick_chunks(n_utt, width, 4096) : 1;
+    const double level = std::isnan(target_db_or_nan) ? -1.0 : std::pow(10.0, (double)target_db_or_nan / 10.0);
     finalize_metrics_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
-        sums, (const long long*)lengths, (int)T, target_db_or_nan, wav, wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks);
+        sums, (const long long*)lengths, (int)T, level, wav, wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks);
     return secommon::check_launch("finalize_metrics_kernel");
 }
 
