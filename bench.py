@@ -259,24 +259,40 @@ def main():
     # inputs; no CPU launch gaps between the launches) and timed with CUDA events around the replays.
     window = pre._frame_window
     wpad = engine._padded_weight()
+    LD = ops.round4(K)
+    fused = engine.precision == 1 and ops.linear_head_tma_supported(N_UTT, F, K, K, LD, wpad.shape[1], LD)
     slots = []
     with torch.no_grad():
         for lengths, wavs in ring:
-            feats = ops.stft_padded(wavs, 0, N_FFT, HOP, window, logpower=True)
-            mean, std = ops.cmvn_stats_padded(feats, K)
-            mask = ops.linear_head_padded(feats, K, wpad, head.linear.bias, head.activation, mean, std, head.eps, precision=engine.precision)
-            wav, sums = ops.mask_istft(wavs, 0, 1, mask, lengths, N_FFT, HOP, window, pad_to=T, mask_padded=True)
-            slots.append(dict(lengths=lengths, wavs=wavs, feats=feats, mean=mean, std=std, mask=mask, wav=wav, sums=sums))
+            sl = dict(lengths=lengths, wavs=wavs)
+            if fused:
+                sl["stat_sums"] = torch.zeros(N_UTT, LD, 2, device=dev, dtype=torch.float64)
+                sl["feats"], _ = ops.stft_features(wavs, 0, N_FFT, HOP, window, logpower=True, stat_sums=sl["stat_sums"])
+                sl["mask"] = ops.linear_head_tma(sl["feats"], K, wpad, head.linear.bias, head.activation, sl["stat_sums"], head.eps)
+            else:
+                sl["feats"] = ops.stft_padded(wavs, 0, N_FFT, HOP, window, logpower=True)
+                sl["mean"], sl["std"] = ops.cmvn_stats_padded(sl["feats"], K)
+                sl["mask"] = ops.linear_head_padded(sl["feats"], K, wpad, head.linear.bias, head.activation, sl["mean"], sl["std"], head.eps,
+                                                    precision=engine.precision)
+            sl["wav"], sl["sums"] = ops.mask_istft(wavs, 0, 1, sl["mask"], lengths, N_FFT, HOP, window, pad_to=T, mask_padded=True)
+            slots.append(sl)
     torch.cuda.synchronize()
-    launchers = {
-        "stft": lambda s: ops.stft_padded(s["wavs"], 0, N_FFT, HOP, window, logpower=True),
-        "cmvn_stats": lambda s: ops.cmvn_stats_padded(s["feats"], K),
-        "head": lambda s: ops.linear_head_padded(s["feats"], K, wpad, head.linear.bias, head.activation, s["mean"], s["std"], head.eps,
-                                                 precision=engine.precision),
-        "mask_istft": lambda s: ops.mask_istft(s["wavs"], 0, 1, s["mask"], s["lengths"], N_FFT, HOP, window, pad_to=T, mask_padded=True,
-                                               out=s["wav"], sums=s["sums"]),
-        "finalize": lambda s: ops.finalize_metrics(s["sums"], s["lengths"], T, wav=s["wav"]),
-    }
+    if fused:
+        # (the sums buffer keeps accumulating across timing launches: the values are not used here)
+        launchers = {
+            "stft": lambda s: ops.stft_features(s["wavs"], 0, N_FFT, HOP, window, logpower=True, stat_sums=s["stat_sums"]),
+            "head": lambda s: ops.linear_head_tma(s["feats"], K, wpad, head.linear.bias, head.activation, s["stat_sums"], head.eps),
+        }
+    else:
+        launchers = {
+            "stft": lambda s: ops.stft_padded(s["wavs"], 0, N_FFT, HOP, window, logpower=True),
+            "cmvn_stats": lambda s: ops.cmvn_stats_padded(s["feats"], K),
+            "head": lambda s: ops.linear_head_padded(s["feats"], K, wpad, head.linear.bias, head.activation, s["mean"], s["std"], head.eps,
+                                                     precision=engine.precision),
+        }
+    launchers["mask_istft"] = lambda s: ops.mask_istft(s["wavs"], 0, 1, s["mask"], s["lengths"], N_FFT, HOP, window, pad_to=T,
+                                                       mask_padded=True, out=s["wav"], sums=s["sums"])
+    launchers["finalize"] = lambda s: ops.finalize_metrics(s["sums"], s["lengths"], T, wav=s["wav"])
     kernel_ms = {}
     reps = max(3, min(20, args.steps // len(slots)))
     for name, fn in launchers.items():
@@ -358,7 +374,7 @@ def main():
                            "parallelism": f"dp{world} (utterance-sharded, no data-path collective)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                         "ms_per_step": 1e3 * t.item() / args.steps, "pipeline_depth": 2},
-                "gpu_launches": 5 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "gpu_launches": engine.launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "check": {"mean_sisdr_db": mean_sisdr, "mean_loss": mean_loss}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -99,6 +99,14 @@ int se_mask_istft_strided(const float* noisy, const float* clean, int64_t utt_st
                           const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, double* sums,
                           int want_spec, void* stream);
 
+/* flags of the _ex / fused entry points */
+#define SE_FLAG_WANT_SPEC 1        /* se_mask_istft_ex: also accumulate the spectral SI-SDR sums (= want_spec) */
+#define SE_FLAG_SUMS_ZEROED 2      /* the caller has zeroed the sums buffer on this stream: skip the library's memset, so
+                                      that consecutive kernels of the fused step keep their programmatic (PDL) edges */
+int se_mask_istft_ex(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
+                     const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
+                     float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags, void* stream);
+
 /* ---- K3 epilogue: level normalisation + metrics from the sums --------------------
  * Per utterance: gain so that the masked mean-square of wav matches the clean
  * reference's (target_db_or_nan = NaN; runner.py:570 + utils.py:38-40) or a fixed level
@@ -177,6 +185,28 @@ int se_linear_head_fwd_strided(const float* x, int64_t ldx, const float* mean, c
 int se_linear_head_bwd(const float* x, const float* mean, const float* std, float cmvn_eps, const float* W,
                        const float* offset, const float* grad_offset, int64_t n_utt, int64_t n_frames,
                        int64_t D_in, int64_t D_out, int act, float* grad_W, float* grad_b, void* stream);
+
+/* ---- K1 + K2 of the fused evaluation step ------------------------------------------
+ * se_stft_features: STFT of one channel -> ONE feature tensor feat (n_utt, n_frames, feat_stride): power (take_log = 0)
+ *   or log(power + log_eps) (take_log = 1), AND stat_sums (n_utt, ld_stats, 2) doubles += [sum_f x, sum_f x^2] per
+ *   (utterance, bin) over all n_frames -- the CMVN statistics of model.py:30 in one-pass form.  stat_sums is zeroed
+ *   first unless flags has SE_FLAG_SUMS_ZEROED.  (runner.py:433,558 preprocessor call + model.py:30.)
+ * se_feature_sums: the same sums from an existing feature tensor x (rows ldx floats apart); overwrites sums.
+ * se_linear_head_fused: offset = act(((x - mean)/(std + cmvn_eps)) W^T + b) with mean / unbiased std derived from
+ *   stat_sums (NULL = no CMVN); tcgen05 TF32 (W is read as TF32: pass it pre-rounded for round-to-nearest).
+ *   One CTA per <=128-row tile, TMA tensor-map loads, accumulators in tensor memory, bulk-store epilogue.
+ *   Returns SE_ERR_UNSUPPORTED outside its shape range (se_linear_head_fused_supported(...) == 0):
+ *   D_in <= 288, D_out <= 272, n_frames >= 8, ldx and ldw multiples of 4, 16-byte aligned x and W. */
+int se_stft_features(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
+                     float log_eps, int take_log, float* feat, int64_t feat_stride, double* stat_sums, int64_t ld_stats,
+                     int flags, void* stream);
+int se_feature_sums(const float* x, int64_t ldx, int64_t n_utt, int64_t n_frames, int64_t D, double* sums, int64_t ld_stats,
+                    void* stream);
+int se_linear_head_fused_supported(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int64_t ldx, int64_t ldw,
+                                   int64_t ld_out);
+int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps,
+                         const float* W, int64_t ldw, const float* b, int64_t n_utt, int64_t n_frames, int64_t D_in,
+                         int64_t D_out, int act, float* offset_out, int64_t ld_out, void* stream);
 
 /* ---- K1b: feature post-processing (S3PRL OnlinePreprocessor feature configs:
  * config/pretrain_sample.yaml:54-65, config/pseudo_noise.yaml:10-15) ------------------

@@ -29,6 +29,11 @@ _SIGNATURES = {
     "se_istft": [c_f, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f],
     "se_mask_istft": [c_f, c_f, i64, c_f, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
     "se_mask_istft_strided": [c_f, c_f, i64, c_f, i64, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
+    "se_mask_istft_ex": [c_f, c_f, i64, c_f, i64, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
+    "se_stft_features": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_int, c_f, i64, c_f, i64, c_int, c_f],
+    "se_feature_sums": [c_f, i64, i64, i64, i64, c_f, i64, c_f],
+    "se_linear_head_fused_supported": [i64, i64, i64, i64, i64, i64, i64],
+    "se_linear_head_fused": [c_f, i64, c_f, i64, c_float, c_f, i64, c_f, i64, i64, i64, i64, c_int, c_f, i64, c_f],
     "se_finalize_metrics": [c_f, c_f, i64, i64, c_float, c_f, i64, i64, c_f, c_f, c_f, c_f],
     "se_sisdr_spec_fwd": [c_f, c_f, c_f, i64, i64, i64, c_float, c_f, c_f, c_f],
     "se_sisdr_spec_bwd": [c_f, c_f, c_f, i64, i64, i64, c_float, c_f, c_f, c_f, c_f],

@@ -143,8 +143,17 @@ constexpr int kWarps1 = 8, kThreads1 = kWarps1 * 32;
 // dynamic shared memory of K1: transpose buffers [16][256] float2, frame staging [16][2][512] float, window pairs
 constexpr size_t kSmem1 = (size_t)(kWarps1 * 2) * (M * 8 + 2 * N * 4) + M * 8;
 
-template <bool POWER, bool PHASE, bool LOGP>
-__global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long long total_frames) {
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Frames are dealt to CTAs in contiguous ranges [blockIdx.x * per_cta, ...): iteration `it` of a CTA transforms the 16
+// consecutive frames first + 16 it + hw (one per half-warp).  With STATS the CTA also accumulates, per (utterance, bin),
+// the sum and the sum of squares of the feature it writes (log-power if LOGP, else power) -- the CMVN statistics of the
+// mask head (model.py:30) -- so that no separate pass over the features is needed: every half-warp leaves its feature row
+// in its (now idle) transpose buffer, thread t sums column t over the 16 rows in double precision, and the running sums
+// are flushed with one double atomicAdd pair per (CTA, utterance, bin).
+template <bool POWER, bool PHASE, bool LOGP, bool STATS>
+__global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long long total_frames, int per_cta) {
     extern __shared__ __align__(16) unsigned char smem1[];
     const int lane = threadIdx.x & 31, j = lane & 15;
     const int hw = (threadIdx.x >> 4);
@@ -155,49 +164,93 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
     float2 tw[15], twn[8];
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     __syncthreads();
-    const long long n_hw = (long long)gridDim.x * (kThreads1 / 16);
-    const long long first = (long long)blockIdx.x * (kThreads1 / 16) + hw;
+    griddep_launch();                                   // a dependent kernel may start its prologue (it waits for our completion)
+    const long long cta_lo = (long long)blockIdx.x * per_cta;
+    const long long cta_hi = cta_lo + per_cta < total_frames ? cta_lo + per_cta : total_frames;
     const unsigned hmask = half_mask(lane);
     auto prefetch = [&](long long gg, int buf) {
         const int u = (int)(gg / a.n_frames), f = (int)(gg - (long long)u * a.n_frames);
         stage_wave(stage + buf * N, a.wav + (long long)u * a.utt_stride, a.T, f * a.hop - N / 2, N, j);
         cp_async_commit();
     };
-    if (first < total_frames) prefetch(first, 0);
+    if (cta_lo + hw < cta_hi) prefetch(cta_lo + hw, 0);
     int buf = 0;
+    double st_s = 0.0, st_q = 0.0, st_s2 = 0.0, st_q2 = 0.0;      // column threadIdx.x (and, in thread 0, column 256)
+    int st_u = -1;
+    auto flush = [&]() {
+        if (st_u >= 0) {
+            double* p = a.stat_sums + ((long long)st_u * a.ld_stats + threadIdx.x) * 2;
+            atomicAdd(p, st_s);
+            atomicAdd(p + 1, st_q);
+            if (threadIdx.x == 0) {
+                double* p2 = a.stat_sums + ((long long)st_u * a.ld_stats + M) * 2;
+                atomicAdd(p2, st_s2);
+                atomicAdd(p2 + 1, st_q2);
+            }
+        }
+        st_s = st_q = st_s2 = st_q2 = 0.0;
+    };
 #pragma unroll 1
-    for (long long gg = first; gg < total_frames; gg += n_hw, buf ^= 1) {
-        if (gg + n_hw < total_frames) { prefetch(gg + n_hw, buf ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncwarp(hmask);
-        float2 v[16];
-        frame_from_stage(stage + buf * N, j, s_win2, v);
-        fft256<-1>(v, xbuf, j, tw, hmask);
-        float2 zm[8];
-        fetch_mirror(v, lane, zm);
-        const long long o = gg * a.spec_stride;
-        float* pw = POWER ? a.power + o : nullptr;
-        float* lg = LOGP ? a.logp + o : nullptr;
-        float* ph = PHASE ? a.phase + o : nullptr;
+    for (long long g0 = cta_lo; g0 < cta_hi; g0 += kThreads1 / 16, buf ^= 1) {
+        const long long gg = g0 + hw;
+        float* frow = reinterpret_cast<float*>(xbuf);
+        if (gg < cta_hi) {
+            if (gg + kThreads1 / 16 < cta_hi) { prefetch(gg + kThreads1 / 16, buf ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncwarp(hmask);
+            float2 v[16];
+            frame_from_stage(stage + buf * N, j, s_win2, v);
+            fft256<-1>(v, xbuf, j, tw, hmask);
+            float2 zm[8];
+            fetch_mirror(v, lane, zm);
+            const long long o = gg * a.spec_stride;
+            float* pw = POWER ? a.power + o : nullptr;
+            float* lg = LOGP ? a.logp + o : nullptr;
+            float* ph = PHASE ? a.phase + o : nullptr;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int k = j + 16 * q;
-            float2 xa, xb;
-            split_pair(v[q], zm[q], twn[q], xa, xb);
-            const float pa = xa.x * xa.x + xa.y * xa.y, pb = xb.x * xb.x + xb.y * xb.y;
-            if (POWER) { pw[k] = pa; pw[M - k] = pb; }
-            if (LOGP) { lg[k] = __logf(pa + a.log_eps); lg[M - k] = __logf(pb + a.log_eps); }
-            if (PHASE) { ph[k] = atan2f(k == 0 ? 0.0f : xa.y, xa.x); ph[M - k] = atan2f(k == 0 ? 0.0f : xb.y, xb.x); }
+            for (int q = 0; q < 8; ++q) {
+                const int k = j + 16 * q;
+                float2 xa, xb;
+                split_pair(v[q], zm[q], twn[q], xa, xb);
+                const float pa = xa.x * xa.x + xa.y * xa.y, pb = xb.x * xb.x + xb.y * xb.y;
+                if (POWER) { pw[k] = pa; pw[M - k] = pb; }
+                float la = 0.f, lb = 0.f;
+                if (LOGP) { la = __logf(pa + a.log_eps); lb = __logf(pb + a.log_eps); lg[k] = la; lg[M - k] = lb; }
+                if (PHASE) { ph[k] = atan2f(k == 0 ? 0.0f : xa.y, xa.x); ph[M - k] = atan2f(k == 0 ? 0.0f : xb.y, xb.x); }
+                if (STATS) { frow[k] = LOGP ? la : pa; frow[M - k] = LOGP ? lb : pb; }
+            }
+            if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
+                const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
+                const float p = x.x * x.x + x.y * x.y;
+                float l = 0.f;
+                if (POWER) pw[128] = p;
+                if (LOGP) { l = __logf(p + a.log_eps); lg[128] = l; }
+                if (PHASE) ph[128] = atan2f(x.y, x.x);
+                if (STATS) frow[128] = LOGP ? l : p;
+            }
+            __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
         }
-        if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
-            const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
-            const float p = x.x * x.x + x.y * x.y;
-            if (POWER) pw[128] = p;
-            if (LOGP) lg[128] = __logf(p + a.log_eps);
-            if (PHASE) ph[128] = atan2f(x.y, x.x);
+        if (STATS) {
+            __syncthreads();                                            // the feature rows of this iteration are in shared memory
+            const int nrows = (int)(cta_hi - g0 < kThreads1 / 16 ? cta_hi - g0 : kThreads1 / 16);
+            const float* col = reinterpret_cast<const float*>(smem1) + threadIdx.x;
+            int r = 0;
+            while (r < nrows) {
+                const int u = (int)((g0 + r) / a.n_frames);
+                const long long u_end = (long long)(u + 1) * a.n_frames - g0;        // first row of the next utterance
+                const int r_end = u_end < nrows ? (int)u_end : nrows;
+                if (u != st_u) { flush(); st_u = u; }
+                for (; r < r_end; ++r) {
+                    const double x = (double)col[r * 2 * M];
+                    st_s += x;
+                    st_q += x * x;
+                    if (threadIdx.x == 0) { const double y = (double)col[r * 2 * M + M]; st_s2 += y; st_q2 += y * y; }
+                }
+            }
+            __syncthreads();                                            // rows consumed: the transpose buffers may be reused
         }
-        __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
     }
+    if (STATS) flush();
 }
 
 // ------------------------------------------------------------------ K3: fused mask -> iSTFT, hop = 256
@@ -236,6 +289,8 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     float2 tw[15], twn[8];
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     __syncthreads();
+    griddep_launch();
+    griddep_wait();                                               // the mask (and the zeroed sums) come from upstream kernels
     float2* xbuf = reinterpret_cast<float2*>(smem3) + hw * M;
     float* stage = reinterpret_cast<float*>(smem3 + (size_t)(kWarps3 * 2) * M * 8) + hw * 2 * kStageFloats3;
     const long long unit = (long long)blockIdx.x * (kThreads3 / 16) + hw;
@@ -391,13 +446,15 @@ int num_sms() {
 // opt the kernels into their dynamic shared-memory sizes (called once per device from se_prepare / first use)
 int prepare512() {
 #define SE_OPT(K, BYTES) SE_CUDA_CHECK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)))
-    SE_OPT((stft512_kernel<true, false, false>), kSmem1);
-    SE_OPT((stft512_kernel<false, true, false>), kSmem1);
-    SE_OPT((stft512_kernel<true, true, false>), kSmem1);
-    SE_OPT((stft512_kernel<false, false, true>), kSmem1);
-    SE_OPT((stft512_kernel<true, false, true>), kSmem1);
-    SE_OPT((stft512_kernel<false, true, true>), kSmem1);
-    SE_OPT((stft512_kernel<true, true, true>), kSmem1);
+    SE_OPT((stft512_kernel<true, false, false, false>), kSmem1);
+    SE_OPT((stft512_kernel<false, true, false, false>), kSmem1);
+    SE_OPT((stft512_kernel<true, true, false, false>), kSmem1);
+    SE_OPT((stft512_kernel<false, false, true, false>), kSmem1);
+    SE_OPT((stft512_kernel<true, false, true, false>), kSmem1);
+    SE_OPT((stft512_kernel<false, true, true, false>), kSmem1);
+    SE_OPT((stft512_kernel<true, true, true, false>), kSmem1);
+    SE_OPT((stft512_kernel<true, false, false, true>), kSmem1);
+    SE_OPT((stft512_kernel<false, false, true, true>), kSmem1);
     SE_OPT(mask_istft512_kernel, kSmem3);
 #undef SE_OPT
     return SE_OK;
@@ -405,18 +462,29 @@ int prepare512() {
 
 int launch_stft512(const StftArgs& a, cudaStream_t st) {
     const long long total = (long long)a.n_utt * a.n_frames;
-    const long long want = (total + (kThreads1 / 16) - 1) / (kThreads1 / 16);
+    const int per_it = kThreads1 / 16;
+    const long long want = (total + per_it - 1) / per_it;
     const long long cap = 2LL * num_sms();
     const unsigned grid = (unsigned)(want < cap ? want : cap);
+    const long long per = (total + grid - 1) / grid;
+    if (per > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "too many frames");
+    const int per_cta = (int)per;
     const int sel = (a.power ? 1 : 0) | (a.phase ? 2 : 0) | (a.logp ? 4 : 0);
+    if (a.stat_sums) {
+        // statistics of the ONE feature written: log-power (sel 4) or power (sel 1)
+        if (sel == 4) stft512_kernel<false, false, true, true><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta);
+        else if (sel == 1) stft512_kernel<true, false, false, true><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta);
+        else return secommon::fail(SE_ERR_BAD_ARG, "statistics need exactly one of power / logpower");
+        return secommon::check_launch("stft512_kernel");
+    }
     switch (sel) {
-        case 1: stft512_kernel<true, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
-        case 2: stft512_kernel<false, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
-        case 3: stft512_kernel<true, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
-        case 4: stft512_kernel<false, false, true><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
-        case 5: stft512_kernel<true, false, true><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
-        case 6: stft512_kernel<false, true, true><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
-        case 7: stft512_kernel<true, true, true><<<grid, kThreads1, kSmem1, st>>>(a, total); break;
+        case 1: stft512_kernel<true, false, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 2: stft512_kernel<false, true, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 3: stft512_kernel<true, true, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 4: stft512_kernel<false, false, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 5: stft512_kernel<true, false, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 6: stft512_kernel<false, true, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 7: stft512_kernel<true, true, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
         default: return SE_OK;                                   // nothing requested
     }
     return secommon::check_launch("stft512_kernel");
@@ -454,7 +522,17 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     plan.total_runs = (long long)a.n_utt * plan.runs_per_utt;
     const long long grid = (plan.total_runs + (kThreads3 / 16) - 1) / (kThreads3 / 16);
     if (grid > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "grid too large");
-    mask_istft512_kernel<<<(unsigned)grid, kThreads3, kSmem3, st>>>(a, plan);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads3);
+    cfg.dynamicSmemBytes = kSmem3;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // prologue overlaps the upstream kernel's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel, a, plan));
     return secommon::check_launch("mask_istft512_kernel");
 }
 

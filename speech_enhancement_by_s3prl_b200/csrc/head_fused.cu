@@ -1,0 +1,438 @@
+// libse_b200.so -- fused CMVN + mask head for the evaluation step (model.py:28-34):
+//
+//     offset = act( ((x - mean) / (std + eps)) W^T + b )
+//
+// with mean / std taken from the per-(utterance, feature) sums that the STFT kernel accumulates
+// (se_stft_stats), so no separate statistics pass runs between the STFT and the head.
+//
+// One CTA owns ONE tile of up to 128 consecutive rows (frames) and ALL output columns:
+//   * warp 9 (one lane)  TMA producer: SWIZZLE_128B tensor-map loads of the whole A tile (every
+//                        32-float k-block lands in its own 16 KB K-major tile) and of the weight
+//                        k-blocks through a 2-stage ring
+//   * warps 0-7          normalise the A tile IN PLACE in shared memory (CMVN scale/shift from the
+//                        sums, round to TF32), later run the epilogue
+//   * warp 8 (one lane)  tcgen05.mma kind::tf32, fp32 accumulators in tensor memory: columns
+//                        [0,256) by one N=256 instruction, the remaining <= 16 by a second one
+//   * epilogue           tcgen05.ld -> +bias -> activation -> row-major staging tile in shared
+//                        memory (reusing the A tile) -> ONE bulk async store per 32-row quadrant:
+//                        with ld_out == padded row length the CTA's output is contiguous in HBM
+// The kernel is launched with programmatic stream serialisation: barrier init, TMEM allocation and
+// the first weight loads overlap the tail of the upstream kernel (griddepcontrol.wait guards the
+// first read of its outputs).
+#include <cuda.h>
+#include "se_common.cuh"
+
+using secommon::fail;
+
+namespace {
+
+constexpr int BM = 128, BK = 32, kMaxKB = 9, kWStages = 2;
+constexpr int kWorkWarps = 8, kWorkThreads = kWorkWarps * 32, kThreads = kWorkThreads + 64;   // + MMA warp + TMA warp
+constexpr int kATileBytes = BM * BK * 4;                       // 16 KB per k-block
+constexpr int kMaxWRows = 272;
+constexpr int kWStageBytes = kMaxWRows * BK * 4;               // 34 816 (multiple of 1024)
+constexpr int kStatLd = kMaxKB * BK;                           // 288
+constexpr int kOffA = 0;
+constexpr int kOffW = kOffA + kMaxKB * kATileBytes;            // 147 456
+constexpr int kOffScale = kOffW + kWStages * kWStageBytes;     // 217 088
+constexpr int kOffShift = kOffScale + 2 * kStatLd * 4;
+constexpr int kOffBias = kOffShift + 2 * kStatLd * 4;
+constexpr int kOffBar = kOffBias + kStatLd * 4;
+constexpr int kNumBars = 2 * kMaxKB + 2 * kWStages + 1;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmem + 16;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr unsigned kSpinLimit = 1u << 22;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > kSpinLimit) __trap();                          // never hang the GPU on a protocol bug
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows 128 B apart, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {           // kind::tf32, fp32 accumulate, A/B K-major, M = 128
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float activate(float z, int act) {
+    if (act == SE_ACT_RELU) return z > 0.f ? z : 0.f;
+    if (act == SE_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-z));
+    return z;
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+struct Head2Args {
+    const double* sums;        // (n_utt, ld_stats, 2): sum x, sum x^2 over the utterance's frames; null = no CMVN
+    long long ld_stats;
+    float cmvn_eps;
+    const float* bias;
+    long long R;               // n_utt * n_frames
+    int n_utt, n_frames, Din, Dout, act;
+    float* out;
+    long long ld_out;
+    int tile_rows;             // rows per CTA: multiple of 8, <= 128, <= n_frames (a tile touches <= 2 utterances)
+    int kblocks;               // ceil(Din / 32) <= 9
+    int w_rows;                // Dout rounded up to 16, <= 272
+    int n_main, n_tail;        // MMA column split: [0, n_main) and [n_main, n_main + n_tail)
+    int w_box_rows, w_boxes;   // weight tensor-map box rows and boxes per k-block
+    int sld;                   // floats per row of the staging tile
+    int bulk_out;              // staging rows == output rows and 16-byte aligned: one bulk store per quadrant
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Head2Args a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    float* s_scale = reinterpret_cast<float*>(smem + kOffScale);
+    float* s_shift = reinterpret_cast<float*>(smem + kOffShift);
+    float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+    const uint32_t bar_a_full = sbase + kOffBar;                       // [kMaxKB]  TMA landed k-block kb of A
+    const uint32_t bar_a_norm = bar_a_full + 8 * kMaxKB;               // [kMaxKB]  k-block kb normalised in place
+    const uint32_t bar_w_full = bar_a_norm + 8 * kMaxKB;               // [kWStages]
+    const uint32_t bar_w_empty = bar_w_full + 8 * kWStages;            // [kWStages]
+    const uint32_t bar_accum = bar_w_empty + 8 * kWStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r0 = (long long)blockIdx.x * a.tile_rows;
+    const uint32_t w_bytes = (uint32_t)a.w_rows * BK * 4;
+
+    if (threadIdx.x == 0) {
+        if (sbase & 1023) __trap();
+        for (int kb = 0; kb < kMaxKB; ++kb) { mbar_init(bar_a_full + 8 * kb, 1); mbar_init(bar_a_norm + 8 * kb, kWorkWarps); }
+        for (int s = 0; s < kWStages; ++s) { mbar_init(bar_w_full + 8 * s, 1); mbar_init(bar_w_empty + 8 * s, 1); }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWorkWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();                                   // the next kernel may start its own prologue
+
+    if (warp == kWorkWarps + 1) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            auto load_w = [&](int kb, int s) {
+                const uint32_t dst = sbase + kOffW + s * kWStageBytes;
+                mbar_expect_tx(bar_w_full + 8 * s, w_bytes);
+                for (int b = 0; b < a.w_boxes; ++b)
+                    tma_load_2d(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, b * a.w_box_rows, bar_w_full + 8 * s);
+            };
+            for (int s = 0; s < kWStages && s < a.kblocks; ++s) load_w(s, s);     // weights do not depend on the upstream kernel
+            griddep_wait();
+            for (int kb = 0; kb < a.kblocks; ++kb) {
+                mbar_expect_tx(bar_a_full + 8 * kb, (uint32_t)a.tile_rows * BK * 4);
+                tma_load_2d(sbase + kOffA + kb * kATileBytes, &tmA, kb * BK, (int)r0, bar_a_full + 8 * kb);
+            }
+            for (int kb = kWStages; kb < a.kblocks; ++kb) {
+                const int s = kb % kWStages;
+                mbar_wait(bar_w_empty + 8 * s, ((kb / kWStages) - 1) & 1);          // MMAs of k-block kb - kWStages have read the stage
+                load_w(kb, s);
+            }
+        }
+    } else if (warp == kWorkWarps) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc_main = make_idesc(a.n_main), idesc_tail = make_idesc(a.n_tail > 0 ? a.n_tail : 16);
+            for (int kb = 0; kb < a.kblocks; ++kb) {
+                const int s = kb % kWStages;
+                mbar_wait(bar_a_norm + 8 * kb, 0);
+                mbar_wait(bar_w_full + 8 * s, (kb / kWStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = sbase + kOffA + kb * kATileBytes;
+                const uint32_t b_addr = sbase + kOffW + s * kWStageBytes;
+                const int kvalid = a.Din - kb * BK;
+                const int ksteps = kvalid >= BK ? BK / 8 : (kvalid + 7) / 8;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint64_t ad = make_desc(a_addr + kk * 32);
+                    umma_tf32(tmem_base, ad, make_desc(b_addr + kk * 32), idesc_main, (kb | kk) ? 1u : 0u);
+                    if (a.n_tail > 0)
+                        umma_tf32(tmem_base + (uint32_t)a.n_main, ad, make_desc(b_addr + a.n_main * BK * 4 + kk * 32), idesc_tail,
+                                  (kb | kk) ? 1u : 0u);
+                }
+                umma_commit(bar_w_empty + 8 * s);
+            }
+            umma_commit(bar_accum);
+        }
+    } else {
+        // ===================== CMVN in place, then epilogue =====================
+        const int t = threadIdx.x;
+        griddep_wait();                                                   // the sums come from the upstream kernel
+        const long long u0 = r0 / a.n_frames;
+        const int split = (int)((u0 + 1) * a.n_frames - r0);              // first tile row of the next utterance
+        for (int i = t; i < 2 * kStatLd; i += kWorkThreads) {
+            const int ul = i / kStatLd, k = i - ul * kStatLd;
+            const long long u = u0 + ul;
+            float sc = 0.f, sh = 0.f;
+            if (k < a.Din) {
+                sc = 1.f;
+                if (a.sums && u < a.n_utt) {
+                    const double* p = a.sums + (u * a.ld_stats + k) * 2;
+                    const double n = (double)a.n_frames, s1 = p[0], s2 = p[1];
+                    const double mean = s1 / n;
+                    double var = (s2 - s1 * mean) / (n - 1.0);               // unbiased (model.py:30)
+                    var = var > 0.0 ? var : 0.0;
+                    const float inv = 1.0f / ((float)sqrt(var) + a.cmvn_eps);
+                    sc = inv;
+                    sh = -(float)mean * inv;
+                }
+            }
+            s_scale[i] = sc;
+            s_shift[i] = sh;
+        }
+        for (int i = t; i < kStatLd; i += kWorkThreads) s_bias[i] = (a.bias && i < a.Dout) ? __ldg(a.bias + i) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
+
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+            mbar_wait(bar_a_full + 8 * kb, 0);
+            float4* tile = reinterpret_cast<float4*>(smem + kOffA + kb * kATileBytes);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = t + kWorkThreads * i;                     // physical 16-byte chunk: conflict-free LDS/STS.128
+                const int row = idx >> 3;
+                if (row < a.tile_rows) {
+                    const int c = (idx & 7) ^ (row & 7);                  // logical chunk (SWIZZLE_128B)
+                    const int so = (row >= split ? kStatLd : 0) + kb * BK + 4 * c;
+                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + so);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + so);
+                    float4 v = tile[idx];
+                    v.x = to_tf32(fmaf(v.x, sc.x, sh.x));
+                    v.y = to_tf32(fmaf(v.y, sc.y, sh.y));
+                    v.z = to_tf32(fmaf(v.z, sc.z, sh.z));
+                    v.w = to_tf32(fmaf(v.w, sc.w, sh.w));
+                    tile[idx] = v;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_norm + 8 * kb);
+        }
+
+        // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31, column half (w >> 2)
+        mbar_wait(bar_accum, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* stage = reinterpret_cast<float*>(smem + kOffA);
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        const int ncol16 = a.w_rows / 16;
+        const int c_lo = 16 * (half == 0 ? 0 : ncol16 / 2), c_hi = 16 * (half == 0 ? ncol16 / 2 : ncol16);
+        float* srow = stage + (long long)row * a.sld;
+        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            uint32_t acc[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                if (c0 + j < a.sld) {
+                    const float4 bz = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                    float4 o;
+                    o.x = activate(__uint_as_float(acc[j]) + bz.x, a.act);
+                    o.y = activate(__uint_as_float(acc[j + 1]) + bz.y, a.act);
+                    o.z = activate(__uint_as_float(acc[j + 2]) + bz.z, a.act);
+                    o.w = activate(__uint_as_float(acc[j + 3]) + bz.w, a.act);
+                    *reinterpret_cast<float4*>(srow + c0 + j) = o;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");        // both warps of the quadrant have staged their columns
+        long long rows_left = a.R - r0;
+        if (rows_left > a.tile_rows) rows_left = a.tile_rows;
+        int rows_valid = (int)rows_left - quad * 32;
+        rows_valid = rows_valid > 32 ? 32 : rows_valid;
+        if (rows_valid > 0) {
+            float* gdst = a.out + (r0 + quad * 32) * a.ld_out;
+            const float* ssrc = stage + (long long)quad * 32 * a.sld;
+            if (a.bulk_out) {
+                if (half == 0 && lane == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(gdst), "r"(smem_u32(ssrc)), "r"((uint32_t)(rows_valid * a.sld * 4)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+            } else {
+                for (int r = half; r < rows_valid; r += 2)
+                    for (int c = lane; c < a.Dout; c += 32) gdst[(long long)r * a.ld_out + c] = ssrc[(long long)r * a.sld + c];
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == kWorkWarps) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: `cols` x `rows` elements, `ld` floats between rows, box = 32 floats x box_rows, SWIZZLE_128B,
+// out-of-bounds elements read as zero
+int make_map(CUtensorMap* map, const float* base, long long cols, long long rows, long long ld, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(SE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SE_OK;
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int se_linear_head_fused_supported(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int64_t ldx, int64_t ldw,
+                                   int64_t ld_out) {
+    if (n_utt <= 0 || n_frames < 8 || D_in <= 0 || D_out <= 0) return 0;
+    if (D_in > kMaxKB * BK || D_out > kMaxWRows) return 0;
+    if (ldx % 4 || ldw % 4 || ldx < D_in || ldw < D_in || ld_out < D_out) return 0;
+    const int64_t dout4 = (D_out + 3) / 4 * 4;
+    if ((ld_out == dout4 ? ld_out : dout4 + 4) * 4 * BM > kMaxKB * kATileBytes) return 0;        // staging tile must fit in the A region
+    return 1;
+}
+
+int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps,
+                         const float* W, int64_t ldw, const float* b, int64_t n_utt, int64_t n_frames, int64_t D_in,
+                         int64_t D_out, int act, float* offset_out, int64_t ld_out, void* stream) {
+    SE_REQUIRE(x && W && offset_out, "null pointer");
+    SE_REQUIRE(act >= SE_ACT_IDENTITY && act <= SE_ACT_SIGMOID, "unknown activation %d", act);
+    SE_REQUIRE(!stat_sums || ld_stats >= D_in, "ld_stats smaller than D_in");
+    if (!se_linear_head_fused_supported(n_utt, n_frames, D_in, D_out, ldx, ldw, ld_out) || !aligned16(x) || !aligned16(W))
+        return fail(SE_ERR_UNSUPPORTED, "fused head: shape / alignment outside the fast path (D_in=%lld, D_out=%lld, n_frames=%lld)",
+                    (long long)D_in, (long long)D_out, (long long)n_frames);
+    Head2Args a{};
+    a.sums = stat_sums; a.ld_stats = ld_stats; a.cmvn_eps = cmvn_eps; a.bias = b;
+    a.R = n_utt * n_frames; a.n_utt = (int)n_utt; a.n_frames = (int)n_frames; a.Din = (int)D_in; a.Dout = (int)D_out; a.act = act;
+    a.out = offset_out; a.ld_out = ld_out;
+    long long rows = (a.R + num_sms() - 1) / num_sms();                     // one tile per SM when the batch is small
+    rows = (rows + 7) / 8 * 8;
+    if (rows > BM) rows = BM;
+    if (rows > n_frames) rows = n_frames / 8 * 8;                           // a tile may touch at most two utterances
+    a.tile_rows = (int)rows;
+    a.kblocks = (int)((D_in + BK - 1) / BK);
+    a.w_rows = (int)((D_out + 15) / 16 * 16);
+    a.n_main = a.w_rows > 256 ? 256 : a.w_rows;
+    a.n_tail = a.w_rows - a.n_main;
+    a.w_boxes = a.w_rows > 256 ? 2 : 1;
+    a.w_box_rows = a.w_rows / a.w_boxes;
+    const int dout4 = (int)((D_out + 3) / 4 * 4);
+    a.bulk_out = (ld_out == dout4 && aligned16(offset_out)) ? 1 : 0;
+    a.sld = a.bulk_out ? (int)ld_out : dout4 + 4;
+    CUtensorMap tmA, tmW;
+    int rc = make_map(&tmA, x, D_in, a.R, ldx, a.tile_rows);
+    if (rc != SE_OK) return rc;
+    if ((rc = make_map(&tmW, W, D_in, D_out, ldw, a.w_box_rows)) != SE_OK) return rc;
+    static bool opted = false;
+    if (!opted) {
+        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        opted = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((a.R + a.tile_rows - 1) / a.tile_rows));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, linear_head_fused_kernel, tmA, tmW, a));
+    return secommon::check_launch("linear_head_fused_kernel");
+}
+
+}  // extern "C"

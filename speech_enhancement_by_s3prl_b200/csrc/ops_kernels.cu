@@ -38,6 +38,7 @@ __global__ void finalize_metrics_kernel(const double* __restrict__ sums, const l
                                         int T, double level_or_neg, float* __restrict__ wav, long long wav_stride,
                                         int width, float* __restrict__ gain_out, float* __restrict__ sisdr_wave,
                                         float* __restrict__ loss_spec, int chunks) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");                   // sums and wav come from the upstream kernel
     const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
     const double* s = sums + (long long)u * SE_NSUMS;
     const double len = lengths ? (double)lengths[u] : (double)T;
@@ -268,6 +269,30 @@ __global__ void cmvn_stats_kernel(const float* __restrict__ x, long long ldx, in
     }
 }
 
+// sums[(u, d)] = [sum_f x, sum_f x^2] (double), the form the fused head consumes (head_fused.cu)
+__global__ void feature_sums_kernel(const float* __restrict__ x, long long ldx, int n_frames, int D, double* __restrict__ sums,
+                                    long long ld_stats) {
+    const int dchunks = (D + 31) / 32;
+    const int u = blockIdx.x / dchunks, dc = blockIdx.x - u * dchunks;
+    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, nrows = blockDim.x >> 5;
+    const int d = dc * 32 + lane;
+    const float* base = x + (long long)u * n_frames * ldx + d;
+    __shared__ double red1[8][33], red2[8][33];
+    double s = 0.0, q = 0.0;
+    if (d < D)
+        for (int f = row; f < n_frames; f += nrows) { const double v = (double)base[(long long)f * ldx]; s += v; q += v * v; }
+    red1[row][lane] = s;
+    red2[row][lane] = q;
+    __syncthreads();
+    if (row == 0 && d < D) {
+        double st = 0.0, qt = 0.0;
+        for (int r = 0; r < nrows; ++r) { st += red1[r][lane]; qt += red2[r][lane]; }
+        double* p = sums + ((long long)u * ld_stats + d) * 2;
+        p[0] = st;
+        p[1] = qt;
+    }
+}
+
 __global__ void cmvn_apply_kernel(float* __restrict__ x, long long n_frames, int D, const float* __restrict__ mean,
                                   const float* __restrict__ stdv, float eps, long long total) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -487,8 +512,17 @@ int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_ut
     SE_REQUIRE(sums && n_utt > 0, "sums must not be null");
     const int chunks = wav ? pick_chunks(n_utt, width, 4096) : 1;
     const double level = std::isnan(target_db_or_nan) ? -1.0 : std::pow(10.0, (double)target_db_or_nan / 10.0);
-    finalize_metrics_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
-        sums, (const long long*)lengths, (int)T, level, wav, wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_utt * chunks));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // CTAs become resident while the upstream kernel drains
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, finalize_metrics_kernel, sums, (const long long*)lengths, (int)T, level, wav,
+                                     (long long)wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks));
     return secommon::check_launch("finalize_metrics_kernel");
 }
 
@@ -588,6 +622,14 @@ int se_cmvn_stats_strided(const float* x, int64_t ldx, int64_t n_utt, int64_t n_
     const long long blocks = n_utt * ((D + 31) / 32);
     cmvn_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, (int)n_frames, (int)D, mean, std, ld_stats);
     return secommon::check_launch("cmvn_stats_kernel");
+}
+
+int se_feature_sums(const float* x, int64_t ldx, int64_t n_utt, int64_t n_frames, int64_t D, double* sums, int64_t ld_stats,
+                    void* stream) {
+    SE_REQUIRE(x && sums && n_utt > 0 && n_frames > 0 && D > 0 && ldx >= D && ld_stats >= D, "bad argument");
+    const long long blocks = n_utt * ((D + 31) / 32);
+    feature_sums_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, (int)n_frames, (int)D, sums, ld_stats);
+    return secommon::check_launch("feature_sums_kernel");
 }
 
 int se_cmvn_apply(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const float* mean, const float* std, float eps,

@@ -193,6 +193,33 @@ int se_stft_strided(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t
     SE_DISPATCH_NFFT(n_fft, launch_stft, a, st)
 }
 
+int se_stft_features(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
+                     float log_eps, int take_log, float* feat, int64_t feat_stride, double* stat_sums, int64_t ld_stats,
+                     int flags, void* stream) {
+    SE_REQUIRE(wav && window && feat && stat_sums, "null pointer");
+    SE_REQUIRE(feat_stride >= n_fft / 2 + 1 && ld_stats >= n_fft / 2 + 1, "feat_stride / ld_stats smaller than K");
+    int rc = check_geometry(n_utt, T, n_fft, hop);
+    if (rc != SE_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(stat_sums, 0, sizeof(double) * 2 * ld_stats * n_utt, st));
+    if (n_fft == 512 && !g_force_generic) {
+        DeviceTables t;
+        if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
+        StftArgs a{};
+        a.wav = wav; a.utt_stride = utt_stride; a.n_utt = (int)n_utt; a.T = (int)T; a.hop = hop;
+        a.n_frames = (int)(T / hop) + 1;
+        a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
+        a.power = take_log ? nullptr : feat; a.logp = take_log ? feat : nullptr; a.log_eps = log_eps; a.spec_stride = feat_stride;
+        a.stat_sums = stat_sums; a.ld_stats = ld_stats;
+        return sefast::launch_stft512(a, st);
+    }
+    // other n_fft: generic STFT, then one pass over the features for the sums
+    rc = se_stft_strided(wav, n_utt, utt_stride, T, n_fft, hop, window, log_eps, take_log ? nullptr : feat, nullptr,
+                         take_log ? feat : nullptr, feat_stride, stream);
+    if (rc != SE_OK) return rc;
+    return se_feature_sums(feat, feat_stride, n_utt, T / hop + 1, n_fft / 2 + 1, stat_sums, ld_stats, stream);
+}
+
 int se_istft(const float* power, const float* phase, int64_t n_utt, int64_t n_frames, int n_fft, int hop,
              const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, void* stream) {
     SE_REQUIRE(power && phase && window && wav_out, "null pointer");
@@ -220,6 +247,14 @@ int se_mask_istft(const float* noisy, const float* clean, int64_t utt_stride, co
 int se_mask_istft_strided(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
                           const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
                           float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int want_spec, void* stream) {
+    return se_mask_istft_ex(noisy, clean, utt_stride, mask, mask_stride, lengths, n_utt, T, n_fft, hop, window, wav_out, out_stride,
+                            pad_to, sums, want_spec ? SE_FLAG_WANT_SPEC : 0, stream);
+}
+
+int se_mask_istft_ex(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
+                     const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
+                     float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags, void* stream) {
+    const int want_spec = (flags & SE_FLAG_WANT_SPEC) ? 1 : 0;
     SE_REQUIRE(noisy && mask && window && wav_out, "null pointer");
     SE_REQUIRE(mask_stride >= n_fft / 2 + 1, "mask_stride=%lld smaller than K", (long long)mask_stride);
     int rc = check_geometry(n_utt, T, n_fft, hop);
@@ -235,7 +270,7 @@ int se_mask_istft_strided(const float* noisy, const float* clean, int64_t utt_st
     a.sums = sums; a.want_spec = (want_spec && clean && sums) ? 1 : 0; a.mask_stride = mask_stride;
     SE_REQUIRE(out_stride >= a.out_len && out_stride >= pad_to, "out_stride=%lld too small", (long long)out_stride);
     cudaStream_t st = (cudaStream_t)stream;
-    if (sums) SE_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * SE_NSUMS * n_utt, st));
+    if (sums && !(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * SE_NSUMS * n_utt, st));
     if (n_fft == 512 && hop == 256 && a.n_frames >= 2 && !g_force_generic) return sefast::launch_mask_istft512(a, st);
     SE_DISPATCH_NFFT(n_fft, launch_mask_istft, a, st)
 }

@@ -41,6 +41,8 @@ struct StftArgs {
     float* logp;               // log(power + log_eps), idem or null
     float log_eps;
     long long spec_stride;     // floats between consecutive frames of an output (>= K; K = dense)
+    double* stat_sums;         // (n_utt, ld_stats, 2) += [sum x, sum x^2] over frames of the feature written, or null
+    long long ld_stats;
 };
 
 struct IstftArgs {

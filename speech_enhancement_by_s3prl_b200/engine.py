@@ -32,6 +32,7 @@ class EnhancementEngine:
         self.ch_inp = int(getattr(preprocessor, "channel_inp", 0))
         self.ch_tar = int(getattr(preprocessor, "channel_tar", 1))
         self._graphs = {}
+        self.launches_per_step = 5          # library kernels per eval_step (set by eval_step: 4 on the fused path)
 
     # ------------------------------------------------------------------ device-resident step
     def eval_step(self, lengths, wavs, want_spec_loss=True):
@@ -46,16 +47,35 @@ class EnhancementEngine:
         head = self.head
         K = self.n_fft // 2 + 1
         with torch.no_grad():
-            # internal tensors use rows padded to 16 bytes (K = 257 -> 260 floats) so that the tensor-core head can
-            # read them with 128-bit loads; nothing outside this function sees the padding
-            feats = ops.stft_padded(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=self.log_features, log_eps=self.pre.eps)
-            mean = std = None
-            if head.cmvn:
-                mean, std = ops.cmvn_stats_padded(feats, K)
-            mask = ops.linear_head_padded(feats, K, self._padded_weight(), head.linear.bias, head.activation, mean, std,
-                                          head.eps, precision=self.precision)
-            wav, sums = ops.mask_istft(wavs, self.ch_inp, self.ch_tar, mask, lengths, self.n_fft, self.hop, window,
-                                       pad_to=T, want_sums=True, want_spec=want_spec_loss, mask_padded=True)
+            # internal tensors use rows padded to 16 bytes (K = 257 -> 260 floats): TMA / 128-bit loads for the
+            # tensor-core head; nothing outside this function sees the padding
+            LD = ops.round4(K)
+            F = T // self.hop + 1
+            wpad = self._padded_weight()
+            Dout = wpad.shape[0]
+            if self.precision == 1 and ops.linear_head_tma_supported(B, F, K, Dout, LD, wpad.shape[1], ops.round4(Dout)):
+                # K1 (+ CMVN sums) -> K2 (TMA + tcgen05 head) -> K3 -> K3': one zeroed workspace, no other memset, so
+                # the four kernels are chained by programmatic dependent launches
+                self.launches_per_step = 4      # K1, K2, K3, K3' (+ torch's fill of the workspace)
+                ws = torch.zeros(B * (2 * LD + ops.NSUMS), device=dev, dtype=torch.float64)
+                stat_sums = ws[:B * 2 * LD].view(B, LD, 2)
+                sums = ws[B * 2 * LD:].view(B, ops.NSUMS)
+                feats, _ = ops.stft_features(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=self.log_features,
+                                             log_eps=self.pre.eps, stat_sums=stat_sums)
+                mask = ops.linear_head_tma(feats, K, wpad, head.linear.bias, head.activation,
+                                             stat_sums if head.cmvn else None, head.eps)
+                wav, sums = ops.mask_istft(wavs, self.ch_inp, self.ch_tar, mask, lengths, self.n_fft, self.hop, window,
+                                           pad_to=T, want_sums=True, want_spec=want_spec_loss, mask_padded=True, sums=sums,
+                                           sums_zeroed=True)
+            else:
+                feats = ops.stft_padded(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=self.log_features, log_eps=self.pre.eps)
+                mean = std = None
+                if head.cmvn:
+                    mean, std = ops.cmvn_stats_padded(feats, K)
+                mask = ops.linear_head_padded(feats, K, wpad, head.linear.bias, head.activation, mean, std,
+                                              head.eps, precision=self.precision)
+                wav, sums = ops.mask_istft(wavs, self.ch_inp, self.ch_tar, mask, lengths, self.n_fft, self.hop, window,
+                                           pad_to=T, want_sums=True, want_spec=want_spec_loss, mask_padded=True)
             gain, sisdr, loss = ops.finalize_metrics(sums, lengths, T, wav=wav, target_db=None)
         return {"loss_per_utt": loss, "sisdr": sisdr, "wav_predicted": wav, "gain": gain, "mask": mask[..., :K]}
 
@@ -66,6 +86,8 @@ class EnhancementEngine:
         if getattr(self, "_wpad_key", None) != key:
             with torch.no_grad():
                 self._wpad = ops.pad_weight(w.detach())
+                if self.precision == 1:
+                    self._wpad = ops.round_tf32(self._wpad)         # the tensor cores read TF32: round to nearest once
             self._wpad_key = key
         return self._wpad
 

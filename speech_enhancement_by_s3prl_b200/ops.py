@@ -102,6 +102,68 @@ def stft_padded(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10)
     return out
 
 
+FLAG_WANT_SPEC, FLAG_SUMS_ZEROED = 1, 2
+
+
+def stft_features(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10, stat_sums=None):
+    """Fused-step K1: ONE feature tensor (B, F, round4(K)) -- log-power or power -- plus the CMVN sums
+    (B, round4(K), 2) float64 = [sum_f x, sum_f x^2].  If ``stat_sums`` is given it must already be zero
+    (the caller zeroed its workspace once for the whole step); otherwise it is allocated and zeroed here."""
+    wavs = _chk(wavs, "wavs")
+    B, C, T = wavs.shape
+    F, K = T // hop + 1, n_fft // 2 + 1
+    LD = round4(K)
+    window = _c(window, "window")
+    with torch.cuda.device(wavs.device):
+        out = torch.empty(B, F, LD, device=wavs.device, dtype=torch.float32)
+        flags = FLAG_SUMS_ZEROED
+        if stat_sums is None:
+            stat_sums = torch.empty(B, LD, 2, device=wavs.device, dtype=torch.float64)
+            flags = 0
+        assert stat_sums.shape == (B, LD, 2) and stat_sums.dtype == torch.float64 and stat_sums.is_contiguous()
+        rc = _lib.load().se_stft_features(wavs.data_ptr() + 4 * int(channel) * T, B, C * T, T, n_fft, hop, window.data_ptr(),
+                                          float(log_eps), int(bool(logpower)), out.data_ptr(), LD, stat_sums.data_ptr(), LD,
+                                          flags, _stream())
+        _lib.check(rc, "se_stft_features")
+    return out, stat_sums
+
+
+def feature_sums(x, D):
+    """x (B, F, LD) -> (B, LD, 2) float64 sums [sum_f x, sum_f x^2] of columns [0, D)."""
+    x = _chk(x, "x")
+    B, F, LD = x.shape
+    with torch.cuda.device(x.device):
+        sums = torch.zeros(B, LD, 2, device=x.device, dtype=torch.float64)
+        rc = _lib.load().se_feature_sums(x.data_ptr(), LD, B, F, int(D), sums.data_ptr(), LD, _stream())
+        _lib.check(rc, "se_feature_sums")
+    return sums
+
+
+def round_tf32(w):
+    """Round fp32 values to the nearest TF32 (10-bit mantissa, ties away from zero, as cvt.rna.tf32.f32)."""
+    bits = w.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def linear_head_tma_supported(B, F, D_in, D_out, ldx, ldw, ld_out):
+    return bool(_lib.load().se_linear_head_fused_supported(B, F, D_in, D_out, ldx, ldw, ld_out))
+
+
+def linear_head_tma(x, D_in, weight_padded, bias, activation, stat_sums, cmvn_eps):
+    """x (B, F, LDx), weight_padded (Dout, LDw) pre-rounded to TF32, stat_sums (B, LDs, 2) float64 or None
+    -> mask (B, F, round4(Dout)) through the TMA / tcgen05 head (columns >= Dout unspecified)."""
+    B, F, LDx = x.shape
+    Dout, LDw = weight_padded.shape
+    LDo = round4(Dout)
+    with torch.cuda.device(x.device):
+        out = torch.empty(B, F, LDo, device=x.device)
+        rc = _lib.load().se_linear_head_fused(x.data_ptr(), LDx, _p(stat_sums), 0 if stat_sums is None else stat_sums.shape[1],
+                                              float(cmvn_eps), weight_padded.data_ptr(), LDw, _p(bias), B, F, int(D_in), Dout,
+                                              ACT[activation], out.data_ptr(), LDo, _stream())
+        _lib.check(rc, "se_linear_head_fused")
+    return out
+
+
 def cmvn_stats_padded(x, D):
     """x (B, F, LD) with D valid columns -> mean, std (B, LD) (valid columns [0, D))."""
     B, F, LD = x.shape
@@ -152,7 +214,7 @@ def istft(power, phase, n_fft, hop, window, pad_to=0):
 
 
 def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, want_sums=True, want_spec=True,
-               out=None, sums=None, mask_padded=False):
+               out=None, sums=None, mask_padded=False, sums_zeroed=False):
     """Fused ``istft(linear_inp * mask, phase_inp)`` straight from the noisy waveform.
 
     wavs (B, C, T); mask (B, F, K); lengths (B,) int64 or None.  Returns (wav (B, width), sums (B, 6) float64|None)."""
@@ -171,10 +233,11 @@ def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, 
         if want_sums and sums is None:
             sums = torch.empty(B, NSUMS, device=wavs.device, dtype=torch.float64)
         clean = None if ch_tar is None else wavs.data_ptr() + 4 * int(ch_tar) * T
-        rc = _lib.load().se_mask_istft_strided(wavs.data_ptr() + 4 * int(ch_inp) * T, clean, C * T, mask.data_ptr(), mask_stride,
-                                               _p(lengths), B, T, n_fft, hop, window.data_ptr(), out.data_ptr(), out.stride(0),
-                                               int(pad_to), _p(sums) if want_sums else None, int(bool(want_spec)), _stream())
-        _lib.check(rc, "se_mask_istft_strided")
+        flags = (FLAG_WANT_SPEC if want_spec else 0) | (FLAG_SUMS_ZEROED if sums_zeroed else 0)
+        rc = _lib.load().se_mask_istft_ex(wavs.data_ptr() + 4 * int(ch_inp) * T, clean, C * T, mask.data_ptr(), mask_stride,
+                                          _p(lengths), B, T, n_fft, hop, window.data_ptr(), out.data_ptr(), out.stride(0),
+                                          int(pad_to), _p(sums) if want_sums else None, flags, _stream())
+        _lib.check(rc, "se_mask_istft_ex")
     return out, (sums if want_sums else None)
 
 

@@ -497,3 +497,62 @@ def test_eval_step_with_tensor_core_head_keeps_sisdr_parity(se, golden_dir):
         scores.append(out["sisdr"].mean().item())
     assert np.mean(losses) == pytest.approx(float(g["loss"]), abs=5e-3)
     assert np.mean(scores) == pytest.approx(float(g["scores"][0]), abs=SISDR_TOL_DB)
+
+
+# ------------------------------------------------------------------------------ fused step: K1 with CMVN sums, TMA head
+@pytest.mark.parametrize("n_fft,B,T,logp", [(512, 3, 16000, True), (512, 5, 9999, True), (512, 2, 64000, False),
+                                            (512, 64, 4096, True), (400, 2, 16000, True)])
+def test_stft_features_and_cmvn_sums(se, n_fft, B, T, logp):
+    from speech_enhancement_by_s3prl_b200 import ops
+    _, mine = make_pair(se, n_fft)
+    hop = mine._win_args["hop_length"]
+    K = n_fft // 2 + 1
+    _, wavs = synth(B, T, seed=T + B)
+    wavs = wavs.cuda()
+    feats, sums = ops.stft_features(wavs, 0, n_fft, hop, mine._frame_window, logpower=logp)
+    ref = ops.stft(wavs, 0, n_fft, hop, mine._frame_window, power=not logp, logpower=logp)["logpower" if logp else "power"]
+    torch.cuda.synchronize()
+    assert torch.equal(feats[..., :K], ref)                                     # same kernel body: bit-identical features
+    s1 = ref.double().sum(1)
+    s2 = (ref.double() ** 2).sum(1)
+    np.testing.assert_allclose(sums[:, :K, 0].cpu().numpy(), s1.cpu().numpy(), rtol=1e-9, atol=1e-9 * s2.max().item() ** 0.5)
+    np.testing.assert_allclose(sums[:, :K, 1].cpu().numpy(), s2.cpu().numpy(), rtol=1e-9)
+    # and the standalone sums entry point
+    sums2 = ops.feature_sums(feats, K)
+    np.testing.assert_allclose(sums2[:, :K].cpu().numpy(), sums[:, :K].cpu().numpy(), rtol=1e-9, atol=1e-9 * s2.max().item() ** 0.5)
+
+
+@pytest.mark.parametrize("B,F,Din,Dout,act,cmvn", [(3, 101, 257, 257, "Sigmoid", True), (2, 300, 201, 201, "ReLU", False),
+                                                   (2, 128, 120, 201, "Identity", True), (64, 251, 257, 257, "Sigmoid", True),
+                                                   (1, 9, 257, 257, "Sigmoid", True), (700, 40, 129, 129, "Sigmoid", True)])
+def test_tma_head_matches_fp32_head(se, B, F, Din, Dout, act, cmvn):
+    from speech_enhancement_by_s3prl_b200 import ops
+    g = torch.Generator().manual_seed(Din + F)
+    LDx = ops.round4(Din)
+    feats = torch.full((B, F, LDx), float("nan"))                            # padding columns must never leak into the result
+    feats[..., :Din] = torch.randn(B, F, Din, generator=g) * 2 - 3
+    feats = feats.cuda()
+    torch.manual_seed(2)
+    lin = torch.nn.Linear(Din, Dout).cuda()
+    dense = feats[..., :Din].contiguous()
+    mean = std = sums = None
+    if cmvn:
+        mean, std = ops.cmvn_stats(dense)
+        sums = ops.feature_sums(feats, Din)
+    off0, _ = ops.linear_head_fused(dense, lin.weight, lin.bias, act, mean, std, 1e-6, precision=0)
+    assert ops.linear_head_tma_supported(B, F, Din, Dout, LDx, LDx, ops.round4(Dout))
+    wpad = ops.round_tf32(ops.pad_weight(lin.weight.detach()))
+    off1 = ops.linear_head_tma(feats, Din, wpad, lin.bias, act, sums, 1e-6)[..., :Dout]
+    torch.cuda.synchronize()
+    scale = max(1.0, dense.abs().max().item() * 0.1)
+    assert torch.isfinite(off1).all()
+    assert (off1 - off0).abs().max().item() < 3e-3 * scale
+    assert (off1 - off0).abs().mean().item() < 3e-4 * scale
+
+
+def test_round_tf32_matches_cvt_rna(se):
+    from speech_enhancement_by_s3prl_b200 import ops
+    w = torch.randn(1000).cuda()
+    r = ops.round_tf32(w)
+    assert ((r.view(torch.int32) & 0x1FFF) == 0).all()
+    assert ((r - w).abs() <= w.abs() * 2.0 ** -11 * 1.0001).all()
