@@ -53,6 +53,11 @@ extern "C" {
 int se_version(void);
 int se_last_error(char* h_buf, int n);
 int se_set_option(int key, int value);
+/* Debugging aid: CTA timeline of the fused-step kernels.  d_buf = device buffer of 1 + 4*capacity uint64 (first word = record
+ * count, zeroed by the caller) or NULL to switch tracing off; records are {kernel id << 32 | block, SM id, t_start, t_end}
+ * (globaltimer ns; kernel ids 1 = STFT, 2 = head, 3 = mask->iSTFT, 4 = finalize).  Applies to launches (and graph captures)
+ * made after the call. */
+int se_set_trace(unsigned long long* d_buf);
 
 /* Create the per-device twiddle tables for n_fft and opt the kernels into their
  * shared-memory size.  Idempotent.  Call once before capturing a CUDA graph. */

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "se_last_error": [ctypes.c_char_p, c_int],
     "se_prepare": [c_int],
     "se_set_option": [c_int, c_int],
+    "se_set_trace": [c_f],
     "se_stft": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_f, c_f, c_f, c_f],
     "se_stft_strided": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_f, c_f, c_f, i64, c_f],
     "se_istft": [c_f, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f],

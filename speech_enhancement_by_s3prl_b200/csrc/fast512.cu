@@ -44,6 +44,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_PENDING> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
@@ -56,12 +60,14 @@ __device__ __forceinline__ void stage_wave(float* __restrict__ dst, const float*
     if ((t0 >= 0) && (t0 + count <= T) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
         for (int c = j; c < count / 4; c += 16) cp_async16(dst + 4 * c, src + 4 * c);
     } else {
-#pragma unroll 1
+        // utterance edges (reflection) and rows that are not 16-byte aligned: element-wise, but still asynchronous -- a
+        // synchronous loop here serialises ~32 L2 round trips and stretches the whole CTA (seen as a bimodal CTA timeline)
+#pragma unroll 4
         for (int i = j; i < count; i += 16) {
             int t = t0 + i;
             t = t < 0 ? -t : t;
             t = t >= T ? 2 * (T - 1) - t : t;
-            dst[i] = __ldg(row + t);
+            cp_async4(dst + i, row + t);
         }
     }
 }
@@ -70,8 +76,8 @@ __device__ __forceinline__ void stage_row(float* __restrict__ dst, const float* 
     if (padded && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {                              // padded: row stride >= round4(count)
         for (int c = j; c < (count + 3) / 4; c += 16) cp_async16(dst + 4 * c, src + 4 * c);
     } else {
-#pragma unroll 1
-        for (int i = j; i < count; i += 16) dst[i] = __ldg(src + i);
+#pragma unroll 4
+        for (int i = j; i < count; i += 16) cp_async4(dst + i, src + i);
     }
 }
 
@@ -80,9 +86,7 @@ __device__ __forceinline__ void frame_from_stage(const float* __restrict__ st, i
     const float2* s2 = reinterpret_cast<const float2*>(st);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-        const float2 x = s2[j + 16 * r];
-        const float2 w = win2[j + 16 * r];
-        v[r] = make_float2(x.x * w.x, x.y * w.y);
+        v[r] = pmul(s2[j + 16 * r], win2[j + 16 * r]);
     }
 }
 
@@ -120,21 +124,22 @@ __device__ __forceinline__ void load_frame(const float* __restrict__ row, int T,
 // One pair of bins (k, M-k) of the real-input split.  zk = Z[k], zm = Z[M-k] (of the 1/2-scaled frame),
 // w = exp(-2*pi*i*k/N).  xa = X[k], xb = X[M-k].
 __device__ __forceinline__ void split_pair(float2 zk, float2 zm, float2 w, float2& xa, float2& xb) {
-    const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
-    const float2 o = make_float2(zk.y + zm.y, zm.x - zk.x);                 // -i * (Z[k] - conj Z[M-k])
+    const float2 e = cadd(zk, make_float2(zm.x, -zm.y));
+    const float2 o = cadd(make_float2(zk.y, -zk.x), make_float2(zm.y, zm.x));   // -i * (Z[k] - conj Z[M-k])
     const float2 t = cmul(o, w);
-    xa = make_float2(e.x + t.x, e.y + t.y);
-    xb = make_float2(e.x - t.x, t.y - e.y);
+    xa = cadd(e, t);
+    xb = cconj(csub(e, t));
 }
 // Inverse of split_pair up to a factor 2: from Y[k], Y[M-k] the values conj(Zinv[k]), conj(Zinv[M-k])
 // that feed the forward FFT used as an inverse.
 __device__ __forceinline__ void merge_pair_conj(float2 ya, float2 yb, float2 w, float2& ca, float2& cb) {
-    const float2 e = make_float2(ya.x + yb.x, ya.y - yb.y);
-    const float2 d = make_float2(ya.x - yb.x, ya.y + yb.y);
+    const float2 ybc = make_float2(yb.x, -yb.y);
+    const float2 e = cadd(ya, ybc);
+    const float2 d = csub(ya, ybc);
     const float2 o = cmul(d, make_float2(w.x, -w.y));
     const float2 u = make_float2(-o.y, o.x);                                  // i * o
-    ca = make_float2(e.x + u.x, -(e.y + u.y));                                // conj(Zinv[k])   = conj(e + u)
-    cb = make_float2(e.x - u.x, e.y - u.y);                                   // conj(Zinv[M-k]) = e - u
+    ca = cconj(cadd(e, u));                                                   // conj(Zinv[k])   = conj(e + u)
+    cb = csub(e, u);                                                          // conj(Zinv[M-k]) = e - u
 }
 
 // ------------------------------------------------------------------ K1
@@ -155,6 +160,7 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 template <bool POWER, bool PHASE, bool LOGP, bool STATS>
 __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long long total_frames, int per_cta) {
     extern __shared__ __align__(16) unsigned char smem1[];
+    secommon::TraceScope trace(a.trace, 1);
     const int lane = threadIdx.x & 31, j = lane & 15;
     const int hw = (threadIdx.x >> 4);
     float2* xbuf = reinterpret_cast<float2*>(smem1) + hw * M;
@@ -165,34 +171,40 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     __syncthreads();
     griddep_launch();                                   // a dependent kernel may start its prologue (it waits for our completion)
-    const long long cta_lo = (long long)blockIdx.x * per_cta;
-    const long long cta_hi = cta_lo + per_cta < total_frames ? cta_lo + per_cta : total_frames;
+    const int total = (int)total_frames;                              // < 2^31 (checked by the launcher): 32-bit index math
+    const int cta_lo = blockIdx.x * per_cta;
+    const int cta_hi = cta_lo + per_cta < total ? cta_lo + per_cta : total;
     const unsigned hmask = half_mask(lane);
-    auto prefetch = [&](long long gg, int buf) {
-        const int u = (int)(gg / a.n_frames), f = (int)(gg - (long long)u * a.n_frames);
+    auto prefetch = [&](int gg, int buf) {
+        const int u = gg / a.n_frames, f = gg - u * a.n_frames;
         stage_wave(stage + buf * N, a.wav + (long long)u * a.utt_stride, a.T, f * a.hop - N / 2, N, j);
         cp_async_commit();
     };
     if (cta_lo + hw < cta_hi) prefetch(cta_lo + hw, 0);
     int buf = 0;
-    double st_s = 0.0, st_q = 0.0, st_s2 = 0.0, st_q2 = 0.0;      // column threadIdx.x (and, in thread 0, column 256)
-    int st_u = -1;
+    // statistics: thread t owns bin t (column sums over the 16 rows of an iteration); bin 256 lives in lane j == 0 of every
+    // half-warp and is accumulated there, frame by frame
+    double st_s = 0.0, st_q = 0.0, ny_s = 0.0, ny_q = 0.0;
+    int st_u = -1, ny_u = -1;
     auto flush = [&]() {
         if (st_u >= 0) {
             double* p = a.stat_sums + ((long long)st_u * a.ld_stats + threadIdx.x) * 2;
             atomicAdd(p, st_s);
             atomicAdd(p + 1, st_q);
-            if (threadIdx.x == 0) {
-                double* p2 = a.stat_sums + ((long long)st_u * a.ld_stats + M) * 2;
-                atomicAdd(p2, st_s2);
-                atomicAdd(p2 + 1, st_q2);
-            }
         }
-        st_s = st_q = st_s2 = st_q2 = 0.0;
+        st_s = st_q = 0.0;
+    };
+    auto flush_nyquist = [&]() {
+        if (ny_u >= 0) {
+            double* p = a.stat_sums + ((long long)ny_u * a.ld_stats + M) * 2;
+            atomicAdd(p, ny_s);
+            atomicAdd(p + 1, ny_q);
+        }
+        ny_s = ny_q = 0.0;
     };
 #pragma unroll 1
-    for (long long g0 = cta_lo; g0 < cta_hi; g0 += kThreads1 / 16, buf ^= 1) {
-        const long long gg = g0 + hw;
+    for (int g0 = cta_lo; g0 < cta_hi; g0 += kThreads1 / 16, buf ^= 1) {
+        const int gg = g0 + hw;
         float* frow = reinterpret_cast<float*>(xbuf);
         if (gg < cta_hi) {
             if (gg + kThreads1 / 16 < cta_hi) { prefetch(gg + kThreads1 / 16, buf ^ 1); cp_async_wait<1>(); }
@@ -203,7 +215,7 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
             fft256<-1>(v, xbuf, j, tw, hmask);
             float2 zm[8];
             fetch_mirror(v, lane, zm);
-            const long long o = gg * a.spec_stride;
+            const long long o = (long long)gg * a.spec_stride;
             float* pw = POWER ? a.power + o : nullptr;
             float* lg = LOGP ? a.logp + o : nullptr;
             float* ph = PHASE ? a.phase + o : nullptr;
@@ -217,7 +229,17 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
                 float la = 0.f, lb = 0.f;
                 if (LOGP) { la = __logf(pa + a.log_eps); lb = __logf(pb + a.log_eps); lg[k] = la; lg[M - k] = lb; }
                 if (PHASE) { ph[k] = atan2f(k == 0 ? 0.0f : xa.y, xa.x); ph[M - k] = atan2f(k == 0 ? 0.0f : xb.y, xb.x); }
-                if (STATS) { frow[k] = LOGP ? la : pa; frow[M - k] = LOGP ? lb : pb; }
+                if (STATS) {
+                    frow[k] = LOGP ? la : pa;
+                    if (k != 0) frow[M - k] = LOGP ? lb : pb;
+                    else {                                              // bin 256 (lane j == 0, q == 0)
+                        const int u = gg / a.n_frames;
+                        if (u != ny_u) { flush_nyquist(); ny_u = u; }
+                        const double y = (double)(LOGP ? lb : pb);
+                        ny_s += y;
+                        ny_q = fma(y, y, ny_q);
+                    }
+                }
             }
             if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
                 const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
@@ -232,25 +254,28 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
         }
         if (STATS) {
             __syncthreads();                                            // the feature rows of this iteration are in shared memory
-            const int nrows = (int)(cta_hi - g0 < kThreads1 / 16 ? cta_hi - g0 : kThreads1 / 16);
+            const int nrows = cta_hi - g0 < kThreads1 / 16 ? cta_hi - g0 : kThreads1 / 16;
             const float* col = reinterpret_cast<const float*>(smem1) + threadIdx.x;
+            int u = g0 / a.n_frames;
+            int r_end = (u + 1) * a.n_frames - g0;                      // first row of the next utterance
             int r = 0;
             while (r < nrows) {
-                const int u = (int)((g0 + r) / a.n_frames);
-                const long long u_end = (long long)(u + 1) * a.n_frames - g0;        // first row of the next utterance
-                const int r_end = u_end < nrows ? (int)u_end : nrows;
+                if (r_end > nrows) r_end = nrows;
                 if (u != st_u) { flush(); st_u = u; }
+#pragma unroll 4
                 for (; r < r_end; ++r) {
                     const double x = (double)col[r * 2 * M];
                     st_s += x;
-                    st_q += x * x;
-                    if (threadIdx.x == 0) { const double y = (double)col[r * 2 * M + M]; st_s2 += y; st_q2 += y * y; }
+                    st_q = fma(x, x, st_q);
                 }
+                ++u;
+                r_end += a.n_frames;
             }
             __syncthreads();                                            // rows consumed: the transpose buffers may be reused
         }
     }
-    if (STATS) flush();
+    if (STATS) { flush(); if (j == 0) flush_nyquist(); }
+    if (a.trace) { __syncthreads(); trace.finish(); }
 }
 
 // ------------------------------------------------------------------ K3: fused mask -> iSTFT, hop = 256
@@ -274,6 +299,7 @@ constexpr size_t kSmem3 = (size_t)(kWarps3 * 2) * (M * 8 + 2 * kStageFloats3 * 4
 
 __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem3[];
+    secommon::TraceScope trace(a.trace, 3);
     float2* s_win2 = reinterpret_cast<float2*>(smem3 + (size_t)(kWarps3 * 2) * (M * 8 + 2 * kStageFloats3 * 4));
     float2* s_bw2 = s_win2 + M;
     for (int i = threadIdx.x; i < M; i += kThreads3) {
@@ -294,7 +320,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     float2* xbuf = reinterpret_cast<float2*>(smem3) + hw * M;
     float* stage = reinterpret_cast<float*>(smem3 + (size_t)(kWarps3 * 2) * M * 8) + hw * 2 * kStageFloats3;
     const long long unit = (long long)blockIdx.x * (kThreads3 / 16) + hw;
-    if (unit >= plan.total_runs) return;                          // no block-level barrier below
+    if (unit >= plan.total_runs) return;                          // no block-level barrier below (tracing: approximate for ragged CTAs)
     const int u = (int)(unit / plan.runs_per_utt), ri = (int)(unit - (long long)u * plan.runs_per_utt);
     const int F = a.n_frames;
     const int b0 = 1 + ri * plan.run_len;
@@ -391,7 +417,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
             for (int q = 0; q < 8; ++q) {
                 const int m = j + 16 * q;
                 const float2 bw = s_bw2[m];
-                const float2 y = make_float2(carry[q].x + bw.x * v[q].x, carry[q].y + bw.y * v[q].y);
+                const float2 y = pfma(bw, v[q], carry[q]);
                 const int t = t0 + 2 * m;
                 if (out_aligned) *reinterpret_cast<float2*>(orow + t) = y;
                 else { orow[t] = y.x; orow[t + 1] = y.y; }
@@ -406,7 +432,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const float2 bw = s_bw2[j + 16 * q + 128];
-            carry[q] = make_float2(bw.x * v[q + 8].x, bw.y * v[q + 8].y);
+            carry[q] = pmul(bw, v[q + 8]);
         }
         __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
     }
@@ -426,6 +452,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
             if (j == 0 && s != 0.0f) atomicAdd(a.sums + (long long)u * sekern::NSUMS + i, (double)s);
         }
     }
+    if (a.trace) { __syncthreads(); trace.finish(); }
 }
 
 }  // namespace
@@ -467,7 +494,7 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
     const long long cap = 2LL * num_sms();
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     const long long per = (total + grid - 1) / grid;
-    if (per > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "too many frames");
+    if (total > 0x7fffff00LL) return secommon::fail(SE_ERR_BAD_ARG, "too many frames (%lld)", total);
     const int per_cta = (int)per;
     const int sel = (a.power ? 1 : 0) | (a.phase ? 2 : 0) | (a.logp ? 4 : 0);
     if (a.stat_sums) {
@@ -529,7 +556,7 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // prologue overlaps the upstream kernel's tail
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = (secommon::pdl_mask() & 2) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel, a, plan));

@@ -25,11 +25,40 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 
 namespace sefft {
 
+#if defined(__CUDA_ARCH__)
+// sm_100 packed fp32 arithmetic: one FADD2 / FMUL2 / FFMA2 works on a (re, im) register pair, and ptxas folds the
+// component shuffles below (broadcast, swap, per-half negation) into the operand selectors of those instructions
+// (R.F32, R.F32x2.LO_HI, .NP ...), so a complex add is ONE instruction and a complex multiply is TWO.  The rounding is
+// that of the scalar forms with the usual mul+add contraction.
+typedef unsigned long long se_u64;
+__device__ __forceinline__ se_u64 pk2(float lo, float hi) { se_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 upk2(se_u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ se_u64 add2(se_u64 a, se_u64 b) { se_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ se_u64 sub2(se_u64 a, se_u64 b) { se_u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ se_u64 mul2(se_u64 a, se_u64 b) { se_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ se_u64 fma2(se_u64 a, se_u64 b, se_u64 c) { se_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return upk2(sub2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return upk2(fma2(pk2(a.y, a.y), pk2(-b.y, b.x), mul2(pk2(a.x, a.x), pk2(b.x, b.y))));
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return upk2(mul2(pk2(a.x, a.y), pk2(s, s))); }
+// a * b + c (complex), and element-wise a * b / a * b + c on (x, y) pairs
+__device__ __forceinline__ float2 cmadd(float2 a, float2 b, float2 c) {
+    return upk2(fma2(pk2(a.y, a.y), pk2(-b.y, b.x), fma2(pk2(a.x, a.x), pk2(b.x, b.y), pk2(c.x, c.y))));
+}
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return upk2(mul2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return upk2(fma2(pk2(a.x, a.y), pk2(b.x, b.y), pk2(c.x, c.y))); }
+#else
 SE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SE_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 SE_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-SE_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 SE_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+SE_HD float2 cmadd(float2 a, float2 b, float2 c) { return cadd(cmul(a, b), c); }
+SE_HD float2 pmul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+SE_HD float2 pfma(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#endif
+SE_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiply by DIR * i  (forward: by -i, inverse: by +i)
 template <int DIR> SE_HD float2 mul_dir_i(float2 a) {
     return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
@@ -69,11 +98,11 @@ template <int DIR> SE_HD void bfly5(float2& a0, float2& a1, float2& a2, float2& 
 // multiply by exp(DIR * 2*pi*i * q / 8), q = 1, 3  (q = 2 is mul_dir_i)
 template <int DIR> SE_HD float2 mul_w8_1(float2 a) {
     const float h = 0.70710678118654752f;
-    return DIR < 0 ? make_float2(h * (a.x + a.y), h * (a.y - a.x)) : make_float2(h * (a.x - a.y), h * (a.x + a.y));
+    return cscale(cadd(a, mul_dir_i<DIR>(a)), h);            // (1 + DIR i) a / sqrt 2
 }
 template <int DIR> SE_HD float2 mul_w8_3(float2 a) {
     const float h = 0.70710678118654752f;
-    return DIR < 0 ? make_float2(h * (a.y - a.x), -h * (a.x + a.y)) : make_float2(-h * (a.x + a.y), h * (a.x - a.y));
+    return cscale(csub(a, mul_dir_i<DIR>(a)), -h);           // (-1 + DIR i) a / sqrt 2
 }
 
 // in-place 8-point DFT of v[0..7] (stride S in the array), natural order out
@@ -98,7 +127,7 @@ template <int DIR> SE_HD float2 mul_w16(float2 a, int q) {   // exp(DIR*2*pi*i*q
         default: wr = -c1; wi = s1; break;
     }
     wi = DIR < 0 ? -wi : wi;
-    return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+    return cmul(a, make_float2(wr, wi));
 }
 
 template <int DIR> SE_HD void bfly16(float2* v) {

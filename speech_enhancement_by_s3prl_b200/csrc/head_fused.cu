@@ -6,9 +6,9 @@
 // (se_stft_stats), so no separate statistics pass runs between the STFT and the head.
 //
 // One CTA owns ONE tile of up to 128 consecutive rows (frames) and ALL output columns:
-//   * warp 9 (one lane)  TMA producer: SWIZZLE_128B tensor-map loads of the whole A tile (every
-//                        32-float k-block lands in its own 16 KB K-major tile) and of the weight
-//                        k-blocks through a 2-stage ring
+//   * warp 9 (one lane)  TMA producer: SWIZZLE_128B tensor-map loads through a 4-stage ring; a stage is one
+//                        32-float k-block of the A tile (16 KB K-major tile) plus the same k-block of all
+//                        weight rows (34 KB)
 //   * warps 0-7          normalise the A tile IN PLACE in shared memory (CMVN scale/shift from the
 //                        sums, round to TF32), later run the epilogue
 //   * warp 8 (one lane)  tcgen05.mma kind::tf32, fp32 accumulators in tensor memory: columns
@@ -26,22 +26,23 @@ using secommon::fail;
 
 namespace {
 
-constexpr int BM = 128, BK = 32, kMaxKB = 9, kWStages = 2;
+constexpr int BM = 128, BK = 32, kMaxKB = 9, kStages = 4;
 constexpr int kWorkWarps = 8, kWorkThreads = kWorkWarps * 32, kThreads = kWorkThreads + 64;   // + MMA warp + TMA warp
-constexpr int kATileBytes = BM * BK * 4;                       // 16 KB per k-block
+constexpr int kATileBytes = BM * BK * 4;                       // 16 KB: one 32-float k-block of the A tile
 constexpr int kMaxWRows = 272;
-constexpr int kWStageBytes = kMaxWRows * BK * 4;               // 34 816 (multiple of 1024)
+constexpr int kWTileBytes = kMaxWRows * BK * 4;                // 34 816: the same k-block of all weight rows
+constexpr int kStageBytes = kATileBytes + kWTileBytes;         // 51 200 (multiple of 1024: SWIZZLE_128B atoms stay aligned)
 constexpr int kStatLd = kMaxKB * BK;                           // 288
-constexpr int kOffA = 0;
-constexpr int kOffW = kOffA + kMaxKB * kATileBytes;            // 147 456
-constexpr int kOffScale = kOffW + kWStages * kWStageBytes;     // 217 088
+constexpr int kOffRing = 0;
+constexpr int kOffScale = kOffRing + kStages * kStageBytes;    // 204 800
 constexpr int kOffShift = kOffScale + 2 * kStatLd * 4;
 constexpr int kOffBias = kOffShift + 2 * kStatLd * 4;
 constexpr int kOffBar = kOffBias + kStatLd * 4;
-constexpr int kNumBars = 2 * kMaxKB + 2 * kWStages + 1;
+constexpr int kNumBars = 3 * kStages + 1;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kStageBytes % 1024 == 0 && kATileBytes % 1024 == 0, "swizzle atom alignment");
 constexpr unsigned kSpinLimit = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,8 +111,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float activate(float z, int act) {
     if (act == SE_ACT_RELU) return z > 0.f ? z : 0.f;
     if (act == SE_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-z));
@@ -124,6 +125,7 @@ struct Head2Args {
     const double* sums;        // (n_utt, ld_stats, 2): sum x, sum x^2 over the utterance's frames; null = no CMVN
     long long ld_stats;
     float cmvn_eps;
+    double inv_n, inv_nm1;     // 1 / n_frames, 1 / (n_frames - 1)
     const float* bias;
     long long R;               // n_utt * n_frames
     int n_utt, n_frames, Din, Dout, act;
@@ -136,21 +138,22 @@ struct Head2Args {
     int w_box_rows, w_boxes;   // weight tensor-map box rows and boxes per k-block
     int sld;                   // floats per row of the staging tile
     int bulk_out;              // staging rows == output rows and 16-byte aligned: one bulk store per quadrant
+    unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Head2Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    secommon::TraceScope trace(a.trace, 2);
     const uint32_t sbase = smem_u32(smem);
     float* s_scale = reinterpret_cast<float*>(smem + kOffScale);
     float* s_shift = reinterpret_cast<float*>(smem + kOffShift);
     float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
-    const uint32_t bar_a_full = sbase + kOffBar;                       // [kMaxKB]  TMA landed k-block kb of A
-    const uint32_t bar_a_norm = bar_a_full + 8 * kMaxKB;               // [kMaxKB]  k-block kb normalised in place
-    const uint32_t bar_w_full = bar_a_norm + 8 * kMaxKB;               // [kWStages]
-    const uint32_t bar_w_empty = bar_w_full + 8 * kWStages;            // [kWStages]
-    const uint32_t bar_accum = bar_w_empty + 8 * kWStages;
+    const uint32_t bar_full = sbase + kOffBar;                         // [kStages] TMA landed the stage's A and W k-block
+    const uint32_t bar_norm = bar_full + 8 * kStages;                  // [kStages] A k-block normalised in place
+    const uint32_t bar_empty = bar_norm + 8 * kStages;                 // [kStages] the MMAs have read the stage
+    const uint32_t bar_accum = bar_empty + 8 * kStages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r0 = (long long)blockIdx.x * a.tile_rows;
@@ -158,8 +161,11 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     if (threadIdx.x == 0) {
         if (sbase & 1023) __trap();
-        for (int kb = 0; kb < kMaxKB; ++kb) { mbar_init(bar_a_full + 8 * kb, 1); mbar_init(bar_a_norm + 8 * kb, kWorkWarps); }
-        for (int s = 0; s < kWStages; ++s) { mbar_init(bar_w_full + 8 * s, 1); mbar_init(bar_w_empty + 8 * s, 1); }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_norm + 8 * s, kWorkWarps);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
         mbar_init(bar_accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,26 +178,34 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     griddep_launch();                                   // the next kernel may start its own prologue
+    if (threadIdx.x == 0) trace.mark(11);
 
     if (warp == kWorkWarps + 1) {
         // ===================== TMA producer =====================
+        // ring of kStages stages, each holding one 32-float k-block of the A tile and of all weight rows
         if (lane == 0) {
+            const uint32_t a_bytes = (uint32_t)a.tile_rows * BK * 4;
             auto load_w = [&](int kb, int s) {
-                const uint32_t dst = sbase + kOffW + s * kWStageBytes;
-                mbar_expect_tx(bar_w_full + 8 * s, w_bytes);
+                const uint32_t dst = sbase + kOffRing + s * kStageBytes + kATileBytes;
                 for (int b = 0; b < a.w_boxes; ++b)
-                    tma_load_2d(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, b * a.w_box_rows, bar_w_full + 8 * s);
+                    tma_load_2d(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, b * a.w_box_rows, bar_full + 8 * s);
             };
-            for (int s = 0; s < kWStages && s < a.kblocks; ++s) load_w(s, s);     // weights do not depend on the upstream kernel
-            griddep_wait();
-            for (int kb = 0; kb < a.kblocks; ++kb) {
-                mbar_expect_tx(bar_a_full + 8 * kb, (uint32_t)a.tile_rows * BK * 4);
-                tma_load_2d(sbase + kOffA + kb * kATileBytes, &tmA, kb * BK, (int)r0, bar_a_full + 8 * kb);
+            auto load_a = [&](int kb, int s) {
+                tma_load_2d(sbase + kOffRing + s * kStageBytes, &tmA, kb * BK, (int)r0, bar_full + 8 * s);
+            };
+            const int first = a.kblocks < kStages ? a.kblocks : kStages;
+            for (int s = 0; s < first; ++s) {                              // weights do not depend on the upstream kernel
+                mbar_expect_tx(bar_full + 8 * s, a_bytes + w_bytes);
+                load_w(s, s);
             }
-            for (int kb = kWStages; kb < a.kblocks; ++kb) {
-                const int s = kb % kWStages;
-                mbar_wait(bar_w_empty + 8 * s, ((kb / kWStages) - 1) & 1);          // MMAs of k-block kb - kWStages have read the stage
+            griddep_wait();
+            for (int s = 0; s < first; ++s) load_a(s, s);
+            for (int kb = kStages; kb < a.kblocks; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(bar_empty + 8 * s, ((kb / kStages) - 1) & 1);     // MMAs of k-block kb - kStages have read the stage
+                mbar_expect_tx(bar_full + 8 * s, a_bytes + w_bytes);
                 load_w(kb, s);
+                load_a(kb, s);
             }
         }
     } else if (warp == kWorkWarps) {
@@ -199,12 +213,11 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) {
             const uint32_t idesc_main = make_idesc(a.n_main), idesc_tail = make_idesc(a.n_tail > 0 ? a.n_tail : 16);
             for (int kb = 0; kb < a.kblocks; ++kb) {
-                const int s = kb % kWStages;
-                mbar_wait(bar_a_norm + 8 * kb, 0);
-                mbar_wait(bar_w_full + 8 * s, (kb / kWStages) & 1);
+                const int s = kb % kStages;
+                mbar_wait(bar_norm + 8 * s, (kb / kStages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = sbase + kOffA + kb * kATileBytes;
-                const uint32_t b_addr = sbase + kOffW + s * kWStageBytes;
+                const uint32_t a_addr = sbase + kOffRing + s * kStageBytes;
+                const uint32_t b_addr = a_addr + kATileBytes;
                 const int kvalid = a.Din - kb * BK;
                 const int ksteps = kvalid >= BK ? BK / 8 : (kvalid + 7) / 8;
                 for (int kk = 0; kk < ksteps; ++kk) {
@@ -214,7 +227,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         umma_tf32(tmem_base + (uint32_t)a.n_main, ad, make_desc(b_addr + a.n_main * BK * 4 + kk * 32), idesc_tail,
                                   (kb | kk) ? 1u : 0u);
                 }
-                umma_commit(bar_w_empty + 8 * s);
+                umma_commit(bar_empty + 8 * s);
             }
             umma_commit(bar_accum);
         }
@@ -224,32 +237,50 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         griddep_wait();                                                   // the sums come from the upstream kernel
         const long long u0 = r0 / a.n_frames;
         const int split = (int)((u0 + 1) * a.n_frames - r0);              // first tile row of the next utterance
-        for (int i = t; i < 2 * kStatLd; i += kWorkThreads) {
-            const int ul = i / kStatLd, k = i - ul * kStatLd;
-            const long long u = u0 + ul;
-            float sc = 0.f, sh = 0.f;
-            if (k < a.Din) {
-                sc = 1.f;
-                if (a.sums && u < a.n_utt) {
-                    const double* p = a.sums + (u * a.ld_stats + k) * 2;
-                    const double n = (double)a.n_frames, s1 = p[0], s2 = p[1];
-                    const double mean = s1 / n;
-                    double var = (s2 - s1 * mean) / (n - 1.0);               // unbiased (model.py:30)
-                    var = var > 0.0 ? var : 0.0;
-                    const float inv = 1.0f / ((float)sqrt(var) + a.cmvn_eps);
-                    sc = inv;
-                    sh = -(float)mean * inv;
+        // per-utterance CMVN scale / shift for the (at most two) utterances of the tile; loads first, then the arithmetic
+        {
+            constexpr int kPer = (2 * kStatLd + kWorkThreads - 1) / kWorkThreads;
+            double2 p[kPer];
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+                const int i = t + q * kWorkThreads, ul = i / kStatLd, k = i - ul * kStatLd;
+                const long long u = u0 + ul;
+                p[q] = make_double2(0.0, 0.0);
+                if (i < 2 * kStatLd && k < a.Din && a.sums && u < a.n_utt)
+                    p[q] = *reinterpret_cast<const double2*>(a.sums + (u * a.ld_stats + k) * 2);
+            }
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+                const int i = t + q * kWorkThreads, ul = i / kStatLd, k = i - ul * kStatLd;
+                if (i < 2 * kStatLd) {
+                    float sc = 0.f, sh = 0.f;
+                    if (k < a.Din) {
+                        sc = 1.f;
+                        if (a.sums && u0 + ul < a.n_utt) {
+                            const double mean = p[q].x * a.inv_n;
+                            const float var = (float)((p[q].y - p[q].x * mean) * a.inv_nm1);   // unbiased (model.py:30); cancellation in double
+                            const float inv = __fdividef(1.0f, sqrtf(fmaxf(var, 0.0f)) + a.cmvn_eps);
+                            sc = inv;
+                            sh = -(float)mean * inv;
+                        }
+                    }
+                    s_scale[i] = sc;
+                    s_shift[i] = sh;
                 }
             }
-            s_scale[i] = sc;
-            s_shift[i] = sh;
         }
-        for (int i = t; i < kStatLd; i += kWorkThreads) s_bias[i] = (a.bias && i < a.Dout) ? __ldg(a.bias + i) : 0.f;
+        {
+            const float bscale = a.act == SE_ACT_SIGMOID ? -1.4426950408889634f : 1.0f;     // see the epilogue
+            for (int i = t; i < kStatLd; i += kWorkThreads) s_bias[i] = (a.bias && i < a.Dout) ? bscale * __ldg(a.bias + i) : 0.f;
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
+        if (t == 0) trace.mark(12);
 
         for (int kb = 0; kb < a.kblocks; ++kb) {
-            mbar_wait(bar_a_full + 8 * kb, 0);
-            float4* tile = reinterpret_cast<float4*>(smem + kOffA + kb * kATileBytes);
+            const int s = kb % kStages;
+            mbar_wait(bar_full + 8 * s, (kb / kStages) & 1);
+            if (t == 0 && kb == 0) trace.mark(13);
+            float4* tile = reinterpret_cast<float4*>(smem + kOffRing + s * kStageBytes);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int idx = t + kWorkThreads * i;                     // physical 16-byte chunk: conflict-free LDS/STS.128
@@ -269,36 +300,68 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a_norm + 8 * kb);
+            if (lane == 0) mbar_arrive(bar_norm + 8 * s);
         }
 
         // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31, column half (w >> 2)
+        if (t == 0) trace.mark(14);
         mbar_wait(bar_accum, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* stage = reinterpret_cast<float*>(smem + kOffA);
+        if (t == 0) trace.mark(15);
+        float* stage = reinterpret_cast<float*>(smem + kOffRing);           // every stage has been consumed: reuse the ring
         const int quad = warp & 3, half = warp >> 2;
         const int row = quad * 32 + lane;
         const int ncol16 = a.w_rows / 16;
         const int c_lo = 16 * (half == 0 ? 0 : ncol16 / 2), c_hi = 16 * (half == 0 ? ncol16 / 2 : ncol16);
         float* srow = stage + (long long)row * a.sld;
-        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-            uint32_t acc[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
+        // two 16-column chunks in flight: the tensor-memory load of chunk c+1 overlaps the activation of chunk c
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
+        // The activation of a chunk is written stage by stage over all 16 values (all exponentials, then all adds, then
+        // all reciprocals): a warp issues in order, so element-by-element code would expose the SFU latency 16 times.
+        // Sigmoid: s_bias holds -log2(e) * bias and z is scaled by -log2(e) in the same FFMA: 1 / (1 + 2^t).
+        const int act = a.act;
+        const float zscale = act == SE_ACT_SIGMOID ? -1.4426950408889634f : 1.0f;
+        auto emit = [&](const uint32_t (&acc)[16], int c0) {
+            float v[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                if (c0 + j < a.sld) {
-                    const float4 bz = *reinterpret_cast<const float4*>(s_bias + c0 + j);
-                    float4 o;
-                    o.x = activate(__uint_as_float(acc[j]) + bz.x, a.act);
-                    o.y = activate(__uint_as_float(acc[j + 1]) + bz.y, a.act);
-                    o.z = activate(__uint_as_float(acc[j + 2]) + bz.z, a.act);
-                    o.w = activate(__uint_as_float(acc[j + 3]) + bz.w, a.act);
-                    *reinterpret_cast<float4*>(srow + c0 + j) = o;
-                }
+                const float4 bz = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                v[j] = fmaf(__uint_as_float(acc[j]), zscale, bz.x);
+                v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), zscale, bz.y);
+                v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), zscale, bz.z);
+                v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), zscale, bz.w);
+            }
+            if (act == SE_ACT_SIGMOID) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v[j]) : "f"(v[j]));
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += 1.0f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(v[j]) : "f"(v[j]));
+            } else if (act == SE_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                if (c0 + j < a.sld) *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        };
+        uint32_t acc0[16], acc1[16];
+        tmem_ld16(tbase + (uint32_t)c_lo, acc0);
+        tmem_ld_wait();
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+            if (c0 + 16 < c_hi) tmem_ld16(tbase + (uint32_t)(c0 + 16), acc1);
+            emit(acc0, c0);
+            tmem_ld_wait();
+            if (c0 + 16 < c_hi) {
+                if (c0 + 32 < c_hi) tmem_ld16(tbase + (uint32_t)(c0 + 32), acc0);
+                emit(acc1, c0 + 16);
+                tmem_ld_wait();
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");        // both warps of the quadrant have staged their columns
+        if (t == 0) trace.mark(16);
         long long rows_left = a.R - r0;
         if (rows_left > a.tile_rows) rows_left = a.tile_rows;
         int rows_valid = (int)rows_left - quad * 32;
@@ -321,6 +384,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
+    trace.finish();
     if (warp == kWorkWarps) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -381,7 +445,7 @@ int se_linear_head_fused_supported(int64_t n_utt, int64_t n_frames, int64_t D_in
     if (D_in > kMaxKB * BK || D_out > kMaxWRows) return 0;
     if (ldx % 4 || ldw % 4 || ldx < D_in || ldw < D_in || ld_out < D_out) return 0;
     const int64_t dout4 = (D_out + 3) / 4 * 4;
-    if ((ld_out == dout4 ? ld_out : dout4 + 4) * 4 * BM > kMaxKB * kATileBytes) return 0;        // staging tile must fit in the A region
+    if ((ld_out == dout4 ? ld_out : dout4 + 4) * 4 * BM > kStages * kStageBytes) return 0;      // staging tile must fit in the ring
     return 1;
 }
 
@@ -398,6 +462,9 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     a.sums = stat_sums; a.ld_stats = ld_stats; a.cmvn_eps = cmvn_eps; a.bias = b;
     a.R = n_utt * n_frames; a.n_utt = (int)n_utt; a.n_frames = (int)n_frames; a.Din = (int)D_in; a.Dout = (int)D_out; a.act = act;
     a.out = offset_out; a.ld_out = ld_out;
+    a.trace = secommon::trace_ptr();
+    a.inv_n = 1.0 / (double)n_frames;
+    a.inv_nm1 = 1.0 / (double)(n_frames - 1);
     long long rows = (a.R + num_sms() - 1) / num_sms();                     // one tile per SM when the batch is small
     rows = (rows + 7) / 8 * 8;
     if (rows > BM) rows = BM;
@@ -428,7 +495,7 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = (secommon::pdl_mask() & 1) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, linear_head_fused_kernel, tmA, tmW, a));

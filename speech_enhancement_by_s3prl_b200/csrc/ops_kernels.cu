@@ -37,9 +37,23 @@ __device__ __forceinline__ double sisdr_from_sums(double st, double tt, double s
 __global__ void finalize_metrics_kernel(const double* __restrict__ sums, const long long* __restrict__ lengths,
                                         int T, double level_or_neg, float* __restrict__ wav, long long wav_stride,
                                         int width, float* __restrict__ gain_out, float* __restrict__ sisdr_wave,
-                                        float* __restrict__ loss_spec, int chunks) {
+                                        float* __restrict__ loss_spec, int chunks, unsigned long long* trace_buf) {
+    secommon::TraceScope trace(trace_buf, 4);
     asm volatile("griddepcontrol.wait;" ::: "memory");                   // sums and wav come from the upstream kernel
     const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    // the first batch of waveform loads does not depend on the gain: issue it before the (double precision) gain arithmetic
+    float* row = wav ? wav + (long long)u * wav_stride : nullptr;
+    const int per = (((width + chunks - 1) / chunks) + 3) & ~3;
+    const int lo = chunk * per, hi = min(width, lo + per);
+    const bool vec = wav && (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+    float4* r4 = reinterpret_cast<float4*>(row);
+    const int n4 = (hi & ~3) / 4, bd = blockDim.x;
+    const int i0 = lo / 4 + threadIdx.x;
+    float4 v[8];
+    if (vec) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (i0 + q * bd < n4) v[q] = r4[i0 + q * bd];
+    }
     const double* s = sums + (long long)u * SE_NSUMS;
     const double len = lengths ? (double)lengths[u] : (double)T;
     const double eps_mean = 1e-8;                                       // utils.py:26, utils.py:31
@@ -51,30 +65,26 @@ __global__ void finalize_metrics_kernel(const double* __restrict__ sums, const l
         if (sisdr_wave) sisdr_wave[u] = (float)sisdr_from_sums(gain * s[SE_SUM_YC], s[SE_SUM_CC], gain * gain * s[SE_SUM_YY], 1e-10);
         if (loss_spec) loss_spec[u] = (float)(-sisdr_from_sums(s[SE_SUM_SPEC_ST], s[SE_SUM_SPEC_TT], s[SE_SUM_SPEC_SS], 1e-10));
     }
-    if (!wav) return;
+    if (!wav) { trace.finish(); return; }
     const float g = (float)gain;
-    float* row = wav + (long long)u * wav_stride;
-    const int per = (((width + chunks - 1) / chunks) + 3) & ~3;
-    const int lo = chunk * per, hi = min(width, lo + per);
-    if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
-        float4* r4 = reinterpret_cast<float4*>(row);
-        const int hi4 = hi & ~3;
-        int i = lo / 4 + threadIdx.x;
-        for (; i + 3 * (int)blockDim.x < hi4 / 4; i += 4 * blockDim.x) {       // four loads in flight per thread
-            float4 v0 = r4[i], v1 = r4[i + blockDim.x], v2 = r4[i + 2 * blockDim.x], v3 = r4[i + 3 * blockDim.x];
-            v0.x *= g; v0.y *= g; v0.z *= g; v0.w *= g;  v1.x *= g; v1.y *= g; v1.z *= g; v1.w *= g;
-            v2.x *= g; v2.y *= g; v2.z *= g; v2.w *= g;  v3.x *= g; v3.y *= g; v3.z *= g; v3.w *= g;
-            r4[i] = v0; r4[i + blockDim.x] = v1; r4[i + 2 * blockDim.x] = v2; r4[i + 3 * blockDim.x] = v3;
+    if (vec) {
+        for (int i = i0; i < n4; i += 8 * bd) {                              // eight (predicated) loads in flight per thread
+            if (i != i0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (i + q * bd < n4) v[q] = r4[i + q * bd];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (i + q * bd < n4) {
+                    v[q].x *= g; v[q].y *= g; v[q].z *= g; v[q].w *= g;
+                    r4[i + q * bd] = v[q];
+                }
         }
-        for (; i < hi4 / 4; i += blockDim.x) {
-            float4 v = r4[i];
-            v.x *= g; v.y *= g; v.z *= g; v.w *= g;
-            r4[i] = v;
-        }
-        for (int k = hi4 + threadIdx.x; k < hi; k += blockDim.x) row[k] *= g;
+        for (int k = (hi & ~3) + threadIdx.x; k < hi; k += blockDim.x) row[k] *= g;
     } else {
         for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) row[k] *= g;
     }
+    if (trace_buf) { __syncthreads(); trace.finish(); }
 }
 
 // ------------------------------------------------------------------ spectral SI-SDR objective
@@ -510,7 +520,12 @@ int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_ut
                         float* wav, int64_t wav_stride, int64_t width, float* gain, float* sisdr_wave, float* loss_spec,
                         void* stream) {
     SE_REQUIRE(sums && n_utt > 0, "sums must not be null");
-    const int chunks = wav ? pick_chunks(n_utt, width, 4096) : 1;
+    // two CTAs per SM in one wave: the launch ramp of ~1000 small CTAs costs more than the scaling itself
+    int chunks = 1;
+    if (wav) {
+        long long want = (2LL * 148 + n_utt - 1) / n_utt, cap = width / 4096;
+        chunks = (int)(want < 1 ? 1 : (cap >= 1 && want > cap ? cap : want));
+    }
     const double level = std::isnan(target_db_or_nan) ? -1.0 : std::pow(10.0, (double)target_db_or_nan / 10.0);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n_utt * chunks));
@@ -518,11 +533,11 @@ int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_ut
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // CTAs become resident while the upstream kernel drains
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = (secommon::pdl_mask() & 4) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, finalize_metrics_kernel, sums, (const long long*)lengths, (int)T, level, wav,
-                                     (long long)wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks));
+                                     (long long)wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks, secommon::trace_ptr()));
     return secommon::check_launch("finalize_metrics_kernel");
 }
 

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "../../include/se_b200.h"
 
@@ -35,13 +36,63 @@ inline int fail(int code, const char* fmt, ...) {
         if (!(cond)) return secommon::fail(SE_ERR_BAD_ARG, __VA_ARGS__);   \
     } while (0)
 
+// Programmatic-dependent-launch mask (experiments): SE_B200_PDL bit 0 = head, bit 1 = mask->iSTFT, bit 2 = finalize; default all.
+inline int pdl_mask() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("SE_B200_PDL"); m = e ? atoi(e) : 7; }
+    return m;
+}
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return SE_OK;
 }
 
+// Optional CTA timeline (debugging aid, se_set_trace): when a trace buffer is set, every CTA of the fused-step kernels
+// appends {kernel id << 32 | blockIdx.x, SM id, globaltimer at start, globaltimer at end} to it.
+inline unsigned long long*& trace_ptr() {
+    static unsigned long long* p = nullptr;
+    return p;
+}
+
 #if defined(__CUDACC__)
+struct TraceScope {
+    unsigned long long* buf;
+    unsigned long long t0;
+    int kernel_id;
+    __device__ __forceinline__ static unsigned long long now() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    }
+    __device__ __forceinline__ TraceScope(unsigned long long* b, int id) : buf(b), t0(0), kernel_id(id) {
+        if (buf && threadIdx.x == 0) t0 = now();
+    }
+    __device__ __forceinline__ void mark(int id) {        // intermediate timestamp (calling thread), record id = `id`
+        if (buf) {
+            const unsigned long long i = atomicAdd(buf, 1ULL);
+            unsigned long long* r = buf + 1 + 4 * i;
+            r[0] = ((unsigned long long)id << 32) | blockIdx.x;
+            r[1] = 0;
+            r[2] = t0;
+            r[3] = now();
+        }
+    }
+    __device__ __forceinline__ void finish() {           // call from thread 0 when the CTA's work is done
+        if (buf && threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const unsigned long long i = atomicAdd(buf, 1ULL);
+            unsigned long long* r = buf + 1 + 4 * i;
+            r[0] = ((unsigned long long)kernel_id << 32) | blockIdx.x;
+            r[1] = smid;
+            r[2] = t0;
+            r[3] = now();
+        }
+    }
+};
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -158,6 +158,11 @@ int se_set_option(int key, int value) {
     return fail(SE_ERR_BAD_ARG, "unknown option %d", key);
 }
 
+int se_set_trace(unsigned long long* d_buf) {
+    secommon::trace_ptr() = d_buf;
+    return SE_OK;
+}
+
 int se_last_error(char* h_buf, int n) {
     if (!h_buf || n <= 0) return SE_ERR_BAD_ARG;
     strncpy(h_buf, secommon::last_error_buf(), (size_t)n);
@@ -211,6 +216,7 @@ int se_stft_features(const float* wav, int64_t n_utt, int64_t utt_stride, int64_
         a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
         a.power = take_log ? nullptr : feat; a.logp = take_log ? feat : nullptr; a.log_eps = log_eps; a.spec_stride = feat_stride;
         a.stat_sums = stat_sums; a.ld_stats = ld_stats;
+        a.trace = secommon::trace_ptr();
         return sefast::launch_stft512(a, st);
     }
     // other n_fft: generic STFT, then one pass over the features for the sums
@@ -268,6 +274,7 @@ int se_mask_istft_ex(const float* noisy, const float* clean, int64_t utt_stride,
     a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
     a.wav_out = wav_out; a.out_stride = out_stride; a.out_len = hop * (a.n_frames - 1); a.pad_to = (int)pad_to;
     a.sums = sums; a.want_spec = (want_spec && clean && sums) ? 1 : 0; a.mask_stride = mask_stride;
+    a.trace = secommon::trace_ptr();
     SE_REQUIRE(out_stride >= a.out_len && out_stride >= pad_to, "out_stride=%lld too small", (long long)out_stride);
     cudaStream_t st = (cudaStream_t)stream;
     if (sums && !(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * SE_NSUMS * n_utt, st));

@@ -43,6 +43,7 @@ struct StftArgs {
     long long spec_stride;     // floats between consecutive frames of an output (>= K; K = dense)
     double* stat_sums;         // (n_utt, ld_stats, 2) += [sum x, sum x^2] over frames of the feature written, or null
     long long ld_stats;
+    unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
 };
 
 struct IstftArgs {
@@ -74,6 +75,7 @@ struct MaskIstftArgs {
     double* sums;              // (n_utt, NSUMS) or null
     int want_spec;             // also accumulate the spectral SI-SDR sums (needs clean)
     long long mask_stride;     // floats between consecutive frames of mask (>= K)
+    unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
 };
 
 SE_HD int imin(int a, int b) { return a < b ? a : b; }
