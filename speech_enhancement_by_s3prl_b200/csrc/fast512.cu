@@ -286,21 +286,63 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
 // atomics.  Frame b0-1 is a halo frame (recomputed by the neighbouring run).
 // Synthesis table: bw[n] = s(n) * w[n] / (2 M (w[n mod H]^2 + w[n mod H + H]^2)) with s = +1 for even n
 // and -1 for odd n (the conjugation of the forward-as-inverse FFT); the 2 undoes merge_pair_conj's factor.
+//
+// Staging (cp.async) is sized for THREE resident CTAs per SM -- the kernel is bound by dependent-issue
+// latency, so resident warps are what buys throughput.  Consecutive frames share half of their samples,
+// so a half-warp keeps two 256-sample slots per waveform: frame f reads (first, second) = (slot p, slot p^1),
+// and as soon as the frame is in registers the dead first slot receives the second half of frame f+1.  Every
+// prefetch therefore has a full frame of work to land behind.  Pass order per frame:
+//   0: noisy frame -> rFFT -> x sqrt(mask) (mask row slot, refilled right after) -> merged spectrum
+//   1: inverse FFT -> window -> overlap-add with the carry -> store, waveform sums (clean first slot)
+//   2: clean frame -> rFFT -> spectral SI-SDR sums against the masked noisy power kept from pass 0
+// The three transforms run through ONE copy of the FFT code inside a non-unrolled pass loop.
+// cp.async groups are committed in the fixed order N(oisy) M(ask) C(lean) once per frame (empty groups at the
+// end of a run), so "all but the two most recent groups" is exactly the data the next consumer needs.
 constexpr int kWarps3 = 4, kThreads3 = kWarps3 * 32;
 
-struct RunPlan { int run_len; int runs_per_utt; long long total_runs; };
+struct RunPlan { int blocks_per_utt; int runs_per_utt; long long total_runs; };   // run ri = blocks (ri*bpu/rpu, (ri+1)*bpu/rpu]
 
 #ifndef SE_K3_MIN_BLOCKS
 #define SE_K3_MIN_BLOCKS 3
 #endif
-// per half-warp, per stage: noisy frame (512) | clean frame (512) | mask row (272) floats
-constexpr int kStageFloats3 = N + N + 272;
-constexpr size_t kSmem3 = (size_t)(kWarps3 * 2) * (M * 8 + 2 * kStageFloats3 * 4) + 2 * M * 8;
+constexpr int kMaskFloats3 = 272;
+// per half-warp: transpose buffer | noisy slots 2 x 256 | clean slots 2 x 256 | mask row
+constexpr int kHwBytes3 = M * 8 + 4 * H * 4 + kMaskFloats3 * 4;
+constexpr size_t kSmem3 = (size_t)(kWarps3 * 2) * kHwBytes3 + 2 * M * 8;
+static_assert(kHwBytes3 % 16 == 0, "16-byte aligned cp.async destinations");
+
+// stage H floats of a waveform row starting at original coordinate t0 (reflect outside [0, T))
+__device__ __forceinline__ void stage_half(float* __restrict__ dst, const float* __restrict__ row, int T, int t0, int j) {
+    const float* src = row + t0;
+    if ((t0 >= 0) && (t0 + H <= T) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+        for (int c = 0; c < H / 64; ++c) cp_async16(dst + 4 * (j + 16 * c), src + 4 * (j + 16 * c));
+    } else {
+#pragma unroll 4
+        for (int i = j; i < H; i += 16) {
+            int t = t0 + i;
+            t = t < 0 ? -t : t;
+            t = t >= T ? 2 * (T - 1) - t : t;
+            cp_async4(dst + i, row + t);
+        }
+    }
+}
+// v[r] = (x[2m], x[2m+1]) * win2[m], m = j + 16 r: r < 8 from the first-half slot, r >= 8 from the second-half slot
+__device__ __forceinline__ void frame_from_slots(const float* __restrict__ first, const float* __restrict__ second, int j,
+                                                 const float2* __restrict__ win2, float2 (&v)[16]) {
+    const float2* f2 = reinterpret_cast<const float2*>(first);
+    const float2* s2 = reinterpret_cast<const float2*>(second);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        v[r] = pmul(f2[j + 16 * r], win2[j + 16 * r]);
+        v[r + 8] = pmul(s2[j + 16 * r], win2[j + 16 * r + 128]);
+    }
+}
 
 __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem3[];
     secommon::TraceScope trace(a.trace, 3);
-    float2* s_win2 = reinterpret_cast<float2*>(smem3 + (size_t)(kWarps3 * 2) * (M * 8 + 2 * kStageFloats3 * 4));
+    float2* s_win2 = reinterpret_cast<float2*>(smem3 + (size_t)(kWarps3 * 2) * kHwBytes3);
     float2* s_bw2 = s_win2 + M;
     for (int i = threadIdx.x; i < M; i += kThreads3) {
         const float w0 = a.tab.window[2 * i], w1 = a.tab.window[2 * i + 1];
@@ -317,21 +359,27 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     __syncthreads();
     griddep_launch();
     griddep_wait();                                               // the mask (and the zeroed sums) come from upstream kernels
-    float2* xbuf = reinterpret_cast<float2*>(smem3) + hw * M;
-    float* stage = reinterpret_cast<float*>(smem3 + (size_t)(kWarps3 * 2) * M * 8) + hw * 2 * kStageFloats3;
+    unsigned char* mine = smem3 + (size_t)hw * kHwBytes3;
+    float2* xbuf = reinterpret_cast<float2*>(mine);
+    float* nb = reinterpret_cast<float*>(mine + M * 8);            // noisy slots
+    float* cb = nb + 2 * H;                                        // clean slots
+    float* mb = cb + 2 * H;                                        // mask row
     const long long unit = (long long)blockIdx.x * (kThreads3 / 16) + hw;
     if (unit >= plan.total_runs) return;                          // no block-level barrier below (tracing: approximate for ragged CTAs)
     const int u = (int)(unit / plan.runs_per_utt), ri = (int)(unit - (long long)u * plan.runs_per_utt);
     const int F = a.n_frames;
-    const int b0 = 1 + ri * plan.run_len;
-    const int b1 = min(F - 1, b0 + plan.run_len - 1);
+    const int b0 = 1 + (int)(((long long)ri * plan.blocks_per_utt) / plan.runs_per_utt);
+    const int b1 = (int)(((long long)(ri + 1) * plan.blocks_per_utt) / plan.runs_per_utt);
     const float* nrow = a.noisy + (long long)u * a.utt_stride;
     const float* crow = a.clean ? a.clean + (long long)u * a.utt_stride : nullptr;
     float* orow = a.wav_out + (long long)u * a.out_stride;
     const int len = a.lengths ? (int)a.lengths[u] : a.T;
     const int valid_frames = min(F, len / H + 1);                  // runner.py:455
     const bool spec = a.want_spec && crow && a.sums;
+    const bool need_clean = crow && a.sums;
     const bool out_aligned = (reinterpret_cast<uintptr_t>(orow) & 7) == 0;
+    const bool mask_padded = a.mask_stride >= 260;
+    const float* mrow0 = a.mask + (long long)u * F * a.mask_stride;
     float acc[sekern::NSUMS];
 #pragma unroll
     for (int i = 0; i < sekern::NSUMS; ++i) acc[i] = 0.0f;
@@ -339,103 +387,117 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
 #pragma unroll
     for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.0f, 0.0f);
 
-    const bool mask_padded = a.mask_stride >= 260;
-    // stage frame f: noisy samples, clean samples (when they are needed: spectral sums or waveform sums) and the mask row
-    auto prefetch = [&](int f, int buf) {
-        float* st = stage + buf * kStageFloats3;
-        stage_wave(st, nrow, a.T, f * H - N / 2, N, j);
-        const bool halo_f = (f == b0 - 1);
-        if (crow && a.sums && (!halo_f || (spec && f == 0))) stage_wave(st + N, crow, a.T, f * H - N / 2, N, j);
-        stage_row(st + 2 * N, a.mask + ((long long)u * F + f) * a.mask_stride, M + 1, j, mask_padded);
-        cp_async_commit();
-    };
-    prefetch(b0 - 1, 0);
-    int buf = 0;
+    // prologue: both halves of the first (halo) frame, its mask row, both clean halves -- groups N, M, C
+    const int f0 = b0 - 1;
+    stage_half(nb, nrow, a.T, (f0 - 1) * H, j);
+    stage_half(nb + H, nrow, a.T, f0 * H, j);
+    cp_async_commit();
+    stage_row(mb, mrow0 + (long long)f0 * a.mask_stride, M + 1, j, mask_padded);
+    cp_async_commit();
+    if (need_clean) {
+        stage_half(cb, crow, a.T, (f0 - 1) * H, j);
+        stage_half(cb + H, crow, a.T, f0 * H, j);
+    }
+    cp_async_commit();
+
+    int p = 0;                                                      // slot holding the first half of the current frame
 #pragma unroll 1
-    for (int f = b0 - 1; f <= b1; ++f, buf ^= 1) {
-        const bool halo = (f == b0 - 1);
+    for (int f = f0; f <= b1; ++f, p ^= 1) {
+        const bool halo = (f == f0);
         const bool own = spec && (!halo || f == 0) && f < valid_frames;
-        if (f < b1) { prefetch(f + 1, buf ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncwarp(hmask);
-        const float* st = stage + buf * kStageFloats3;
-        const float* mk = st + 2 * N;
-        float pta[8], ptb[8], pt128 = 0.0f;
+        const bool more = f < b1;
+        float ra[8], rb[8], r128 = 0.0f;                            // relu(mask * |X|^2) of this frame (objective.py:89)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { pta[q] = 0.0f; ptb[q] = 0.0f; }
+        for (int q = 0; q < 8; ++q) { ra[q] = 0.0f; rb[q] = 0.0f; }
         float2 v[16];
-        // pass 0: clean frame (spectral sums only), pass 1: noisy frame -> masked spectrum, pass 2: inverse
 #pragma unroll 1
-        for (int pass = own ? 0 : 1; pass < 3; ++pass) {
-            if (pass < 2) frame_from_stage(pass == 0 ? st + N : st, j, s_win2, v);
-            fft256<-1>(v, xbuf, j, tw, hmask);
-            if (pass == 2) break;
-            float2 zm[8];
-            fetch_mirror(v, lane, zm);
+        for (int pass = 0; pass < (own ? 3 : 2); ++pass) {
             if (pass == 0) {
+                cp_async_wait<2>();                                 // N(f) has landed
+                __syncwarp(hmask);
+                frame_from_slots(nb + p * H, nb + (p ^ 1) * H, j, s_win2, v);
+                __syncwarp(hmask);
+                if (more) stage_half(nb + p * H, nrow, a.T, (f + 1) * H, j);       // second half of frame f+1 -> the dead first slot
+                cp_async_commit();
+            } else if (pass == 2) {
+                frame_from_slots(cb + p * H, cb + (p ^ 1) * H, j, s_win2, v);        // C(f) landed before pass 1's overlap-add
+            }
+            fft256<-1>(v, xbuf, j, tw, hmask);
+            if (pass == 0) {
+                float2 zm[8];
+                fetch_mirror(v, lane, zm);
+                cp_async_wait<2>();                                 // M(f) has landed
+                __syncwarp(hmask);
+                float2 ca[8], cbv[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float2 xa, xb;
-                    split_pair(v[q], zm[q], twn[q], xa, xb);
-                    pta[q] = xa.x * xa.x + xa.y * xa.y;
-                    ptb[q] = xb.x * xb.x + xb.y * xb.y;
-                }
-                pt128 = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
-            } else {
-                float2 ca[8], cb[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float ga = mk[j + 16 * q], gb = mk[M - j - 16 * q];
+                    const float ga = mb[j + 16 * q], gb = mb[M - j - 16 * q];
                     float2 xa, xb;
                     split_pair(v[q], zm[q], twn[q], xa, xb);
                     if (own) {
-                        const float ra = fmaxf(ga * (xa.x * xa.x + xa.y * xa.y), 0.0f);      // relu(predicted), objective.py:89
-                        const float rb = fmaxf(gb * (xb.x * xb.x + xb.y * xb.y), 0.0f);
-                        acc[sekern::SUM_SPEC_ST] += fast_sqrt(ra * pta[q]) + fast_sqrt(rb * ptb[q]);
-                        acc[sekern::SUM_SPEC_TT] += pta[q] + ptb[q];
-                        acc[sekern::SUM_SPEC_SS] += ra + rb;
+                        ra[q] = fmaxf(ga * (xa.x * xa.x + xa.y * xa.y), 0.0f);
+                        rb[q] = fmaxf(gb * (xb.x * xb.x + xb.y * xb.y), 0.0f);
                     }
-                    merge_pair_conj(cscale(xa, fast_sqrt(ga)), cscale(xb, fast_sqrt(gb)), twn[q], ca[q], cb[q]);
+                    merge_pair_conj(cscale(xa, fast_sqrt(ga)), cscale(xb, fast_sqrt(gb)), twn[q], ca[q], cbv[q]);
                 }
-                const float g128 = mk[128];
-                const float2 x128 = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
-                if (own && j == 0) {
-                    const float r = fmaxf(g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
-                    acc[sekern::SUM_SPEC_ST] += fast_sqrt(r * pt128);
-                    acc[sekern::SUM_SPEC_TT] += pt128;
-                    acc[sekern::SUM_SPEC_SS] += r;
-                }
+                const float g128 = mb[128];
+                const float2 x128 = make_float2(2.0f * v[8].x, -2.0f * v[8].y);    // k = 128 pairs with itself: X = 2 conj(Z[128])
+                if (own) r128 = fmaxf(g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
+                __syncwarp(hmask);
+                if (more) stage_row(mb, mrow0 + (long long)(f + 1) * a.mask_stride, M + 1, j, mask_padded);
+                cp_async_commit();
                 // Zinv[128] = 2 conj(Y[128]) (same factor 2 as merge_pair_conj); its conjugate feeds the FFT
                 const float s128 = 2.0f * fast_sqrt(g128);
-                scatter_mirror(ca, cb, make_float2(s128 * x128.x, s128 * x128.y), lane, v);
-            }
-        }
-        // v[q] = conj(z[m]), z[m] = (x[2m], x[2m+1]) unnormalised, m = j + 16 q; signs and scales are in s_bw2
-        if (!halo) {
-            const int t0 = (f - 1) * H;
+                scatter_mirror(ca, cbv, make_float2(s128 * x128.x, s128 * x128.y), lane, v);
+            } else if (pass == 1) {
+                // v[q] = conj(z[m]), z[m] = (x[2m], x[2m+1]) unnormalised, m = j + 16 q; signs and scales are in s_bw2
+                cp_async_wait<2>();                                 // C(f) has landed
+                __syncwarp(hmask);
+                if (!halo) {
+                    const int t0 = (f - 1) * H;
+                    const float* cfirst = cb + p * H;               // first half of the clean frame = this output block
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int m = j + 16 * q;
-                const float2 bw = s_bw2[m];
-                const float2 y = pfma(bw, v[q], carry[q]);
-                const int t = t0 + 2 * m;
-                if (out_aligned) *reinterpret_cast<float2*>(orow + t) = y;
-                else { orow[t] = y.x; orow[t + 1] = y.y; }
-                if (a.sums) {
-                    float2 c = make_float2(0.0f, 0.0f);
-                    if (crow) c = *reinterpret_cast<const float2*>(st + N + 2 * m);           // first half of the clean frame = this block
-                    if (t < len) { acc[sekern::SUM_YY] += y.x * y.x; acc[sekern::SUM_YC] += y.x * c.x; acc[sekern::SUM_CC] += c.x * c.x; }
-                    if (t + 1 < len) { acc[sekern::SUM_YY] += y.y * y.y; acc[sekern::SUM_YC] += y.y * c.y; acc[sekern::SUM_CC] += c.y * c.y; }
+                    for (int q = 0; q < 8; ++q) {
+                        const int m = j + 16 * q;
+                        const float2 y = pfma(s_bw2[m], v[q], carry[q]);
+                        const int t = t0 + 2 * m;
+                        if (out_aligned) *reinterpret_cast<float2*>(orow + t) = y;
+                        else { orow[t] = y.x; orow[t + 1] = y.y; }
+                        if (a.sums) {
+                            float2 c = make_float2(0.0f, 0.0f);
+                            if (crow) c = *reinterpret_cast<const float2*>(cfirst + 2 * m);
+                            if (t < len) { acc[sekern::SUM_YY] += y.x * y.x; acc[sekern::SUM_YC] += y.x * c.x; acc[sekern::SUM_CC] += c.x * c.x; }
+                            if (t + 1 < len) { acc[sekern::SUM_YY] += y.y * y.y; acc[sekern::SUM_YC] += y.y * c.y; acc[sekern::SUM_CC] += c.y * c.y; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) carry[q] = pmul(s_bw2[j + 16 * q + 128], v[q + 8]);
+            } else {
+                float2 zm[8];
+                fetch_mirror(v, lane, zm);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float2 xa, xb;
+                    split_pair(v[q], zm[q], twn[q], xa, xb);
+                    const float pta = xa.x * xa.x + xa.y * xa.y, ptb = xb.x * xb.x + xb.y * xb.y;
+                    acc[sekern::SUM_SPEC_ST] += fast_sqrt(ra[q] * pta) + fast_sqrt(rb[q] * ptb);
+                    acc[sekern::SUM_SPEC_TT] += pta + ptb;
+                    acc[sekern::SUM_SPEC_SS] += ra[q] + rb[q];
+                }
+                if (j == 0) {
+                    const float pt128 = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
+                    acc[sekern::SUM_SPEC_ST] += fast_sqrt(r128 * pt128);
+                    acc[sekern::SUM_SPEC_TT] += pt128;
+                    acc[sekern::SUM_SPEC_SS] += r128;
                 }
             }
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float2 bw = s_bw2[j + 16 * q + 128];
-            carry[q] = pmul(bw, v[q + 8]);
-        }
-        __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
+        __syncwarp(hmask);                                          // the clean first slot is dead now
+        if (need_clean && more) stage_half(cb + p * H, crow, a.T, (f + 1) * H, j);
+        cp_async_commit();
     }
+    cp_async_wait<0>();
     // the last run of an utterance also zero-fills [out_len, pad_to) and finishes sum c^2 over [out_len, len)
     if (b1 == F - 1) {
         for (int t = a.out_len + j; t < max(a.pad_to, len); t += 16) {
@@ -518,34 +580,26 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
 }
 
 int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
-    // Run length: long enough that the halo frame is a small overhead, short enough to fill the GPU, and chosen so
-    // that the number of CTAs is (just under) a whole number of waves -- with ~2 CTAs per SM a ragged last wave
-    // leaves a third of the SMs idle for half of the kernel.
+    // Runs: every utterance's F-1 output blocks are cut into runs_per_utt near-equal runs (lengths differ by at most one).
+    // Small batches: as many runs as there are resident half-warps (SE_K3_MIN_BLOCKS CTAs per SM), so that ONE balanced
+    // wave covers the GPU -- but at least 4 blocks per run (the halo frame costs 2/3 of a frame).  Large batches: runs of
+    // about 32 blocks, many waves.
     const int blocks_per_utt = a.n_frames - 1;
-    const long long hw_per_wave = 2LL * num_sms() * (kThreads3 / 16);          // 2 CTAs/SM resident (shared memory)
+    const long long slots = (long long)SE_K3_MIN_BLOCKS * num_sms() * (kThreads3 / 16);
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("SE_B200_RUN_LEN"); forced = e ? atoi(e) : 0; }
     RunPlan plan;
-    if (forced > 0) {
-        plan.runs_per_utt = (blocks_per_utt + forced - 1) / forced;
-    } else {
-        // candidates: runs_per_utt such that n_utt * runs_per_utt fills w waves, w = 1, 2, ...; take the first whose
-        // run length is <= 64 blocks, but never go below 6 blocks per run (halo overhead 1/6)
-        int best = 0;
-        for (int w = 1; w <= 4096; ++w) {
-            const int rpu = (int)((w * hw_per_wave) / a.n_utt);
-            if (rpu < 1) continue;
-            const int rl = (blocks_per_utt + rpu - 1) / rpu;
-            if (rl < 6) break;
-            best = rpu;
-            if (rl <= 64) break;
-        }
-        if (best == 0) best = (blocks_per_utt + 5) / 6 > 0 ? (blocks_per_utt + 5) / 6 : 1;
-        plan.runs_per_utt = best;
-    }
-    if (plan.runs_per_utt > blocks_per_utt) plan.runs_per_utt = blocks_per_utt;
-    plan.run_len = (blocks_per_utt + plan.runs_per_utt - 1) / plan.runs_per_utt;
-    plan.runs_per_utt = (blocks_per_utt + plan.run_len - 1) / plan.run_len;
+    plan.blocks_per_utt = blocks_per_utt;
+    long long rpu;
+    if (forced > 0) rpu = (blocks_per_utt + forced - 1) / forced;
+    else if ((long long)a.n_utt * blocks_per_utt <= slots * 32) {
+        rpu = slots / a.n_utt;
+        const long long cap = blocks_per_utt / 4;
+        if (rpu > cap) rpu = cap;
+    } else rpu = (blocks_per_utt + 31) / 32;
+    if (rpu < 1) rpu = 1;
+    if (rpu > blocks_per_utt) rpu = blocks_per_utt;
+    plan.runs_per_utt = (int)rpu;
     plan.total_runs = (long long)a.n_utt * plan.runs_per_utt;
     const long long grid = (plan.total_runs + (kThreads3 / 16) - 1) / (kThreads3 / 16);
     if (grid > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "grid too large");
