@@ -74,7 +74,10 @@ __device__ __forceinline__ void stage_wave(float* __restrict__ dst, const float*
 // stage a row of `count` floats (any alignment) that needs no reflection
 __device__ __forceinline__ void stage_row(float* __restrict__ dst, const float* __restrict__ src, int count, int j, bool padded) {
     if (padded && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {                              // padded: row stride >= round4(count)
-        for (int c = j; c < (count + 3) / 4; c += 16) cp_async16(dst + 4 * c, src + 4 * c);
+        const int n16 = (count + 3) / 4;
+#pragma unroll
+        for (int c = 0; c < 5; ++c)                                                              // count <= 320 here (K = 257)
+            if (j + 16 * c < n16) cp_async16(dst + 4 * (j + 16 * c), src + 4 * (j + 16 * c));
     } else {
 #pragma unroll 4
         for (int i = j; i < count; i += 16) cp_async4(dst + i, src + i);
@@ -90,34 +93,31 @@ __device__ __forceinline__ void frame_from_stage(const float* __restrict__ st, i
     }
 }
 
-// v[r] = (x[2m], x[2m+1]) * win2[m], m = j + 16 r, for the frame whose first sample is row[t0]
-// (t0 may run over either end of the row -> reflect, as torch.stft pad_mode='reflect')
-__device__ __forceinline__ void load_frame(const float* __restrict__ row, int T, int t0, int j, const float2* __restrict__ win2,
-                                           float2* __restrict__ xbuf, unsigned hmask, float2 (&v)[16]) {
+// stage H floats of a waveform row starting at original coordinate t0 (reflect outside [0, T))
+__device__ __forceinline__ void stage_half(float* __restrict__ dst, const float* __restrict__ row, int T, int t0, int j) {
     const float* src = row + t0;
-    if ((t0 >= 0) && (t0 + N <= T) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0)) {
-        const float2* s2 = reinterpret_cast<const float2*>(src);
+    if ((t0 >= 0) && (t0 + H <= T) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = __ldg(s2 + j + 16 * r);
-    } else {                                           // rare: rolled loop through the half-warp's buffer
-        float* xf = reinterpret_cast<float*>(xbuf);
-#pragma unroll 1
-        for (int i = j; i < N; i += 16) {
+        for (int c = 0; c < H / 64; ++c) cp_async16(dst + 4 * (j + 16 * c), src + 4 * (j + 16 * c));
+    } else {
+#pragma unroll 4
+        for (int i = j; i < H; i += 16) {
             int t = t0 + i;
             t = t < 0 ? -t : t;
             t = t >= T ? 2 * (T - 1) - t : t;
-            xf[i] = __ldg(row + t);
+            cp_async4(dst + i, row + t);
         }
-        __syncwarp(hmask);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = xbuf[j + 16 * r];
-        __syncwarp(hmask);
     }
+}
+// v[r] = (x[2m], x[2m+1]) * win2[m], m = j + 16 r: r < 8 from the first-half slot, r >= 8 from the second-half slot
+__device__ __forceinline__ void frame_from_slots(const float* __restrict__ first, const float* __restrict__ second, int j,
+                                                 const float2* __restrict__ win2, float2 (&v)[16]) {
+    const float2* f2 = reinterpret_cast<const float2*>(first);
+    const float2* s2 = reinterpret_cast<const float2*>(second);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const float2 w = win2[j + 16 * r];
-        v[r].x *= w.x;
-        v[r].y *= w.y;
+    for (int r = 0; r < 8; ++r) {
+        v[r] = pmul(f2[j + 16 * r], win2[j + 16 * r]);
+        v[r + 8] = pmul(s2[j + 16 * r], win2[j + 16 * r + 128]);
     }
 }
 
@@ -151,16 +151,46 @@ constexpr size_t kSmem1 = (size_t)(kWarps1 * 2) * (M * 8 + 2 * N * 4) + M * 8;
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Frames are dealt to CTAs in contiguous ranges [blockIdx.x * per_cta, ...): iteration `it` of a CTA transforms the 16
-// consecutive frames first + 16 it + hw (one per half-warp).  With STATS the CTA also accumulates, per (utterance, bin),
-// the sum and the sum of squares of the feature it writes (log-power if LOGP, else power) -- the CMVN statistics of the
-// mask head (model.py:30) -- so that no separate pass over the features is needed: every half-warp leaves its feature row
-// in its (now idle) transpose buffer, thread t sums column t over the 16 rows in double precision, and the running sums
-// are flushed with one double atomicAdd pair per (CTA, utterance, bin).
+// write the requested outputs of one frame (lane j of a half-warp holds Z[j + 16 q] and the mirrored bins);
+// `acc` (STATS): the half-warp's private (sum x, sum x^2) accumulators in shared memory, updated for the feature written
 template <bool POWER, bool PHASE, bool LOGP, bool STATS>
+__device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (&zm)[8], const float2 (&twn)[8], int j,
+                                           const StftArgs& a, long long o, float2* __restrict__ acc) {
+    float* pw = POWER ? a.power + o : nullptr;
+    float* lg = LOGP ? a.logp + o : nullptr;
+    float* ph = PHASE ? a.phase + o : nullptr;
+    auto stat = [&](int k, float x) {
+        if (STATS) acc[k] = pfma(make_float2(x, x), make_float2(1.0f, x), acc[k]);
+    };
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int k = j + 16 * q;
+        float2 xa, xb;
+        split_pair(v[q], zm[q], twn[q], xa, xb);
+        const float pa = xa.x * xa.x + xa.y * xa.y, pb = xb.x * xb.x + xb.y * xb.y;
+        if (POWER) { pw[k] = pa; pw[M - k] = pb; }
+        float la = 0.f, lb = 0.f;
+        if (LOGP) { la = __logf(pa + a.log_eps); lb = __logf(pb + a.log_eps); lg[k] = la; lg[M - k] = lb; }
+        if (PHASE) { ph[k] = atan2f(k == 0 ? 0.0f : xa.y, xa.x); ph[M - k] = atan2f(k == 0 ? 0.0f : xb.y, xb.x); }
+        stat(k, LOGP ? la : pa);
+        stat(M - k, LOGP ? lb : pb);
+    }
+    if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
+        const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
+        const float p = x.x * x.x + x.y * x.y;
+        float l = 0.f;
+        if (POWER) pw[128] = p;
+        if (LOGP) { l = __logf(p + a.log_eps); lg[128] = l; }
+        if (PHASE) ph[128] = atan2f(x.y, x.x);
+        stat(128, LOGP ? l : p);
+    }
+}
+
+// General hop: frames are dealt to CTAs in contiguous ranges [blockIdx.x * per_cta, ...); iteration `it` of a CTA transforms
+// the 16 consecutive frames first + 16 it + hw (one per half-warp), whole frames double-buffered through cp.async.
+template <bool POWER, bool PHASE, bool LOGP>
 __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long long total_frames, int per_cta) {
     extern __shared__ __align__(16) unsigned char smem1[];
-    secommon::TraceScope trace(a.trace, 1);
     const int lane = threadIdx.x & 31, j = lane & 15;
     const int hw = (threadIdx.x >> 4);
     float2* xbuf = reinterpret_cast<float2*>(smem1) + hw * M;
@@ -170,7 +200,7 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
     float2 tw[15], twn[8];
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     __syncthreads();
-    griddep_launch();                                   // a dependent kernel may start its prologue (it waits for our completion)
+    griddep_launch();
     const int total = (int)total_frames;                              // < 2^31 (checked by the launcher): 32-bit index math
     const int cta_lo = blockIdx.x * per_cta;
     const int cta_hi = cta_lo + per_cta < total ? cta_lo + per_cta : total;
@@ -182,99 +212,114 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
     };
     if (cta_lo + hw < cta_hi) prefetch(cta_lo + hw, 0);
     int buf = 0;
-    // statistics: thread t owns bin t (column sums over the 16 rows of an iteration); bin 256 lives in lane j == 0 of every
-    // half-warp and is accumulated there, frame by frame
-    double st_s = 0.0, st_q = 0.0, ny_s = 0.0, ny_q = 0.0;
-    int st_u = -1, ny_u = -1;
-    auto flush = [&]() {
-        if (st_u >= 0) {
-            double* p = a.stat_sums + ((long long)st_u * a.ld_stats + threadIdx.x) * 2;
-            atomicAdd(p, st_s);
-            atomicAdd(p + 1, st_q);
-        }
-        st_s = st_q = 0.0;
-    };
-    auto flush_nyquist = [&]() {
-        if (ny_u >= 0) {
-            double* p = a.stat_sums + ((long long)ny_u * a.ld_stats + M) * 2;
-            atomicAdd(p, ny_s);
-            atomicAdd(p + 1, ny_q);
-        }
-        ny_s = ny_q = 0.0;
-    };
 #pragma unroll 1
-    for (int g0 = cta_lo; g0 < cta_hi; g0 += kThreads1 / 16, buf ^= 1) {
-        const int gg = g0 + hw;
-        float* frow = reinterpret_cast<float*>(xbuf);
-        if (gg < cta_hi) {
-            if (gg + kThreads1 / 16 < cta_hi) { prefetch(gg + kThreads1 / 16, buf ^ 1); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
+    for (int gg = cta_lo + hw; gg < cta_hi; gg += kThreads1 / 16, buf ^= 1) {
+        if (gg + kThreads1 / 16 < cta_hi) { prefetch(gg + kThreads1 / 16, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp(hmask);
+        float2 v[16];
+        frame_from_stage(stage + buf * N, j, s_win2, v);
+        fft256<-1>(v, xbuf, j, tw, hmask);
+        float2 zm[8];
+        fetch_mirror(v, lane, zm);
+        emit_frame<POWER, PHASE, LOGP, false>(v, zm, twn, j, a, (long long)gg * a.spec_stride, nullptr);
+        __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
+    }
+}
+
+// hop = 256 (= N/2): every half-warp owns a RUN of consecutive frames of one utterance -- run ri of an utterance is frames
+// [ri F / rpu, (ri+1) F / rpu) -- and keeps two 256-sample slots: frame f reads (first, second) = (slot p, slot p^1), and
+// as soon as the frame is in registers the dead first slot receives the second half of frame f+1 (cp.async), which has a
+// whole transform to land behind.  No block-level barrier in the frame loop.
+// STATS: the sum and the sum of squares per (utterance, bin) of the feature written (log-power if LOGP, else power) -- the
+// CMVN statistics of the mask head (model.py:30) -- are accumulated in the half-warp's private shared-memory row (fp32 over
+// the few frames of a run), combined over the CTA's half-warps in double precision after ONE barrier at the end, and added
+// to stat_sums with one double atomicAdd pair per (CTA, utterance, bin).
+constexpr int kAccFloat2 = M + 2;                                         // bins 0..256, padded to a 16-byte multiple
+constexpr int kHwBytes1 = M * 8 + 2 * H * 4 + kAccFloat2 * 8;             // transpose buffer | two sample slots | accumulators
+constexpr size_t kSmem1Run = (size_t)(kWarps1 * 2) * kHwBytes1 + M * 8 + (kWarps1 * 2) * 4;
+
+struct StftRunPlan { int runs_per_utt; long long total_runs; };
+
+template <bool POWER, bool PHASE, bool LOGP, bool STATS>
+__global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, StftRunPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem1[];
+    secommon::TraceScope trace(a.trace, 1);
+    const int lane = threadIdx.x & 31, j = lane & 15;
+    const int hw = (threadIdx.x >> 4);
+    unsigned char* mine = smem1 + (size_t)hw * kHwBytes1;
+    float2* xbuf = reinterpret_cast<float2*>(mine);
+    float* slot = reinterpret_cast<float*>(mine + M * 8);
+    float2* acc = reinterpret_cast<float2*>(mine + M * 8 + 2 * H * 4);
+    float2* s_win2 = reinterpret_cast<float2*>(smem1 + (size_t)(kWarps1 * 2) * kHwBytes1);
+    int* s_utt = reinterpret_cast<int*>(s_win2 + M);                  // utterance of every half-warp's run (-1: none)
+    for (int i = threadIdx.x; i < M; i += kThreads1) s_win2[i] = make_float2(0.5f * a.tab.window[2 * i], 0.5f * a.tab.window[2 * i + 1]);
+    float2 tw[15], twn[8];
+    load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
+    const unsigned hmask = half_mask(lane);
+    const long long unit = (long long)blockIdx.x * (kThreads1 / 16) + hw;
+    const bool active = unit < plan.total_runs;
+    const int u = active ? (int)(unit / plan.runs_per_utt) : -1;
+    if (STATS) {
+        for (int i = j; i < kAccFloat2; i += 16) acc[i] = make_float2(0.0f, 0.0f);
+        if (j == 0) s_utt[hw] = u;
+    }
+    __syncthreads();
+    griddep_launch();                                   // a dependent kernel may start its prologue (it waits for our completion)
+    if (active) {
+        const int ri = (int)(unit - (long long)u * plan.runs_per_utt);
+        const int F = a.n_frames;
+        const int fa = (int)(((long long)ri * F) / plan.runs_per_utt), fb = (int)(((long long)(ri + 1) * F) / plan.runs_per_utt);
+        const float* row = a.wav + (long long)u * a.utt_stride;
+        stage_half(slot, row, a.T, (fa - 1) * H, j);
+        stage_half(slot + H, row, a.T, fa * H, j);
+        cp_async_commit();
+        int p = 0;
+#pragma unroll 1
+        for (int f = fa; f < fb; ++f, p ^= 1) {
+            cp_async_wait<0>();
             __syncwarp(hmask);
             float2 v[16];
-            frame_from_stage(stage + buf * N, j, s_win2, v);
+            frame_from_slots(slot + p * H, slot + (p ^ 1) * H, j, s_win2, v);
+            __syncwarp(hmask);
+            if (f + 1 < fb) stage_half(slot + p * H, row, a.T, (f + 1) * H, j);   // second half of frame f+1 -> the dead first slot
+            cp_async_commit();
             fft256<-1>(v, xbuf, j, tw, hmask);
             float2 zm[8];
             fetch_mirror(v, lane, zm);
-            const long long o = (long long)gg * a.spec_stride;
-            float* pw = POWER ? a.power + o : nullptr;
-            float* lg = LOGP ? a.logp + o : nullptr;
-            float* ph = PHASE ? a.phase + o : nullptr;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k = j + 16 * q;
-                float2 xa, xb;
-                split_pair(v[q], zm[q], twn[q], xa, xb);
-                const float pa = xa.x * xa.x + xa.y * xa.y, pb = xb.x * xb.x + xb.y * xb.y;
-                if (POWER) { pw[k] = pa; pw[M - k] = pb; }
-                float la = 0.f, lb = 0.f;
-                if (LOGP) { la = __logf(pa + a.log_eps); lb = __logf(pb + a.log_eps); lg[k] = la; lg[M - k] = lb; }
-                if (PHASE) { ph[k] = atan2f(k == 0 ? 0.0f : xa.y, xa.x); ph[M - k] = atan2f(k == 0 ? 0.0f : xb.y, xb.x); }
-                if (STATS) {
-                    frow[k] = LOGP ? la : pa;
-                    if (k != 0) frow[M - k] = LOGP ? lb : pb;
-                    else {                                              // bin 256 (lane j == 0, q == 0)
-                        const int u = gg / a.n_frames;
-                        if (u != ny_u) { flush_nyquist(); ny_u = u; }
-                        const double y = (double)(LOGP ? lb : pb);
-                        ny_s += y;
-                        ny_q = fma(y, y, ny_q);
-                    }
-                }
-            }
-            if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
-                const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
-                const float p = x.x * x.x + x.y * x.y;
-                float l = 0.f;
-                if (POWER) pw[128] = p;
-                if (LOGP) { l = __logf(p + a.log_eps); lg[128] = l; }
-                if (PHASE) ph[128] = atan2f(x.y, x.x);
-                if (STATS) frow[128] = LOGP ? l : p;
-            }
-            __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
-        }
-        if (STATS) {
-            __syncthreads();                                            // the feature rows of this iteration are in shared memory
-            const int nrows = cta_hi - g0 < kThreads1 / 16 ? cta_hi - g0 : kThreads1 / 16;
-            const float* col = reinterpret_cast<const float*>(smem1) + threadIdx.x;
-            int u = g0 / a.n_frames;
-            int r_end = (u + 1) * a.n_frames - g0;                      // first row of the next utterance
-            int r = 0;
-            while (r < nrows) {
-                if (r_end > nrows) r_end = nrows;
-                if (u != st_u) { flush(); st_u = u; }
-#pragma unroll 4
-                for (; r < r_end; ++r) {
-                    const double x = (double)col[r * 2 * M];
-                    st_s += x;
-                    st_q = fma(x, x, st_q);
-                }
-                ++u;
-                r_end += a.n_frames;
-            }
-            __syncthreads();                                            // rows consumed: the transpose buffers may be reused
+            emit_frame<POWER, PHASE, LOGP, STATS>(v, zm, twn, j, a, ((long long)u * F + f) * a.spec_stride, acc);
         }
     }
-    if (STATS) { flush(); if (j == 0) flush_nyquist(); }
+    if (STATS) {
+        __syncthreads();                                            // every half-warp's accumulators are final
+        // thread t owns bin t (thread 0 also bin 256); the CTA's runs are consecutive, so utterances are non-decreasing
+        const float2* base = reinterpret_cast<const float2*>(smem1 + M * 8 + 2 * H * 4);
+        constexpr int kStride = kHwBytes1 / 8;
+        for (int bin = threadIdx.x; bin <= M; bin += kThreads1) {
+            double s1 = 0.0, s2 = 0.0;
+            int cur = -1;
+            for (int h = 0; h < kThreads1 / 16; ++h) {
+                const int uh = s_utt[h];
+                if (uh < 0) break;
+                if (uh != cur) {
+                    if (cur >= 0) {
+                        double* pdst = a.stat_sums + ((long long)cur * a.ld_stats + bin) * 2;
+                        atomicAdd(pdst, s1);
+                        atomicAdd(pdst + 1, s2);
+                    }
+                    cur = uh; s1 = 0.0; s2 = 0.0;
+                }
+                const float2 t = base[h * kStride + bin];
+                s1 += (double)t.x;
+                s2 += (double)t.y;
+            }
+            if (cur >= 0) {
+                double* pdst = a.stat_sums + ((long long)cur * a.ld_stats + bin) * 2;
+                atomicAdd(pdst, s1);
+                atomicAdd(pdst + 1, s2);
+            }
+        }
+    }
     if (a.trace) { __syncthreads(); trace.finish(); }
 }
 
@@ -311,34 +356,6 @@ constexpr int kHwBytes3 = M * 8 + 4 * H * 4 + kMaskFloats3 * 4;
 constexpr size_t kSmem3 = (size_t)(kWarps3 * 2) * kHwBytes3 + 2 * M * 8;
 static_assert(kHwBytes3 % 16 == 0, "16-byte aligned cp.async destinations");
 
-// stage H floats of a waveform row starting at original coordinate t0 (reflect outside [0, T))
-__device__ __forceinline__ void stage_half(float* __restrict__ dst, const float* __restrict__ row, int T, int t0, int j) {
-    const float* src = row + t0;
-    if ((t0 >= 0) && (t0 + H <= T) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-#pragma unroll
-        for (int c = 0; c < H / 64; ++c) cp_async16(dst + 4 * (j + 16 * c), src + 4 * (j + 16 * c));
-    } else {
-#pragma unroll 4
-        for (int i = j; i < H; i += 16) {
-            int t = t0 + i;
-            t = t < 0 ? -t : t;
-            t = t >= T ? 2 * (T - 1) - t : t;
-            cp_async4(dst + i, row + t);
-        }
-    }
-}
-// v[r] = (x[2m], x[2m+1]) * win2[m], m = j + 16 r: r < 8 from the first-half slot, r >= 8 from the second-half slot
-__device__ __forceinline__ void frame_from_slots(const float* __restrict__ first, const float* __restrict__ second, int j,
-                                                 const float2* __restrict__ win2, float2 (&v)[16]) {
-    const float2* f2 = reinterpret_cast<const float2*>(first);
-    const float2* s2 = reinterpret_cast<const float2*>(second);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        v[r] = pmul(f2[j + 16 * r], win2[j + 16 * r]);
-        v[r + 8] = pmul(s2[j + 16 * r], win2[j + 16 * r + 128]);
-    }
-}
-
 __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem3[];
     secommon::TraceScope trace(a.trace, 3);
@@ -358,14 +375,13 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     __syncthreads();
     griddep_launch();
-    griddep_wait();                                               // the mask (and the zeroed sums) come from upstream kernels
     unsigned char* mine = smem3 + (size_t)hw * kHwBytes3;
     float2* xbuf = reinterpret_cast<float2*>(mine);
     float* nb = reinterpret_cast<float*>(mine + M * 8);            // noisy slots
     float* cb = nb + 2 * H;                                        // clean slots
     float* mb = cb + 2 * H;                                        // mask row
     const long long unit = (long long)blockIdx.x * (kThreads3 / 16) + hw;
-    if (unit >= plan.total_runs) return;                          // no block-level barrier below (tracing: approximate for ragged CTAs)
+    if (unit >= plan.total_runs) { griddep_wait(); return; }      // no block-level barrier below (tracing: approximate for ragged CTAs)
     const int u = (int)(unit / plan.runs_per_utt), ri = (int)(unit - (long long)u * plan.runs_per_utt);
     const int F = a.n_frames;
     const int b0 = 1 + (int)(((long long)ri * plan.blocks_per_utt) / plan.runs_per_utt);
@@ -386,12 +402,15 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     float2 carry[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.0f, 0.0f);
+    float2 yy2 = make_float2(0.0f, 0.0f), yc2 = yy2, cc2 = yy2;     // (even, odd) sample partial sums of the fast overlap-add path
 
-    // prologue: both halves of the first (halo) frame, its mask row, both clean halves -- groups N, M, C
+    // prologue: both halves of the first (halo) frame, its mask row, both clean halves -- groups N, M, C.  The waveforms
+    // are inputs of the step, so their first loads are issued before waiting for the upstream kernel (the mask's producer).
     const int f0 = b0 - 1;
     stage_half(nb, nrow, a.T, (f0 - 1) * H, j);
     stage_half(nb + H, nrow, a.T, f0 * H, j);
     cp_async_commit();
+    griddep_wait();                                               // the mask (and the zeroed sums) come from upstream kernels
     stage_row(mb, mrow0 + (long long)f0 * a.mask_stride, M + 1, j, mask_padded);
     cp_async_commit();
     if (need_clean) {
@@ -456,18 +475,35 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 if (!halo) {
                     const int t0 = (f - 1) * H;
                     const float* cfirst = cb + p * H;               // first half of the clean frame = this output block
+                    if (out_aligned && t0 + H <= len) {             // whole block inside the utterance: no per-sample predicates
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int m = j + 16 * q;
-                        const float2 y = pfma(s_bw2[m], v[q], carry[q]);
-                        const int t = t0 + 2 * m;
-                        if (out_aligned) *reinterpret_cast<float2*>(orow + t) = y;
-                        else { orow[t] = y.x; orow[t + 1] = y.y; }
-                        if (a.sums) {
-                            float2 c = make_float2(0.0f, 0.0f);
-                            if (crow) c = *reinterpret_cast<const float2*>(cfirst + 2 * m);
-                            if (t < len) { acc[sekern::SUM_YY] += y.x * y.x; acc[sekern::SUM_YC] += y.x * c.x; acc[sekern::SUM_CC] += c.x * c.x; }
-                            if (t + 1 < len) { acc[sekern::SUM_YY] += y.y * y.y; acc[sekern::SUM_YC] += y.y * c.y; acc[sekern::SUM_CC] += c.y * c.y; }
+                        for (int q = 0; q < 8; ++q) {
+                            const int m = j + 16 * q;
+                            const float2 y = pfma(s_bw2[m], v[q], carry[q]);
+                            *reinterpret_cast<float2*>(orow + t0 + 2 * m) = y;
+                            if (a.sums) {
+                                yy2 = pfma(y, y, yy2);
+                                if (crow) {
+                                    const float2 c = *reinterpret_cast<const float2*>(cfirst + 2 * m);
+                                    yc2 = pfma(y, c, yc2);
+                                    cc2 = pfma(c, c, cc2);
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int m = j + 16 * q;
+                            const float2 y = pfma(s_bw2[m], v[q], carry[q]);
+                            const int t = t0 + 2 * m;
+                            if (out_aligned) *reinterpret_cast<float2*>(orow + t) = y;
+                            else { orow[t] = y.x; orow[t + 1] = y.y; }
+                            if (a.sums) {
+                                float2 c = make_float2(0.0f, 0.0f);
+                                if (crow) c = *reinterpret_cast<const float2*>(cfirst + 2 * m);
+                                if (t < len) { acc[sekern::SUM_YY] += y.x * y.x; acc[sekern::SUM_YC] += y.x * c.x; acc[sekern::SUM_CC] += c.x * c.x; }
+                                if (t + 1 < len) { acc[sekern::SUM_YY] += y.y * y.y; acc[sekern::SUM_YC] += y.y * c.y; acc[sekern::SUM_CC] += c.y * c.y; }
+                            }
                         }
                     }
                 }
@@ -506,6 +542,9 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
         }
     }
     if (a.sums) {
+        acc[sekern::SUM_YY] += yy2.x + yy2.y;
+        acc[sekern::SUM_YC] += yc2.x + yc2.y;
+        acc[sekern::SUM_CC] += cc2.x + cc2.y;
 #pragma unroll
         for (int i = 0; i < sekern::NSUMS; ++i) {
             float s = acc[i];
@@ -535,15 +574,22 @@ int num_sms() {
 // opt the kernels into their dynamic shared-memory sizes (called once per device from se_prepare / first use)
 int prepare512() {
 #define SE_OPT(K, BYTES) SE_CUDA_CHECK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)))
-    SE_OPT((stft512_kernel<true, false, false, false>), kSmem1);
-    SE_OPT((stft512_kernel<false, true, false, false>), kSmem1);
-    SE_OPT((stft512_kernel<true, true, false, false>), kSmem1);
-    SE_OPT((stft512_kernel<false, false, true, false>), kSmem1);
-    SE_OPT((stft512_kernel<true, false, true, false>), kSmem1);
-    SE_OPT((stft512_kernel<false, true, true, false>), kSmem1);
-    SE_OPT((stft512_kernel<true, true, true, false>), kSmem1);
-    SE_OPT((stft512_kernel<true, false, false, true>), kSmem1);
-    SE_OPT((stft512_kernel<false, false, true, true>), kSmem1);
+    SE_OPT((stft512_kernel<true, false, false>), kSmem1);
+    SE_OPT((stft512_kernel<false, true, false>), kSmem1);
+    SE_OPT((stft512_kernel<true, true, false>), kSmem1);
+    SE_OPT((stft512_kernel<false, false, true>), kSmem1);
+    SE_OPT((stft512_kernel<true, false, true>), kSmem1);
+    SE_OPT((stft512_kernel<false, true, true>), kSmem1);
+    SE_OPT((stft512_kernel<true, true, true>), kSmem1);
+    SE_OPT((stft512_run_kernel<true, false, false, false>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<false, true, false, false>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<true, true, false, false>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<false, false, true, false>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<true, false, true, false>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<false, true, true, false>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<true, true, true, false>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<true, false, false, true>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<false, false, true, true>), kSmem1Run);
     SE_OPT(mask_istft512_kernel, kSmem3);
 #undef SE_OPT
     return SE_OK;
@@ -551,30 +597,57 @@ int prepare512() {
 
 int launch_stft512(const StftArgs& a, cudaStream_t st) {
     const long long total = (long long)a.n_utt * a.n_frames;
+    if (total > 0x7fffff00LL) return secommon::fail(SE_ERR_BAD_ARG, "too many frames (%lld)", total);
+    const int sel = (a.power ? 1 : 0) | (a.phase ? 2 : 0) | (a.logp ? 4 : 0);
+    if (sel == 0) return SE_OK;                                  // nothing requested
     const int per_it = kThreads1 / 16;
+    if (a.hop == H) {
+        // runs: one balanced wave of 2 CTAs per SM when the batch is small, runs of about 32 frames otherwise
+        const long long slots = 2LL * num_sms() * per_it;
+        long long rpu;
+        if (total <= slots * 32) {
+            rpu = slots / a.n_utt;
+            if (rpu > a.n_frames) rpu = a.n_frames;
+        } else rpu = (a.n_frames + 31) / 32;
+        if (rpu < 1) rpu = 1;
+        StftRunPlan plan;
+        plan.runs_per_utt = (int)rpu;
+        plan.total_runs = (long long)a.n_utt * rpu;
+        const long long grid = (plan.total_runs + per_it - 1) / per_it;
+        if (grid > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "grid too large");
+#define SE_RUN(P, Q, L, S) stft512_run_kernel<P, Q, L, S><<<(unsigned)grid, kThreads1, kSmem1Run, st>>>(a, plan)
+        if (a.stat_sums) {
+            // statistics of the ONE feature written: log-power (sel 4) or power (sel 1)
+            if (sel == 4) SE_RUN(false, false, true, true);
+            else if (sel == 1) SE_RUN(true, false, false, true);
+            else return secommon::fail(SE_ERR_BAD_ARG, "statistics need exactly one of power / logpower");
+        } else {
+            switch (sel) {
+                case 1: SE_RUN(true, false, false, false); break;
+                case 2: SE_RUN(false, true, false, false); break;
+                case 3: SE_RUN(true, true, false, false); break;
+                case 4: SE_RUN(false, false, true, false); break;
+                case 5: SE_RUN(true, false, true, false); break;
+                case 6: SE_RUN(false, true, true, false); break;
+                default: SE_RUN(true, true, true, false); break;
+            }
+        }
+#undef SE_RUN
+        return secommon::check_launch("stft512_run_kernel");
+    }
+    if (a.stat_sums) return secommon::fail(SE_ERR_UNSUPPORTED, "fused statistics need hop = 256");
     const long long want = (total + per_it - 1) / per_it;
     const long long cap = 2LL * num_sms();
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    const long long per = (total + grid - 1) / grid;
-    if (total > 0x7fffff00LL) return secommon::fail(SE_ERR_BAD_ARG, "too many frames (%lld)", total);
-    const int per_cta = (int)per;
-    const int sel = (a.power ? 1 : 0) | (a.phase ? 2 : 0) | (a.logp ? 4 : 0);
-    if (a.stat_sums) {
-        // statistics of the ONE feature written: log-power (sel 4) or power (sel 1)
-        if (sel == 4) stft512_kernel<false, false, true, true><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta);
-        else if (sel == 1) stft512_kernel<true, false, false, true><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta);
-        else return secommon::fail(SE_ERR_BAD_ARG, "statistics need exactly one of power / logpower");
-        return secommon::check_launch("stft512_kernel");
-    }
+    const int per_cta = (int)((total + grid - 1) / grid);
     switch (sel) {
-        case 1: stft512_kernel<true, false, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
-        case 2: stft512_kernel<false, true, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
-        case 3: stft512_kernel<true, true, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
-        case 4: stft512_kernel<false, false, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
-        case 5: stft512_kernel<true, false, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
-        case 6: stft512_kernel<false, true, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
-        case 7: stft512_kernel<true, true, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
-        default: return SE_OK;                                   // nothing requested
+        case 1: stft512_kernel<true, false, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 2: stft512_kernel<false, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 3: stft512_kernel<true, true, false><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 4: stft512_kernel<false, false, true><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 5: stft512_kernel<true, false, true><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        case 6: stft512_kernel<false, true, true><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
+        default: stft512_kernel<true, true, true><<<grid, kThreads1, kSmem1, st>>>(a, total, per_cta); break;
     }
     return secommon::check_launch("stft512_kernel");
 }

@@ -207,7 +207,7 @@ int se_stft_features(const float* wav, int64_t n_utt, int64_t utt_stride, int64_
     if (rc != SE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (!(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(stat_sums, 0, sizeof(double) * 2 * ld_stats * n_utt, st));
-    if (n_fft == 512 && !g_force_generic) {
+    if (n_fft == 512 && hop == 256 && !g_force_generic) {
         DeviceTables t;
         if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
         StftArgs a{};

@@ -515,11 +515,20 @@ def test_stft_features_and_cmvn_sums(se, n_fft, B, T, logp):
     assert torch.equal(feats[..., :K], ref)                                     # same kernel body: bit-identical features
     s1 = ref.double().sum(1)
     s2 = (ref.double() ** 2).sum(1)
-    np.testing.assert_allclose(sums[:, :K, 0].cpu().numpy(), s1.cpu().numpy(), rtol=1e-9, atol=1e-9 * s2.max().item() ** 0.5)
-    np.testing.assert_allclose(sums[:, :K, 1].cpu().numpy(), s2.cpu().numpy(), rtol=1e-9)
-    # and the standalone sums entry point
+    # the fused kernel adds up a run's few frames in fp32 before the double-precision combine: ~1e-7 relative per partial
+    F = ref.shape[1]
+    a1 = 1e-6 * (s2.max().item() * F) ** 0.5
+    np.testing.assert_allclose(sums[:, :K, 0].cpu().numpy(), s1.cpu().numpy(), rtol=2e-6, atol=a1)
+    np.testing.assert_allclose(sums[:, :K, 1].cpu().numpy(), s2.cpu().numpy(), rtol=2e-6)
+    # and the standalone sums entry point (double precision throughout)
     sums2 = ops.feature_sums(feats, K)
-    np.testing.assert_allclose(sums2[:, :K].cpu().numpy(), sums[:, :K].cpu().numpy(), rtol=1e-9, atol=1e-9 * s2.max().item() ** 0.5)
+    np.testing.assert_allclose(sums2[:, :K, 0].cpu().numpy(), s1.cpu().numpy(), rtol=1e-9, atol=1e-3 * a1)
+    np.testing.assert_allclose(sums2[:, :K, 1].cpu().numpy(), s2.cpu().numpy(), rtol=1e-9)
+    # what the head derives from the sums: mean / unbiased std against torch
+    mean = (sums[:, :K, 0] / F).float()
+    var = ((sums[:, :K, 1] - sums[:, :K, 0] ** 2 / F) / (F - 1)).clamp_min(0)
+    assert (mean - ref.mean(1)).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    np.testing.assert_allclose(var.sqrt().float().cpu().numpy(), ref.std(1).cpu().numpy(), rtol=2e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("B,F,Din,Dout,act,cmvn", [(3, 101, 257, 257, "Sigmoid", True), (2, 300, 201, 201, "ReLU", False),
