@@ -506,7 +506,8 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     a.n_main = a.w_rows > 256 ? 256 : a.w_rows;
     a.n_tail = a.w_rows - a.n_main;
     static int want_cluster = -1;
-    if (want_cluster < 0) { const char* e = getenv("SE_B200_HEAD_CLUSTER"); want_cluster = e ? atoi(e) : 1;        // measured: no gain from halving the weight L2 traffic (the MMA rate bounds the main loop) }
+    // default 1: halving the weight L2 traffic gave no measured gain (the TF32 MMA rate bounds the main loop)
+    if (want_cluster < 0) { const char* e = getenv("SE_B200_HEAD_CLUSTER"); want_cluster = e ? atoi(e) : 1; }
     a.cluster = want_cluster >= 2 ? 2 : 1;
     a.w_boxes = (a.w_rows > 256 || a.cluster == 2) ? 2 : 1;           // w_rows is a multiple of 16: both boxes are whole 8-row atoms
     a.w_box_rows = a.w_rows / a.w_boxes;
