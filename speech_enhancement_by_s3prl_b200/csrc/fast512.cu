@@ -253,13 +253,25 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
     float2* acc = reinterpret_cast<float2*>(mine + M * 8 + 2 * H * 4);
     float2* s_win2 = reinterpret_cast<float2*>(smem1 + (size_t)(kWarps1 * 2) * kHwBytes1);
     int* s_utt = reinterpret_cast<int*>(s_win2 + M);                  // utterance of every half-warp's run (-1: none)
-    for (int i = threadIdx.x; i < M; i += kThreads1) s_win2[i] = make_float2(0.5f * a.tab.window[2 * i], 0.5f * a.tab.window[2 * i + 1]);
-    float2 tw[15], twn[8];
-    load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     const unsigned hmask = half_mask(lane);
     const long long unit = (long long)blockIdx.x * (kThreads1 / 16) + hw;
     const bool active = unit < plan.total_runs;
     const int u = active ? (int)(unit / plan.runs_per_utt) : -1;
+    // the first frame's samples come from HBM: put those loads in flight before anything else (tables, accumulators)
+    int fa = 0, fb = 0;
+    const float* row = a.wav;
+    if (active) {
+        const int ri = (int)(unit - (long long)u * plan.runs_per_utt);
+        fa = (int)(((long long)ri * a.n_frames) / plan.runs_per_utt);
+        fb = (int)(((long long)(ri + 1) * a.n_frames) / plan.runs_per_utt);
+        row = a.wav + (long long)u * a.utt_stride;
+        stage_half(slot, row, a.T, (fa - 1) * H, j);
+        stage_half(slot + H, row, a.T, fa * H, j);
+        cp_async_commit();
+    }
+    for (int i = threadIdx.x; i < M; i += kThreads1) s_win2[i] = make_float2(0.5f * a.tab.window[2 * i], 0.5f * a.tab.window[2 * i + 1]);
+    float2 tw[15], twn[8];
+    load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
     if (STATS) {
         for (int i = j; i < kAccFloat2; i += 16) acc[i] = make_float2(0.0f, 0.0f);
         if (j == 0) s_utt[hw] = u;
@@ -267,13 +279,7 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
     __syncthreads();
     griddep_launch();                                   // a dependent kernel may start its prologue (it waits for our completion)
     if (active) {
-        const int ri = (int)(unit - (long long)u * plan.runs_per_utt);
         const int F = a.n_frames;
-        const int fa = (int)(((long long)ri * F) / plan.runs_per_utt), fb = (int)(((long long)(ri + 1) * F) / plan.runs_per_utt);
-        const float* row = a.wav + (long long)u * a.utt_stride;
-        stage_half(slot, row, a.T, (fa - 1) * H, j);
-        stage_half(slot + H, row, a.T, fa * H, j);
-        cp_async_commit();
         int p = 0;
 #pragma unroll 1
         for (int f = fa; f < fb; ++f, p ^= 1) {
@@ -361,6 +367,19 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     secommon::TraceScope trace(a.trace, 3);
     float2* s_win2 = reinterpret_cast<float2*>(smem3 + (size_t)(kWarps3 * 2) * kHwBytes3);
     float2* s_bw2 = s_win2 + M;
+    {   // the first frame's noisy samples come from HBM and do not depend on the upstream kernel: loads in flight first
+        const int hw0 = threadIdx.x >> 4, j0 = threadIdx.x & 15;
+        const long long unit0 = (long long)blockIdx.x * (kThreads3 / 16) + hw0;
+        if (unit0 < plan.total_runs) {
+            const int u0 = (int)(unit0 / plan.runs_per_utt), ri0 = (int)(unit0 - (long long)u0 * plan.runs_per_utt);
+            const int f00 = (int)(((long long)ri0 * plan.blocks_per_utt) / plan.runs_per_utt);      // = b0 - 1
+            float* nb0 = reinterpret_cast<float*>(smem3 + (size_t)hw0 * kHwBytes3 + M * 8);
+            const float* nrow0 = a.noisy + (long long)u0 * a.utt_stride;
+            stage_half(nb0, nrow0, a.T, (f00 - 1) * H, j0);
+            stage_half(nb0 + H, nrow0, a.T, f00 * H, j0);
+        }
+        cp_async_commit();
+    }
     for (int i = threadIdx.x; i < M; i += kThreads3) {
         const float w0 = a.tab.window[2 * i], w1 = a.tab.window[2 * i + 1];
         s_win2[i] = make_float2(0.5f * w0, 0.5f * w1);
@@ -406,10 +425,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
 
     // prologue: both halves of the first (halo) frame, its mask row, both clean halves -- groups N, M, C.  The waveforms
     // are inputs of the step, so their first loads are issued before waiting for the upstream kernel (the mask's producer).
-    const int f0 = b0 - 1;
-    stage_half(nb, nrow, a.T, (f0 - 1) * H, j);
-    stage_half(nb + H, nrow, a.T, f0 * H, j);
-    cp_async_commit();
+    const int f0 = b0 - 1;                                        // (its noisy samples were requested at the top: group N)
     griddep_wait();                                               // the mask (and the zeroed sums) come from upstream kernels
     stage_row(mb, mrow0 + (long long)f0 * a.mask_stride, M + 1, j, mask_padded);
     cp_async_commit();
