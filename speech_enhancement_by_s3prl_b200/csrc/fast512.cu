@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
     }
 }
 
-// hop = 256 (= N/2): every half-warp owns a RUN of consecutive frames of one utterance -- run ri of an utterance is frames
-// [ri F / rpu, (ri+1) F / rpu) -- and keeps two 256-sample slots: frame f reads (first, second) = (slot p, slot p^1), and
+// hop = 256 (= N/2): every half-warp owns a RUN of consecutive frames of one utterance (F / rpu frames, the first F mod rpu
+// runs one more) and keeps two 256-sample slots: frame f reads (first, second) = (slot p, slot p^1), and
 // as soon as the frame is in registers the dead first slot receives the second half of frame f+1 (cp.async), which has a
 // whole transform to land behind.  No block-level barrier in the frame loop.
 // STATS: the sum and the sum of squares per (utterance, bin) of the feature written (log-power if LOGP, else power) -- the
@@ -262,8 +262,11 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
     const float* row = a.wav;
     if (active) {
         const int ri = (int)(unit - (long long)u * plan.runs_per_utt);
-        fa = (int)(((long long)ri * a.n_frames) / plan.runs_per_utt);
-        fb = (int)(((long long)(ri + 1) * a.n_frames) / plan.runs_per_utt);
+        // the first (F mod rpu) runs are one frame longer; rpu is even, so the two half-warps of a warp (runs 2k, 2k+1 of
+        // one utterance) have equal lengths except for one pair per utterance
+        const int base_len = a.n_frames / plan.runs_per_utt, rem_runs = a.n_frames - base_len * plan.runs_per_utt;
+        fa = ri * base_len + min(ri, rem_runs);
+        fb = fa + base_len + (ri < rem_runs ? 1 : 0);
         row = a.wav + (long long)u * a.utt_stride;
         stage_half(slot, row, a.T, (fa - 1) * H, j);
         stage_half(slot + H, row, a.T, fa * H, j);
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
 // end of a run), so "all but the two most recent groups" is exactly the data the next consumer needs.
 constexpr int kWarps3 = 4, kThreads3 = kWarps3 * 32;
 
-struct RunPlan { int blocks_per_utt; int runs_per_utt; long long total_runs; };   // run ri = blocks (ri*bpu/rpu, (ri+1)*bpu/rpu]
+struct RunPlan { int blocks_per_utt; int runs_per_utt; long long total_runs; };   // run ri: bpu/rpu blocks, the first bpu%rpu runs one more
 
 #ifndef SE_K3_MIN_BLOCKS
 #define SE_K3_MIN_BLOCKS 3
@@ -372,7 +375,8 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
         const long long unit0 = (long long)blockIdx.x * (kThreads3 / 16) + hw0;
         if (unit0 < plan.total_runs) {
             const int u0 = (int)(unit0 / plan.runs_per_utt), ri0 = (int)(unit0 - (long long)u0 * plan.runs_per_utt);
-            const int f00 = (int)(((long long)ri0 * plan.blocks_per_utt) / plan.runs_per_utt);      // = b0 - 1
+            const int base0 = plan.blocks_per_utt / plan.runs_per_utt, rem0 = plan.blocks_per_utt - base0 * plan.runs_per_utt;
+            const int f00 = ri0 * base0 + min(ri0, rem0);                                            // = b0 - 1
             float* nb0 = reinterpret_cast<float*>(smem3 + (size_t)hw0 * kHwBytes3 + M * 8);
             const float* nrow0 = a.noisy + (long long)u0 * a.utt_stride;
             stage_half(nb0, nrow0, a.T, (f00 - 1) * H, j0);
@@ -403,8 +407,11 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     if (unit >= plan.total_runs) { griddep_wait(); return; }      // no block-level barrier below (tracing: approximate for ragged CTAs)
     const int u = (int)(unit / plan.runs_per_utt), ri = (int)(unit - (long long)u * plan.runs_per_utt);
     const int F = a.n_frames;
-    const int b0 = 1 + (int)(((long long)ri * plan.blocks_per_utt) / plan.runs_per_utt);
-    const int b1 = (int)(((long long)(ri + 1) * plan.blocks_per_utt) / plan.runs_per_utt);
+    // the first (bpu mod rpu) runs of an utterance are one block longer; with an even rpu the two half-warps of a warp
+    // (runs 2k, 2k+1 of the same utterance) get equal lengths except for one pair, so no warp idles half its lanes
+    const int base_len = plan.blocks_per_utt / plan.runs_per_utt, rem_runs = plan.blocks_per_utt - base_len * plan.runs_per_utt;
+    const int b0 = 1 + ri * base_len + min(ri, rem_runs);
+    const int b1 = b0 + base_len - 1 + (ri < rem_runs ? 1 : 0);
     const float* nrow = a.noisy + (long long)u * a.utt_stride;
     const float* crow = a.clean ? a.clean + (long long)u * a.utt_stride : nullptr;
     float* orow = a.wav_out + (long long)u * a.out_stride;
@@ -422,6 +429,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
 #pragma unroll
     for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.0f, 0.0f);
     float2 yy2 = make_float2(0.0f, 0.0f), yc2 = yy2, cc2 = yy2;     // (even, odd) sample partial sums of the fast overlap-add path
+    float2 st2 = yy2, tt2 = yy2, ss2 = yy2;                         // (bin k, bin M-k) partial spectral sums
 
     // prologue: both halves of the first (halo) frame, its mask row, both clean halves -- groups N, M, C.  The waveforms
     // are inputs of the step, so their first loads are issued before waiting for the upstream kernel (the mask's producer).
@@ -491,20 +499,26 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 if (!halo) {
                     const int t0 = (f - 1) * H;
                     const float* cfirst = cb + p * H;               // first half of the clean frame = this output block
-                    if (out_aligned && t0 + H <= len) {             // whole block inside the utterance: no per-sample predicates
+                    if (out_aligned && t0 + H <= len && need_clean) {   // whole block inside the utterance, all sums wanted:
+                        float2* o2 = reinterpret_cast<float2*>(orow + t0) + j;     // straight-line code, no per-sample predicates
+                        const float2* c2 = reinterpret_cast<const float2*>(cfirst) + j;
+                        const float2* bw2 = s_bw2 + j;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float2 y = pfma(bw2[16 * q], v[q], carry[q]);
+                            const float2 c = c2[16 * q];
+                            o2[16 * q] = y;
+                            yy2 = pfma(y, y, yy2);
+                            yc2 = pfma(y, c, yc2);
+                            cc2 = pfma(c, c, cc2);
+                        }
+                    } else if (out_aligned && t0 + H <= len) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int m = j + 16 * q;
                             const float2 y = pfma(s_bw2[m], v[q], carry[q]);
                             *reinterpret_cast<float2*>(orow + t0 + 2 * m) = y;
-                            if (a.sums) {
-                                yy2 = pfma(y, y, yy2);
-                                if (crow) {
-                                    const float2 c = *reinterpret_cast<const float2*>(cfirst + 2 * m);
-                                    yc2 = pfma(y, c, yc2);
-                                    cc2 = pfma(c, c, cc2);
-                                }
-                            }
+                            if (a.sums) yy2 = pfma(y, y, yy2);
                         }
                     } else {
 #pragma unroll
@@ -532,10 +546,12 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 for (int q = 0; q < 8; ++q) {
                     float2 xa, xb;
                     split_pair(v[q], zm[q], twn[q], xa, xb);
-                    const float pta = xa.x * xa.x + xa.y * xa.y, ptb = xb.x * xb.x + xb.y * xb.y;
-                    acc[sekern::SUM_SPEC_ST] += fast_sqrt(ra[q] * pta) + fast_sqrt(rb[q] * ptb);
-                    acc[sekern::SUM_SPEC_TT] += pta + ptb;
-                    acc[sekern::SUM_SPEC_SS] += ra[q] + rb[q];
+                    const float2 pt = make_float2(xa.x * xa.x + xa.y * xa.y, xb.x * xb.x + xb.y * xb.y);
+                    const float2 r = make_float2(ra[q], rb[q]);
+                    const float2 rt = pmul(r, pt);
+                    st2 = cadd(st2, make_float2(fast_sqrt(rt.x), fast_sqrt(rt.y)));
+                    tt2 = cadd(tt2, pt);
+                    ss2 = cadd(ss2, r);
                 }
                 if (j == 0) {
                     const float pt128 = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
@@ -561,6 +577,9 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
         acc[sekern::SUM_YY] += yy2.x + yy2.y;
         acc[sekern::SUM_YC] += yc2.x + yc2.y;
         acc[sekern::SUM_CC] += cc2.x + cc2.y;
+        acc[sekern::SUM_SPEC_ST] += st2.x + st2.y;
+        acc[sekern::SUM_SPEC_TT] += tt2.x + tt2.y;
+        acc[sekern::SUM_SPEC_SS] += ss2.x + ss2.y;
 #pragma unroll
         for (int i = 0; i < sekern::NSUMS; ++i) {
             float s = acc[i];
@@ -625,6 +644,7 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
             rpu = slots / a.n_utt;
             if (rpu > a.n_frames) rpu = a.n_frames;
         } else rpu = (a.n_frames + 31) / 32;
+        if (rpu > 2) rpu &= ~1LL;
         if (rpu < 1) rpu = 1;
         StftRunPlan plan;
         plan.runs_per_utt = (int)rpu;
@@ -686,6 +706,7 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
         const long long cap = blocks_per_utt / 4;
         if (rpu > cap) rpu = cap;
     } else rpu = (blocks_per_utt + 31) / 32;
+    if (rpu > 2) rpu &= ~1LL;                                        // even: warps pair runs of the same utterance
     if (rpu < 1) rpu = 1;
     if (rpu > blocks_per_utt) rpu = blocks_per_utt;
     plan.runs_per_utt = (int)rpu;
