@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
     }
     __syncthreads();
     griddep_launch();                                   // a dependent kernel may start its prologue (it waits for our completion)
+    if (threadIdx.x == 0) trace.mark(17);
     if (active) {
         const int F = a.n_frames;
         int p = 0;
@@ -299,8 +300,10 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
             emit_frame<POWER, PHASE, LOGP, STATS>(v, zm, twn, j, a, ((long long)u * F + f) * a.spec_stride, acc);
         }
     }
+    if (threadIdx.x == 0) trace.mark(18);
     if (STATS) {
         __syncthreads();                                            // every half-warp's accumulators are final
+        if (threadIdx.x == 0) trace.mark(19);
         // thread t owns bin t (thread 0 also bin 256); the CTA's runs are consecutive, so utterances are non-decreasing
         const float2* base = reinterpret_cast<const float2*>(smem1 + M * 8 + 2 * H * 4);
         constexpr int kStride = kHwBytes1 / 8;
@@ -354,6 +357,27 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
 // end of a run), so "all but the two most recent groups" is exactly the data the next consumer needs.
 constexpr int kWarps3 = 4, kThreads3 = kWarps3 * 32;
 
+// Run partition of one utterance's `bpu` output blocks into `rpu` runs: base = bpu / rpu blocks each, `rem` = bpu mod rpu
+// runs get one more.  Runs come in pairs (2k, 2k+1) -- the two half-warps of a warp -- and both runs of a pair have the
+// same length (so no warp idles half its lanes) except for one mixed pair when rem is odd; long and short pairs are
+// interleaved evenly (Bresenham), so every CTA -- and every SM -- gets the same mix of long and short runs.
+// Returns the first block (1-based) of run ri and its length.
+__host__ __device__ __forceinline__ void run_bounds(int ri, int bpu, int rpu, int& b0, int& len) {
+    const int base = bpu / rpu, rem = bpu - base * rpu;
+    if (rpu & 1) {                                                  // odd run count (tiny problems): longer runs first
+        b0 = 1 + ri * base + (ri < rem ? ri : rem);
+        len = base + (ri < rem ? 1 : 0);
+        return;
+    }
+    const int P = rpu >> 1, L = rem >> 1, odd = rem & 1;            // pairs, long pairs, one extra long run
+    const int k = ri >> 1, h = ri & 1;
+    const int nl = (int)(((long long)k * L) / P), nl1 = (int)(((long long)(k + 1) * L) / P);
+    const int is_long = nl1 - nl;                                   // 0 or 1; pair 0 is always short (L < P)
+    // odd rem: the extra block makes run 0 (first run of the short pair 0) long -- the one mixed pair
+    b0 = 1 + 2 * (k * base + nl) + h * (base + is_long) + (ri > 0 ? odd : 0);
+    len = base + is_long + (ri == 0 ? odd : 0);
+}
+
 struct RunPlan { int blocks_per_utt; int runs_per_utt; long long total_runs; };   // run ri: bpu/rpu blocks, the first bpu%rpu runs one more
 
 #ifndef SE_K3_MIN_BLOCKS
@@ -375,8 +399,9 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
         const long long unit0 = (long long)blockIdx.x * (kThreads3 / 16) + hw0;
         if (unit0 < plan.total_runs) {
             const int u0 = (int)(unit0 / plan.runs_per_utt), ri0 = (int)(unit0 - (long long)u0 * plan.runs_per_utt);
-            const int base0 = plan.blocks_per_utt / plan.runs_per_utt, rem0 = plan.blocks_per_utt - base0 * plan.runs_per_utt;
-            const int f00 = ri0 * base0 + min(ri0, rem0);                                            // = b0 - 1
+            int b00, len00;
+            run_bounds(ri0, plan.blocks_per_utt, plan.runs_per_utt, b00, len00);
+            const int f00 = b00 - 1;
             float* nb0 = reinterpret_cast<float*>(smem3 + (size_t)hw0 * kHwBytes3 + M * 8);
             const float* nrow0 = a.noisy + (long long)u0 * a.utt_stride;
             stage_half(nb0, nrow0, a.T, (f00 - 1) * H, j0);
@@ -407,11 +432,9 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     if (unit >= plan.total_runs) { griddep_wait(); return; }      // no block-level barrier below (tracing: approximate for ragged CTAs)
     const int u = (int)(unit / plan.runs_per_utt), ri = (int)(unit - (long long)u * plan.runs_per_utt);
     const int F = a.n_frames;
-    // the first (bpu mod rpu) runs of an utterance are one block longer; with an even rpu the two half-warps of a warp
-    // (runs 2k, 2k+1 of the same utterance) get equal lengths except for one pair, so no warp idles half its lanes
-    const int base_len = plan.blocks_per_utt / plan.runs_per_utt, rem_runs = plan.blocks_per_utt - base_len * plan.runs_per_utt;
-    const int b0 = 1 + ri * base_len + min(ri, rem_runs);
-    const int b1 = b0 + base_len - 1 + (ri < rem_runs ? 1 : 0);
+    int b0, run_len;
+    run_bounds(ri, plan.blocks_per_utt, plan.runs_per_utt, b0, run_len);
+    const int b1 = b0 + run_len - 1;
     const float* nrow = a.noisy + (long long)u * a.utt_stride;
     const float* crow = a.clean ? a.clean + (long long)u * a.utt_stride : nullptr;
     float* orow = a.wav_out + (long long)u * a.out_stride;

@@ -85,7 +85,7 @@ def main():
             print("    end percentiles 5/25/50/75/95:", " ".join(f"{x:6.2f}" for x in pct))
             print("    end by block (every 16th):", " ".join(f"{x:5.1f}" for x in b[o][::16]))
             print("    start by block (every 16th):", " ".join(f"{x:5.1f}" for x in a[o][::16]))
-    marks = {11: "head: prologue done", 12: "head: stats+bias ready", 13: "head: first stage landed", 14: "head: A normalised",
+    marks = {17: "K1: prologue done", 18: "K1: thread 0 frames done", 19: "K1: all frames done", 11: "head: prologue done", 12: "head: stats+bias ready", 13: "head: first stage landed", 14: "head: A normalised",
              15: "head: accumulator ready", 16: "head: tile staged", 41: "fin: dependency released", 42: "fin: gain ready"}
     for k, name in marks.items():
         m = sel & (kid == k)
