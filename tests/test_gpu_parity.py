@@ -565,3 +565,94 @@ def test_round_tf32_matches_cvt_rna(se):
     r = ops.round_tf32(w)
     assert ((r.view(torch.int32) & 0x1FFF) == 0).all()
     assert ((r - w).abs() <= w.abs() * 2.0 ** -11 * 1.0001).all()
+
+
+# ------------------------------------------------------------------------------ the bench configuration at full size
+@pytest.fixture(scope="module")
+def bench_case(se):
+    """BASELINE.json configs[1]: 64 x 4 s, 16 kHz, n_fft 512 / hop 256, LinearResidual(257) on log-power -- the exact batch
+    bench.py times, with ragged lengths added for half of the utterances.  The oracle runs it in well under a second."""
+    from speech_enhancement_by_s3prl_b200 import synth as synth_mod
+    ora, mine = make_pair(se, 512)
+    lengths, wavs = synth_mod.batch(64, 4.0)
+    g = torch.Generator().manual_seed(9)
+    lengths = lengths.clone()
+    cut = torch.randint(20000, 64000, (32,), generator=g)
+    lengths[::2] = cut
+    for b, n in enumerate(lengths.tolist()):
+        wavs[b, :, n:] = 0                                                  # collate_fn zero-pads (dataset.py:175)
+    torch.manual_seed(1337)
+    head = se.LinearResidual(input_size=257, output_size=257).cuda()
+    c = ora.get_feat_config
+    ora.feat_list = [c("linear", 0, log=True), c("linear", 0, log=True), c("linear", 0), c("phase", 0), c("linear", 1), c("phase", 1)]
+    with torch.no_grad():
+        ref = sp.eval_step(ora, dict(weight=head.linear.weight.detach().cpu(), bias=head.linear.bias.detach().cpu()), lengths, wavs)
+    return dict(mine=mine, head=head, lengths=lengths, wavs=wavs, ref=ref)
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph", "host_pipeline"])
+def test_bench_configuration_matches_oracle_at_full_size(se, bench_case, mode):
+    bc = bench_case
+    eng = se.EnhancementEngine(bc["mine"], bc["head"], log_features=True, precision=1)       # the path bench.py times
+    lengths, wavs, ref = bc["lengths"], bc["wavs"], bc["ref"]
+    if mode == "eager":
+        out = eng.eval_step(lengths.cuda(), wavs.cuda())
+        sisdr, loss = out["sisdr"].cpu(), out["loss_per_utt"].mean().item()
+    elif mode == "graph":
+        st = eng.capture_bound(lengths.cuda(), wavs.cuda())
+        for _ in range(3):                                                  # replays must not accumulate into the workspaces
+            st["graph"].replay()
+        torch.cuda.synchronize()
+        sisdr, loss = st["sisdr"].cpu(), st["loss_per_utt"].mean().item()
+        out = st
+    else:
+        pipe = eng.host_pipeline(64, 3, 64000, depth=2)
+        lp, wp = lengths.clone().pin_memory(), wavs.clone().pin_memory()
+        for _ in range(3):
+            pipe.submit(lp, wp)
+        res = pipe.drain()
+        assert len(res) == 3
+        for r in res[1:]:                                                   # every slot of the pipeline gives the same answer
+            assert torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1])
+        sisdr, loss = res[0][1], res[0][0].mean().item()
+        out = None
+    np.testing.assert_allclose(sisdr.numpy(), ref["sisdr"].numpy(), atol=SISDR_TOL_DB)
+    assert loss == pytest.approx(ref["loss"].item(), abs=5e-3)              # TF32 head: 10-bit mantissa operands
+    if out is not None:
+        for b in (0, 1, 31, 63):
+            n = int(lengths[b])
+            assert sisdr_db(out["wav_predicted"][b, :n].cpu(), ref["wav_predicted"][b, :n]) > 40.0
+
+
+def test_fused_step_properties_at_full_size(se, bench_case):
+    """Size-independent properties of the fused kernels on the full bench batch (no oracle involved)."""
+    from speech_enhancement_by_s3prl_b200 import ops
+    mine, wavs = bench_case["mine"], bench_case["wavs"].cuda()
+    B, _, T = wavs.shape
+    F, K = T // 256 + 1, 257
+    win = mine._frame_window
+    # (1) an all-ones mask reconstructs the noisy waveform: iSTFT(STFT(x)) = x through the fused mask->iSTFT kernel
+    ones = torch.ones(B, F, K, device=wavs.device)
+    wav, sums = ops.mask_istft(wavs, 0, 0, ones, None, 512, 256, win, pad_to=T)
+    assert (wav - wavs[:, 0]).abs().max().item() < 5e-6
+    # ... and its sums are the waveform's energy three times over (y = c = noisy), spectral sums tie: st = tt = ss
+    e = (wavs[:, 0].double() ** 2).sum(1)
+    for col in (0, 1, 2):
+        np.testing.assert_allclose(sums[:, col].cpu().numpy(), e.cpu().numpy(), rtol=2e-5)
+    np.testing.assert_allclose(sums[:, 3].cpu().numpy(), sums[:, 4].cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(sums[:, 5].cpu().numpy(), sums[:, 4].cpu().numpy(), rtol=1e-5)
+    # (2) a constant mask g scales the output by sqrt(g) (the mask multiplies the POWER spectrum, model.py:33)
+    wav_q, _ = ops.mask_istft(wavs, 0, None, ones * 0.25, None, 512, 256, win, pad_to=T, want_sums=False)
+    assert (wav_q - 0.5 * wav).abs().max().item() < 5e-6
+    # (3) Parseval on the analysis side: sum_k c_k |X_k|^2 = N * sum_n (w_n x_n)^2 per frame, checked in aggregate
+    feats, st_sums = ops.stft_features(wavs, 0, 512, 256, win, logpower=False)
+    p = feats[..., :K].double()
+    wgt = torch.full((K,), 2.0, dtype=torch.float64, device=p.device)
+    wgt[0] = wgt[-1] = 1.0
+    lhs = (p * wgt).sum((1, 2))
+    x = torch.nn.functional.pad(wavs[:, 0:1].double(), (256, 256), mode="reflect")[:, 0]
+    frames = x.unfold(1, 512, 256)[:, :F]
+    rhs = 512.0 * ((frames * win.double()) ** 2).sum((1, 2))
+    np.testing.assert_allclose(lhs.cpu().numpy(), rhs.cpu().numpy(), rtol=2e-5)
+    # (4) the CMVN sums of K1 are the column sums of what it wrote
+    np.testing.assert_allclose(st_sums[:, :K, 0].cpu().numpy(), p.sum(1).cpu().numpy(), rtol=5e-6, atol=1e-9)
