@@ -146,6 +146,21 @@ int se_l1_logspec_bwd(const float* log_predicted, const float* linear_tar, const
                       int64_t n_frames, int64_t K, float eps, double count, const float* grad_out,
                       float* grad_log_predicted, void* stream);
 
+/* ---- K4d: weighted speech distortion objective (objective.py:120-153) ------------------
+ * loss = alpha * mean_u sum_{f<len,k} ((S - G S) voiced)^2 + (1 - alpha) * mean_u sum (G max(X - S, 0))^2 with
+ * S = linear_tar, X = linear_inp, G = offset; voiced[u,f] = 10 log10(sum_k S + eps) > 10 log10(max_{u,f} sum_k S + eps)
+ * - db_interval (the maximum runs over the whole padded batch, as in the reference).  Workspaces (caller-owned):
+ * ws_energy (n_utt * n_frames) floats, ws_max 1 float, ws_sums2 (n_utt, 2) doubles; loss: 1 float.
+ * bwd: grad_offset = grad_loss[0] * d loss / d offset (0 on padded frames), from the forward's workspaces.
+ * Under data parallelism the batch maximum needs an all-reduce(max) of ws_max between the two forward kernels; the
+ * single-process form here is what the reference computes. */
+int se_wsd_fwd(const float* linear_inp, const float* offset, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+               int64_t n_frames, int64_t K, float alpha, float db_interval, float eps, float* ws_energy, float* ws_max,
+               double* ws_sums2, float* loss, void* stream);
+int se_wsd_bwd(const float* linear_inp, const float* offset, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+               int64_t n_frames, int64_t K, float alpha, float db_interval, float eps, const float* ws_energy,
+               const float* ws_max, const float* grad_loss, float* grad_offset, void* stream);
+
 /* ---- K4c: batched waveform SI-SDR (evaluation.py:5-10 over runner.py:587-602) -----
  * sisdr[u] = sisdr_eval(src[u, :len[u]], tar[u, :len[u]]).  ws_sums3: caller workspace of
  * n_utt x 3 doubles (overwritten: <s,t>, <t,t>, <s,s>). */

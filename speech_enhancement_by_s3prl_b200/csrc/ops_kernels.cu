@@ -186,6 +186,87 @@ __global__ void l1_logspec_bwd_kernel(const float* __restrict__ logp, const floa
     }
 }
 
+// ------------------------------------------------------------------ weighted speech distortion objective (objective.py:120-153)
+// energy[u,f] = sum_k S[u,f,k] for EVERY frame (the reference takes energy.max() over the whole padded batch), and the
+// batch maximum.  One warp per frame; energies are >= 0 in practice (power spectra), so the maximum is an atomicMax on
+// the float's bit pattern, with negative sums clamped out of the comparison the way max() of mixed signs would need.
+__global__ void wsd_energy_kernel(const float* __restrict__ tar, long long n_rows, int K, float* __restrict__ energy,
+                                  float* __restrict__ max_energy) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float best = -INFINITY;
+    for (long long r = warp; r < n_rows; r += nwarps) {
+        const float* t = tar + r * K;
+        float s = 0.0f;
+        for (int k = lane; k < K; k += 32) s += t[k];
+        s = secommon::warp_sum(s);
+        if (lane == 0) energy[r] = s;
+        best = fmaxf(best, s);
+    }
+    if (lane == 0 && best > -INFINITY) {
+        // order-preserving integer image of a float: flip all bits of negatives, the sign bit of non-negatives
+        const unsigned bits = __float_as_uint(best);
+        atomicMax(reinterpret_cast<unsigned*>(max_energy), (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u));
+    }
+}
+__device__ __forceinline__ float wsd_decode_max(const float* max_energy) {
+    const unsigned key = *reinterpret_cast<const unsigned*>(max_energy);
+    return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
+// per-utterance sums over valid frames: sums2[u] = { sum ((S - G S) voiced)^2, sum (G N)^2 }, N = max(X - S, 0)
+__global__ void wsd_sums_kernel(const float* __restrict__ inp, const float* __restrict__ off, const float* __restrict__ tar,
+                                const long long* __restrict__ stft_len, int n_frames, int K, float db_interval, float eps,
+                                const float* __restrict__ energy, const float* __restrict__ max_energy,
+                                double* __restrict__ sums2, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const long long valid = (long long)min((long long)n_frames, stft_len ? stft_len[u] : (long long)n_frames) * K;
+    const long long per = (valid + chunks - 1) / chunks;
+    const long long lo = chunk * per, hi = min(valid, lo + per);
+    const long long base = (long long)u * n_frames * K;
+    const float thres = 10.0f * log10f(wsd_decode_max(max_energy) + eps) - db_interval;
+    float acc[2] = {0.f, 0.f};
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int f = (int)(i / K);
+        const float S = tar[base + i], G = off[base + i], X = inp[base + i];
+        const bool voiced = 10.0f * log10f(energy[(long long)u * n_frames + f] + eps) > thres;
+        const float d = voiced ? S - G * S : 0.0f;
+        const float n = G * fmaxf(X - S, 0.0f);
+        acc[0] += d * d;
+        acc[1] += n * n;
+    }
+    block_accumulate_to<2, float>(acc, sums2 + (long long)u * 2);
+}
+__global__ void wsd_finish_kernel(const double* __restrict__ sums2, int n_utt, float alpha, float* __restrict__ loss) {
+    double sp = 0.0, no = 0.0;
+    for (int u = threadIdx.x; u < n_utt; u += blockDim.x) { sp += sums2[2 * u]; no += sums2[2 * u + 1]; }
+    sp = secommon::warp_sum(sp);
+    no = secommon::warp_sum(no);
+    if (threadIdx.x == 0) loss[0] = (float)(((double)alpha * sp + (1.0 - (double)alpha) * no) / n_utt);
+}
+// d loss / d G = grad * (1/B) * ( alpha * 2 (S - G S)(-S) voiced + (1 - alpha) * 2 G N^2 ) on valid frames, else 0
+__global__ void wsd_bwd_kernel(const float* __restrict__ inp, const float* __restrict__ off, const float* __restrict__ tar,
+                               const long long* __restrict__ stft_len, int n_utt, int n_frames, int K, float alpha,
+                               float db_interval, float eps, const float* __restrict__ energy,
+                               const float* __restrict__ max_energy, const float* __restrict__ grad_out,
+                               float* __restrict__ grad_off, long long total) {
+    const float thres = 10.0f * log10f(wsd_decode_max(max_energy) + eps) - db_interval;
+    const float scale = grad_out[0] / (float)n_utt;
+    const long long per_utt = (long long)n_frames * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long u = i / per_utt, r = i - u * per_utt;
+        const int f = (int)(r / K);
+        const long long nvalid = min((long long)n_frames, stft_len ? stft_len[u] : (long long)n_frames);
+        float g = 0.0f;
+        if (f < nvalid) {
+            const float S = tar[i], G = off[i], X = inp[i];
+            const bool voiced = 10.0f * log10f(energy[u * n_frames + f] + eps) > thres;
+            const float n = fmaxf(X - S, 0.0f);
+            g = scale * ((voiced ? alpha * 2.0f * (S - G * S) * (-S) : 0.0f) + (1.0f - alpha) * 2.0f * G * n * n);
+        }
+        grad_off[i] = g;
+    }
+}
+
 // ------------------------------------------------------------------ waveform-level reductions
 // sums3[u] += (<s,t>, <t,t>, <s,s>) over t < len[u]
 __global__ void wave_sums_kernel(const float* __restrict__ src, long long src_stride, const float* __restrict__ tar,
@@ -563,6 +644,40 @@ int se_sisdr_spec_bwd(const float* predicted, const float* linear_tar, const int
     sisdr_spec_bwd_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
         predicted, linear_tar, (const long long*)stft_len, (int)n_utt, (int)n_frames, (int)K, eps, sums3, grad_out, grad_predicted, chunks);
     return secommon::check_launch("sisdr_spec_bwd_kernel");
+}
+
+int se_wsd_fwd(const float* linear_inp, const float* offset, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+               int64_t n_frames, int64_t K, float alpha, float db_interval, float eps, float* ws_energy, float* ws_max,
+               double* ws_sums2, float* loss, void* stream) {
+    SE_REQUIRE(linear_inp && offset && linear_tar && ws_energy && ws_max && ws_sums2 && loss && n_utt > 0 && n_frames > 0 && K > 0,
+               "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemsetAsync(ws_max, 0, sizeof(float), st));                 // key 0 = below every float
+    SE_CUDA_CHECK(cudaMemsetAsync(ws_sums2, 0, sizeof(double) * 2 * n_utt, st));
+    const long long rows = n_utt * n_frames;
+    const long long want = (rows + 7) / 8;
+    wsd_energy_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(linear_tar, rows, (int)K, ws_energy, ws_max);
+    int rc = secommon::check_launch("wsd_energy_kernel");
+    if (rc != SE_OK) return rc;
+    const int chunks = pick_chunks(n_utt, n_frames * K, 8192);
+    wsd_sums_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, st>>>(linear_inp, offset, linear_tar, (const long long*)stft_len,
+                                                                     (int)n_frames, (int)K, db_interval, eps, ws_energy, ws_max,
+                                                                     ws_sums2, chunks);
+    if ((rc = secommon::check_launch("wsd_sums_kernel")) != SE_OK) return rc;
+    wsd_finish_kernel<<<1, 32, 0, st>>>(ws_sums2, (int)n_utt, alpha, loss);
+    return secommon::check_launch("wsd_finish_kernel");
+}
+
+int se_wsd_bwd(const float* linear_inp, const float* offset, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,
+               int64_t n_frames, int64_t K, float alpha, float db_interval, float eps, const float* ws_energy,
+               const float* ws_max, const float* grad_loss, float* grad_offset, void* stream) {
+    SE_REQUIRE(linear_inp && offset && linear_tar && ws_energy && ws_max && grad_loss && grad_offset && n_utt > 0, "bad argument");
+    const long long total = n_utt * n_frames * K;
+    const long long want = (total + 1023) / 1024;
+    wsd_bwd_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        linear_inp, offset, linear_tar, (const long long*)stft_len, (int)n_utt, (int)n_frames, (int)K, alpha, db_interval, eps,
+        ws_energy, ws_max, grad_loss, grad_offset, total);
+    return secommon::check_launch("wsd_bwd_kernel");
 }
 
 int se_l1_logspec_fwd(const float* log_predicted, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,

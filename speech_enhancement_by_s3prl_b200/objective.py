@@ -44,19 +44,15 @@ class L1(nn.Module):
 
 
 class WSD(nn.Module):
-    """objective.py:120-153 -- weighted speech distortion.  SURVEY.md 8f row 1 ("next"): kept on
-    stock torch ops for now so the config key keeps working; not yet a fused kernel."""
+    """objective.py:120-153 -- weighted speech distortion: alpha * speech distortion on voiced frames + (1 - alpha) *
+    residual noise, both summed per utterance over valid frames and averaged over the batch.  Fused forward and
+    backward (w.r.t. ``offset``); ``linear_inp`` / ``linear_tar`` are data and get no gradient, as in the reference's use."""
 
     def __init__(self, alpha=0.5, db_interval=30, eps=1e-10, **kwargs):
         super().__init__()
         self.alpha, self.db_interval, self.eps = alpha, db_interval, eps
 
-    def forward(self, linear_inp, offset, linear_tar, stft_length_masks, **kwargs):
-        m = stft_length_masks.unsqueeze(-1)
-        noise = torch.clamp(linear_inp - linear_tar, min=0.0)
-        energy = linear_tar.sum(dim=-1, keepdim=True)
-        thres = 10.0 * torch.log10(energy.max() + self.eps) - self.db_interval
-        voiced = ((10.0 * torch.log10(energy + self.eps)) > thres).long()
-        speech = ((linear_tar - offset * linear_tar) * voiced * m).pow(2).sum(-1).sum(-1).mean()
-        noise_term = (offset * noise * m).pow(2).sum(-1).sum(-1).mean()
-        return self.alpha * speech + (1.0 - self.alpha) * noise_term, {}
+    def forward(self, linear_inp, offset, linear_tar, stft_length_masks=None, stft_lengths=None, **kwargs):
+        loss = ops.wsd(linear_inp, offset, linear_tar, _frames(stft_length_masks, stft_lengths), self.alpha, self.db_interval,
+                       self.eps)
+        return loss, {}

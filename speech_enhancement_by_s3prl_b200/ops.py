@@ -472,6 +472,74 @@ def l1_logspec_sums(log_predicted, linear_tar, stft_len, eps=1e-10):
 
 
 # --------------------------------------------------------------------------- mask head
+@torch.library.custom_op("se_b200::wsd", mutates_args=())
+def _wsd(linear_inp: torch.Tensor, offset: torch.Tensor, linear_tar: torch.Tensor, stft_len: torch.Tensor, alpha: float,
+         db_interval: float, eps: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """objective.WSD forward -> (loss (1,), frame energies (B, F), batch-maximum key (1,)) -- the last two feed the backward."""
+    linear_inp, offset, linear_tar = _c(linear_inp, "linear_inp"), _c(offset, "offset"), _c(linear_tar, "linear_tar")
+    B, F, K = linear_tar.shape
+    dev = linear_tar.device
+    with torch.cuda.device(dev):
+        energy = torch.empty(B, F, device=dev)
+        emax = torch.empty(1, device=dev)
+        sums2 = torch.empty(B, 2, device=dev, dtype=torch.float64)
+        loss = torch.empty(1, device=dev)
+        rc = _lib.load().se_wsd_fwd(linear_inp.data_ptr(), offset.data_ptr(), linear_tar.data_ptr(), stft_len.data_ptr(), B, F, K,
+                                    alpha, db_interval, eps, energy.data_ptr(), emax.data_ptr(), sums2.data_ptr(),
+                                    loss.data_ptr(), _stream())
+        _lib.check(rc, "se_wsd_fwd")
+    return loss, energy, emax
+
+
+@_wsd.register_fake
+def _(linear_inp, offset, linear_tar, stft_len, alpha, db_interval, eps):
+    B, F, K = linear_tar.shape
+    return linear_tar.new_empty(1), linear_tar.new_empty(B, F), linear_tar.new_empty(1)
+
+
+@torch.library.custom_op("se_b200::wsd_bwd", mutates_args=())
+def _wsd_bwd(linear_inp: torch.Tensor, offset: torch.Tensor, linear_tar: torch.Tensor, stft_len: torch.Tensor, alpha: float,
+             db_interval: float, eps: float, energy: torch.Tensor, emax: torch.Tensor, grad_loss: torch.Tensor) -> torch.Tensor:
+    linear_inp, offset, linear_tar = _c(linear_inp, "linear_inp"), _c(offset, "offset"), _c(linear_tar, "linear_tar")
+    B, F, K = linear_tar.shape
+    with torch.cuda.device(linear_tar.device):
+        grad = torch.empty_like(offset)
+        g = grad_loss.reshape(1).to(torch.float32).contiguous()
+        rc = _lib.load().se_wsd_bwd(linear_inp.data_ptr(), offset.data_ptr(), linear_tar.data_ptr(), stft_len.data_ptr(), B, F, K,
+                                    alpha, db_interval, eps, energy.data_ptr(), emax.data_ptr(), g.data_ptr(), grad.data_ptr(),
+                                    _stream())
+        _lib.check(rc, "se_wsd_bwd")
+    return grad
+
+
+@_wsd_bwd.register_fake
+def _(linear_inp, offset, linear_tar, stft_len, alpha, db_interval, eps, energy, emax, grad_loss):
+    return torch.empty_like(offset)
+
+
+def _wsd_setup(ctx, inputs, output):
+    linear_inp, offset, linear_tar, stft_len, alpha, db_interval, eps = inputs
+    _, energy, emax = output
+    ctx.save_for_backward(linear_inp, offset, linear_tar, stft_len, energy, emax)
+    ctx.cfg = (alpha, db_interval, eps)
+
+
+def _wsd_backward(ctx, grad_loss, grad_energy, grad_emax):
+    linear_inp, offset, linear_tar, stft_len, energy, emax = ctx.saved_tensors
+    alpha, db_interval, eps = ctx.cfg
+    grad = torch.ops.se_b200.wsd_bwd(linear_inp, offset, linear_tar, stft_len, alpha, db_interval, eps, energy, emax, grad_loss)
+    return None, grad, None, None, None, None, None          # the spectra are data: only the head's offset gets a gradient
+
+
+_wsd.register_autograd(_wsd_backward, setup_context=_wsd_setup)
+
+
+def wsd(linear_inp, offset, linear_tar, stft_len, alpha=0.5, db_interval=30.0, eps=1e-10):
+    """objective.py:120-153 as one fused forward (+ backward w.r.t. offset).  Returns the scalar loss."""
+    stft_len = _c(stft_len, "stft_len", torch.int64)
+    return torch.ops.se_b200.wsd(linear_inp, offset, linear_tar, stft_len, float(alpha), float(db_interval), float(eps))[0][0]
+
+
 @torch.library.custom_op("se_b200::linear_head", mutates_args=())
 def _linear_head(x: torch.Tensor, mean: torch.Tensor | None, std: torch.Tensor | None, cmvn_eps: float,
                  weight: torch.Tensor, bias: torch.Tensor | None, act: int, precision: int) -> torch.Tensor:

@@ -656,3 +656,29 @@ def test_fused_step_properties_at_full_size(se, bench_case):
     np.testing.assert_allclose(lhs.cpu().numpy(), rhs.cpu().numpy(), rtol=2e-5)
     # (4) the CMVN sums of K1 are the column sums of what it wrote
     np.testing.assert_allclose(st_sums[:, :K, 0].cpu().numpy(), p.sum(1).cpu().numpy(), rtol=5e-6, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------ fused WSD objective
+@pytest.mark.parametrize("B,F,K,alpha,db", [(3, 40, 201, 0.3, 50.0), (5, 120, 257, 0.5, 30.0), (2, 33, 129, 0.9, 10.0)])
+def test_wsd_matches_oracle_and_autograd(se, B, F, K, alpha, db):
+    g = torch.Generator().manual_seed(B * F + K)
+    tar = (torch.rand(B, F, K, generator=g) ** 4) * 3.0                         # heavy-tailed power spectra
+    tar[:, F // 3:F // 2] *= 1e-4                                               # some frames well below the voicing threshold
+    inp = tar + (torch.rand(B, F, K, generator=g) - 0.3).clamp_min(-0.2) * 0.5  # X - S of both signs
+    off = torch.rand(B, F, K, generator=g)
+    lens = torch.randint(F // 2, F + 1, (B,), generator=g)
+    lens[0] = F
+    masks = (torch.arange(F)[None, :] < lens[:, None]).long()
+    ref_off = off.clone().requires_grad_(True)
+    ref = sp.wsd(inp, ref_off, tar, masks, alpha=alpha, db_interval=db)
+    ref.backward()
+    mine_off = off.cuda().requires_grad_(True)
+    loss, _ = se.WSD(alpha=alpha, db_interval=db)(inp.cuda(), mine_off, tar.cuda(), masks.cuda())
+    loss.backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=2e-5)
+    scale = ref_off.grad.abs().max().item()
+    assert (mine_off.grad.cpu() - ref_off.grad).abs().max().item() < 2e-5 * scale
+    assert torch.count_nonzero(mine_off.grad.cpu()[masks == 0]).item() == 0     # padded frames carry no gradient
+    # frame counts instead of masks (what the fused step passes)
+    loss2, _ = se.WSD(alpha=alpha, db_interval=db)(inp.cuda(), off.cuda(), tar.cuda(), stft_lengths=lens.cuda())
+    assert loss2.item() == pytest.approx(loss.item(), rel=1e-6)
