@@ -241,6 +241,16 @@ int se_delta(float* x, int64_t n_utt, int64_t n_frames, int64_t D, int order, vo
 int se_cmvn_apply(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const float* mean, const float* std,
                   float eps, void* stream);
 
+/* ---- a13 + a1 on the device: batch synthesis (dataset.py:106-111 normalize_wav_decibel, 54-74 add_noise, 128-161
+ * __getitem__, 169-179 collate_fn) ------------------------------------
+ * Per utterance u: speech[u, :speech_len[u]] and noise[u, :noise_len[u]] are RMS-normalised to target_level_db, the noise is
+ * tiled (or cropped) to the speech length and scaled to snr_db[u] (add_noise's formula with eps), and
+ * wavs_out[u] = [noisy, speech, scaled_noise] (3, T_out), zero beyond speech_len[u] -- collate_fn's output for the batch.
+ * The reference's sample lengths are the speech lengths; T_out >= max(speech_len).  ws_sums4: (n_utt, 4) doubles. */
+int se_mix_batch(const float* speech, int64_t speech_stride, const int64_t* speech_len, const float* noise, int64_t noise_stride,
+                 const int64_t* noise_len, const float* snr_db, int64_t n_utt, int64_t T_out, float target_level_db, float eps,
+                 double* ws_sums4, float* wavs_out, void* stream);
+
 /* ---- a1: host batch -> device (dataset.py:169-179 collate_fn output; runner.py:431, 556) ----
  * Copies channels [0, n_ch) of a pinned HOST batch h_wavs (B, C, T) into a compact device batch
  * d_wavs (B, n_ch, T) with one strided async copy (the path consumes the noisy and clean channels

@@ -267,6 +267,60 @@ __global__ void wsd_bwd_kernel(const float* __restrict__ inp, const float* __res
     }
 }
 
+// ------------------------------------------------------------------ on-device batch synthesis (dataset.py:54-74, 106-111, 128-161, 169-179)
+// sums4[u] = { sum s^2 over [0, Ls), sum n^2 over [0, Ln), sum n^2 over [0, Ls mod Ln) (0 if Ls < Ln: crop), unused }
+__global__ void mix_sums_kernel(const float* __restrict__ speech, long long s_stride, const long long* __restrict__ s_len,
+                                const float* __restrict__ noise, long long n_stride, const long long* __restrict__ n_len,
+                                double* __restrict__ sums4, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const long long Ls = s_len[u], Ln = n_len[u];
+    const long long rem = Ls >= Ln ? Ls % Ln : Ls;                      // tiled: the partial last copy; cropped: the kept prefix
+    const long long span = Ls > Ln ? Ls : Ln;
+    const long long per = (span + chunks - 1) / chunks;
+    const long long lo = chunk * per, hi = min(span, lo + per);
+    const float* s = speech + (long long)u * s_stride;
+    const float* n = noise + (long long)u * n_stride;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        if (i < Ls) { const float v = s[i]; acc[0] += v * v; }
+        if (i < Ln) { const float v = n[i]; acc[1] += v * v; if (i < rem) acc[2] += v * v; }
+    }
+    block_accumulate_to<4, float>(acc, sums4 + (long long)u * 4);
+}
+// out[u] = [noisy, speech_n, scaled_noise] (3, T_out), zero beyond Ls (collate_fn's padding)
+__global__ void mix_write_kernel(const float* __restrict__ speech, long long s_stride, const long long* __restrict__ s_len,
+                                 const float* __restrict__ noise, long long n_stride, const long long* __restrict__ n_len,
+                                 const float* __restrict__ snr_db, const double* __restrict__ sums4, int T_out,
+                                 float level, float eps, float* __restrict__ out, int chunks) {
+    const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
+    const long long Ls = s_len[u], Ln = n_len[u];
+    const double ss = sums4[4 * u], nn = sums4[4 * u + 1], nrem = sums4[4 * u + 2];
+    // normalize_wav_decibel (dataset.py:106-111): x * 10^(level/20) / (rms + 1e-10)
+    const float s_gain = level / ((float)sqrt(ss / (double)Ls) + 1e-10f);
+    const float n_gain = level / ((float)sqrt(nn / (double)Ln) + 1e-10f);
+    // add_noise (dataset.py:54-74) on the normalised signals: powers over the speech length, noise tiled or cropped
+    const double reps = Ls >= Ln ? (double)(Ls / Ln) : 0.0;
+    const float p_s = (float)(ss * (double)s_gain * (double)s_gain);
+    const float p_n = (float)((reps * nn + nrem) * (double)n_gain * (double)n_gain);
+    const float ratio = powf(10.0f, snr_db[u] / 10.0f);
+    const float mix_gain = sqrtf(p_s / (ratio * p_n + eps)) * n_gain;     // applied to the raw noise samples
+    const int per = (((T_out + chunks - 1) / chunks) + 3) & ~3;
+    const int lo = chunk * per, hi = min(T_out, lo + per);
+    const float* s = speech + (long long)u * s_stride;
+    const float* n = noise + (long long)u * n_stride;
+    float* o = out + (long long)u * 3 * T_out;
+    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+        float sp = 0.0f, sc = 0.0f;
+        if (t < Ls) {
+            sp = s[t] * s_gain;
+            sc = n[t % Ln] * mix_gain;
+        }
+        o[t] = sp + sc;
+        o[T_out + t] = sp;
+        o[2LL * T_out + t] = sc;
+    }
+}
+
 // ------------------------------------------------------------------ waveform-level reductions
 // sums3[u] += (<s,t>, <t,t>, <s,s>) over t < len[u]
 __global__ void wave_sums_kernel(const float* __restrict__ src, long long src_stride, const float* __restrict__ tar,
@@ -644,6 +698,25 @@ int se_sisdr_spec_bwd(const float* predicted, const float* linear_tar, const int
     sisdr_spec_bwd_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
         predicted, linear_tar, (const long long*)stft_len, (int)n_utt, (int)n_frames, (int)K, eps, sums3, grad_out, grad_predicted, chunks);
     return secommon::check_launch("sisdr_spec_bwd_kernel");
+}
+
+int se_mix_batch(const float* speech, int64_t speech_stride, const int64_t* speech_len, const float* noise, int64_t noise_stride,
+                 const int64_t* noise_len, const float* snr_db, int64_t n_utt, int64_t T_out, float target_level_db, float eps,
+                 double* ws_sums4, float* wavs_out, void* stream) {
+    SE_REQUIRE(speech && speech_len && noise && noise_len && snr_db && ws_sums4 && wavs_out && n_utt > 0 && T_out > 0, "bad argument");
+    SE_REQUIRE(T_out < (1LL << 30), "T_out=%lld too long", (long long)T_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemsetAsync(ws_sums4, 0, sizeof(double) * 4 * n_utt, st));
+    const int chunks = pick_chunks(n_utt, T_out, 8192);
+    mix_sums_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, st>>>(speech, speech_stride, (const long long*)speech_len, noise,
+                                                                     noise_stride, (const long long*)noise_len, ws_sums4, chunks);
+    int rc = secommon::check_launch("mix_sums_kernel");
+    if (rc != SE_OK) return rc;
+    mix_write_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, st>>>(speech, speech_stride, (const long long*)speech_len, noise,
+                                                                      noise_stride, (const long long*)noise_len, snr_db, ws_sums4,
+                                                                      (int)T_out, powf(10.0f, target_level_db / 20.0f), eps,
+                                                                      wavs_out, chunks);
+    return secommon::check_launch("mix_write_kernel");
 }
 
 int se_wsd_fwd(const float* linear_inp, const float* offset, const float* linear_tar, const int64_t* stft_len, int64_t n_utt,

@@ -257,6 +257,29 @@ def finalize_metrics(sums, lengths, T, wav=None, target_db=None, want_gain=True,
     return gain, sisdr, loss
 
 
+# --------------------------------------------------------------------------- on-device batch synthesis
+def mix_batch(speech, speech_len, noise, noise_len, snr_db, target_level=-25.0, eps=1e-8, T_out=None):
+    """The reference's ``OnlineDataset.__getitem__`` + ``collate_fn`` for a whole batch on the GPU.
+
+    speech (B, Ts) / noise (B, Tn) fp32 zero-padded rows with their true lengths (B,) int64, snr_db (B,) fp32.
+    Returns (lengths (B,) int64, wavs (B, 3, T_out) = [noisy, speech, scaled_noise]); eps = the dataset's eps
+    (dataset.py:80, 158)."""
+    speech, noise = _c(speech, "speech"), _c(noise, "noise")
+    speech_len, noise_len = _c(speech_len, "speech_len", torch.int64), _c(noise_len, "noise_len", torch.int64)
+    snr_db = _c(snr_db.to(torch.float32), "snr_db")
+    B, Ts = speech.shape
+    T_out = int(T_out) if T_out is not None else Ts
+    assert T_out >= Ts and noise.shape[0] == B
+    with torch.cuda.device(speech.device):
+        ws = torch.empty(B, 4, device=speech.device, dtype=torch.float64)
+        out = torch.empty(B, 3, T_out, device=speech.device)
+        rc = _lib.load().se_mix_batch(speech.data_ptr(), Ts, speech_len.data_ptr(), noise.data_ptr(), noise.shape[1],
+                                      noise_len.data_ptr(), snr_db.data_ptr(), B, T_out, float(target_level), float(eps),
+                                      ws.data_ptr(), out.data_ptr(), _stream())
+        _lib.check(rc, "se_mix_batch")
+    return speech_len, out
+
+
 # --------------------------------------------------------------------------- waveform-level helpers
 def sisdr_wave(src, tar, lengths=None, eps=1e-10):
     """Batched evaluation.sisdr_eval: src, tar (B, T) -> (B,) dB."""
