@@ -167,6 +167,52 @@ class EnhancementEngine:
         return loss
 
 
+    def train_step_graph(self, lengths, wavs, objective, optimizer, grad_clip=None):
+        """``train_step`` replayed from a CUDA graph: forward, backward, gradient all-reduce, clipping and the optimizer
+        update of one batch shape are captured once (the eager step is launch-bound: ~40 small launches).  The optimizer
+        must be capturable (e.g. ``torch.optim.Adam(..., capturable=True)``).  Returns the loss tensor of the static step
+        (valid until the next call)."""
+        B, C, T = wavs.shape
+        key = ("train", B, C, T, id(objective), id(optimizer), grad_clip)
+        st = self._graphs.get(key)
+        if st is None:
+            dev = wavs.device
+            ops.prepare(self.n_fft)
+            st = {"lengths": lengths.clone(), "wavs": wavs.clone()}
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):                                   # warm-up: lazy state of autograd, NCCL and the optimizer
+                    self.train_step(st["lengths"], st["wavs"], objective, optimizer, grad_clip)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            optimizer.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["loss"] = self._train_body(st["lengths"], st["wavs"], objective, optimizer, grad_clip)
+            st["graph"] = graph
+            self._graphs[key] = st
+        st["lengths"].copy_(lengths, non_blocking=True)
+        st["wavs"].copy_(wavs, non_blocking=True)
+        st["graph"].replay()
+        return st["loss"]
+
+    def _train_body(self, lengths, wavs, objective, optimizer, grad_clip):
+        """forward + backward + update without ``zero_grad`` (inside a graph the gradients live in the graph's pool)."""
+        c = self.pre.get_feat_config
+        feat_cfg = c("linear", self.ch_inp, log=self.log_features)
+        feats, linear_inp, linear_tar = self.pre(wavs, [feat_cfg, c("linear", self.ch_inp), c("linear", self.ch_tar)])
+        predicted, extra = self.head(features=feats, linears=linear_inp)
+        frames = lengths // self.hop + 1
+        loss, _ = objective(predicted=predicted, linear_tar=linear_tar, linear_inp=linear_inp, stft_lengths=frames, **extra)
+        loss.backward()
+        dp.allreduce_gradients(self.head.parameters())
+        if grad_clip is not None:
+            torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
+        optimizer.step()
+        return loss
+
+
 class HostPipeline:
     """Host-facing evaluation loop: pinned host batches in, per-utterance (loss term, SI-SDR) out.
 

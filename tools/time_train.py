@@ -26,3 +26,18 @@ for nfreq, win, hop in [(257, 32, 16), (201, 25, 10)]:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         print(f"n_freq {nfreq} hop_ms {hop} precision {precision}: {ms:.3f} ms/step  {256 / ms * 1e3:.0f} audio-s/s  loss {loss.item():.4f}")
+        del loss                                   # (keeps the eager autograd graph -- and its default-stream nodes -- alive)
+        torch.manual_seed(1337)
+        head2 = se.LinearResidual(input_size=nfreq, output_size=nfreq).to(dev)
+        eng = se.EnhancementEngine(pre, head2, log_features=True, precision=precision)
+        opt2 = torch.optim.Adam(head2.parameters(), lr=1e-4, capturable=True)
+        for _ in range(3):
+            loss = eng.train_step_graph(lengths, wavs, obj, opt2, grad_clip=1.0)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            loss = eng.train_step_graph(lengths, wavs, obj, opt2, grad_clip=1.0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"   graph replay: {ms:.3f} ms/step  {256 / ms * 1e3:.0f} audio-s/s  loss {loss.item():.4f}")
