@@ -228,6 +228,15 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
                          const float* W, int64_t ldw, const float* b, int64_t n_utt, int64_t n_frames, int64_t D_in,
                          int64_t D_out, int act, float* offset_out, int64_t ld_out, void* stream);
 
+/* Tensor-core form of se_linear_head_bwd (tcgen05 TF32 split-K GEMM; grad_b from a ones column of the same GEMM).
+ * ws_partials: caller workspace of se_linear_head_bwd_tc_workspace(...) floats (0 = shape unsupported: D_in <= 271 and a
+ * split of the rows may touch at most 4 utterances); ldx / ld_off = floats between rows of x / of offset and grad_offset. */
+int64_t se_linear_head_bwd_tc_workspace(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out);
+int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const float* std, int64_t ld_stats, float cmvn_eps,
+                          const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt, int64_t n_frames,
+                          int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats, float* grad_W,
+                          float* grad_b, void* stream);
+
 /* ---- K1b: feature post-processing (S3PRL OnlinePreprocessor feature configs:
  * config/pretrain_sample.yaml:54-65, config/pseudo_noise.yaml:10-15) ------------------
  * se_mel: out[u,f,m] = log?(sum_k power[u,f,k] * fb[k,m] (+eps)), fb (K, n_mels) row-major

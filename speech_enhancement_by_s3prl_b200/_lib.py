@@ -51,6 +51,8 @@ _SIGNATURES = {
     "se_cmvn_stats_strided": [c_f, i64, i64, i64, i64, c_f, c_f, i64, c_f],
     "se_linear_head_fwd_strided": [c_f, i64, c_f, c_f, i64, c_float, c_f, i64, c_f, i64, i64, i64, i64, c_int, c_f, c_f, c_f, i64, c_int, c_f],
     "se_linear_head_bwd": [c_f, c_f, c_f, c_float, c_f, c_f, c_f, i64, i64, i64, i64, c_int, c_f, c_f, c_f],
+    "se_linear_head_bwd_tc_workspace": [i64, i64, i64, i64],
+    "se_linear_head_bwd_tc": [c_f, i64, c_f, c_f, i64, c_float, c_f, c_f, i64, i64, i64, i64, i64, c_int, c_f, i64, c_f, c_f, c_f],
     "se_mel": [c_f, i64, i64, c_f, i64, c_int, c_float, c_f, i64, c_f],
     "se_delta": [c_f, i64, i64, i64, c_int, c_f],
     "se_cmvn_apply": [c_f, i64, i64, i64, c_f, c_f, c_float, c_f],
@@ -82,7 +84,7 @@ def load():
             for name, argtypes in _SIGNATURES.items():
                 fn = getattr(lib, name)            # AttributeError if the symbol is not exported
                 fn.argtypes = argtypes
-                fn.restype = c_int
+                fn.restype = i64 if name.endswith("_workspace") else c_int
             _lib = lib
     return _lib
 

@@ -1,0 +1,358 @@
+// libse_b200.so -- tensor-core weight gradient of the mask head (autograd of model.py:14-17, 28-34):
+//
+//     grad_W[n, k] = sum_r dZ[r, n] * xhat[r, k]        grad_b[n] = sum_r dZ[r, n]
+//     dZ = grad_offset * act'(offset)                   xhat = (x - mean) / (std + eps)   (the head's CMVN input)
+//
+// A split-K tcgen05 GEMM: CTA (split s, m-tile mt) owns rows [ra, rb) of the batch and output features
+// [128 mt, 128 mt + 128), and accumulates D[128 n][272 k] in tensor memory over its row blocks of 32.
+//   * warps 0-7  producers: both operands are row-major in r (the reduction index), so they are TRANSPOSED on the way
+//                into shared memory: thread -> one n (or k), four consecutive rows per 16-byte chunk, coalesced 128-byte
+//                loads across the warp, one conflict-free STS.128 into the K-major SWIZZLE_128B tile; dZ's activation
+//                derivative and xhat's CMVN are applied here, operands rounded to TF32 (cvt.rna).  Column k = D_in of
+//                the B tile is the constant 1, so grad_b falls out of the GEMM as column D_in of D.
+//   * warp 8     tcgen05.mma kind::tf32 (M = 128, N = 256 + 16), commits stages back to the producers
+//   * epilogue   tcgen05.ld -> staging tile -> coalesced stores of the CTA's partial into the workspace
+// A second kernel sums the partials over the splits into grad_W / grad_b.
+#include "se_common.cuh"
+
+using secommon::fail;
+
+namespace {
+
+constexpr int BM = 128, BK = 32, kStages = 4;
+constexpr int kProdWarps = 8, kProdThreads = kProdWarps * 32, kThreads = kProdThreads + 32;
+constexpr int kATileBytes = BM * BK * 4;                       // 16 KB
+constexpr int kMaxBRows = 272;
+constexpr int kBTileBytes = kMaxBRows * BK * 4;                // 34 816
+constexpr int kStageBytes = kATileBytes + kBTileBytes;         // 51 200
+constexpr int kMaxUtt = 4;                                     // utterances one CTA's row range may touch
+constexpr int kOffRing = 0;
+constexpr int kOffStats = kOffRing + kStages * kStageBytes;    // [kMaxUtt][272] (mean, 1/(std+eps))
+constexpr int kOffBar = kOffStats + kMaxUtt * kMaxBRows * 8;
+constexpr int kNumBars = 2 * kStages + 1;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmem + 16;
+constexpr int kStageLd = 276;                                  // staging row stride (floats): conflict-free STS.128 by row
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(BM * kStageLd * 4 <= kStages * kStageBytes, "staging tile fits in the ring");
+constexpr unsigned kSpinLimit = 1u << 22;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > kSpinLimit) __trap();                          // never hang the GPU on a protocol bug
+    }
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major SWIZZLE_128B: rows 128 B apart, 8-row groups 1024 B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {           // kind::tf32, fp32 accumulate, A/B K-major, M = 128
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct BwdArgs {
+    const float* x; long long ldx;
+    const float* mean; const float* stdv; long long ld_stats; float cmvn_eps;
+    const float* offset; const float* grad_offset; long long ld_off;
+    long long R; int n_frames, Din, Dout, act;
+    long long rows_per_split;      // multiple of 32
+    int b_rows;                    // round16(Din + 1) <= 272
+    int n_main, n_tail;
+    float* partials;               // (splits, m_tiles * 128, 272)
+    int m_rows;                    // m_tiles * 128
+};
+
+__global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const BwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    float2* s_stats = reinterpret_cast<float2*>(smem + kOffStats);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, n0 = blockIdx.y * BM;
+    const long long ra = (long long)split * a.rows_per_split;
+    const long long rb = ra + a.rows_per_split < a.R ? ra + a.rows_per_split : a.R;
+    const int nkb = rb > ra ? (int)((rb - ra + BK - 1) / BK) : 0;
+
+    if (threadIdx.x == 0) {
+        if (sbase & 1023) __trap();
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, kProdWarps); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProdWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // CMVN constants of the (at most kMaxUtt) utterances this CTA's rows touch
+    const long long u_first = ra / a.n_frames;
+    for (int i = threadIdx.x; i < kMaxUtt * kMaxBRows; i += kThreads) {
+        const int ul = i / kMaxBRows, k = i - ul * kMaxBRows;
+        const long long u = u_first + ul;
+        float2 st = make_float2(0.0f, 1.0f);
+        if (a.mean && k < a.Din && u * a.n_frames < a.R) {
+            st.x = __ldg(a.mean + u * a.ld_stats + k);
+            st.y = 1.0f / (__ldg(a.stdv + u * a.ld_stats + k) + a.cmvn_eps);
+        }
+        s_stats[i] = st;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kProdWarps) {
+        // ===================== producers: transpose both operands into K-major tiles =====================
+        const int t = threadIdx.x;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kStages;
+            if (kb >= kStages) mbar_wait(bar_empty + 8 * s, ((kb / kStages) - 1) & 1);
+            unsigned char* At = smem + kOffRing + s * kStageBytes;
+            unsigned char* Bt = At + kATileBytes;
+            const long long r0 = ra + (long long)kb * BK;
+            // A tile: dZ^T.  item -> (n = item & 127, chunk c = item >> 7): rows r0 + 4c .. + 3
+#pragma unroll
+            for (int i = 0; i < (BM * 8) / kProdThreads; ++i) {
+                const int item = t + kProdThreads * i;
+                const int n = item & (BM - 1), c = item >> 7;
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
+                if (n0 + n < a.Dout) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const long long r = r0 + 4 * c + jj;
+                        if (r < rb) {
+                            const float o = __ldg(a.offset + r * a.ld_off + n0 + n);
+                            float v = __ldg(a.grad_offset + r * a.ld_off + n0 + n);
+                            if (a.act == SE_ACT_SIGMOID) v *= o * (1.0f - o);
+                            else if (a.act == SE_ACT_RELU) v = o > 0.f ? v : 0.f;
+                            g[jj] = v;
+                        }
+                    }
+                }
+                *reinterpret_cast<float4*>(At + n * 128 + ((c ^ (n & 7)) << 4)) =
+                    make_float4(to_tf32(g[0]), to_tf32(g[1]), to_tf32(g[2]), to_tf32(g[3]));
+            }
+            // B tile: xhat^T with the ones column at k = Din.  item -> (k = item % b_rows, chunk c = item / b_rows)
+            const long long uq = r0 / a.n_frames;                          // utterance of the block's first row
+            const int ul0 = (int)(uq - u_first), bnd = (int)((uq + 1) * a.n_frames - r0);   // rows of the block before the next one
+            for (int item = t; item < a.b_rows * 8; item += kProdThreads) {
+                const int c = item / a.b_rows, k = item - c * a.b_rows;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const long long r = r0 + 4 * c + jj;
+                    if (r < rb) {
+                        if (k < a.Din) {
+                            const int ul = a.n_frames >= BK ? ul0 + (4 * c + jj >= bnd ? 1 : 0) : (int)(r / a.n_frames - u_first);
+                            const float2 st = s_stats[ul * kMaxBRows + k];
+                            v[jj] = (__ldg(a.x + r * a.ldx + k) - st.x) * st.y;
+                        } else if (k == a.Din) {
+                            v[jj] = 1.0f;
+                        }
+                    }
+                }
+                *reinterpret_cast<float4*>(Bt + k * 128 + ((c ^ (k & 7)) << 4)) =
+                    make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        }
+        // ===================== epilogue: the CTA's partial D -> workspace =====================
+        if (nkb > 0) {
+            mbar_wait(bar_accum, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        float* stage = reinterpret_cast<float*>(smem + kOffRing);
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        const int ncol16 = a.b_rows / 16;
+        const int c_lo = 16 * (half == 0 ? 0 : ncol16 / 2), c_hi = 16 * (half == 0 ? ncol16 / 2 : ncol16);
+        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            uint32_t acc[16];
+            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4)
+                *reinterpret_cast<float4*>(stage + row * kStageLd + c0 + jj) =
+                    nkb > 0 ? make_float4(__uint_as_float(acc[jj]), __uint_as_float(acc[jj + 1]), __uint_as_float(acc[jj + 2]),
+                                          __uint_as_float(acc[jj + 3]))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
+        float* dst = a.partials + ((long long)split * a.m_rows + n0) * kMaxBRows;
+        for (int rr = warp; rr < BM; rr += kProdWarps)
+            for (int c = lane; c < a.b_rows; c += 32) dst[(long long)rr * kMaxBRows + c] = stage[rr * kStageLd + c];
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===================== MMA issuer =====================
+        if (lane == 0 && nkb > 0) {
+            const uint32_t idesc_main = make_idesc(a.n_main), idesc_tail = make_idesc(a.n_tail > 0 ? a.n_tail : 16);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(bar_full + 8 * s, (kb / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = sbase + kOffRing + s * kStageBytes;
+                const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint64_t ad = make_desc(a_addr + kk * 32);
+                    umma_tf32(tmem_base, ad, make_desc(b_addr + kk * 32), idesc_main, (kb | kk) ? 1u : 0u);
+                    if (a.n_tail > 0)
+                        umma_tf32(tmem_base + (uint32_t)a.n_main, ad, make_desc(b_addr + a.n_main * BK * 4 + kk * 32), idesc_tail,
+                                  (kb | kk) ? 1u : 0u);
+                }
+                umma_commit(bar_empty + 8 * s);
+            }
+            umma_commit(bar_accum);
+        }
+    }
+    __syncthreads();
+    if (warp == kProdWarps) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// grad_W[n, k] = sum_s partials[s, n, k], grad_b[n] = sum_s partials[s, n, Din]
+__global__ void head_bwd_reduce_kernel(const float* __restrict__ partials, int splits, int m_rows, int Din, int Dout,
+                                       float* __restrict__ grad_W, float* __restrict__ grad_b) {
+    const int cols = Din + 1;
+    const long long total = (long long)Dout * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / cols), k = (int)(i - (long long)n * cols);
+        const float* p = partials + (long long)n * kMaxBRows + k;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int s = 0;
+        const long long stride = (long long)m_rows * kMaxBRows;
+        for (; s + 3 < splits; s += 4) {
+            s0 += p[(long long)s * stride]; s1 += p[(long long)(s + 1) * stride];
+            s2 += p[(long long)(s + 2) * stride]; s3 += p[(long long)(s + 3) * stride];
+        }
+        for (; s < splits; ++s) s0 += p[(long long)s * stride];
+        const float v = (s0 + s1) + (s2 + s3);
+        if (k < Din) grad_W[(long long)n * Din + k] = v;
+        else if (grad_b) grad_b[n] = v;
+    }
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+struct Geometry { int m_tiles, splits; long long rows_per_split; };
+
+bool plan(long long R, long long n_frames, long long Din, long long Dout, Geometry* g) {
+    if (R <= 0 || n_frames <= 0 || Din <= 0 || Dout <= 0 || Din + 1 > kMaxBRows) return false;
+    g->m_tiles = (int)((Dout + BM - 1) / BM);
+    long long splits = num_sms() / g->m_tiles;
+    if (splits < 1) splits = 1;
+    long long rows = (R + splits - 1) / splits;
+    rows = (rows + BK - 1) / BK * BK;
+    g->rows_per_split = rows;
+    g->splits = (int)((R + rows - 1) / rows);
+    // a split may touch at most kMaxUtt utterances (their CMVN constants are staged in shared memory)
+    return (rows + n_frames - 1) / n_frames + 1 <= kMaxUtt;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t se_linear_head_bwd_tc_workspace(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out) {
+    Geometry g;
+    if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g)) return 0;
+    return (int64_t)g.splits * g.m_tiles * BM * kMaxBRows;
+}
+
+int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const float* std, int64_t ld_stats, float cmvn_eps,
+                          const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt, int64_t n_frames,
+                          int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats, float* grad_W,
+                          float* grad_b, void* stream) {
+    SE_REQUIRE(x && offset && grad_offset && ws_partials && grad_W && n_utt > 0 && n_frames > 0, "bad argument");
+    SE_REQUIRE((mean == nullptr) == (std == nullptr), "mean and std go together");
+    SE_REQUIRE(ldx >= D_in && ld_off >= D_out && (!mean || ld_stats >= D_in), "row stride smaller than the row");
+    SE_REQUIRE(act >= SE_ACT_IDENTITY && act <= SE_ACT_SIGMOID, "unknown activation %d", act);
+    Geometry g;
+    if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g))
+        return fail(SE_ERR_UNSUPPORTED, "tensor-core head backward: shape outside its range (D_in=%lld, n_frames=%lld)",
+                    (long long)D_in, (long long)n_frames);
+    SE_REQUIRE(ws_floats >= (int64_t)g.splits * g.m_tiles * BM * kMaxBRows, "workspace too small");
+    BwdArgs a{};
+    a.x = x; a.ldx = ldx; a.mean = mean; a.stdv = std; a.ld_stats = ld_stats; a.cmvn_eps = cmvn_eps;
+    a.offset = offset; a.grad_offset = grad_offset; a.ld_off = ld_off;
+    a.R = n_utt * n_frames; a.n_frames = (int)n_frames; a.Din = (int)D_in; a.Dout = (int)D_out; a.act = act;
+    a.rows_per_split = g.rows_per_split;
+    a.b_rows = (int)((D_in + 1 + 15) / 16 * 16);
+    a.n_main = a.b_rows > 256 ? 256 : a.b_rows;
+    a.n_tail = a.b_rows - a.n_main;
+    a.partials = ws_partials;
+    a.m_rows = g.m_tiles * BM;
+    static bool opted = false;
+    if (!opted) {
+        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        opted = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    linear_head_bwd_tc_kernel<<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kThreads, kSmemBytes, st>>>(a);
+    int rc = secommon::check_launch("linear_head_bwd_tc_kernel");
+    if (rc != SE_OK) return rc;
+    const long long total = D_out * (D_in + 1);
+    head_bwd_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws_partials, g.splits, a.m_rows, (int)D_in, (int)D_out,
+                                                                          grad_W, grad_b);
+    return secommon::check_launch("head_bwd_reduce_kernel");
+}
+
+}  // extern "C"

@@ -585,33 +585,43 @@ def _(x, mean, std, cmvn_eps, weight, bias, act, precision):
 
 @torch.library.custom_op("se_b200::linear_head_bwd", mutates_args=())
 def _linear_head_bwd(x: torch.Tensor, mean: torch.Tensor | None, std: torch.Tensor | None, cmvn_eps: float,
-                     weight: torch.Tensor, offset: torch.Tensor, grad_offset: torch.Tensor, act: int) -> tuple[torch.Tensor, torch.Tensor]:
+                     weight: torch.Tensor, offset: torch.Tensor, grad_offset: torch.Tensor, act: int,
+                     precision: int) -> tuple[torch.Tensor, torch.Tensor]:
     x, offset, grad_offset = _c(x, "features"), _c(offset, "offset"), _c(grad_offset, "grad_offset")
     B, F, Din = x.shape
     Dout = weight.shape[0]
     with torch.cuda.device(x.device):
         gw = torch.empty(Dout, Din, device=x.device)
         gb = torch.empty(Dout, device=x.device)
-        rc = _lib.load().se_linear_head_bwd(x.data_ptr(), _p(mean), _p(std), cmvn_eps, weight.data_ptr(), offset.data_ptr(),
+        lib = _lib.load()
+        ws_floats = lib.se_linear_head_bwd_tc_workspace(B, F, Din, Dout) if precision == 1 else 0
+        if ws_floats > 0:                                   # tensor-core split-K GEMM (TF32 operands, fp32 accumulate)
+            ws = torch.empty(ws_floats, device=x.device)
+            rc = lib.se_linear_head_bwd_tc(x.data_ptr(), Din, _p(mean), _p(std), Din, cmvn_eps, offset.data_ptr(),
+                                           grad_offset.data_ptr(), Dout, B, F, Din, Dout, act, ws.data_ptr(), ws_floats,
+                                           gw.data_ptr(), gb.data_ptr(), _stream())
+            _lib.check(rc, "se_linear_head_bwd_tc")
+            return gw, gb
+        rc = lib.se_linear_head_bwd(x.data_ptr(), _p(mean), _p(std), cmvn_eps, weight.data_ptr(), offset.data_ptr(),
                                             grad_offset.data_ptr(), B, F, Din, Dout, act, gw.data_ptr(), gb.data_ptr(), _stream())
         _lib.check(rc, "se_linear_head_bwd")
     return gw, gb
 
 
 @_linear_head_bwd.register_fake
-def _(x, mean, std, cmvn_eps, weight, offset, grad_offset, act):
+def _(x, mean, std, cmvn_eps, weight, offset, grad_offset, act, precision):
     return torch.empty_like(weight), weight.new_empty(weight.shape[0])
 
 
 def _head_setup(ctx, inputs, output):
     x, mean, std, cmvn_eps, weight, bias, act, precision = inputs
     ctx.save_for_backward(x, mean, std, weight, output)
-    ctx.cmvn_eps, ctx.act, ctx.has_bias = cmvn_eps, act, bias is not None
+    ctx.cmvn_eps, ctx.act, ctx.has_bias, ctx.precision = cmvn_eps, act, bias is not None, precision
 
 
 def _head_backward(ctx, grad_out):
     x, mean, std, weight, offset = ctx.saved_tensors
-    gw, gb = torch.ops.se_b200.linear_head_bwd(x, mean, std, ctx.cmvn_eps, weight, offset, grad_out, ctx.act)
+    gw, gb = torch.ops.se_b200.linear_head_bwd(x, mean, std, ctx.cmvn_eps, weight, offset, grad_out, ctx.act, ctx.precision)
     return None, None, None, None, gw, (gb if ctx.has_bias else None), None, None
 
 

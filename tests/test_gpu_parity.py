@@ -735,3 +735,62 @@ def test_train_step_graph_matches_eager_training(se):
     # what must hold is that graph replays keep optimising from wherever they start and match eager numerics step for step
     assert (w_e - init).abs().max().item() > 1e-4 and (w_g - init).abs().max().item() > 1e-4
     assert np.isfinite(l_g) and l_g < l_e + 0.5
+
+
+# ------------------------------------------------------------------------------ tensor-core head backward (tcgen05 split-K)
+@pytest.mark.parametrize("B,F,Din,Dout,act,cmvn", [(3, 101, 257, 257, "Sigmoid", True), (64, 251, 257, 257, "Sigmoid", True),
+                                                   (2, 300, 201, 201, "ReLU", False), (5, 64, 120, 201, "Identity", True),
+                                                   (9, 40, 129, 300, "Sigmoid", True)])
+def test_tensor_core_head_backward_matches_torch(se, B, F, Din, Dout, act, cmvn):
+    """The backward kernel in isolation: same offset / grad_offset into the fp32 SIMT kernel, the tcgen05 kernel and torch."""
+    from speech_enhancement_by_s3prl_b200 import ops
+    assert ops._lib.load().se_linear_head_bwd_tc_workspace(B, F, Din, Dout) > 0
+    g = torch.Generator().manual_seed(Din + F + B)
+    feats = (torch.randn(B, F, Din, generator=g) * 2 - 3).cuda()
+    offset = torch.rand(B, F, Dout, generator=g).cuda()
+    if act == "ReLU":
+        offset = (offset - 0.3).clamp_min(0.0)                                # exact zeros where the unit is off
+    grad_offset = torch.randn(B, F, Dout, generator=g).cuda()
+    weight = torch.randn(Dout, Din, generator=g).cuda()
+    mean = std = None
+    if cmvn:
+        mean, std = ops.cmvn_stats(feats)
+    code = ops.ACT[act]
+    gw0, gb0 = torch.ops.se_b200.linear_head_bwd(feats, mean, std, 1e-6, weight, offset, grad_offset, code, 0)
+    gw1, gb1 = torch.ops.se_b200.linear_head_bwd(feats, mean, std, 1e-6, weight, offset, grad_offset, code, 1)
+    torch.cuda.synchronize()
+    # torch reference in float64
+    xh = feats.double()
+    if cmvn:
+        xh = (xh - mean.double()[:, None, :]) / (std.double()[:, None, :] + 1e-6)
+    dz = grad_offset.double()
+    if act == "Sigmoid":
+        dz = dz * offset.double() * (1 - offset.double())
+    elif act == "ReLU":
+        dz = dz * (offset > 0).double()
+    gw_ref = torch.einsum("bfn,bfk->nk", dz, xh)
+    gb_ref = dz.sum((0, 1))
+    sw, sb = gw_ref.abs().max().item(), gb_ref.abs().max().item()
+    assert (gw0.double() - gw_ref).abs().max().item() < 2e-4 * sw             # fp32 kernel
+    assert torch.isfinite(gw1).all() and torch.isfinite(gb1).all()
+    # TF32 operands (2^-11 relative rounding each) in a length B*F reduction of random-sign terms
+    assert (gw1.double() - gw_ref).abs().max().item() < 2e-3 * sw
+    assert (gw1.double() - gw_ref).abs().mean().item() < 2e-4 * sw
+    assert (gb1.double() - gb_ref).abs().max().item() < 2e-3 * sb
+
+
+def test_tensor_core_head_trains_like_fp32_head(se):
+    """End to end through autograd: a few Adam steps with the tensor-core forward + backward track the fp32 head's loss."""
+    _, mine = make_pair(se, 512)
+    lengths, wavs = synth(4, 16000, seed=31)
+    lengths, wavs = lengths.cuda(), wavs.cuda()
+    losses = []
+    for precision in (0, 1):
+        torch.manual_seed(5)
+        head = se.LinearResidual(input_size=257, output_size=257, precision=precision).cuda()
+        eng = se.EnhancementEngine(mine, head, log_features=True, precision=precision)
+        opt = torch.optim.Adam(head.parameters(), lr=1e-3)
+        for _ in range(6):
+            loss = eng.train_step(lengths, wavs, se.SISDR(), opt, 1.0)
+        losses.append(loss.item())
+    assert losses[1] == pytest.approx(losses[0], abs=0.05)

@@ -8,8 +8,9 @@ for nfreq, win, hop in [(257, 32, 16), (201, 25, 10)]:
     pre = se.OnlinePreprocessor(sample_rate=16000, win_ms=win, hop_ms=hop, n_freq=nfreq).to(dev)
     pre.channel_inp, pre.channel_tar = 0, 1
     torch.manual_seed(1337)
-    head = se.LinearResidual(input_size=nfreq, output_size=nfreq).to(dev)
     for precision in (0, 1):
+        torch.manual_seed(1337)
+        head = se.LinearResidual(input_size=nfreq, output_size=nfreq, precision=precision).to(dev)
         eng = se.EnhancementEngine(pre, head, log_features=True, precision=precision)
         opt = torch.optim.Adam(head.parameters(), lr=1e-4)
         lengths, wavs = synth.batch(64, 4.0)
@@ -28,7 +29,7 @@ for nfreq, win, hop in [(257, 32, 16), (201, 25, 10)]:
         print(f"n_freq {nfreq} hop_ms {hop} precision {precision}: {ms:.3f} ms/step  {256 / ms * 1e3:.0f} audio-s/s  loss {loss.item():.4f}")
         del loss                                   # (keeps the eager autograd graph -- and its default-stream nodes -- alive)
         torch.manual_seed(1337)
-        head2 = se.LinearResidual(input_size=nfreq, output_size=nfreq).to(dev)
+        head2 = se.LinearResidual(input_size=nfreq, output_size=nfreq, precision=precision).to(dev)
         eng = se.EnhancementEngine(pre, head2, log_features=True, precision=precision)
         opt2 = torch.optim.Adam(head2.parameters(), lr=1e-4, capturable=True)
         for _ in range(3):
