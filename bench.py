@@ -282,26 +282,31 @@ def main():
     wpad = engine._padded_weight()
     LD = ops.round4(K)
     fused = engine.precision == 1 and ops.linear_head_tma_supported(N_UTT, F, K, K, LD, wpad.shape[1], LD)
+    use_ws = fused and engine.use_spec_ws and ops.spec_ws_supported(N_FFT, HOP)
     slots = []
     with torch.no_grad():
         for lengths, wavs in ring:
             sl = dict(lengths=lengths, wavs=wavs)
             if fused:
                 sl["stat_sums"] = torch.zeros(N_UTT, LD, 2, device=dev, dtype=torch.float64)
-                sl["feats"], _ = ops.stft_features(wavs, 0, N_FFT, HOP, window, logpower=True, stat_sums=sl["stat_sums"])
+                sl["spec_ws"] = torch.empty(N_UTT, F, ops.SPEC_WS_FLOATS, device=dev) if use_ws else None
+                sl["feats"], _ = ops.stft_features(wavs, 0, N_FFT, HOP, window, logpower=True, stat_sums=sl["stat_sums"],
+                                                   spec_ws=sl["spec_ws"])
                 sl["mask"] = ops.linear_head_tma(sl["feats"], K, wpad, head.linear.bias, head.activation, sl["stat_sums"], head.eps)
             else:
                 sl["feats"] = ops.stft_padded(wavs, 0, N_FFT, HOP, window, logpower=True)
                 sl["mean"], sl["std"] = ops.cmvn_stats_padded(sl["feats"], K)
                 sl["mask"] = ops.linear_head_padded(sl["feats"], K, wpad, head.linear.bias, head.activation, sl["mean"], sl["std"], head.eps,
                                                     precision=engine.precision)
-            sl["wav"], sl["sums"] = ops.mask_istft(wavs, 0, 1, sl["mask"], lengths, N_FFT, HOP, window, pad_to=T, mask_padded=True)
+            sl["wav"], sl["sums"] = ops.mask_istft(wavs, 0, 1, sl["mask"], lengths, N_FFT, HOP, window, pad_to=T, mask_padded=True,
+                                                   spec_ws=sl.get("spec_ws"))
             slots.append(sl)
     torch.cuda.synchronize()
     if fused:
         # (the sums buffer keeps accumulating across timing launches: the values are not used here)
         launchers = {
-            "stft": lambda s: ops.stft_features(s["wavs"], 0, N_FFT, HOP, window, logpower=True, stat_sums=s["stat_sums"]),
+            "stft": lambda s: ops.stft_features(s["wavs"], 0, N_FFT, HOP, window, logpower=True, stat_sums=s["stat_sums"],
+                                                spec_ws=s["spec_ws"]),
             "head": lambda s: ops.linear_head_tma(s["feats"], K, wpad, head.linear.bias, head.activation, s["stat_sums"], head.eps),
         }
     else:
@@ -312,7 +317,7 @@ def main():
                                                      precision=engine.precision),
         }
     launchers["mask_istft"] = lambda s: ops.mask_istft(s["wavs"], 0, 1, s["mask"], s["lengths"], N_FFT, HOP, window, pad_to=T,
-                                                       mask_padded=True, out=s["wav"], sums=s["sums"])
+                                                       mask_padded=True, out=s["wav"], sums=s["sums"], spec_ws=s.get("spec_ws"))
     launchers["finalize"] = lambda s: ops.finalize_metrics(s["sums"], s["lengths"], T, wav=s["wav"])
     kernel_ms = {}
     reps = max(3, min(20, args.steps // len(slots)))

@@ -153,9 +153,13 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 
 // write the requested outputs of one frame (lane j of a half-warp holds Z[j + 16 q] and the mirrored bins);
 // `acc` (STATS): the half-warp's private (sum x, sum x^2) accumulators in shared memory, updated for the feature written
-template <bool POWER, bool PHASE, bool LOGP, bool STATS>
+// CSPEC: the complex spectrum goes to the workspace row `cs` in the layout K3 consumes (kSpecFloats per frame):
+// float4 (X[k], X[M-k]) at index 16 q + j for k = j + 16 q < 128, and X[128] at floats 512, 513.
+constexpr int kSpecFloats = SE_SPEC_WS_FLOATS;
+template <bool POWER, bool PHASE, bool LOGP, bool STATS, bool CSPEC = false>
 __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (&zm)[8], const float2 (&twn)[8], int j,
-                                           const StftArgs& a, long long o, float2* __restrict__ acc) {
+                                           const StftArgs& a, long long o, float2* __restrict__ acc,
+                                           float* __restrict__ cs = nullptr) {
     float* pw = POWER ? a.power + o : nullptr;
     float* lg = LOGP ? a.logp + o : nullptr;
     float* ph = PHASE ? a.phase + o : nullptr;
@@ -167,6 +171,7 @@ __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (
         const int k = j + 16 * q;
         float2 xa, xb;
         split_pair(v[q], zm[q], twn[q], xa, xb);
+        if (CSPEC) reinterpret_cast<float4*>(cs)[16 * q + j] = make_float4(xa.x, xa.y, xb.x, xb.y);
         const float pa = xa.x * xa.x + xa.y * xa.y, pb = xb.x * xb.x + xb.y * xb.y;
         if (POWER) { pw[k] = pa; pw[M - k] = pb; }
         float la = 0.f, lb = 0.f;
@@ -177,6 +182,7 @@ __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (
     }
     if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
         const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
+        if (CSPEC) reinterpret_cast<float2*>(cs)[256] = x;
         const float p = x.x * x.x + x.y * x.y;
         float l = 0.f;
         if (POWER) pw[128] = p;
@@ -241,7 +247,7 @@ constexpr size_t kSmem1Run = (size_t)(kWarps1 * 2) * kHwBytes1 + M * 8 + (kWarps
 
 struct StftRunPlan { int runs_per_utt; long long total_runs; };
 
-template <bool POWER, bool PHASE, bool LOGP, bool STATS>
+template <bool POWER, bool PHASE, bool LOGP, bool STATS, bool CSPEC = false>
 __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, StftRunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem1[];
     secommon::TraceScope trace(a.trace, 1);
@@ -297,7 +303,8 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
             fft256<-1>(v, xbuf, j, tw, hmask);
             float2 zm[8];
             fetch_mirror(v, lane, zm);
-            emit_frame<POWER, PHASE, LOGP, STATS>(v, zm, twn, j, a, ((long long)u * F + f) * a.spec_stride, acc);
+            emit_frame<POWER, PHASE, LOGP, STATS, CSPEC>(v, zm, twn, j, a, ((long long)u * F + f) * a.spec_stride, acc,
+                                                         CSPEC ? a.cspec + ((long long)u * F + f) * kSpecFloats : nullptr);
         }
     }
     if (threadIdx.x == 0) trace.mark(18);
@@ -384,17 +391,31 @@ struct RunPlan { int blocks_per_utt; int runs_per_utt; long long total_runs; }; 
 #define SE_K3_MIN_BLOCKS 3
 #endif
 constexpr int kMaskFloats3 = 272;
-// per half-warp: transpose buffer | noisy slots 2 x 256 | clean slots 2 x 256 | mask row
-constexpr int kHwBytes3 = M * 8 + 4 * H * 4 + kMaskFloats3 * 4;
+// per half-warp: transpose buffer | noisy slots 2 x 256 (CS: one spectrum row of K1's workspace) | clean slots 2 x 256 | mask row
+constexpr int kNoisyBytes3 = kSpecFloats * 4 > 2 * H * 4 ? kSpecFloats * 4 : 2 * H * 4;
+constexpr int kHwBytes3 = M * 8 + kNoisyBytes3 + 2 * H * 4 + kMaskFloats3 * 4;
 constexpr size_t kSmem3 = (size_t)(kWarps3 * 2) * kHwBytes3 + 2 * M * 8;
-static_assert(kHwBytes3 % 16 == 0, "16-byte aligned cp.async destinations");
+static_assert(kHwBytes3 % 16 == 0 && kNoisyBytes3 % 16 == 0, "16-byte aligned cp.async destinations");
 
+// One masked pair of bins: spectral-loss terms (own) and the merged, conjugated inverse-FFT input
+__device__ __forceinline__ void mask_merge(float2 xa, float2 xb, float ga, float gb, float2 w, bool own, float& ra, float& rb,
+                                           float2& ca, float2& cb) {
+    if (own) {
+        ra = fmaxf(ga * (xa.x * xa.x + xa.y * xa.y), 0.0f);
+        rb = fmaxf(gb * (xb.x * xb.x + xb.y * xb.y), 0.0f);
+    }
+    merge_pair_conj(cscale(xa, fast_sqrt(ga)), cscale(xb, fast_sqrt(gb)), w, ca, cb);
+}
+
+// CS: the noisy spectrum comes from K1's workspace (a.cspec) instead of being recomputed from the waveform -- one transform
+// less per frame.  cp.async groups are then [spectrum row + mask row], [clean] per frame.
+template <bool CS>
 __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem3[];
     secommon::TraceScope trace(a.trace, 3);
     float2* s_win2 = reinterpret_cast<float2*>(smem3 + (size_t)(kWarps3 * 2) * kHwBytes3);
     float2* s_bw2 = s_win2 + M;
-    {   // the first frame's noisy samples come from HBM and do not depend on the upstream kernel: loads in flight first
+    if (!CS) {   // the first frame's noisy samples come from HBM and do not depend on the upstream kernel: loads in flight first
         const int hw0 = threadIdx.x >> 4, j0 = threadIdx.x & 15;
         const long long unit0 = (long long)blockIdx.x * (kThreads3 / 16) + hw0;
         if (unit0 < plan.total_runs) {
@@ -425,8 +446,8 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     griddep_launch();
     unsigned char* mine = smem3 + (size_t)hw * kHwBytes3;
     float2* xbuf = reinterpret_cast<float2*>(mine);
-    float* nb = reinterpret_cast<float*>(mine + M * 8);            // noisy slots
-    float* cb = nb + 2 * H;                                        // clean slots
+    float* nb = reinterpret_cast<float*>(mine + M * 8);            // noisy slots (CS: spectrum row)
+    float* cb = reinterpret_cast<float*>(mine + M * 8 + kNoisyBytes3);   // clean slots
     float* mb = cb + 2 * H;                                        // mask row
     const long long unit = (long long)blockIdx.x * (kThreads3 / 16) + hw;
     if (unit >= plan.total_runs) { griddep_wait(); return; }      // no block-level barrier below (tracing: approximate for ragged CTAs)
@@ -458,6 +479,14 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
     // are inputs of the step, so their first loads are issued before waiting for the upstream kernel (the mask's producer).
     const int f0 = b0 - 1;                                        // (its noisy samples were requested at the top: group N)
     griddep_wait();                                               // the mask (and the zeroed sums) come from upstream kernels
+    const float* srow0 = CS ? a.cspec + (long long)u * F * kSpecFloats : nullptr;
+    auto stage_spec = [&](int f) {                                // one workspace row: 129 x 16 bytes
+        const float* src = srow0 + (long long)f * kSpecFloats;
+#pragma unroll
+        for (int c = 0; c < 9; ++c)
+            if (j + 16 * c < kSpecFloats / 4) cp_async16(nb + 4 * (j + 16 * c), src + 4 * (j + 16 * c));
+    };
+    if (CS) stage_spec(f0);
     stage_row(mb, mrow0 + (long long)f0 * a.mask_stride, M + 1, j, mask_padded);
     cp_async_commit();
     if (need_clean) {
@@ -476,9 +505,33 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
 #pragma unroll
         for (int q = 0; q < 8; ++q) { ra[q] = 0.0f; rb[q] = 0.0f; }
         float2 v[16];
+        if (CS) {
+            // pass 0 without a transform: X[k], X[M-k] from the staged workspace row
+            cp_async_wait<1>();                                     // spectrum + mask rows of frame f have landed
+            __syncwarp(hmask);
+            float2 ca[8], cbv[8];
+            const float4* s4 = reinterpret_cast<const float4*>(nb);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 x = s4[16 * q + j];
+                mask_merge(make_float2(x.x, x.y), make_float2(x.z, x.w), mb[j + 16 * q], mb[M - j - 16 * q], twn[q], own,
+                           ra[q], rb[q], ca[q], cbv[q]);
+            }
+            const float g128 = mb[128];
+            const float2 x128 = reinterpret_cast<const float2*>(nb)[256];
+            if (own) r128 = fmaxf(g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
+            __syncwarp(hmask);
+            if (more) {
+                stage_spec(f + 1);
+                stage_row(mb, mrow0 + (long long)(f + 1) * a.mask_stride, M + 1, j, mask_padded);
+            }
+            cp_async_commit();
+            const float s128 = 2.0f * fast_sqrt(g128);
+            scatter_mirror(ca, cbv, make_float2(s128 * x128.x, s128 * x128.y), lane, v);
+        }
 #pragma unroll 1
-        for (int pass = 0; pass < (own ? 3 : 2); ++pass) {
-            if (pass == 0) {
+        for (int pass = CS ? 1 : 0; pass < (own ? 3 : 2); ++pass) {
+            if (!CS && pass == 0) {
                 cp_async_wait<2>();                                 // N(f) has landed
                 __syncwarp(hmask);
                 frame_from_slots(nb + p * H, nb + (p ^ 1) * H, j, s_win2, v);
@@ -489,7 +542,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 frame_from_slots(cb + p * H, cb + (p ^ 1) * H, j, s_win2, v);        // C(f) landed before pass 1's overlap-add
             }
             fft256<-1>(v, xbuf, j, tw, hmask);
-            if (pass == 0) {
+            if (!CS && pass == 0) {
                 float2 zm[8];
                 fetch_mirror(v, lane, zm);
                 cp_async_wait<2>();                                 // M(f) has landed
@@ -497,14 +550,9 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 float2 ca[8], cbv[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float ga = mb[j + 16 * q], gb = mb[M - j - 16 * q];
                     float2 xa, xb;
                     split_pair(v[q], zm[q], twn[q], xa, xb);
-                    if (own) {
-                        ra[q] = fmaxf(ga * (xa.x * xa.x + xa.y * xa.y), 0.0f);
-                        rb[q] = fmaxf(gb * (xb.x * xb.x + xb.y * xb.y), 0.0f);
-                    }
-                    merge_pair_conj(cscale(xa, fast_sqrt(ga)), cscale(xb, fast_sqrt(gb)), twn[q], ca[q], cbv[q]);
+                    mask_merge(xa, xb, mb[j + 16 * q], mb[M - j - 16 * q], twn[q], own, ra[q], rb[q], ca[q], cbv[q]);
                 }
                 const float g128 = mb[128];
                 const float2 x128 = make_float2(2.0f * v[8].x, -2.0f * v[8].y);    // k = 128 pairs with itself: X = 2 conj(Z[128])
@@ -517,7 +565,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 scatter_mirror(ca, cbv, make_float2(s128 * x128.x, s128 * x128.y), lane, v);
             } else if (pass == 1) {
                 // v[q] = conj(z[m]), z[m] = (x[2m], x[2m+1]) unnormalised, m = j + 16 q; signs and scales are in s_bw2
-                cp_async_wait<2>();                                 // C(f) has landed
+                if (CS) cp_async_wait<1>(); else cp_async_wait<2>();   // C(f) has landed
                 __syncwarp(hmask);
                 if (!halo) {
                     const int t0 = (f - 1) * H;
@@ -648,7 +696,10 @@ int prepare512() {
     SE_OPT((stft512_run_kernel<true, true, true, false>), kSmem1Run);
     SE_OPT((stft512_run_kernel<true, false, false, true>), kSmem1Run);
     SE_OPT((stft512_run_kernel<false, false, true, true>), kSmem1Run);
-    SE_OPT(mask_istft512_kernel, kSmem3);
+    SE_OPT((stft512_run_kernel<true, false, false, true, true>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<false, false, true, true, true>), kSmem1Run);
+    SE_OPT(mask_istft512_kernel<false>, kSmem3);
+    SE_OPT(mask_istft512_kernel<true>, kSmem3);
 #undef SE_OPT
     return SE_OK;
 }
@@ -675,12 +726,14 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
         const long long grid = (plan.total_runs + per_it - 1) / per_it;
         if (grid > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "grid too large");
 #define SE_RUN(P, Q, L, S) stft512_run_kernel<P, Q, L, S><<<(unsigned)grid, kThreads1, kSmem1Run, st>>>(a, plan)
+#define SE_RUN_CS(P, Q, L) stft512_run_kernel<P, Q, L, true, true><<<(unsigned)grid, kThreads1, kSmem1Run, st>>>(a, plan)
         if (a.stat_sums) {
             // statistics of the ONE feature written: log-power (sel 4) or power (sel 1)
-            if (sel == 4) SE_RUN(false, false, true, true);
-            else if (sel == 1) SE_RUN(true, false, false, true);
+            if (sel == 4) { if (a.cspec) SE_RUN_CS(false, false, true); else SE_RUN(false, false, true, true); }
+            else if (sel == 1) { if (a.cspec) SE_RUN_CS(true, false, false); else SE_RUN(true, false, false, true); }
             else return secommon::fail(SE_ERR_BAD_ARG, "statistics need exactly one of power / logpower");
         } else {
+            if (a.cspec) return secommon::fail(SE_ERR_UNSUPPORTED, "the spectrum workspace is written by the statistics variants only");
             switch (sel) {
                 case 1: SE_RUN(true, false, false, false); break;
                 case 2: SE_RUN(false, true, false, false); break;
@@ -692,9 +745,10 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
             }
         }
 #undef SE_RUN
+#undef SE_RUN_CS
         return secommon::check_launch("stft512_run_kernel");
     }
-    if (a.stat_sums) return secommon::fail(SE_ERR_UNSUPPORTED, "fused statistics need hop = 256");
+    if (a.stat_sums || a.cspec) return secommon::fail(SE_ERR_UNSUPPORTED, "fused statistics / spectrum workspace need hop = 256");
     const long long want = (total + per_it - 1) / per_it;
     const long long cap = 2LL * num_sms();
     const unsigned grid = (unsigned)(want < cap ? want : cap);
@@ -746,7 +800,8 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = (secommon::pdl_mask() & 2) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel, a, plan));
+    if (a.cspec) SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<true>, a, plan));
+    else SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<false>, a, plan));
     return secommon::check_launch("mask_istft512_kernel");
 }
 

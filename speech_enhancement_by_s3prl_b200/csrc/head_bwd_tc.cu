@@ -12,7 +12,9 @@
 //                the B tile is the constant 1, so grad_b falls out of the GEMM as column D_in of D.
 //   * warp 8     tcgen05.mma kind::tf32 (M = 128, N = 256 + 16), commits stages back to the producers
 //   * epilogue   tcgen05.ld -> staging tile -> coalesced stores of the CTA's partial into the workspace
-// A second kernel sums the partials over the splits into grad_W / grad_b.
+// Output rows that do not fill a 128-row tile are few when D_out = 257 (one row): up to kMaxSimtRows such rows go through a
+// SIMT dot-product pass (by the CTAs of the first tile, after their epilogue) instead of a third tensor-core tile that would
+// transpose the whole B operand again for one useful row.  A second kernel sums the partials over the splits into grad_W / grad_b.
 #include "se_common.cuh"
 
 using secommon::fail;
@@ -26,6 +28,7 @@ constexpr int kMaxBRows = 272;
 constexpr int kBTileBytes = kMaxBRows * BK * 4;                // 34 816
 constexpr int kStageBytes = kATileBytes + kBTileBytes;         // 51 200
 constexpr int kMaxUtt = 4;                                     // utterances one CTA's row range may touch
+constexpr int kMaxSimtRows = 4;                                // leftover output rows handled without the tensor cores
 constexpr int kOffRing = 0;
 constexpr int kOffStats = kOffRing + kStages * kStageBytes;    // [kMaxUtt][272] (mean, 1/(std+eps))
 constexpr int kOffBar = kOffStats + kMaxUtt * kMaxBRows * 8;
@@ -104,9 +107,45 @@ struct BwdArgs {
     long long rows_per_split;      // multiple of 32
     int b_rows;                    // round16(Din + 1) <= 272
     int n_main, n_tail;
-    float* partials;               // (splits, m_tiles * 128, 272)
-    int m_rows;                    // m_tiles * 128
+    float* partials;               // (splits, m_rows, 272)
+    int m_rows;                    // m_tiles * 128 + simt_rows
+    int m_tiles, simt_rows;        // tensor-core tiles; leftover rows [128 m_tiles, 128 m_tiles + simt_rows) done by SIMT CTAs
 };
+
+// dZ = grad_offset * act'(offset)
+__device__ __forceinline__ float dact(float g, float o, int act) {
+    if (act == SE_ACT_SIGMOID) return g * (o * (1.0f - o));
+    if (act == SE_ACT_RELU) return o > 0.f ? g : 0.f;
+    return g;
+}
+
+// leftover rows: partial[n][k] = sum_r dZ[r, n] * xhat[r, k] for n in [n_base, n_base + nrows), thread per k
+__device__ __forceinline__ void simt_rows_block(const BwdArgs& a, long long ra, long long rb, int n_base, int nrows, float* dst) {
+    for (int k = threadIdx.x; k <= a.Din; k += kThreads) {
+        float acc[kMaxSimtRows];
+#pragma unroll
+        for (int i = 0; i < kMaxSimtRows; ++i) acc[i] = 0.0f;
+        long long r = ra;
+        while (r < rb) {
+            const long long u = r / a.n_frames;
+            long long r_end = (u + 1) * a.n_frames;
+            if (r_end > rb) r_end = rb;
+            float m = 0.0f, rs = 1.0f;
+            if (a.mean && k < a.Din) { m = __ldg(a.mean + u * a.ld_stats + k); rs = 1.0f / (__ldg(a.stdv + u * a.ld_stats + k) + a.cmvn_eps); }
+#pragma unroll 4
+            for (; r < r_end; ++r) {
+                const float xh = k < a.Din ? (__ldg(a.x + r * a.ldx + k) - m) * rs : 1.0f;
+#pragma unroll
+                for (int i = 0; i < kMaxSimtRows; ++i)
+                    if (i < nrows)
+                        acc[i] += dact(__ldg(a.grad_offset + r * a.ld_off + n_base + i), __ldg(a.offset + r * a.ld_off + n_base + i), a.act) * xh;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxSimtRows; ++i)
+            if (i < nrows) dst[(long long)i * kMaxBRows + k] = acc[i];
+    }
+}
 
 __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const BwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -156,49 +195,74 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
             unsigned char* At = smem + kOffRing + s * kStageBytes;
             unsigned char* Bt = At + kATileBytes;
             const long long r0 = ra + (long long)kb * BK;
-            // A tile: dZ^T.  item -> (n = item & 127, chunk c = item >> 7): rows r0 + 4c .. + 3
+            const bool full = r0 + BK <= rb;                               // all 32 rows of the block exist
+            // A tile: dZ^T.  thread -> one n, the chunks c = (t >> 7) + 2 i: 16 row-strided loads in flight per pass
+            {
+                const int n = t & (BM - 1), ch = t >> 7;
+                const bool nvalid = n0 + n < a.Dout;
+                const float* po = a.offset + r0 * a.ld_off + n0 + n;
+                const float* pg = a.grad_offset + r0 * a.ld_off + n0 + n;
 #pragma unroll
-            for (int i = 0; i < (BM * 8) / kProdThreads; ++i) {
-                const int item = t + kProdThreads * i;
-                const int n = item & (BM - 1), c = item >> 7;
-                float g[4] = {0.f, 0.f, 0.f, 0.f};
-                if (n0 + n < a.Dout) {
+                for (int pass = 0; pass < 2; ++pass) {
+                    float o[8], g[8];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const long long r = r0 + 4 * c + jj;
-                        if (r < rb) {
-                            const float o = __ldg(a.offset + r * a.ld_off + n0 + n);
-                            float v = __ldg(a.grad_offset + r * a.ld_off + n0 + n);
-                            if (a.act == SE_ACT_SIGMOID) v *= o * (1.0f - o);
-                            else if (a.act == SE_ACT_RELU) v = o > 0.f ? v : 0.f;
-                            g[jj] = v;
-                        }
+                    for (int e = 0; e < 8; ++e) {
+                        const int rr = 4 * (ch + 2 * (2 * pass + (e >> 2))) + (e & 3);
+                        const bool ok = nvalid && (full || r0 + rr < rb);
+                        o[e] = ok ? __ldg(po + (long long)rr * a.ld_off) : 0.0f;
+                        g[e] = ok ? __ldg(pg + (long long)rr * a.ld_off) : 0.0f;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = ch + 2 * (2 * pass + h);
+                        *reinterpret_cast<float4*>(At + n * 128 + ((c ^ (n & 7)) << 4)) =
+                            make_float4(to_tf32(dact(g[4 * h], o[4 * h], a.act)), to_tf32(dact(g[4 * h + 1], o[4 * h + 1], a.act)),
+                                        to_tf32(dact(g[4 * h + 2], o[4 * h + 2], a.act)), to_tf32(dact(g[4 * h + 3], o[4 * h + 3], a.act)));
                     }
                 }
-                *reinterpret_cast<float4*>(At + n * 128 + ((c ^ (n & 7)) << 4)) =
-                    make_float4(to_tf32(g[0]), to_tf32(g[1]), to_tf32(g[2]), to_tf32(g[3]));
             }
-            // B tile: xhat^T with the ones column at k = Din.  item -> (k = item % b_rows, chunk c = item / b_rows)
+            // B tile: xhat^T with the ones column at k = Din.  thread -> column k = t (all 8 chunks, 32 rows); the columns
+            // 256 .. b_rows - 1 are shared out afterwards as (k = 256 + (t & 15), chunk t >> 4) over the first 128 threads
             const long long uq = r0 / a.n_frames;                          // utterance of the block's first row
-            const int ul0 = (int)(uq - u_first), bnd = (int)((uq + 1) * a.n_frames - r0);   // rows of the block before the next one
-            for (int item = t; item < a.b_rows * 8; item += kProdThreads) {
-                const int c = item / a.b_rows, k = item - c * a.b_rows;
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const int ul0 = (int)(uq - u_first);
+            const int bnd = (int)((uq + 1) * a.n_frames - r0);             // rows of the block before the next utterance (n_frames >= 32)
+            auto b_column = [&](int k, int c_lo, int c_hi) {
+                const bool isx = k < a.Din;
+                const float2 st0 = s_stats[ul0 * kMaxBRows + k];
+                const float2 st1 = bnd < BK ? s_stats[(ul0 + 1) * kMaxBRows + k] : st0;
+                const float* px = a.x + r0 * a.ldx + (isx ? k : 0);
+                const float fill = k == a.Din ? 1.0f : 0.0f;
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const long long r = r0 + 4 * c + jj;
-                    if (r < rb) {
-                        if (k < a.Din) {
-                            const int ul = a.n_frames >= BK ? ul0 + (4 * c + jj >= bnd ? 1 : 0) : (int)(r / a.n_frames - u_first);
-                            const float2 st = s_stats[ul * kMaxBRows + k];
-                            v[jj] = (__ldg(a.x + r * a.ldx + k) - st.x) * st.y;
-                        } else if (k == a.Din) {
-                            v[jj] = 1.0f;
+                for (int c4 = c_lo; c4 < c_hi; c4 += 4) {
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int rr = 4 * c4 + e;
+                        const bool ok = (c4 + (e >> 2) < c_hi) && (full || r0 + rr < rb);
+                        v[e] = (ok && isx) ? __ldg(px + (long long)rr * a.ldx) : (ok ? fill : 0.0f);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int c = c4 + h;
+                        if (c < c_hi) {
+                            float w[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int rr = 4 * c + jj;
+                                const float2 st = rr >= bnd ? st1 : st0;
+                                w[jj] = isx ? (v[4 * h + jj] - st.x) * st.y : v[4 * h + jj];
+                                if (!full && r0 + rr >= rb) w[jj] = 0.0f;
+                            }
+                            *reinterpret_cast<float4*>(Bt + k * 128 + ((c ^ (k & 7)) << 4)) =
+                                make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
                         }
                     }
                 }
-                *reinterpret_cast<float4*>(Bt + k * 128 + ((c ^ (k & 7)) << 4)) =
-                    make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+            };
+            if (t < a.b_rows) b_column(t, 0, 8);
+            if (a.b_rows > kProdThreads && t < 16 * 8) {
+                const int k = kProdThreads + (t & 15), c = t >> 4;
+                if (k < a.b_rows) b_column(k, c, c + 1);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
             __syncwarp();
@@ -257,6 +321,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
+    // leftover output rows of this split (the CTAs of the first tile take them: a few L2-resident dot products)
+    if (a.simt_rows > 0 && blockIdx.y == 0)
+        simt_rows_block(a, ra, rb, a.m_tiles * BM, a.simt_rows, a.partials + ((long long)split * a.m_rows + a.m_tiles * BM) * kMaxBRows);
 }
 
 // grad_W[n, k] = sum_s partials[s, n, k], grad_b[n] = sum_s partials[s, n, Din]
@@ -292,11 +359,14 @@ int num_sms() {
     return sms;
 }
 
-struct Geometry { int m_tiles, splits; long long rows_per_split; };
+struct Geometry { int m_tiles, simt_rows, m_rows, splits; long long rows_per_split; };
 
 bool plan(long long R, long long n_frames, long long Din, long long Dout, Geometry* g) {
-    if (R <= 0 || n_frames <= 0 || Din <= 0 || Dout <= 0 || Din + 1 > kMaxBRows) return false;
-    g->m_tiles = (int)((Dout + BM - 1) / BM);
+    if (R <= 0 || n_frames < BK || Din <= 0 || Dout <= 0 || Din + 1 > kMaxBRows) return false;
+    const int rem = (int)(Dout % BM);
+    g->simt_rows = (Dout > BM && rem > 0 && rem <= kMaxSimtRows) ? rem : 0;
+    g->m_tiles = (int)((Dout - g->simt_rows + BM - 1) / BM);
+    g->m_rows = g->m_tiles * BM + g->simt_rows;
     long long splits = num_sms() / g->m_tiles;
     if (splits < 1) splits = 1;
     long long rows = (R + splits - 1) / splits;
@@ -314,7 +384,7 @@ extern "C" {
 int64_t se_linear_head_bwd_tc_workspace(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out) {
     Geometry g;
     if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g)) return 0;
-    return (int64_t)g.splits * g.m_tiles * BM * kMaxBRows;
+    return (int64_t)g.splits * g.m_rows * kMaxBRows;
 }
 
 int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const float* std, int64_t ld_stats, float cmvn_eps,
@@ -329,7 +399,7 @@ int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const 
     if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g))
         return fail(SE_ERR_UNSUPPORTED, "tensor-core head backward: shape outside its range (D_in=%lld, n_frames=%lld)",
                     (long long)D_in, (long long)n_frames);
-    SE_REQUIRE(ws_floats >= (int64_t)g.splits * g.m_tiles * BM * kMaxBRows, "workspace too small");
+    SE_REQUIRE(ws_floats >= (int64_t)g.splits * g.m_rows * kMaxBRows, "workspace too small");
     BwdArgs a{};
     a.x = x; a.ldx = ldx; a.mean = mean; a.stdv = std; a.ld_stats = ld_stats; a.cmvn_eps = cmvn_eps;
     a.offset = offset; a.grad_offset = grad_offset; a.ld_off = ld_off;
@@ -339,7 +409,7 @@ int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const 
     a.n_main = a.b_rows > 256 ? 256 : a.b_rows;
     a.n_tail = a.b_rows - a.n_main;
     a.partials = ws_partials;
-    a.m_rows = g.m_tiles * BM;
+    a.m_rows = g.m_rows; a.m_tiles = g.m_tiles; a.simt_rows = g.simt_rows;
     static bool opted = false;
     if (!opted) {
         SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
