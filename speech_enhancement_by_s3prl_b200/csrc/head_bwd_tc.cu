@@ -13,8 +13,8 @@
 //   * warp 8     tcgen05.mma kind::tf32 (M = 128, N = 256 + 16), commits stages back to the producers
 //   * epilogue   tcgen05.ld -> staging tile -> coalesced stores of the CTA's partial into the workspace
 // Output rows that do not fill a 128-row tile are few when D_out = 257 (one row): up to kMaxSimtRows such rows go through a
-// SIMT dot-product pass (by the CTAs of the first tile, after their epilogue) instead of a third tensor-core tile that would
-// transpose the whole B operand again for one useful row.  A second kernel sums the partials over the splits into grad_W / grad_b.
+// fp32 dot products accumulated by the B-operand producers of the first tile's CTAs (they hold xhat in registers anyway)
+// instead of a third tensor-core tile that would transpose the whole B operand again for one useful row.  A second kernel sums the partials over the splits into grad_W / grad_b.
 #include "se_common.cuh"
 
 using secommon::fail;
@@ -31,12 +31,15 @@ constexpr int kMaxUtt = 4;                                     // utterances one
 constexpr int kMaxSimtRows = 4;                                // leftover output rows handled without the tensor cores
 constexpr int kOffRing = 0;
 constexpr int kOffStats = kOffRing + kStages * kStageBytes;    // [kMaxUtt][272] (mean, 1/(std+eps))
-constexpr int kOffBar = kOffStats + kMaxUtt * kMaxBRows * 8;
+constexpr int kOffDz = kOffStats + kMaxUtt * kMaxBRows * 8;    // [2][kMaxSimtRows][32] dZ of the leftover rows, double-buffered
+constexpr int kOffTail = kOffDz + 2 * 4 * 32 * 4;              // [kMaxSimtRows][16][8] partial sums of the shared-out columns
+constexpr int kOffBar = kOffTail + 4 * 16 * 8 * 4;
 constexpr int kNumBars = 2 * kStages + 1;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 constexpr int kStageLd = 276;                                  // staging row stride (floats): conflict-free STS.128 by row
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kMaxSimtRows == 4, "kOffDz / kOffTail are sized for 4 leftover rows");
 static_assert(BM * kStageLd * 4 <= kStages * kStageBytes, "staging tile fits in the ring");
 constexpr unsigned kSpinLimit = 1u << 22;
 
@@ -119,38 +122,12 @@ __device__ __forceinline__ float dact(float g, float o, int act) {
     return g;
 }
 
-// leftover rows: partial[n][k] = sum_r dZ[r, n] * xhat[r, k] for n in [n_base, n_base + nrows), thread per k
-__device__ __forceinline__ void simt_rows_block(const BwdArgs& a, long long ra, long long rb, int n_base, int nrows, float* dst) {
-    for (int k = threadIdx.x; k <= a.Din; k += kThreads) {
-        float acc[kMaxSimtRows];
-#pragma unroll
-        for (int i = 0; i < kMaxSimtRows; ++i) acc[i] = 0.0f;
-        long long r = ra;
-        while (r < rb) {
-            const long long u = r / a.n_frames;
-            long long r_end = (u + 1) * a.n_frames;
-            if (r_end > rb) r_end = rb;
-            float m = 0.0f, rs = 1.0f;
-            if (a.mean && k < a.Din) { m = __ldg(a.mean + u * a.ld_stats + k); rs = 1.0f / (__ldg(a.stdv + u * a.ld_stats + k) + a.cmvn_eps); }
-#pragma unroll 4
-            for (; r < r_end; ++r) {
-                const float xh = k < a.Din ? (__ldg(a.x + r * a.ldx + k) - m) * rs : 1.0f;
-#pragma unroll
-                for (int i = 0; i < kMaxSimtRows; ++i)
-                    if (i < nrows)
-                        acc[i] += dact(__ldg(a.grad_offset + r * a.ld_off + n_base + i), __ldg(a.offset + r * a.ld_off + n_base + i), a.act) * xh;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kMaxSimtRows; ++i)
-            if (i < nrows) dst[(long long)i * kMaxBRows + k] = acc[i];
-    }
-}
-
 __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const BwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     float2* s_stats = reinterpret_cast<float2*>(smem + kOffStats);
+    float* s_dz = reinterpret_cast<float*>(smem + kOffDz);
+    float* s_tail = reinterpret_cast<float*>(smem + kOffTail);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
     const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -189,84 +166,141 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
     if (warp < kProdWarps) {
         // ===================== producers: transpose both operands into K-major tiles =====================
         const int t = threadIdx.x;
+        // leftover output rows [128 m_tiles, +simt_rows): the thread that normalises column k of a block also accumulates
+        // sum_r dZ[r, n_left] * xhat[r, k] in fp32 (dZ of the block's 32 rows is shared through s_dz); first-tile CTAs only
+        const bool do_left = a.simt_rows > 0 && blockIdx.y == 0;
+        const int n_left = a.m_tiles * BM;
+        float acc_l[kMaxSimtRows], acc_t[kMaxSimtRows];
+#pragma unroll
+        for (int i = 0; i < kMaxSimtRows; ++i) { acc_l[i] = 0.0f; acc_t[i] = 0.0f; }
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % kStages;
-            if (kb >= kStages) mbar_wait(bar_empty + 8 * s, ((kb / kStages) - 1) & 1);
             unsigned char* At = smem + kOffRing + s * kStageBytes;
             unsigned char* Bt = At + kATileBytes;
             const long long r0 = ra + (long long)kb * BK;
             const bool full = r0 + BK <= rb;                               // all 32 rows of the block exist
-            // A tile: dZ^T.  thread -> one n, the chunks c = (t >> 7) + 2 i: 16 row-strided loads in flight per pass
+            const int n = t & (BM - 1), ch = t >> 7;
+            const bool nvalid = n0 + n < a.Dout;
+            const bool kvalid = t < a.b_rows, isx = t < a.Din;
+            // ---- every global load of the block is issued before anything is consumed (96 per thread in flight)
+            float ao[32], ag[32], bv[32];
             {
-                const int n = t & (BM - 1), ch = t >> 7;
-                const bool nvalid = n0 + n < a.Dout;
                 const float* po = a.offset + r0 * a.ld_off + n0 + n;
                 const float* pg = a.grad_offset + r0 * a.ld_off + n0 + n;
+                const float* px = a.x + r0 * a.ldx + (isx ? t : 0);
 #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    float o[8], g[8];
+                for (int e = 0; e < 16; ++e) {                             // A: chunks c = ch + 2 (e >> 2), rows 4 c + (e & 3)
+                    const int rr = 4 * (ch + 2 * (e >> 2)) + (e & 3);
+                    const bool ok = nvalid && (full || r0 + rr < rb);
+                    ao[e] = ok ? __ldg(po + (long long)rr * a.ld_off) : 0.0f;
+                    ag[e] = ok ? __ldg(pg + (long long)rr * a.ld_off) : 0.0f;
+                }
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int rr = 4 * (ch + 2 * (2 * pass + (e >> 2))) + (e & 3);
-                        const bool ok = nvalid && (full || r0 + rr < rb);
-                        o[e] = ok ? __ldg(po + (long long)rr * a.ld_off) : 0.0f;
-                        g[e] = ok ? __ldg(pg + (long long)rr * a.ld_off) : 0.0f;
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int c = ch + 2 * (2 * pass + h);
-                        *reinterpret_cast<float4*>(At + n * 128 + ((c ^ (n & 7)) << 4)) =
-                            make_float4(to_tf32(dact(g[4 * h], o[4 * h], a.act)), to_tf32(dact(g[4 * h + 1], o[4 * h + 1], a.act)),
-                                        to_tf32(dact(g[4 * h + 2], o[4 * h + 2], a.act)), to_tf32(dact(g[4 * h + 3], o[4 * h + 3], a.act)));
-                    }
+                for (int rr = 0; rr < 32; ++rr) {                          // B: column t, rows 0..31
+                    const bool ok = isx && (full || r0 + rr < rb);
+                    bv[rr] = ok ? __ldg(px + (long long)rr * a.ldx) : 0.0f;
                 }
             }
-            // B tile: xhat^T with the ones column at k = Din.  thread -> column k = t (all 8 chunks, 32 rows); the columns
-            // 256 .. b_rows - 1 are shared out afterwards as (k = 256 + (t & 15), chunk t >> 4) over the first 128 threads
+            if (do_left && t < 32 * a.simt_rows) {                         // dZ of the leftover rows for this block
+                const int rr = t & 31, i = t >> 5;
+                float dz = 0.0f;
+                if (full || r0 + rr < rb)
+                    dz = dact(__ldg(a.grad_offset + (r0 + rr) * a.ld_off + n_left + i), __ldg(a.offset + (r0 + rr) * a.ld_off + n_left + i), a.act);
+                s_dz[((kb & 1) * kMaxSimtRows + i) * 32 + rr] = dz;
+            }
+            if (kb >= kStages) mbar_wait(bar_empty + 8 * s, ((kb / kStages) - 1) & 1);   // the MMAs that read this stage are done
+            // ---- A tile: dZ^T
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int c = ch + 2 * h;
+                *reinterpret_cast<float4*>(At + n * 128 + ((c ^ (n & 7)) << 4)) =
+                    make_float4(to_tf32(dact(ag[4 * h], ao[4 * h], a.act)), to_tf32(dact(ag[4 * h + 1], ao[4 * h + 1], a.act)),
+                                to_tf32(dact(ag[4 * h + 2], ao[4 * h + 2], a.act)), to_tf32(dact(ag[4 * h + 3], ao[4 * h + 3], a.act)));
+            }
+            // ---- B tile: xhat^T with the ones column at k = Din.  thread -> column k = t; the columns 256 .. b_rows - 1 are
+            // shared out afterwards as (k = 256 + (t & 15), chunk t >> 4) over the first 128 threads
             const long long uq = r0 / a.n_frames;                          // utterance of the block's first row
             const int ul0 = (int)(uq - u_first);
             const int bnd = (int)((uq + 1) * a.n_frames - r0);             // rows of the block before the next utterance (n_frames >= 32)
-            auto b_column = [&](int k, int c_lo, int c_hi) {
-                const bool isx = k < a.Din;
-                const float2 st0 = s_stats[ul0 * kMaxBRows + k];
-                const float2 st1 = bnd < BK ? s_stats[(ul0 + 1) * kMaxBRows + k] : st0;
-                const float* px = a.x + r0 * a.ldx + (isx ? k : 0);
-                const float fill = k == a.Din ? 1.0f : 0.0f;
+            if (do_left) asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");   // s_dz[kb & 1] is complete
+            const float* dzb = s_dz + (kb & 1) * kMaxSimtRows * 32;
+            if (kvalid) {
+                const float2 st0 = s_stats[ul0 * kMaxBRows + t];
+                const float2 st1 = bnd < BK ? s_stats[(ul0 + 1) * kMaxBRows + t] : st0;
+                const float fill = t == a.Din ? 1.0f : 0.0f;
 #pragma unroll
-                for (int c4 = c_lo; c4 < c_hi; c4 += 4) {
-                    float v[16];
+                for (int c = 0; c < 8; ++c) {
+                    float w[4];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int rr = 4 * c4 + e;
-                        const bool ok = (c4 + (e >> 2) < c_hi) && (full || r0 + rr < rb);
-                        v[e] = (ok && isx) ? __ldg(px + (long long)rr * a.ldx) : (ok ? fill : 0.0f);
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int rr = 4 * c + jj;
+                        const float2 st = rr >= bnd ? st1 : st0;
+                        w[jj] = isx ? (bv[rr] - st.x) * st.y : fill;
+                        if (!full && r0 + rr >= rb) w[jj] = 0.0f;
                     }
+                    *reinterpret_cast<float4*>(Bt + t * 128 + ((c ^ (t & 7)) << 4)) =
+                        make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
+                    if (do_left) {
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const int c = c4 + h;
-                        if (c < c_hi) {
-                            float w[4];
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int rr = 4 * c + jj;
-                                const float2 st = rr >= bnd ? st1 : st0;
-                                w[jj] = isx ? (v[4 * h + jj] - st.x) * st.y : v[4 * h + jj];
-                                if (!full && r0 + rr >= rb) w[jj] = 0.0f;
+                        for (int i = 0; i < kMaxSimtRows; ++i)
+                            if (i < a.simt_rows) {
+                                const float4 d = *reinterpret_cast<const float4*>(dzb + i * 32 + 4 * c);
+                                acc_l[i] += w[0] * d.x + w[1] * d.y + w[2] * d.z + w[3] * d.w;
                             }
-                            *reinterpret_cast<float4*>(Bt + k * 128 + ((c ^ (k & 7)) << 4)) =
-                                make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
-                        }
                     }
                 }
-            };
-            if (t < a.b_rows) b_column(t, 0, 8);
+            }
             if (a.b_rows > kProdThreads && t < 16 * 8) {
                 const int k = kProdThreads + (t & 15), c = t >> 4;
-                if (k < a.b_rows) b_column(k, c, c + 1);
+                if (k < a.b_rows) {
+                    const bool tx = k < a.Din;
+                    const float2 st0 = s_stats[ul0 * kMaxBRows + k];
+                    const float2 st1 = bnd < BK ? s_stats[(ul0 + 1) * kMaxBRows + k] : st0;
+                    const float fill = k == a.Din ? 1.0f : 0.0f;
+                    float w[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int rr = 4 * c + jj;
+                        const bool ok = full || r0 + rr < rb;
+                        const float2 st = rr >= bnd ? st1 : st0;
+                        w[jj] = !ok ? 0.0f : (tx ? (__ldg(a.x + (r0 + rr) * a.ldx + k) - st.x) * st.y : fill);
+                    }
+                    *reinterpret_cast<float4*>(Bt + k * 128 + ((c ^ (k & 7)) << 4)) =
+                        make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
+                    if (do_left) {
+#pragma unroll
+                        for (int i = 0; i < kMaxSimtRows; ++i)
+                            if (i < a.simt_rows) {
+                                const float4 d = *reinterpret_cast<const float4*>(dzb + i * 32 + 4 * c);
+                                acc_t[i] += w[0] * d.x + w[1] * d.y + w[2] * d.z + w[3] * d.w;
+                            }
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        }
+        if (do_left) {
+            // partial rows n_left + i of this split: main columns straight from the registers, the shared-out columns
+            // (256 ..) summed over their 8 chunk owners through shared memory
+            float* dst = a.partials + ((long long)split * a.m_rows + n_left) * kMaxBRows;
+            if (t < 16 * 8) {
+#pragma unroll
+                for (int i = 0; i < kMaxSimtRows; ++i) s_tail[(i * 16 + (t & 15)) * 8 + (t >> 4)] = acc_t[i];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
+#pragma unroll
+            for (int i = 0; i < kMaxSimtRows; ++i)
+                if (i < a.simt_rows) {
+                    if (t < a.b_rows && t < kProdThreads) dst[(long long)i * kMaxBRows + t] = acc_l[i];
+                    if (t < 16 && kProdThreads + t < a.b_rows) {
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) sum += s_tail[(i * 16 + t) * 8 + c];
+                        dst[(long long)i * kMaxBRows + kProdThreads + t] = sum;
+                    }
+                }
         }
         // ===================== epilogue: the CTA's partial D -> workspace =====================
         if (nkb > 0) {
@@ -321,9 +355,6 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
-    // leftover output rows of this split (the CTAs of the first tile take them: a few L2-resident dot products)
-    if (a.simt_rows > 0 && blockIdx.y == 0)
-        simt_rows_block(a, ra, rb, a.m_tiles * BM, a.simt_rows, a.partials + ((long long)split * a.m_rows + a.m_tiles * BM) * kMaxBRows);
 }
 
 // grad_W[n, k] = sum_s partials[s, n, k], grad_b[n] = sum_s partials[s, n, Din]
