@@ -223,6 +223,24 @@ int se_linear_head_bwd(const float* x, const float* mean, const float* std, floa
                        const float* offset, const float* grad_offset, int64_t n_utt, int64_t n_frames,
                        int64_t D_in, int64_t D_out, int act, float* grad_W, float* grad_b, void* stream);
 
+/* se_linear_head_bwd_fused: se_linear_head_bwd_tc with the CMVN statistics given as the sums se_stft_features wrote (the
+ * counterpart of se_linear_head_fused: same mean / unbiased std arithmetic); stat_sums NULL = no CMVN. */
+int se_linear_head_bwd_fused(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps,
+                             const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt, int64_t n_frames,
+                             int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats, float* grad_W,
+                             float* grad_b, void* stream);
+
+/* ---- spectral SI-SDR objective on predicted = offset * linear_inp (objective.py:86-100 after model.py:33) ----------------
+ * Same sums / loss as se_sisdr_spec_fwd without materialising `predicted`; rows of the three tensors are ld_* floats apart
+ * (float4 loads when every ld is a multiple of 4 and the pointers are 16-byte aligned).  offset NULL: predicted = linear_inp.
+ * bwd: grad_offset = grad_out[u] * d loss_u / d predicted * linear_inp (0 on padded frames and on columns >= K of a row). */
+int se_sisdr_mask_fwd(const float* offset, int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar,
+                      int64_t ld_tar, const int64_t* stft_len, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
+                      double* sums3, float* loss_per_utt, void* stream);
+int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar,
+                      int64_t ld_tar, const int64_t* stft_len, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
+                      const double* sums3, const float* grad_out, float* grad_offset, int64_t ld_g, void* stream);
+
 /* ---- K1 + K2 of the fused evaluation step ------------------------------------------
  * se_stft_features: STFT of one channel -> ONE feature tensor feat (n_utt, n_frames, feat_stride): power (take_log = 0)
  *   or log(power + log_eps) (take_log = 1), AND stat_sums (n_utt, ld_stats, 2) doubles += [sum_f x, sum_f x^2] per
@@ -244,6 +262,13 @@ int se_linear_head_fused_supported(int64_t n_utt, int64_t n_frames, int64_t D_in
 int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps,
                          const float* W, int64_t ldw, const float* b, int64_t n_utt, int64_t n_frames, int64_t D_in,
                          int64_t D_out, int act, float* offset_out, int64_t ld_out, void* stream);
+
+/* se_stft_features2: se_stft_features with BOTH spectral tensors of the channel -- power ("linear", what the objectives and
+ * `predicted = linears * offset` consume) and log-power (the head's feature) -- from one transform; either may be NULL.
+ * stat_sums holds the sums of logpower if it is given, else of power.  One launch for n_fft 512 / hop 256. */
+int se_stft_features2(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
+                      float log_eps, float* power, float* logpower, int64_t spec_stride, double* stat_sums, int64_t ld_stats,
+                      int flags, void* stream);
 
 /* Tensor-core form of se_linear_head_bwd (tcgen05 TF32 split-K GEMM; grad_b from a ones column of the same GEMM).
  * ws_partials: caller workspace of se_linear_head_bwd_tc_workspace(...) floats (0 = shape unsupported: D_in <= 271, n_frames >= 32

@@ -696,6 +696,7 @@ int prepare512() {
     SE_OPT((stft512_run_kernel<true, true, true, false>), kSmem1Run);
     SE_OPT((stft512_run_kernel<true, false, false, true>), kSmem1Run);
     SE_OPT((stft512_run_kernel<false, false, true, true>), kSmem1Run);
+    SE_OPT((stft512_run_kernel<true, false, true, true>), kSmem1Run);
     SE_OPT((stft512_run_kernel<true, false, false, true, true>), kSmem1Run);
     SE_OPT((stft512_run_kernel<false, false, true, true, true>), kSmem1Run);
     SE_OPT(mask_istft512_kernel<false>, kSmem3);
@@ -731,7 +732,8 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
             // statistics of the ONE feature written: log-power (sel 4) or power (sel 1)
             if (sel == 4) { if (a.cspec) SE_RUN_CS(false, false, true); else SE_RUN(false, false, true, true); }
             else if (sel == 1) { if (a.cspec) SE_RUN_CS(true, false, false); else SE_RUN(true, false, false, true); }
-            else return secommon::fail(SE_ERR_BAD_ARG, "statistics need exactly one of power / logpower");
+            else if (sel == 5 && !a.cspec) SE_RUN(true, false, true, true);        // power + log-power, statistics of log-power
+            else return secommon::fail(SE_ERR_BAD_ARG, "statistics need power and / or logpower (no phase)");
         } else {
             if (a.cspec) return secommon::fail(SE_ERR_UNSUPPORTED, "the spectrum workspace is written by the statistics variants only");
             switch (sel) {

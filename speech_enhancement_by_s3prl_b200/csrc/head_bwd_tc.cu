@@ -105,6 +105,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 struct BwdArgs {
     const float* x; long long ldx;
     const float* mean; const float* stdv; long long ld_stats; float cmvn_eps;
+    const double* sums; double inv_n, inv_nm1;   // alternative to mean / stdv: (n_utt, ld_stats, 2) [sum x, sum x^2] over the frames
     const float* offset; const float* grad_offset; long long ld_off;
     long long R; int n_frames, Din, Dout, act;
     long long rows_per_split;      // multiple of 32
@@ -155,6 +156,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
         if (a.mean && k < a.Din && u * a.n_frames < a.R) {
             st.x = __ldg(a.mean + u * a.ld_stats + k);
             st.y = 1.0f / (__ldg(a.stdv + u * a.ld_stats + k) + a.cmvn_eps);
+        } else if (a.sums && k < a.Din && u * a.n_frames < a.R) {   // same arithmetic as the fused forward head (head_fused.cu)
+            const double2 p = *reinterpret_cast<const double2*>(a.sums + (u * a.ld_stats + k) * 2);
+            const double mean = p.x * a.inv_n;
+            const float var = (float)((p.y - p.x * mean) * a.inv_nm1);
+            st.x = (float)mean;
+            st.y = __fdividef(1.0f, sqrtf(fmaxf(var, 0.0f)) + a.cmvn_eps);
         }
         s_stats[i] = st;
     }
@@ -418,13 +425,35 @@ int64_t se_linear_head_bwd_tc_workspace(int64_t n_utt, int64_t n_frames, int64_t
     return (int64_t)g.splits * g.m_rows * kMaxBRows;
 }
 
+static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums, int64_t ld_stats,
+                         float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt,
+                         int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats,
+                         float* grad_W, float* grad_b, void* stream);
+
 int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const float* std, int64_t ld_stats, float cmvn_eps,
                           const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt, int64_t n_frames,
                           int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats, float* grad_W,
                           float* grad_b, void* stream) {
-    SE_REQUIRE(x && offset && grad_offset && ws_partials && grad_W && n_utt > 0 && n_frames > 0, "bad argument");
     SE_REQUIRE((mean == nullptr) == (std == nullptr), "mean and std go together");
-    SE_REQUIRE(ldx >= D_in && ld_off >= D_out && (!mean || ld_stats >= D_in), "row stride smaller than the row");
+    return head_bwd_impl(x, ldx, mean, std, nullptr, ld_stats, cmvn_eps, offset, grad_offset, ld_off, n_utt, n_frames, D_in, D_out,
+                         act, ws_partials, ws_floats, grad_W, grad_b, stream);
+}
+
+int se_linear_head_bwd_fused(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps,
+                             const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt, int64_t n_frames,
+                             int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats, float* grad_W,
+                             float* grad_b, void* stream) {
+    SE_REQUIRE(!stat_sums || n_frames >= 2, "CMVN statistics need at least two frames");
+    return head_bwd_impl(x, ldx, nullptr, nullptr, stat_sums, ld_stats, cmvn_eps, offset, grad_offset, ld_off, n_utt, n_frames, D_in,
+                         D_out, act, ws_partials, ws_floats, grad_W, grad_b, stream);
+}
+
+static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums, int64_t ld_stats,
+                         float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt,
+                         int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats,
+                         float* grad_W, float* grad_b, void* stream) {
+    SE_REQUIRE(x && offset && grad_offset && ws_partials && grad_W && n_utt > 0 && n_frames > 0, "bad argument");
+    SE_REQUIRE(ldx >= D_in && ld_off >= D_out && ((!mean && !stat_sums) || ld_stats >= D_in), "row stride smaller than the row");
     SE_REQUIRE(act >= SE_ACT_IDENTITY && act <= SE_ACT_SIGMOID, "unknown activation %d", act);
     Geometry g;
     if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g))
@@ -433,6 +462,7 @@ int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const 
     SE_REQUIRE(ws_floats >= (int64_t)g.splits * g.m_rows * kMaxBRows, "workspace too small");
     BwdArgs a{};
     a.x = x; a.ldx = ldx; a.mean = mean; a.stdv = std; a.ld_stats = ld_stats; a.cmvn_eps = cmvn_eps;
+    a.sums = stat_sums; a.inv_n = 1.0 / (double)n_frames; a.inv_nm1 = n_frames > 1 ? 1.0 / (double)(n_frames - 1) : 0.0;
     a.offset = offset; a.grad_offset = grad_offset; a.ld_off = ld_off;
     a.R = n_utt * n_frames; a.n_frames = (int)n_frames; a.Din = (int)D_in; a.Dout = (int)D_out; a.act = act;
     a.rows_per_split = g.rows_per_split;

@@ -148,6 +148,104 @@ __global__ void sisdr_spec_bwd_kernel(const float* __restrict__ pred, const floa
     }
 }
 
+// ---- the same objective on predicted = offset * linear_inp (model.py:33) without materialising `predicted`, on row-strided
+// tensors (rows ld floats apart; V = 4: 16-byte aligned rows read as float4, V = 1: any stride).  The backward writes
+// d loss / d offset = d loss / d predicted * linear_inp directly (0 on padded frames and on the pad columns of a row).
+template <int V> __device__ __forceinline__ void ldv(const float* p, float (&v)[V]) {
+    if (V == 4) { const float4 q = *reinterpret_cast<const float4*>(p); v[0] = q.x; v[1 % V] = q.y; v[2 % V] = q.z; v[3 % V] = q.w; }
+    else v[0] = *p;
+}
+template <int V> __device__ __forceinline__ void stv(float* p, const float (&v)[V]) {
+    if (V == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1 % V], v[2 % V], v[3 % V]);
+    else *p = v[0];
+}
+
+struct SisdrMaskArgs {
+    const float* offset; const float* inp; const float* tar;     // offset may be null (predicted = inp)
+    long long ld_off, ld_inp, ld_tar;
+    const long long* stft_len;
+    int n_utt, n_frames, K, chunks;
+    double* sums3;
+    float eps; const float* grad_out; float* grad_offset; long long ld_g;   // backward only
+};
+
+template <int V>
+__global__ void __launch_bounds__(256) sisdr_mask_sums_kernel(const SisdrMaskArgs a) {
+    const int u = blockIdx.x / a.chunks, chunk = blockIdx.x - u * a.chunks;
+    const int valid = (int)min((long long)a.n_frames, a.stft_len ? a.stft_len[u] : (long long)a.n_frames);
+    const int KV = (a.K + V - 1) / V;
+    const int per = (valid + a.chunks - 1) / a.chunks;
+    const int f_lo = chunk * per, f_hi = min(valid, f_lo + per);
+    const long long row0 = (long long)u * a.n_frames;
+    float acc[3] = {0.f, 0.f, 0.f};
+    const int items = max(f_hi - f_lo, 0) * KV;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int fr = i / KV, c = (i - fr * KV) * V;
+        const long long r = row0 + f_lo + fr;
+        float x[V], t[V], o[V];
+        ldv<V>(a.inp + r * a.ld_inp + c, x);
+        ldv<V>(a.tar + r * a.ld_tar + c, t);
+        if (a.offset) ldv<V>(a.offset + r * a.ld_off + c, o);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+            if (c + e < a.K) {
+                const float rp = relu(a.offset ? o[e] * x[e] : x[e]), rt = relu(t[e]);
+                acc[0] += sqrtf(rp) * sqrtf(rt);
+                acc[1] += rt;
+                acc[2] += rp;
+            }
+    }
+    block_accumulate_to<3, float>(acc, a.sums3 + (long long)u * 3);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) sisdr_mask_bwd_kernel(const SisdrMaskArgs a) {
+    const int u = blockIdx.x / a.chunks, chunk = blockIdx.x - u * a.chunks;
+    const int valid = (int)min((long long)a.n_frames, a.stft_len ? a.stft_len[u] : (long long)a.n_frames);
+    const int KV = (int)(a.ld_g / V) < (a.K + V - 1) / V ? (a.K + V - 1) / V : (int)(a.ld_g / V);   // whole rows of grad_offset
+    const int per = (a.n_frames + a.chunks - 1) / a.chunks;
+    const int f_lo = chunk * per, f_hi = min(a.n_frames, f_lo + per);
+    const double eps = a.eps;
+    const double st = a.sums3[3 * u], tt = a.sums3[3 * u + 1], ss = a.sums3[3 * u + 2];
+    const double al = st / (tt + eps);
+    const double A = al * al * tt;
+    const double D = al * al * tt - 2.0 * al * st + ss + eps;
+    const double R = A / D;
+    const double kappa = -10.0 / (log(10.0) * (R + eps) * D * D);        // see sisdr_spec_bwd_kernel
+    const double ca = 2.0 * al * tt / (tt + eps);
+    const double cd = 2.0 * (al * tt - st) / (tt + eps) - 2.0 * al;
+    const double go = (double)a.grad_out[u];
+    const float c_t = (float)(go * kappa * (ca * D - A * cd));
+    const float c_s = (float)(go * kappa * (-2.0 * A));
+    const long long row0 = (long long)u * a.n_frames;
+    const int items = max(f_hi - f_lo, 0) * KV;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int fr = i / KV, c = (i - fr * KV) * V;
+        const int f = f_lo + fr;
+        const long long r = row0 + f;
+        float g[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) g[e] = 0.0f;
+        if (f < valid && c < a.K) {
+            float x[V], t[V], o[V];
+            ldv<V>(a.inp + r * a.ld_inp + c, x);
+            ldv<V>(a.tar + r * a.ld_tar + c, t);
+            if (a.offset) ldv<V>(a.offset + r * a.ld_off + c, o);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float pi = a.offset ? o[e] * x[e] : x[e];
+                if (c + e < a.K && pi > 0.0f) {
+                    const float sq = sqrtf(pi), ti = sqrtf(relu(t[e]));
+                    g[e] = (c_t * ti + c_s * sq) * (0.5f / sq) * (a.offset ? x[e] : 1.0f);
+                }
+            }
+        }
+        if (c + V <= a.ld_g) stv<V>(a.grad_offset + r * a.ld_g + c, g);
+    }
+}
+
 // ------------------------------------------------------------------ log-spectral L1 objective
 __global__ void l1_logspec_fwd_kernel(const float* __restrict__ logp, const float* __restrict__ tar,
                                       const long long* __restrict__ stft_len, int n_frames, int K, float eps,
@@ -698,6 +796,49 @@ int se_sisdr_spec_bwd(const float* predicted, const float* linear_tar, const int
     sisdr_spec_bwd_kernel<<<(unsigned)(n_utt * chunks), kThreads, 0, (cudaStream_t)stream>>>(
         predicted, linear_tar, (const long long*)stft_len, (int)n_utt, (int)n_frames, (int)K, eps, sums3, grad_out, grad_predicted, chunks);
     return secommon::check_launch("sisdr_spec_bwd_kernel");
+}
+
+static bool vec4_ok(const float* p, long long ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); }
+
+int se_sisdr_mask_fwd(const float* offset, int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar,
+                      int64_t ld_tar, const int64_t* stft_len, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
+                      double* sums3, float* loss_per_utt, void* stream) {
+    SE_REQUIRE(linear_inp && linear_tar && sums3 && n_utt > 0 && n_frames > 0 && K > 0, "bad argument");
+    SE_REQUIRE(ld_inp >= K && ld_tar >= K && (!offset || ld_off >= K), "row stride smaller than K");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemsetAsync(sums3, 0, sizeof(double) * 3 * n_utt, st));
+    SisdrMaskArgs a{};
+    a.offset = offset; a.inp = linear_inp; a.tar = linear_tar; a.ld_off = ld_off; a.ld_inp = ld_inp; a.ld_tar = ld_tar;
+    a.stft_len = (const long long*)stft_len; a.n_utt = (int)n_utt; a.n_frames = (int)n_frames; a.K = (int)K;
+    a.chunks = pick_chunks(n_utt, n_frames * K, 16384); a.sums3 = sums3; a.eps = eps;
+    const long long need = (K + 3) / 4 * 4;
+    const bool v4 = vec4_ok(offset, ld_off) && vec4_ok(linear_inp, ld_inp) && vec4_ok(linear_tar, ld_tar) && ld_inp >= need &&
+                    ld_tar >= need && (!offset || ld_off >= need);
+    if (v4) sisdr_mask_sums_kernel<4><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
+    else sisdr_mask_sums_kernel<1><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
+    int rc = secommon::check_launch("sisdr_mask_sums_kernel");
+    if (rc != SE_OK || !loss_per_utt) return rc;
+    sisdr_spec_finish_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, st>>>(sums3, (int)n_utt, eps, loss_per_utt);
+    return secommon::check_launch("sisdr_spec_finish_kernel");
+}
+
+int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar,
+                      int64_t ld_tar, const int64_t* stft_len, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
+                      const double* sums3, const float* grad_out, float* grad_offset, int64_t ld_g, void* stream) {
+    SE_REQUIRE(linear_inp && linear_tar && sums3 && grad_out && grad_offset && n_utt > 0 && n_frames > 0 && K > 0, "bad argument");
+    SE_REQUIRE(ld_inp >= K && ld_tar >= K && ld_g >= K && (!offset || ld_off >= K), "row stride smaller than K");
+    SisdrMaskArgs a{};
+    a.offset = offset; a.inp = linear_inp; a.tar = linear_tar; a.ld_off = ld_off; a.ld_inp = ld_inp; a.ld_tar = ld_tar;
+    a.stft_len = (const long long*)stft_len; a.n_utt = (int)n_utt; a.n_frames = (int)n_frames; a.K = (int)K;
+    a.chunks = pick_chunks(n_utt, n_frames * K, 16384); a.sums3 = const_cast<double*>(sums3); a.eps = eps;
+    a.grad_out = grad_out; a.grad_offset = grad_offset; a.ld_g = ld_g;
+    const long long need = (K + 3) / 4 * 4;
+    const bool v4 = vec4_ok(offset, ld_off) && vec4_ok(linear_inp, ld_inp) && vec4_ok(linear_tar, ld_tar) && vec4_ok(grad_offset, ld_g) &&
+                    ld_inp >= need && ld_tar >= need && ld_g >= need && (!offset || ld_off >= need);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (v4) sisdr_mask_bwd_kernel<4><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
+    else sisdr_mask_bwd_kernel<1><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
+    return secommon::check_launch("sisdr_mask_bwd_kernel");
 }
 
 int se_mix_batch(const float* speech, int64_t speech_stride, const int64_t* speech_len, const float* noise, int64_t noise_stride,

@@ -249,6 +249,32 @@ static int stft_features_impl(const float* wav, int64_t n_utt, int64_t utt_strid
     return se_feature_sums(feat, feat_stride, n_utt, T / hop + 1, n_fft / 2 + 1, stat_sums, ld_stats, stream);
 }
 
+int se_stft_features2(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
+                      float log_eps, float* power, float* logpower, int64_t spec_stride, double* stat_sums, int64_t ld_stats,
+                      int flags, void* stream) {
+    SE_REQUIRE(wav && window && (power || logpower) && stat_sums, "null pointer");
+    SE_REQUIRE(spec_stride >= n_fft / 2 + 1 && ld_stats >= n_fft / 2 + 1, "spec_stride / ld_stats smaller than K");
+    int rc = check_geometry(n_utt, T, n_fft, hop);
+    if (rc != SE_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(stat_sums, 0, sizeof(double) * 2 * ld_stats * n_utt, st));
+    if (n_fft == 512 && hop == 256 && !g_force_generic) {
+        DeviceTables t;
+        if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
+        StftArgs a{};
+        a.wav = wav; a.utt_stride = utt_stride; a.n_utt = (int)n_utt; a.T = (int)T; a.hop = hop;
+        a.n_frames = (int)(T / hop) + 1;
+        a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
+        a.power = power; a.logp = logpower; a.log_eps = log_eps; a.spec_stride = spec_stride;
+        a.stat_sums = stat_sums; a.ld_stats = ld_stats;
+        a.trace = secommon::trace_ptr();
+        return sefast::launch_stft512(a, st);
+    }
+    rc = se_stft_strided(wav, n_utt, utt_stride, T, n_fft, hop, window, log_eps, power, nullptr, logpower, spec_stride, stream);
+    if (rc != SE_OK) return rc;
+    return se_feature_sums(logpower ? logpower : power, spec_stride, n_utt, T / hop + 1, n_fft / 2 + 1, stat_sums, ld_stats, stream);
+}
+
 int se_istft(const float* power, const float* phase, int64_t n_utt, int64_t n_frames, int n_fft, int hop,
              const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, void* stream) {
     SE_REQUIRE(power && phase && window && wav_out, "null pointer");

@@ -36,6 +36,7 @@ class EnhancementEngine:
         # K1 -> K3 spectrum workspace (512/256): one transform less in K3, but K1 writes / K3 reads 2 KB more per frame.
         # Measured on B200: K3 41 -> 37 us, K1 17.6 -> 21.6 us, and slower once the batch outgrows L2 -- off by default.
         self.use_spec_ws = os.environ.get("SE_B200_SPEC_WS", "0") == "1"
+        self.fused_training = os.environ.get("SE_B200_FUSED_TRAIN", "1") != "0"  # train_step without autograd (see fused_training_supported)
         self.launches_per_step = 5          # library kernels per eval_step (set by eval_step: 4 on the fused path)
 
     # ------------------------------------------------------------------ device-resident step
@@ -157,9 +158,69 @@ class EnhancementEngine:
         return self._graphs[key]
 
     # ------------------------------------------------------------------ training step (head fwd + bwd)
+    def fused_training_supported(self, objective, B, T):
+        """True if train_step can take the fused route: LinearResidual on the (log-)power spectrum with the SISDR
+        objective, tensor-core head, shapes inside the TMA head's / the split-K backward's range."""
+        from . import model, objective as obj
+        if not self.fused_training or self.precision != 1 or type(objective) is not obj.SISDR:
+            return False
+        if type(self.head) is not model.LinearResidual:
+            return False
+        F, K = T // self.hop + 1, self.n_fft // 2 + 1
+        LD = ops.round4(K)
+        w = self.head.linear.weight
+        if w.shape != (K, K):
+            return False
+        return (ops.linear_head_tma_supported(B, F, K, K, LD, ops.round4(K), LD) and ops.linear_head_bwd_fused_supported(B, F, K, K))
+
+    def _fused_forward_backward(self, lengths, wavs, objective):
+        """runner.py:431-460 in seven kernels, no autograd graph: K1 (noisy: power + log-power + CMVN sums), K1 (clean:
+        power), TMA head, SISDR sums + finish on offset * linear_inp, its backward straight to grad_offset, split-K
+        tensor-core weight gradient + reduction.  Leaves the gradients in ``.grad`` and returns the loss."""
+        B, C, T = wavs.shape
+        dev = wavs.device
+        head = self.head
+        window = self.pre._frame_window
+        if window.device != dev:
+            self.pre.to(dev)
+            window = self.pre._frame_window
+        K = self.n_fft // 2 + 1
+        LD = ops.round4(K)
+        with torch.no_grad():
+            ws = torch.zeros(B * (2 * LD + 3), device=dev, dtype=torch.float64)
+            stat_sums = ws[:B * 2 * LD].view(B, LD, 2)
+            sums3 = ws[B * 2 * LD:].view(B, 3)
+            linear_inp, logp, _ = ops.stft_features2(wavs, self.ch_inp, self.n_fft, self.hop, window, want_power=True,
+                                                     want_logpower=self.log_features, log_eps=self.pre.eps, stat_sums=stat_sums)
+            feats = logp if self.log_features else linear_inp
+            linear_tar = ops.stft_padded(wavs, self.ch_tar, self.n_fft, self.hop, window, logpower=False)
+            wpad = self._padded_weight()
+            stats = stat_sums if head.cmvn else None
+            offset = ops.linear_head_tma(feats, K, wpad, head.linear.bias, head.activation, stats, head.eps)
+            frames = lengths // self.hop + 1
+            loss_u, sums3 = ops.sisdr_mask_fwd(offset, linear_inp, linear_tar, frames, K, objective.eps, sums3=sums3)
+            loss = loss_u.mean()
+            grad_out = torch.full((B,), 1.0 / B, device=dev)
+            grad_offset = ops.sisdr_mask_bwd(offset, linear_inp, linear_tar, frames, K, sums3, grad_out, objective.eps)
+            gw, gb = ops.linear_head_bwd_fused(feats, K, stats, head.eps, offset, grad_offset, K, head.activation)
+            for p, g in ((head.linear.weight, gw), (head.linear.bias, gb)):
+                if p.grad is None:
+                    p.grad = g
+                else:
+                    p.grad.add_(g)
+        return loss
+
     def train_step(self, lengths, wavs, objective, optimizer=None, grad_clip=None):
         """runner.py:431-471 on the kernels: preprocessor tensors -> head -> criterion -> backward
         (+ gradient all-reduce under DP) -> optimizer step.  Returns the loss tensor."""
+        if optimizer is not None and self.fused_training_supported(objective, wavs.shape[0], wavs.shape[2]):
+            optimizer.zero_grad(set_to_none=True)
+            loss = self._fused_forward_backward(lengths, wavs, objective)
+            dp.allreduce_gradients(self.head.parameters())
+            if grad_clip is not None:
+                torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
+            optimizer.step()
+            return loss
         c = self.pre.get_feat_config
         feat_cfg = c("linear", self.ch_inp, log=self.log_features)
         feats, linear_inp, linear_tar = self.pre(wavs, [feat_cfg, c("linear", self.ch_inp), c("linear", self.ch_tar)])
@@ -208,6 +269,13 @@ class EnhancementEngine:
 
     def _train_body(self, lengths, wavs, objective, optimizer, grad_clip):
         """forward + backward + update without ``zero_grad`` (inside a graph the gradients live in the graph's pool)."""
+        if self.fused_training_supported(objective, wavs.shape[0], wavs.shape[2]):
+            loss = self._fused_forward_backward(lengths, wavs, objective)
+            dp.allreduce_gradients(self.head.parameters())
+            if grad_clip is not None:
+                torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
+            optimizer.step()
+            return loss
         c = self.pre.get_feat_config
         feat_cfg = c("linear", self.ch_inp, log=self.log_features)
         feats, linear_inp, linear_tar = self.pre(wavs, [feat_cfg, c("linear", self.ch_inp), c("linear", self.ch_tar)])

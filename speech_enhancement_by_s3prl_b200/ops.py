@@ -144,6 +144,87 @@ def stft_features(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-1
     return out, stat_sums
 
 
+def stft_features2(wavs, channel, n_fft, hop, window, want_power=True, want_logpower=True, log_eps=1e-10, stat_sums=None):
+    """Training-step K1: power and / or log-power of one channel, rows padded to round4(K), from ONE transform, plus the
+    CMVN sums (B, round4(K), 2) float64 of log-power (of power if log-power is not requested).  ``stat_sums`` given =
+    already zeroed by the caller.  Returns (power | None, logpower | None, stat_sums)."""
+    wavs = _chk(wavs, "wavs")
+    B, C, T = wavs.shape
+    F, K = T // hop + 1, n_fft // 2 + 1
+    LD = round4(K)
+    window = _c(window, "window")
+    assert want_power or want_logpower
+    with torch.cuda.device(wavs.device):
+        power = torch.empty(B, F, LD, device=wavs.device, dtype=torch.float32) if want_power else None
+        logp = torch.empty(B, F, LD, device=wavs.device, dtype=torch.float32) if want_logpower else None
+        flags = FLAG_SUMS_ZEROED
+        if stat_sums is None:
+            stat_sums = torch.empty(B, LD, 2, device=wavs.device, dtype=torch.float64)
+            flags = 0
+        assert stat_sums.shape == (B, LD, 2) and stat_sums.dtype == torch.float64 and stat_sums.is_contiguous()
+        rc = _lib.load().se_stft_features2(wavs.data_ptr() + 4 * int(channel) * T, B, C * T, T, n_fft, hop, window.data_ptr(),
+                                           float(log_eps), _p(power), _p(logp), LD, stat_sums.data_ptr(), LD, flags, _stream())
+        _lib.check(rc, "se_stft_features2")
+    return power, logp, stat_sums
+
+
+def linear_head_bwd_fused_supported(B, F, D_in, D_out):
+    return _lib.load().se_linear_head_bwd_tc_workspace(B, F, D_in, D_out) > 0
+
+
+def linear_head_bwd_fused(x, D_in, stat_sums, cmvn_eps, offset, grad_offset, D_out, activation):
+    """Weight / bias gradients of the TMA head from its padded operands: x (B, F, LDx), offset and grad_offset (B, F, LDo),
+    stat_sums (B, LDs, 2) float64 or None (no CMVN).  Returns (grad_W (D_out, D_in), grad_b (D_out,))."""
+    B, F, LDx = x.shape
+    LDo = offset.shape[2]
+    assert grad_offset.shape == offset.shape and offset.is_contiguous() and grad_offset.is_contiguous() and x.is_contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        ws_floats = lib.se_linear_head_bwd_tc_workspace(B, F, int(D_in), int(D_out))
+        if ws_floats <= 0:
+            raise RuntimeError(f"se_linear_head_bwd_fused: shape (B={B}, F={F}, D_in={D_in}, D_out={D_out}) is not supported")
+        ws = torch.empty(ws_floats, device=x.device)
+        gw = torch.empty(D_out, D_in, device=x.device)
+        gb = torch.empty(D_out, device=x.device)
+        rc = lib.se_linear_head_bwd_fused(x.data_ptr(), LDx, _p(stat_sums), 0 if stat_sums is None else stat_sums.shape[1],
+                                          float(cmvn_eps), offset.data_ptr(), grad_offset.data_ptr(), LDo, B, F, int(D_in),
+                                          int(D_out), ACT[activation], ws.data_ptr(), ws_floats, gw.data_ptr(), gb.data_ptr(),
+                                          _stream())
+        _lib.check(rc, "se_linear_head_bwd_fused")
+    return gw, gb
+
+
+def sisdr_mask_fwd(offset, linear_inp, linear_tar, stft_lengths, K, eps=1e-10, sums3=None):
+    """objective.SISDR of predicted = offset * linear_inp on (B, F, LD) row-padded tensors (offset None: predicted =
+    linear_inp).  Returns (loss_per_utt (B,), sums3 (B, 3) float64 for the backward)."""
+    B, F, LDi = linear_inp.shape
+    stft_lengths = _c(stft_lengths, "stft_lengths", torch.int64)
+    with torch.cuda.device(linear_inp.device):
+        if sums3 is None:
+            sums3 = torch.empty(B, 3, device=linear_inp.device, dtype=torch.float64)
+        loss = torch.empty(B, device=linear_inp.device)
+        rc = _lib.load().se_sisdr_mask_fwd(_p(offset), 0 if offset is None else offset.shape[2], linear_inp.data_ptr(), LDi,
+                                           linear_tar.data_ptr(), linear_tar.shape[2], _p(stft_lengths), B, F, int(K), float(eps),
+                                           sums3.data_ptr(), loss.data_ptr(), _stream())
+        _lib.check(rc, "se_sisdr_mask_fwd")
+    return loss, sums3
+
+
+def sisdr_mask_bwd(offset, linear_inp, linear_tar, stft_lengths, K, sums3, grad_out, eps=1e-10, ld_out=None):
+    """d (sum_u grad_out[u] * loss_u) / d offset, (B, F, ld_out or LD of linear_inp); pad columns are zero."""
+    B, F, LDi = linear_inp.shape
+    LDg = int(ld_out or (offset.shape[2] if offset is not None else LDi))
+    stft_lengths = _c(stft_lengths, "stft_lengths", torch.int64)
+    grad_out = _c(grad_out, "grad_out")
+    with torch.cuda.device(linear_inp.device):
+        g = torch.empty(B, F, LDg, device=linear_inp.device)
+        rc = _lib.load().se_sisdr_mask_bwd(_p(offset), 0 if offset is None else offset.shape[2], linear_inp.data_ptr(), LDi,
+                                           linear_tar.data_ptr(), linear_tar.shape[2], _p(stft_lengths), B, F, int(K), float(eps),
+                                           sums3.data_ptr(), grad_out.data_ptr(), g.data_ptr(), LDg, _stream())
+        _lib.check(rc, "se_sisdr_mask_bwd")
+    return g
+
+
 def feature_sums(x, D):
     """x (B, F, LD) -> (B, LD, 2) float64 sums [sum_f x, sum_f x^2] of columns [0, D)."""
     x = _chk(x, "x")

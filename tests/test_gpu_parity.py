@@ -851,3 +851,76 @@ def test_eval_step_same_with_and_without_spectrum_workspace(se):
     assert (a["wav_predicted"] - b["wav_predicted"]).abs().max().item() < 1e-6
     assert (a["sisdr"] - b["sisdr"]).abs().max().item() < 1e-4
     assert (a["loss_per_utt"] - b["loss_per_utt"]).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------ fused training step (no autograd graph)
+@pytest.mark.parametrize("B,T,ragged", [(4, 16000, False), (6, 32000, True), (64, 64000, False)])
+def test_fused_training_step_matches_autograd_path(se, B, T, ragged):
+    """K1(power + log-power + sums) -> TMA head -> SISDR on offset * linear_inp -> its backward -> split-K weight gradient
+    against the drop-in modules under autograd (runner.py:431-460), and both against the CPU oracle's gradient at small size."""
+    from speech_enhancement_by_s3prl_b200 import ops
+    ora, mine = make_pair(se, 512)
+    lens = torch.LongTensor([T - 997 * i for i in range(B)]) if ragged else None
+    lengths, wavs = synth(B, T, seed=B + T, lengths=lens)
+    lengths_d, wavs_d = lengths.cuda(), wavs.cuda()
+    grads, losses = [], []
+    for fused in (True, False):
+        torch.manual_seed(11)
+        head = se.LinearResidual(input_size=257, output_size=257, precision=1).cuda()
+        eng = se.EnhancementEngine(mine, head, log_features=True, precision=1)
+        eng.fused_training = fused
+        assert eng.fused_training_supported(se.SISDR(), B, T) == fused
+        opt = torch.optim.SGD(head.parameters(), lr=0.0)                      # lr 0: gradients only
+        loss = eng.train_step(lengths_d, wavs_d, se.SISDR(), opt, None)
+        torch.cuda.synchronize()
+        grads.append((head.linear.weight.grad.clone(), head.linear.bias.grad.clone()))
+        losses.append(loss.item())
+    assert losses[0] == pytest.approx(losses[1], abs=2e-4)                    # TF32 head in both
+    for g_f, g_a in zip(*grads):
+        scale = g_a.abs().max().item()
+        assert (g_f - g_a).abs().max().item() < 4e-3 * scale                  # TF32 operands on both sides, different summation
+        assert (g_f - g_a).abs().mean().item() < 4e-4 * scale
+    if B <= 6:
+        # fp32 oracle on CPU (same weights)
+        torch.manual_seed(11)
+        init = se.LinearResidual(input_size=257, output_size=257)
+        w = init.linear.weight.detach().clone().requires_grad_(True)
+        b = init.linear.bias.detach().clone().requires_grad_(True)
+        c = ora.get_feat_config
+        feats, lin_i, lin_t = ora(wavs, [c("linear", 0, log=True), c("linear", 0), c("linear", 1)])
+        pred, _ = sp.linear_residual_head(feats, lin_i, w, b)
+        masks = sp.length_masks(sp.stft_lengths(lengths, 256))
+        ref_loss, _ = sp.sisdr_spectral(pred, lin_t, masks)
+        ref_loss.backward()
+        assert losses[0] == pytest.approx(ref_loss.item(), abs=2e-3)
+        gw = grads[0][0].cpu()
+        assert torch.nn.functional.cosine_similarity(gw.flatten(), w.grad.flatten(), dim=0).item() > 0.9999
+        assert (gw - w.grad).abs().max().item() < 1e-2 * w.grad.abs().max().item()
+
+
+def test_sisdr_mask_kernels_match_unfused_objective(se):
+    """se_sisdr_mask_fwd / _bwd (strided, float4 and scalar variants) against sisdr_spec on predicted = offset * linear_inp."""
+    from speech_enhancement_by_s3prl_b200 import ops
+    B, F, K = 5, 77, 257
+    g = torch.Generator().manual_seed(2)
+    off = torch.rand(B, F, K, generator=g).cuda()
+    inp = (torch.randn(B, F, K, generator=g) ** 2).cuda()
+    tar = (torch.randn(B, F, K, generator=g) ** 2).cuda()
+    inp[0, 3, 5] = 0.0                                                         # predicted == 0: zero gradient, no NaN
+    frames = torch.LongTensor([77, 60, 1, 77, 33]).cuda()
+    pred = (off * inp).requires_grad_(True)
+    loss_ref = ops.sisdr_spec(pred, tar, frames, 1e-10)
+    loss_ref.mean().backward()
+    g_ref = pred.grad * inp
+    for LD in (K, 260):                                                        # scalar and float4 variants
+        pad = lambda x: torch.nn.functional.pad(x, (0, LD - K), value=float("nan")).contiguous()
+        loss, sums3 = ops.sisdr_mask_fwd(pad(off), pad(inp), pad(tar), frames, K)
+        np.testing.assert_allclose(loss.cpu().numpy(), loss_ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
+        go = torch.full((B,), 1.0 / B, device="cuda")
+        gr = ops.sisdr_mask_bwd(pad(off), pad(inp), pad(tar), frames, K, sums3, go)
+        assert gr.shape == (B, F, LD) and torch.isfinite(gr).all() and (gr[..., K:] == 0).all()
+        scale = g_ref.abs().max().item()
+        assert (gr[..., :K] - g_ref).abs().max().item() < 1e-5 * scale
+        assert (gr[1, 60:] == 0).all() and (gr[2, 1:] == 0).all()
+        loss_p, _ = ops.sisdr_mask_fwd(None, pad(off * inp), pad(tar), frames, K)   # offset = None: predicted given
+        np.testing.assert_allclose(loss_p.cpu().numpy(), loss_ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
