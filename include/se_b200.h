@@ -241,6 +241,15 @@ int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_i
                       int64_t ld_tar, const int64_t* stft_len, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
                       const double* sums3, const float* grad_out, float* grad_offset, int64_t ld_g, void* stream);
 
+/* ---- gradient clipping + Adam on the head's parameters (runner.py:463-466: clip_grad_norm_ then optimizer.step) -------
+ * params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors (<= 8) device pointers, numels their sizes.  Semantics of
+ * torch.nn.utils.clip_grad_norm_(max_norm) (skipped if max_norm <= 0; the scaled gradient is written back) followed by
+ * torch.optim.Adam.step (L2 weight_decay, no amsgrad).  ws_acc: 1 double, ws_state: 2 ints (steps taken, internal), both
+ * zero before the first call and owned by the caller; the step count advances on the device (CUDA-graph replayable). */
+int se_adam_clip_step(float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                      const int64_t* numels, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float max_norm, double* ws_acc, int* ws_state, void* stream);
+
 /* ---- K1 + K2 of the fused evaluation step ------------------------------------------
  * se_stft_features: STFT of one channel -> ONE feature tensor feat (n_utt, n_frames, feat_stride): power (take_log = 0)
  *   or log(power + log_eps) (take_log = 1), AND stat_sums (n_utt, ld_stats, 2) doubles += [sum_f x, sum_f x^2] per

@@ -246,6 +246,62 @@ __global__ void __launch_bounds__(256) sisdr_mask_bwd_kernel(const SisdrMaskArgs
     }
 }
 
+// ------------------------------------------------------------------ gradient clipping + Adam for the head's parameters
+// runner.py:463-466 (clip_grad_norm_ -> optimizer.step) on a handful of small tensors: torch runs ~15 launches for it,
+// here it is two -- the squared gradient norm, then clip + update.  All state (moments, step count, norm accumulator) lives
+// on the device, so the pair replays from a CUDA graph.
+constexpr int kAdamMaxTensors = 8;
+struct AdamArgs {
+    float* p[kAdamMaxTensors]; float* g[kAdamMaxTensors]; float* m[kAdamMaxTensors]; float* v[kAdamMaxTensors];
+    long long n[kAdamMaxTensors];
+    int count;
+    float lr, beta1, beta2, eps, weight_decay, max_norm;   // max_norm <= 0: no clipping
+    double* acc;       // [1] sum of squared gradients of this step (zeroed by the update kernel's last CTA)
+    int* state;        // [0] steps taken, [1] CTAs of the update kernel that have finished
+};
+
+__global__ void __launch_bounds__(256) adam_norm_kernel(const AdamArgs a) {
+    float acc[1] = {0.0f};
+    for (int t = 0; t < a.count; ++t)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * blockDim.x) {
+            const float g = a.g[t][i];
+            acc[0] += g * g;
+        }
+    block_accumulate_to<1, float>(acc, a.acc);
+}
+
+__global__ void __launch_bounds__(256) adam_update_kernel(const AdamArgs a) {
+    const int step = a.state[0] + 1;                                        // torch.optim.Adam: bias corrections use the new count
+    float clip = 1.0f;
+    if (a.max_norm > 0.0f) {
+        const float total = (float)sqrt(*a.acc);
+        clip = fminf(a.max_norm / (total + 1e-6f), 1.0f);                   // torch.nn.utils.clip_grad_norm_
+    }
+    const double bc1 = 1.0 - pow((double)a.beta1, (double)step), bc2 = 1.0 - pow((double)a.beta2, (double)step);
+    const float step_size = (float)(a.lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    for (int t = 0; t < a.count; ++t)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * blockDim.x) {
+            float g = a.g[t][i] * clip;
+            a.g[t][i] = g;                                                  // the clipped gradient stays visible, as in torch
+            const float p = a.p[t][i];
+            if (a.weight_decay != 0.0f) g += a.weight_decay * p;
+            const float m = a.beta1 * a.m[t][i] + (1.0f - a.beta1) * g;
+            const float v = a.beta2 * a.v[t][i] + (1.0f - a.beta2) * g * g;
+            a.m[t][i] = m;
+            a.v[t][i] = v;
+            a.p[t][i] = p - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.state + 1, 1) == (int)gridDim.x - 1) {              // every CTA has read acc and the step count
+            *a.acc = 0.0;
+            a.state[1] = 0;
+            a.state[0] = step;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ log-spectral L1 objective
 __global__ void l1_logspec_fwd_kernel(const float* __restrict__ logp, const float* __restrict__ tar,
                                       const long long* __restrict__ stft_len, int n_frames, int K, float eps,
@@ -810,7 +866,7 @@ int se_sisdr_mask_fwd(const float* offset, int64_t ld_off, const float* linear_i
     SisdrMaskArgs a{};
     a.offset = offset; a.inp = linear_inp; a.tar = linear_tar; a.ld_off = ld_off; a.ld_inp = ld_inp; a.ld_tar = ld_tar;
     a.stft_len = (const long long*)stft_len; a.n_utt = (int)n_utt; a.n_frames = (int)n_frames; a.K = (int)K;
-    a.chunks = pick_chunks(n_utt, n_frames * K, 16384); a.sums3 = sums3; a.eps = eps;
+    a.chunks = pick_chunks(n_utt, n_frames * K, 2048); a.sums3 = sums3; a.eps = eps;
     const long long need = (K + 3) / 4 * 4;
     const bool v4 = vec4_ok(offset, ld_off) && vec4_ok(linear_inp, ld_inp) && vec4_ok(linear_tar, ld_tar) && ld_inp >= need &&
                     ld_tar >= need && (!offset || ld_off >= need);
@@ -830,7 +886,7 @@ int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_i
     SisdrMaskArgs a{};
     a.offset = offset; a.inp = linear_inp; a.tar = linear_tar; a.ld_off = ld_off; a.ld_inp = ld_inp; a.ld_tar = ld_tar;
     a.stft_len = (const long long*)stft_len; a.n_utt = (int)n_utt; a.n_frames = (int)n_frames; a.K = (int)K;
-    a.chunks = pick_chunks(n_utt, n_frames * K, 16384); a.sums3 = const_cast<double*>(sums3); a.eps = eps;
+    a.chunks = pick_chunks(n_utt, n_frames * K, 2048); a.sums3 = const_cast<double*>(sums3); a.eps = eps;
     a.grad_out = grad_out; a.grad_offset = grad_offset; a.ld_g = ld_g;
     const long long need = (K + 3) / 4 * 4;
     const bool v4 = vec4_ok(offset, ld_off) && vec4_ok(linear_inp, ld_inp) && vec4_ok(linear_tar, ld_tar) && vec4_ok(grad_offset, ld_g) &&
@@ -839,6 +895,32 @@ int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_i
     if (v4) sisdr_mask_bwd_kernel<4><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
     else sisdr_mask_bwd_kernel<1><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
     return secommon::check_launch("sisdr_mask_bwd_kernel");
+}
+
+int se_adam_clip_step(float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                      const int64_t* numels, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float max_norm, double* ws_acc, int* ws_state, void* stream) {
+    SE_REQUIRE(params && grads && exp_avg && exp_avg_sq && numels && ws_acc && ws_state, "null pointer");
+    SE_REQUIRE(n_tensors > 0 && n_tensors <= kAdamMaxTensors, "n_tensors=%d must be in [1, %d]", n_tensors, kAdamMaxTensors);
+    AdamArgs a{};
+    long long total = 0;
+    for (int t = 0; t < n_tensors; ++t) {
+        SE_REQUIRE(params[t] && grads[t] && exp_avg[t] && exp_avg_sq[t] && numels[t] > 0, "tensor %d: null pointer or empty", t);
+        a.p[t] = params[t]; a.g[t] = grads[t]; a.m[t] = exp_avg[t]; a.v[t] = exp_avg_sq[t]; a.n[t] = numels[t];
+        total += numels[t];
+    }
+    a.count = n_tensors; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
+    a.acc = ws_acc; a.state = ws_state;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long blocks = (total + 4 * 256 - 1) / (4 * 256);
+    if (blocks > 592) blocks = 592;
+    if (max_norm > 0.0f) {
+        adam_norm_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+        int rc = secommon::check_launch("adam_norm_kernel");
+        if (rc != SE_OK) return rc;
+    }
+    adam_update_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    return secommon::check_launch("adam_update_kernel");
 }
 
 int se_mix_batch(const float* speech, int64_t speech_stride, const int64_t* speech_len, const float* noise, int64_t noise_stride,

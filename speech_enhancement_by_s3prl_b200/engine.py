@@ -194,6 +194,7 @@ class EnhancementEngine:
                                                      want_logpower=self.log_features, log_eps=self.pre.eps, stat_sums=stat_sums)
             feats = logp if self.log_features else linear_inp
             linear_tar = ops.stft_padded(wavs, self.ch_tar, self.n_fft, self.hop, window, logpower=False)
+            self._wpad_key = None                   # the weights change every step (and a captured step must re-derive them)
             wpad = self._padded_weight()
             stats = stat_sums if head.cmvn else None
             offset = ops.linear_head_tma(feats, K, wpad, head.linear.bias, head.activation, stats, head.eps)
@@ -210,6 +211,16 @@ class EnhancementEngine:
                     p.grad.add_(g)
         return loss
 
+    def _clip_and_step(self, optimizer, grad_clip):
+        """runner.py:463-466; two launches with se_b200.ClipAdam, torch's kernels with any other optimizer."""
+        from .optim import ClipAdam
+        if isinstance(optimizer, ClipAdam):
+            optimizer.clip_and_step(grad_clip)
+            return
+        if grad_clip is not None:
+            torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
+        optimizer.step()
+
     def train_step(self, lengths, wavs, objective, optimizer=None, grad_clip=None):
         """runner.py:431-471 on the kernels: preprocessor tensors -> head -> criterion -> backward
         (+ gradient all-reduce under DP) -> optimizer step.  Returns the loss tensor."""
@@ -217,9 +228,7 @@ class EnhancementEngine:
             optimizer.zero_grad(set_to_none=True)
             loss = self._fused_forward_backward(lengths, wavs, objective)
             dp.allreduce_gradients(self.head.parameters())
-            if grad_clip is not None:
-                torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
-            optimizer.step()
+            self._clip_and_step(optimizer, grad_clip)
             return loss
         c = self.pre.get_feat_config
         feat_cfg = c("linear", self.ch_inp, log=self.log_features)
@@ -231,9 +240,7 @@ class EnhancementEngine:
             optimizer.zero_grad(set_to_none=True)
             loss.backward()
             dp.allreduce_gradients(self.head.parameters())
-            if grad_clip is not None:
-                torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
-            optimizer.step()
+            self._clip_and_step(optimizer, grad_clip)
         return loss
 
 
@@ -272,9 +279,7 @@ class EnhancementEngine:
         if self.fused_training_supported(objective, wavs.shape[0], wavs.shape[2]):
             loss = self._fused_forward_backward(lengths, wavs, objective)
             dp.allreduce_gradients(self.head.parameters())
-            if grad_clip is not None:
-                torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
-            optimizer.step()
+            self._clip_and_step(optimizer, grad_clip)
             return loss
         c = self.pre.get_feat_config
         feat_cfg = c("linear", self.ch_inp, log=self.log_features)
@@ -284,9 +289,7 @@ class EnhancementEngine:
         loss, _ = objective(predicted=predicted, linear_tar=linear_tar, linear_inp=linear_inp, stft_lengths=frames, **extra)
         loss.backward()
         dp.allreduce_gradients(self.head.parameters())
-        if grad_clip is not None:
-            torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
-        optimizer.step()
+        self._clip_and_step(optimizer, grad_clip)
         return loss
 
 

@@ -42,3 +42,18 @@ for nfreq, win, hop in [(257, 32, 16), (201, 25, 10)]:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         print(f"   graph replay: {ms:.3f} ms/step  {256 / ms * 1e3:.0f} audio-s/s  loss {loss.item():.4f}")
+        if precision == 1:
+            torch.manual_seed(1337)
+            head3 = se.LinearResidual(input_size=nfreq, output_size=nfreq, precision=precision).to(dev)
+            eng = se.EnhancementEngine(pre, head3, log_features=True, precision=precision)
+            opt3 = se.ClipAdam(head3.parameters(), lr=1e-4)
+            for _ in range(3):
+                loss = eng.train_step_graph(lengths, wavs, obj, opt3, grad_clip=1.0)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                loss = eng.train_step_graph(lengths, wavs, obj, opt3, grad_clip=1.0)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"   graph replay, ClipAdam: {ms:.3f} ms/step  {256 / ms * 1e3:.0f} audio-s/s  loss {loss.item():.4f}")
