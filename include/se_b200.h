@@ -241,6 +241,22 @@ int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_i
                       int64_t ld_tar, const int64_t* stft_len, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
                       const double* sums3, const float* grad_out, float* grad_offset, int64_t ld_g, void* stream);
 
+/* ---- active sampling (sampler.py:59-120, driven by runner.py:383-411) ----------------------------------------------------
+ * se_head_grad_embeddings: per-UTTERANCE gradients of the head -- row u of grads_out (n_utt, D_out*D_in + D_out) is
+ *   [d loss_u / d W (row-major), d loss_u / d b], the vector sampler.scoring builds with one backward call per utterance.
+ *   grad_offset holds d loss_u / d offset for every utterance at once (utterances do not interact, e.g. se_sisdr_mask_bwd
+ *   with grad_out = 1).  The split-K weight-gradient kernel runs with one split per utterance, so its partials are the answer.
+ *   CMVN of x: mean and std, or stat_sums, or neither.  ws: se_head_grad_embeddings_workspace(...) floats (0 = unsupported).
+ * se_match_scores: sampler.matching -- scores[j] = <key_j / (|key_j| + eps), mean_i query_i / (|query_i| + eps)>;
+ *   ws_d: n_query + 2 n_key doubles, ws_qbar: P floats. */
+int64_t se_head_grad_embeddings_workspace(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out);
+int se_head_grad_embeddings(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums,
+                            int64_t ld_stats, float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off,
+                            int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws, int64_t ws_floats,
+                            float* grads_out, void* stream);
+int se_match_scores(const float* query, int64_t n_query, const float* key, int64_t n_key, int64_t P, float eps, double* ws_d,
+                    float* ws_qbar, float* scores, void* stream);
+
 /* ---- gradient clipping + Adam on the head's parameters (runner.py:463-466: clip_grad_norm_ then optimizer.step) -------
  * params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors (<= 8) device pointers, numels their sizes.  Semantics of
  * torch.nn.utils.clip_grad_norm_(max_norm) (skipped if max_norm <= 0; the scaled gradient is written back) followed by

@@ -13,5 +13,6 @@ from .utils import masked_mean, masked_normalize_decibel           # noqa: F401
 from .runner_ops import get_length_masks, decode_wav, stft_lengths  # noqa: F401
 from .engine import EnhancementEngine                              # noqa: F401
 from .optim import ClipAdam                                        # noqa: F401
+from .sampler_ops import scoring, matching, thresholding           # noqa: F401
 
 __version__ = "0.1.0"

@@ -386,6 +386,19 @@ __global__ void head_bwd_reduce_kernel(const float* __restrict__ partials, int s
     }
 }
 
+// per-utterance partials (n_utt, m_rows, 272) -> embeddings (n_utt, Dout * Din + Dout) = [grad_W.view(-1), grad_b] (sampler.py:95-108)
+__global__ void head_grad_pack_kernel(const float* __restrict__ partials, int m_rows, int Din, int Dout, float* __restrict__ out) {
+    const long long P = (long long)Dout * Din + Dout;
+    const float* src = partials + (long long)blockIdx.y * m_rows * kMaxBRows;
+    float* dst = out + (long long)blockIdx.y * P;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const long long wn = (long long)Dout * Din;
+        const int n = i < wn ? (int)(i / Din) : (int)(i - wn);
+        const int k = i < wn ? (int)(i - (long long)n * Din) : Din;
+        dst[i] = src[(long long)n * kMaxBRows + k];
+    }
+}
+
 int num_sms() {
     static int sms = 0;
     if (sms == 0) {
@@ -399,12 +412,19 @@ int num_sms() {
 
 struct Geometry { int m_tiles, simt_rows, m_rows, splits; long long rows_per_split; };
 
-bool plan(long long R, long long n_frames, long long Din, long long Dout, Geometry* g) {
+// per_utt: one split per utterance (its partial IS that utterance's gradient: per-sample gradients for sampler.py:59-110)
+bool plan(long long R, long long n_frames, long long Din, long long Dout, Geometry* g, bool per_utt = false) {
     if (R <= 0 || n_frames < BK || Din <= 0 || Dout <= 0 || Din + 1 > kMaxBRows) return false;
     const int rem = (int)(Dout % BM);
     g->simt_rows = (Dout > BM && rem > 0 && rem <= kMaxSimtRows) ? rem : 0;
     g->m_tiles = (int)((Dout - g->simt_rows + BM - 1) / BM);
     g->m_rows = g->m_tiles * BM + g->simt_rows;
+    if (per_utt) {
+        if (R / n_frames > 0x7fffffffLL) return false;
+        g->rows_per_split = n_frames;
+        g->splits = (int)(R / n_frames);
+        return true;
+    }
     long long splits = num_sms() / g->m_tiles;
     if (splits < 1) splits = 1;
     long long rows = (R + splits - 1) / splits;
@@ -428,7 +448,7 @@ int64_t se_linear_head_bwd_tc_workspace(int64_t n_utt, int64_t n_frames, int64_t
 static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums, int64_t ld_stats,
                          float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt,
                          int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats,
-                         float* grad_W, float* grad_b, void* stream);
+                         float* grad_W, float* grad_b, void* stream, float* per_utt_out = nullptr);
 
 int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const float* std, int64_t ld_stats, float cmvn_eps,
                           const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt, int64_t n_frames,
@@ -448,15 +468,31 @@ int se_linear_head_bwd_fused(const float* x, int64_t ldx, const double* stat_sum
                          D_out, act, ws_partials, ws_floats, grad_W, grad_b, stream);
 }
 
+int64_t se_head_grad_embeddings_workspace(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out) {
+    Geometry g;
+    if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g, true)) return 0;
+    return (int64_t)g.splits * g.m_rows * kMaxBRows;
+}
+
+int se_head_grad_embeddings(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums,
+                            int64_t ld_stats, float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off,
+                            int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws, int64_t ws_floats,
+                            float* grads_out, void* stream) {
+    SE_REQUIRE(grads_out, "null pointer");
+    SE_REQUIRE((mean == nullptr) == (std == nullptr) && !(mean && stat_sums), "CMVN: give mean and std, or stat_sums, or neither");
+    return head_bwd_impl(x, ldx, mean, std, stat_sums, ld_stats, cmvn_eps, offset, grad_offset, ld_off, n_utt, n_frames, D_in, D_out,
+                         act, ws, ws_floats, nullptr, nullptr, stream, grads_out);
+}
+
 static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums, int64_t ld_stats,
                          float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt,
                          int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats,
-                         float* grad_W, float* grad_b, void* stream) {
-    SE_REQUIRE(x && offset && grad_offset && ws_partials && grad_W && n_utt > 0 && n_frames > 0, "bad argument");
+                         float* grad_W, float* grad_b, void* stream, float* per_utt_out) {
+    SE_REQUIRE(x && offset && grad_offset && ws_partials && (grad_W || per_utt_out) && n_utt > 0 && n_frames > 0, "bad argument");
     SE_REQUIRE(ldx >= D_in && ld_off >= D_out && ((!mean && !stat_sums) || ld_stats >= D_in), "row stride smaller than the row");
     SE_REQUIRE(act >= SE_ACT_IDENTITY && act <= SE_ACT_SIGMOID, "unknown activation %d", act);
     Geometry g;
-    if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g))
+    if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g, per_utt_out != nullptr))
         return fail(SE_ERR_UNSUPPORTED, "tensor-core head backward: shape outside its range (D_in=%lld, n_frames=%lld)",
                     (long long)D_in, (long long)n_frames);
     SE_REQUIRE(ws_floats >= (int64_t)g.splits * g.m_rows * kMaxBRows, "workspace too small");
@@ -481,6 +517,11 @@ static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const f
     int rc = secommon::check_launch("linear_head_bwd_tc_kernel");
     if (rc != SE_OK) return rc;
     const long long total = D_out * (D_in + 1);
+    if (per_utt_out) {
+        head_grad_pack_kernel<<<dim3((unsigned)((total + 1023) / 1024), (unsigned)n_utt), 256, 0, st>>>(ws_partials, a.m_rows, (int)D_in,
+                                                                                                      (int)D_out, per_utt_out);
+        return secommon::check_launch("head_grad_pack_kernel");
+    }
     head_bwd_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws_partials, g.splits, a.m_rows, (int)D_in, (int)D_out,
                                                                           grad_W, grad_b);
     return secommon::check_launch("head_bwd_reduce_kernel");

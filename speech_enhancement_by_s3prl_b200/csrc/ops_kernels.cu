@@ -302,6 +302,39 @@ __global__ void __launch_bounds__(256) adam_update_kernel(const AdamArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ active-sampling match scores (sampler.py:113-116)
+// scores[j] = < key_j / (|key_j| + eps),  mean_i query_i / (|query_i| + eps) >
+__global__ void __launch_bounds__(256) row_sumsq_kernel(const float* __restrict__ x, long long P, int chunks, double* __restrict__ out) {
+    const int row = blockIdx.x / chunks, chunk = blockIdx.x - row * chunks;
+    const long long per = (P + chunks - 1) / chunks, lo = chunk * per, hi = min(P, lo + per);
+    const float* r = x + (long long)row * P;
+    float acc[1] = {0.0f};
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) acc[0] += r[i] * r[i];
+    block_accumulate_to<1, float>(acc, out + row);
+}
+__global__ void __launch_bounds__(256) match_qbar_kernel(const float* __restrict__ q, int nq, long long P, float eps,
+                                                         const double* __restrict__ q_sumsq, float* __restrict__ qbar) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        for (int r = 0; r < nq; ++r) s += q[(long long)r * P + i] / ((float)sqrt(q_sumsq[r]) + eps);
+        qbar[i] = s / (float)nq;
+    }
+}
+__global__ void __launch_bounds__(256) match_dot_kernel(const float* __restrict__ k, long long P, int chunks,
+                                                        const float* __restrict__ qbar, double* __restrict__ dots) {
+    const int row = blockIdx.x / chunks, chunk = blockIdx.x - row * chunks;
+    const long long per = (P + chunks - 1) / chunks, lo = chunk * per, hi = min(P, lo + per);
+    const float* r = k + (long long)row * P;
+    float acc[1] = {0.0f};
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) acc[0] += r[i] * qbar[i];
+    block_accumulate_to<1, float>(acc, dots + row);
+}
+__global__ void match_finish_kernel(const double* __restrict__ k_sumsq, const double* __restrict__ dots, int nk, float eps,
+                                    float* __restrict__ scores) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nk) scores[j] = (float)(dots[j] / ((double)((float)sqrt(k_sumsq[j]) + eps)));
+}
+
 // ------------------------------------------------------------------ log-spectral L1 objective
 __global__ void l1_logspec_fwd_kernel(const float* __restrict__ logp, const float* __restrict__ tar,
                                       const long long* __restrict__ stft_len, int n_frames, int K, float eps,
@@ -921,6 +954,26 @@ int se_adam_clip_step(float* const* params, float* const* grads, float* const* e
     }
     adam_update_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     return secommon::check_launch("adam_update_kernel");
+}
+
+int se_match_scores(const float* query, int64_t n_query, const float* key, int64_t n_key, int64_t P, float eps, double* ws_d,
+                    float* ws_qbar, float* scores, void* stream) {
+    SE_REQUIRE(query && key && ws_d && ws_qbar && scores && n_query > 0 && n_key > 0 && P > 0, "bad argument");
+    SE_REQUIRE(n_query < (1 << 20) && n_key < (1 << 20), "too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* q_sumsq = ws_d;                       // [n_query] | k_sumsq [n_key] | dots [n_key]
+    double* k_sumsq = ws_d + n_query;
+    double* dots = k_sumsq + n_key;
+    SE_CUDA_CHECK(cudaMemsetAsync(ws_d, 0, sizeof(double) * (size_t)(n_query + 2 * n_key), st));
+    const int cq = pick_chunks(n_query, P, 4096), ck = pick_chunks(n_key, P, 4096);
+    row_sumsq_kernel<<<(unsigned)(n_query * cq), 256, 0, st>>>(query, P, cq, q_sumsq);
+    row_sumsq_kernel<<<(unsigned)(n_key * ck), 256, 0, st>>>(key, P, ck, k_sumsq);
+    long long blocks = (P + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    match_qbar_kernel<<<(unsigned)blocks, 256, 0, st>>>(query, (int)n_query, P, eps, q_sumsq, ws_qbar);
+    match_dot_kernel<<<(unsigned)(n_key * ck), 256, 0, st>>>(key, P, ck, ws_qbar, dots);
+    match_finish_kernel<<<(unsigned)((n_key + 127) / 128), 128, 0, st>>>(k_sumsq, dots, (int)n_key, eps, scores);
+    return secommon::check_launch("match_scores");
 }
 
 int se_mix_batch(const float* speech, int64_t speech_stride, const int64_t* speech_len, const float* noise, int64_t noise_stride,

@@ -1,0 +1,128 @@
+"""Active-sampling scoring (reference sampler.py:59-120, called from the sampler child process that
+runner.py:383-411 drives): per-utterance gradient embeddings of the mask head and their cosine match
+against the mean query gradient.
+
+``scoring`` in the reference runs one ``backward(retain_graph=True)`` per utterance.  For the
+projection heads of the named path (``Linear`` / ``LinearResidual`` with the spectral SISDR
+objective) every utterance's gradient comes out of ONE pass here: the per-utterance loss terms do
+not interact, so d loss_u / d offset for the whole batch is one launch of the objective's backward
+with grad_out = 1, and the split-K weight-gradient kernel run with one split per utterance leaves
+exactly the per-utterance (grad_W, grad_b) in its partials (``se_head_grad_embeddings``).
+Other heads / objectives (the recurrent ones are cuDNN, outside the path) go through
+``scoring_loop`` -- the reference's loop on the drop-in modules.
+"""
+import torch
+
+from . import _lib, model, objective, ops
+
+get_length_masks = ops.length_masks                                   # sampler.py:35-39
+
+
+def matching(query_scores, key_scores, eps=1e-12):
+    """sampler.py:113-116 in one pass over each matrix: (n_query, P), (n_key, P) -> (n_key,)."""
+    q, k = ops._c(query_scores, "query_scores"), ops._c(key_scores, "key_scores")
+    if q.dim() != 2 or k.dim() != 2 or q.shape[1] != k.shape[1]:
+        raise RuntimeError(f"matching: shapes {tuple(q.shape)} and {tuple(k.shape)} do not agree")
+    nq, P = q.shape
+    nk = k.shape[0]
+    with torch.cuda.device(q.device):
+        ws_d = torch.empty(nq + 2 * nk, device=q.device, dtype=torch.float64)
+        ws_q = torch.empty(P, device=q.device)
+        out = torch.empty(nk, device=q.device)
+        rc = _lib.load().se_match_scores(q.data_ptr(), nq, k.data_ptr(), nk, P, float(eps), ws_d.data_ptr(), ws_q.data_ptr(),
+                                         out.data_ptr(), ops._stream())
+        _lib.check(rc, "se_match_scores")
+    return out
+
+
+def thresholding(match_scores):
+    """sampler.py:119-120."""
+    return match_scores > 0
+
+
+def head_grad_embeddings(features, offset, grad_offset, activation, mean=None, std=None, cmvn_eps=1e-6):
+    """(B, F, Din) features, (B, F, Dout) offset and d loss_u / d offset -> (B, Dout*Din + Dout) rows
+    [grad_W.view(-1), grad_b] per utterance, in ``named_parameters`` order (sampler.py:95-108)."""
+    x, off, go = ops._c(features, "features"), ops._c(offset, "offset"), ops._c(grad_offset, "grad_offset")
+    B, F, Din = x.shape
+    Dout = off.shape[2]
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        ws_floats = lib.se_head_grad_embeddings_workspace(B, F, Din, Dout)
+        if ws_floats <= 0:
+            raise RuntimeError(f"se_head_grad_embeddings: shape (B={B}, F={F}, D_in={Din}, D_out={Dout}) is not supported")
+        ws = torch.empty(ws_floats, device=x.device)
+        out = torch.empty(B, Dout * Din + Dout, device=x.device)
+        rc = lib.se_head_grad_embeddings(x.data_ptr(), Din, ops._p(mean), ops._p(std), None, Din, float(cmvn_eps), off.data_ptr(),
+                                         go.data_ptr(), Dout, B, F, Din, Dout, ops.ACT[activation], ws.data_ptr(), ws_floats,
+                                         out.data_ptr(), ops._stream())
+        _lib.check(rc, "se_head_grad_embeddings")
+    return out
+
+
+def _batched_ok(head, criterion, features):
+    if type(head) not in (model.Linear, model.LinearResidual) or type(criterion) is not objective.SISDR:
+        return False
+    B, F, Din = features.shape
+    return _lib.load().se_head_grad_embeddings_workspace(B, F, Din, head.linear.weight.shape[0]) > 0
+
+
+@torch.no_grad()
+def scoring_batched(head, criterion, features, linear_inp, linear_tar, stft_lengths, mean=False):
+    """Gradient embeddings of a Linear / LinearResidual head under objective.SISDR without a Python loop.
+    mean=False: (B, P), row u = gradient of the loss of utterance u alone (what criterion returns for a batch of one);
+    mean=True: (1, P), gradient of the batch-mean loss."""
+    x = ops._c(features, "features")
+    B, F, Din = x.shape
+    K = head.linear.weight.shape[0]
+    mean_t = std_t = None
+    if isinstance(head, model.LinearResidual):
+        if head.cmvn:
+            mean_t, std_t = ops.cmvn_stats(x)
+        offset = ops.linear_head(x, head.linear.weight, head.linear.bias, head.activation, mean_t, std_t, head.eps,
+                                 precision=head.precision)
+        lin = ops._c(linear_inp, "linear_inp")
+        eps_c = head.eps
+    else:                                                             # Linear: predicted = act(W x + b), no mask multiply
+        offset = ops.linear_head(x, head.linear.weight, head.linear.bias, head.activation, precision=head.precision)
+        lin = None
+        eps_c = 1e-6
+    tar = ops._c(linear_tar, "linear_tar")
+    frames = ops._c(stft_lengths, "stft_lengths", torch.int64)
+    if lin is not None:
+        _, sums3 = ops.sisdr_mask_fwd(offset, lin, tar, frames, K, criterion.eps)
+        go = ops.sisdr_mask_bwd(offset, lin, tar, frames, K, sums3, torch.ones(B, device=x.device), criterion.eps)
+    else:
+        _, sums3 = ops.sisdr_mask_fwd(None, offset, tar, frames, K, criterion.eps)
+        go = ops.sisdr_mask_bwd(None, offset, tar, frames, K, sums3, torch.ones(B, device=x.device), criterion.eps)
+    grads = head_grad_embeddings(x, offset, go, head.activation, mean_t, std_t, eps_c)
+    return grads.mean(dim=0, keepdim=True) if mean else grads
+
+
+def scoring_loop(head, criterion, features, linear_inp, linear_tar, stft_lengths, mean=False):
+    """The reference's loop (sampler.py:77-110) on the drop-in modules: one backward per utterance."""
+    predicted, results = head(features=features, linears=linear_inp)
+    extra = {k: v for k, v in results.items()}
+    idx = [slice(None)] if mean else [slice(u, u + 1) for u in range(predicted.shape[0])]
+    grads = []
+    for sl in idx:
+        kw = {k: v[sl] for k, v in extra.items()}
+        loss, _ = criterion(predicted=predicted[sl], linear_tar=linear_tar[sl], linear_inp=linear_inp[sl],
+                            stft_lengths=stft_lengths[sl], **kw)
+        head.zero_grad()
+        loss.backward(retain_graph=True)
+        grads.append(torch.cat([p.grad.reshape(-1) for _, p in head.named_parameters() if p.grad is not None]).detach())
+        head.zero_grad()
+    return torch.stack(grads, dim=0)
+
+
+def scoring(preprocessor, head, criterion, lengths, wavs, mean=False, feat_log=True):
+    """sampler.py:59-110 for ``--from_rawfeature``: (B, 3, T) batch -> (B, n_params) gradient embeddings
+    ((1, n_params) with mean=True)."""
+    c = preprocessor.get_feat_config
+    ch_i, ch_t = int(getattr(preprocessor, "channel_inp", 0)), int(getattr(preprocessor, "channel_tar", 1))
+    feats, linear_inp, linear_tar = preprocessor(wavs, [c("linear", ch_i, log=feat_log), c("linear", ch_i), c("linear", ch_t)])
+    frames = lengths.to(feats.device) // preprocessor._win_args["hop_length"] + 1
+    if _batched_ok(head, criterion, feats):
+        return scoring_batched(head, criterion, feats, linear_inp, linear_tar, frames, mean=mean)
+    return scoring_loop(head, criterion, feats, linear_inp, linear_tar, frames, mean=mean)

@@ -978,3 +978,72 @@ def test_train_step_graph_with_clip_adam(se):
         finals.append((loss.item(), head.linear.weight.detach().clone()))
     assert finals[0][0] == pytest.approx(finals[1][0], abs=0.02)
     assert (finals[0][1] - finals[1][1]).abs().max().item() < 2e-3       # 8 Adam steps of lr 1e-3: updates of ~8e-3
+
+
+# ------------------------------------------------------------------------------ active sampling: gradient embeddings + matching
+def test_matching_matches_reference_formula(se):
+    g = torch.Generator().manual_seed(9)
+    for nq, nk, P in [(32, 12, 66306), (3, 5, 1000), (1, 1, 7)]:
+        q = torch.randn(nq, P, generator=g).cuda() * 3
+        k = torch.randn(nk, P, generator=g).cuda() * 0.1
+        k[0] = 0.0                                                             # a zero gradient scores 0 (eps in the norm)
+        got = se.matching(q, k)
+        qn = q.double() / (q.double().pow(2).sum(-1, keepdim=True).pow(0.5) + 1e-12)      # sampler.py:113-116
+        kn = k.double() / (k.double().pow(2).sum(-1, keepdim=True).pow(0.5) + 1e-12)
+        ref = torch.mm(kn, qn.mean(0).unsqueeze(1)).reshape(-1)
+        assert (got.double() - ref).abs().max().item() < 2e-6
+        assert torch.equal(se.thresholding(got), got > 0)
+    with pytest.raises(RuntimeError):
+        se.matching(torch.zeros(2, 3), torch.zeros(2, 3))
+
+
+@pytest.mark.parametrize("n_fft,cmvn,act", [(400, True, "Sigmoid"), (512, True, "Sigmoid"), (400, False, "ReLU")])
+def test_scoring_batched_equals_per_utterance_loop(se, n_fft, cmvn, act):
+    """Per-utterance gradient embeddings in one pass (se_head_grad_embeddings) against the reference's loop of backward
+    calls (sampler.py:77-110) on the drop-in modules, and against the CPU oracle's autograd."""
+    from speech_enhancement_by_s3prl_b200 import sampler_ops
+    ora, mine = make_pair(se, n_fft)
+    hop = mine._win_args["hop_length"]
+    K = n_fft // 2 + 1
+    B, T = 5, 12000
+    lengths, wavs = synth(B, T, seed=n_fft, lengths=torch.LongTensor([12000, 9000, 12000, 5000, 11111]))
+    torch.manual_seed(4)
+    head = se.LinearResidual(input_size=K, output_size=K, activation=act, cmvn=cmvn).cuda()
+    crit = se.SISDR()
+    c = mine.get_feat_config
+    feats, lin_i, lin_t = mine(wavs.cuda(), [c("linear", 0, log=True), c("linear", 0), c("linear", 1)])
+    frames = lengths.cuda() // hop + 1
+    assert sampler_ops._batched_ok(head, crit, feats)
+    fast = sampler_ops.scoring_batched(head, crit, feats, lin_i, lin_t, frames)
+    loop = sampler_ops.scoring_loop(head, crit, feats, lin_i, lin_t, frames)
+    assert fast.shape == loop.shape == (B, K * K + K)
+    for u in range(B):
+        scale = loop[u].abs().max().item()
+        assert (fast[u] - loop[u]).abs().max().item() < 2e-3 * scale          # TF32 operands in the batched kernel
+        assert torch.nn.functional.cosine_similarity(fast[u], loop[u], dim=0).item() > 0.99999
+    # mean=True: gradient of the batch-mean loss
+    fast_m = sampler_ops.scoring_batched(head, crit, feats, lin_i, lin_t, frames, mean=True)
+    loop_m = sampler_ops.scoring_loop(head, crit, feats, lin_i, lin_t, frames, mean=True)
+    assert fast_m.shape == (1, K * K + K)
+    assert torch.nn.functional.cosine_similarity(fast_m[0], loop_m[0], dim=0).item() > 0.99999
+    # the public entry point takes the batch
+    top = se.scoring(mine, head, crit, lengths.cuda(), wavs.cuda())
+    assert (top - fast).abs().max().item() <= 1e-6 * fast.abs().max().item()
+    # oracle (CPU autograd, fp32) for one utterance
+    if cmvn and act == "Sigmoid":
+        w = head.linear.weight.detach().cpu().clone().requires_grad_(True)
+        b = head.linear.bias.detach().cpu().clone().requires_grad_(True)
+        oc = ora.get_feat_config
+        f_o, li_o, lt_o = ora(wavs[1:2], [oc("linear", 0, log=True), oc("linear", 0), oc("linear", 1)])
+        pred, _ = sp.linear_residual_head(f_o, li_o, w, b)
+        masks = sp.length_masks(sp.stft_lengths(lengths[1:2], hop))[:, :pred.shape[1]]
+        if masks.shape[1] < pred.shape[1]:
+            masks = torch.nn.functional.pad(masks, (0, pred.shape[1] - masks.shape[1]))
+        ref_loss, _ = sp.sisdr_spectral(pred, lt_o, masks)
+        ref_loss.backward()
+        ref = torch.cat([w.grad.reshape(-1), b.grad.reshape(-1)])
+        assert torch.nn.functional.cosine_similarity(fast[1].cpu(), ref, dim=0).item() > 0.9999
+        # scores: the sampler's decision is the sign / ranking of the match
+        s_fast = se.matching(fast[:2], fast[2:])
+        s_loop = se.matching(loop[:2], loop[2:])
+        assert (s_fast - s_loop).abs().max().item() < 2e-3
