@@ -108,6 +108,9 @@ int se_mask_istft_strided(const float* noisy, const float* clean, int64_t utt_st
 #define SE_FLAG_WANT_SPEC 1        /* se_mask_istft_ex: also accumulate the spectral SI-SDR sums (= want_spec) */
 #define SE_FLAG_SUMS_ZEROED 2      /* the caller has zeroed the sums buffer on this stream: skip the library's memset, so
                                       that consecutive kernels of the fused step keep their programmatic (PDL) edges */
+#define SE_FLAG_MASK_IS_POWER 4    /* se_mask_istft_ex: `mask` holds a TARGET power spectrum P (e.g. the upstream SpecHead's
+                                      output, runner.py:272-281): wav_out = istft(P, phase(STFT(noisy))) = iSTFT(sqrt(P) X / |X|),
+                                      sqrt(P) where X = 0 -- _decode_wav on a predicted spectrum without materialising the phase */
 int se_mask_istft_ex(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
                      const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
                      float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags, void* stream);

@@ -10,7 +10,7 @@ from .model import Linear, LinearResidual, LSTM, Residual          # noqa: F401
 from .objective import SISDR, L1, WSD                              # noqa: F401
 from .evaluation import sisdr_eval, sisdr_eval_batch               # noqa: F401
 from .utils import masked_mean, masked_normalize_decibel           # noqa: F401
-from .runner_ops import get_length_masks, decode_wav, stft_lengths  # noqa: F401
+from .runner_ops import get_length_masks, decode_wav, pseudo_wav, stft_lengths  # noqa: F401
 from .engine import EnhancementEngine                              # noqa: F401
 from .optim import ClipAdam                                        # noqa: F401
 from .sampler_ops import scoring, matching, thresholding           # noqa: F401

@@ -398,18 +398,26 @@ constexpr size_t kSmem3 = (size_t)(kWarps3 * 2) * kHwBytes3 + 2 * M * 8;
 static_assert(kHwBytes3 % 16 == 0 && kNoisyBytes3 % 16 == 0, "16-byte aligned cp.async destinations");
 
 // One masked pair of bins: spectral-loss terms (own) and the merged, conjugated inverse-FFT input
+// PM ("power mode"): ga / gb are the target POWER of the bins, the output keeps the phase of X: Y = sqrt(g) X / |X|, and
+// Y = sqrt(g) where X = 0 (atan2(0, 0) = 0) -- OnlinePreprocessor.istft(linears, phase_inp) without the phase (runner.py:266-281)
+template <bool PM> __device__ __forceinline__ float2 apply_gain(float2 x, float g) {
+    if (!PM) return cscale(x, fast_sqrt(g));
+    const float p = x.x * x.x + x.y * x.y;
+    return p > 0.0f ? cscale(x, fast_sqrt(g) * rsqrtf(p)) : make_float2(fast_sqrt(g), 0.0f);
+}
+template <bool PM>
 __device__ __forceinline__ void mask_merge(float2 xa, float2 xb, float ga, float gb, float2 w, bool own, float& ra, float& rb,
                                            float2& ca, float2& cb) {
     if (own) {
-        ra = fmaxf(ga * (xa.x * xa.x + xa.y * xa.y), 0.0f);
-        rb = fmaxf(gb * (xb.x * xb.x + xb.y * xb.y), 0.0f);
+        ra = fmaxf(PM ? ga : ga * (xa.x * xa.x + xa.y * xa.y), 0.0f);
+        rb = fmaxf(PM ? gb : gb * (xb.x * xb.x + xb.y * xb.y), 0.0f);
     }
-    merge_pair_conj(cscale(xa, fast_sqrt(ga)), cscale(xb, fast_sqrt(gb)), w, ca, cb);
+    merge_pair_conj(apply_gain<PM>(xa, ga), apply_gain<PM>(xb, gb), w, ca, cb);
 }
 
 // CS: the noisy spectrum comes from K1's workspace (a.cspec) instead of being recomputed from the waveform -- one transform
 // less per frame.  cp.async groups are then [spectrum row + mask row], [clean] per frame.
-template <bool CS>
+template <bool CS, bool PM = false>
 __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem3[];
     secommon::TraceScope trace(a.trace, 3);
@@ -514,20 +522,22 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 x = s4[16 * q + j];
-                mask_merge(make_float2(x.x, x.y), make_float2(x.z, x.w), mb[j + 16 * q], mb[M - j - 16 * q], twn[q], own,
+                mask_merge<PM>(make_float2(x.x, x.y), make_float2(x.z, x.w), mb[j + 16 * q], mb[M - j - 16 * q], twn[q], own,
                            ra[q], rb[q], ca[q], cbv[q]);
             }
             const float g128 = mb[128];
             const float2 x128 = reinterpret_cast<const float2*>(nb)[256];
-            if (own) r128 = fmaxf(g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
+            if (own) r128 = fmaxf(PM ? g128 : g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
             __syncwarp(hmask);
             if (more) {
                 stage_spec(f + 1);
                 stage_row(mb, mrow0 + (long long)(f + 1) * a.mask_stride, M + 1, j, mask_padded);
             }
             cp_async_commit();
-            const float s128 = 2.0f * fast_sqrt(g128);
-            scatter_mirror(ca, cbv, make_float2(s128 * x128.x, s128 * x128.y), lane, v);
+            float2 y128;
+            if (PM) { y128 = apply_gain<true>(x128, g128); y128.x *= 2.0f; y128.y *= 2.0f; }
+            else { const float s128 = 2.0f * fast_sqrt(g128); y128 = make_float2(s128 * x128.x, s128 * x128.y); }
+            scatter_mirror(ca, cbv, y128, lane, v);
         }
 #pragma unroll 1
         for (int pass = CS ? 1 : 0; pass < (own ? 3 : 2); ++pass) {
@@ -552,17 +562,19 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_ker
                 for (int q = 0; q < 8; ++q) {
                     float2 xa, xb;
                     split_pair(v[q], zm[q], twn[q], xa, xb);
-                    mask_merge(xa, xb, mb[j + 16 * q], mb[M - j - 16 * q], twn[q], own, ra[q], rb[q], ca[q], cbv[q]);
+                    mask_merge<PM>(xa, xb, mb[j + 16 * q], mb[M - j - 16 * q], twn[q], own, ra[q], rb[q], ca[q], cbv[q]);
                 }
                 const float g128 = mb[128];
                 const float2 x128 = make_float2(2.0f * v[8].x, -2.0f * v[8].y);    // k = 128 pairs with itself: X = 2 conj(Z[128])
-                if (own) r128 = fmaxf(g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
+                if (own) r128 = fmaxf(PM ? g128 : g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
                 __syncwarp(hmask);
                 if (more) stage_row(mb, mrow0 + (long long)(f + 1) * a.mask_stride, M + 1, j, mask_padded);
                 cp_async_commit();
                 // Zinv[128] = 2 conj(Y[128]) (same factor 2 as merge_pair_conj); its conjugate feeds the FFT
-                const float s128 = 2.0f * fast_sqrt(g128);
-                scatter_mirror(ca, cbv, make_float2(s128 * x128.x, s128 * x128.y), lane, v);
+                float2 y128;
+                if (PM) { y128 = apply_gain<true>(x128, g128); y128.x *= 2.0f; y128.y *= 2.0f; }
+                else { const float s128 = 2.0f * fast_sqrt(g128); y128 = make_float2(s128 * x128.x, s128 * x128.y); }
+                scatter_mirror(ca, cbv, y128, lane, v);
             } else if (pass == 1) {
                 // v[q] = conj(z[m]), z[m] = (x[2m], x[2m+1]) unnormalised, m = j + 16 q; signs and scales are in s_bw2
                 if (CS) cp_async_wait<1>(); else cp_async_wait<2>();   // C(f) has landed
@@ -701,6 +713,7 @@ int prepare512() {
     SE_OPT((stft512_run_kernel<false, false, true, true, true>), kSmem1Run);
     SE_OPT(mask_istft512_kernel<false>, kSmem3);
     SE_OPT(mask_istft512_kernel<true>, kSmem3);
+    SE_OPT((mask_istft512_kernel<false, true>), kSmem3);
 #undef SE_OPT
     return SE_OK;
 }
@@ -802,7 +815,9 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = (secommon::pdl_mask() & 2) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (a.cspec) SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<true>, a, plan));
+    if (a.mask_is_power && a.cspec) return secommon::fail(SE_ERR_UNSUPPORTED, "power mode reads the waveform, not the spectrum workspace");
+    if (a.mask_is_power) SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<false, true>, a, plan));
+    else if (a.cspec) SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<true>, a, plan));
     else SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<false>, a, plan));
     return secommon::check_launch("mask_istft512_kernel");
 }

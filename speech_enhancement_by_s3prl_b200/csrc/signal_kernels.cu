@@ -347,6 +347,7 @@ static int mask_istft_impl(const float* noisy, const float* spec_ws, const float
     a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
     a.wav_out = wav_out; a.out_stride = out_stride; a.out_len = hop * (a.n_frames - 1); a.pad_to = (int)pad_to;
     a.sums = sums; a.want_spec = (want_spec && clean && sums) ? 1 : 0; a.mask_stride = mask_stride;
+    a.mask_is_power = (flags & SE_FLAG_MASK_IS_POWER) ? 1 : 0;
     a.trace = secommon::trace_ptr();
     SE_REQUIRE(out_stride >= a.out_len && out_stride >= pad_to, "out_stride=%lld too small", (long long)out_stride);
     cudaStream_t st = (cudaStream_t)stream;

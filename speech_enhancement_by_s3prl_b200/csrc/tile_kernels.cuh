@@ -78,6 +78,7 @@ struct MaskIstftArgs {
     long long mask_stride;     // floats between consecutive frames of mask (>= K)
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
     const float* cspec;        // spectrum workspace written by K1 (then `noisy` is not read), or null (512/256 only)
+    int mask_is_power;         // `mask` holds the TARGET power spectrum: output = iSTFT(sqrt(mask) e^{i phase(noisy)}) (runner.py:266-281)
 };
 
 SE_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -357,15 +358,23 @@ SE_HD void mask_istft_tile(Exec& ex, const MaskIstftArgs& a, int utt, int tile, 
             float2 xb = rfft_split(zb, za, s.twN[k2]);
             if (k == 0) { xa.y = 0.0f; xb.y = 0.0f; }
             const float ga = mk[k], gb = mk[k2];
-            const float2 ya = cscale(xa, sqrtf(ga)), yb = cscale(xb, sqrtf(gb));
+            float2 ya, yb;
+            if (a.mask_is_power) {            // polar(sqrt(power), phase(X)); phase(0) = 0
+                const float qa = xa.x * xa.x + xa.y * xa.y, qb = xb.x * xb.x + xb.y * xb.y;
+                ya = qa > 0.0f ? cscale(xa, sqrtf(ga) * rsqrtf(qa)) : make_float2(sqrtf(ga), 0.0f);
+                yb = qb > 0.0f ? cscale(xb, sqrtf(gb) * rsqrtf(qb)) : make_float2(sqrtf(gb), 0.0f);
+            } else {
+                ya = cscale(xa, sqrtf(ga));
+                yb = cscale(xb, sqrtf(gb));
+            }
             if (spec) {
                 const int f = f_lo + g;
                 if (f >= own_lo && f < own_hi) {
-                    const float pa = ga * (xa.x * xa.x + xa.y * xa.y), ta = ptar[g * K + k];
+                    const float pa = a.mask_is_power ? ga : ga * (xa.x * xa.x + xa.y * xa.y), ta = ptar[g * K + k];
                     const float ra = pa > 0.0f ? pa : 0.0f;            // relu, objective.py:89
                     acc[SUM_SPEC_ST] += sqrtf(ra * ta); acc[SUM_SPEC_TT] += ta; acc[SUM_SPEC_SS] += ra;
                     if (k2 != k) {
-                        const float pb = gb * (xb.x * xb.x + xb.y * xb.y), tb = ptar[g * K + k2];
+                        const float pb = a.mask_is_power ? gb : gb * (xb.x * xb.x + xb.y * xb.y), tb = ptar[g * K + k2];
                         const float rb = pb > 0.0f ? pb : 0.0f;
                         acc[SUM_SPEC_ST] += sqrtf(rb * tb); acc[SUM_SPEC_TT] += tb; acc[SUM_SPEC_SS] += rb;
                     }

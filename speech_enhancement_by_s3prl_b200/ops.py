@@ -102,7 +102,7 @@ def stft_padded(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10)
     return out
 
 
-FLAG_WANT_SPEC, FLAG_SUMS_ZEROED = 1, 2
+FLAG_WANT_SPEC, FLAG_SUMS_ZEROED, FLAG_MASK_IS_POWER = 1, 2, 4
 
 
 SPEC_WS_FLOATS = 516
@@ -311,7 +311,7 @@ def istft(power, phase, n_fft, hop, window, pad_to=0):
 
 
 def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, want_sums=True, want_spec=True,
-               out=None, sums=None, mask_padded=False, sums_zeroed=False, spec_ws=None):
+               out=None, sums=None, mask_padded=False, sums_zeroed=False, spec_ws=None, mask_is_power=False):
     """Fused ``istft(linear_inp * mask, phase_inp)`` straight from the noisy waveform -- or, with ``spec_ws`` (the
     workspace stft_features filled for the same wavs / ch_inp), from the spectrum K1 already computed.
 
@@ -332,6 +332,7 @@ def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, 
             sums = torch.empty(B, NSUMS, device=wavs.device, dtype=torch.float64)
         clean = None if ch_tar is None else wavs.data_ptr() + 4 * int(ch_tar) * T
         flags = (FLAG_WANT_SPEC if want_spec else 0) | (FLAG_SUMS_ZEROED if sums_zeroed else 0)
+        flags |= FLAG_MASK_IS_POWER if mask_is_power else 0     # `mask` = target power; output keeps the noisy phase
         if spec_ws is not None:
             assert spec_ws.shape == (B, F, SPEC_WS_FLOATS) and spec_ws.dtype == torch.float32 and spec_ws.is_contiguous()
             rc = _lib.load().se_mask_istft_ws(spec_ws.data_ptr(), clean, C * T, mask.data_ptr(), mask_stride, _p(lengths), B, T,

@@ -1047,3 +1047,30 @@ def test_scoring_batched_equals_per_utterance_loop(se, n_fft, cmvn, act):
         s_fast = se.matching(fast[:2], fast[2:])
         s_loop = se.matching(loop[:2], loop[2:])
         assert (s_fast - s_loop).abs().max().item() < 2e-3
+
+
+# ------------------------------------------------------------------------------ pseudo-wave generation (runner.py:266-305)
+@pytest.mark.parametrize("n_fft", [512, 400, 1024])
+def test_pseudo_wav_matches_decode_wav_of_the_oracle(se, n_fft):
+    """_pseudo_clean / _pseudo_noise: a predicted power spectrum with the noisy phase -> waveform at -25 dB.  The fused path
+    (no phase tensor) against the oracle's preprocessor.istft(linears, phase_inp) + pad + masked_normalize_decibel, on a
+    zero-padded ragged batch (frames of exact zeros take the atan2(0, 0) = 0 branch)."""
+    ora, mine = make_pair(se, n_fft)
+    B, T = 4, 20000
+    lengths, wavs = synth(B, T, seed=n_fft + 1, lengths=torch.LongTensor([20000, 15000, 9000, 20000]))
+    c = ora.get_feat_config
+    _, lin_i, phase_i, lin_t = ora(wavs, [c("linear", 0), c("linear", 0), c("phase", 0), c("linear", 1)])
+    g = torch.Generator().manual_seed(1)
+    predicted = lin_t * (0.5 + torch.rand(lin_t.shape, generator=g)) + 1e-6       # what a SpecHead (ReLU output) would emit
+    ref = sp.decode_wav(ora, predicted, phase_i, lengths, target_level=-25)
+    got = se.pseudo_wav(mine, predicted.cuda(), wavs.cuda(), lengths.cuda(), target_level=-25)
+    assert got.shape == ref.shape
+    for b in range(B):
+        n = int(lengths[b])
+        assert sisdr_db(got[b, :n].cpu(), ref[b, :n]) > 60.0                     # same waveform to ~1e-3 relative
+        level = 10 * torch.log10(got[b, :n].pow(2).mean()).item()
+        assert level == pytest.approx(-25.0, abs=1e-3)
+    # the unfused drop-in sequence gives the same answer (decode_wav on K1's phase)
+    feats = mine(wavs.cuda(), [mine.get_feat_config("phase", 0)])
+    unfused = se.decode_wav(mine, predicted.cuda(), feats[0], lengths.cuda(), target_level=-25)
+    assert (unfused - got).abs().max().item() < 2e-4 * got.abs().max().item()
