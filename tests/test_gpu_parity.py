@@ -1074,3 +1074,33 @@ def test_pseudo_wav_matches_decode_wav_of_the_oracle(se, n_fft):
     feats = mine(wavs.cuda(), [mine.get_feat_config("phase", 0)])
     unfused = se.decode_wav(mine, predicted.cuda(), feats[0], lengths.cuda(), target_level=-25)
     assert (unfused - got).abs().max().item() < 2e-4 * got.abs().max().item()
+
+
+# ------------------------------------------------------------------------------ BASELINE.json configs[3]: long-form utterances
+@pytest.mark.parametrize("n_fft,secs", [(1024, 60.0), (512, 60.0), (400, 20.0)])
+def test_long_form_eval_step_matches_oracle(se, n_fft, secs):
+    """60 s utterances (960 000 samples; the reference's own length masks stop at 50 s, runner.py:32) through the fused
+    evaluation step at n_fft 1024 / hop 256 -- the long-form configuration -- and the other geometries, against the oracle."""
+    from speech_enhancement_by_s3prl_b200 import synth as synth_mod
+    ora, mine = make_pair(se, n_fft)
+    K = n_fft // 2 + 1
+    lengths, wavs = synth_mod.batch(2, secs)
+    T = wavs.shape[2]
+    lengths = lengths.clone()
+    lengths[1] = T - 12345
+    wavs[1, :, T - 12345:] = 0
+    torch.manual_seed(1337)
+    head = se.LinearResidual(input_size=K, output_size=K).cuda()
+    c = ora.get_feat_config
+    ora.feat_list = [c("linear", 0, log=True), c("linear", 0, log=True), c("linear", 0), c("phase", 0), c("linear", 1), c("phase", 1)]
+    with torch.no_grad():
+        ref = sp.eval_step(ora, dict(weight=head.linear.weight.detach().cpu(), bias=head.linear.bias.detach().cpu()), lengths, wavs)
+    for precision in (0, 1):
+        eng = se.EnhancementEngine(mine, head, log_features=True, precision=precision)
+        out = eng.eval_step(lengths.cuda(), wavs.cuda())
+        np.testing.assert_allclose(out["sisdr"].cpu().numpy(), ref["sisdr"].numpy(), atol=SISDR_TOL_DB)
+        assert out["loss_per_utt"].mean().item() == pytest.approx(ref["loss"].item(), abs=5e-3)
+        for b in range(2):
+            n = int(lengths[b])
+            assert sisdr_db(out["wav_predicted"][b, :n].cpu(), ref["wav_predicted"][b, :n]) > 40.0
+        assert out["wav_predicted"].shape == (2, T)
