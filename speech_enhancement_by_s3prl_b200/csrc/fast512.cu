@@ -38,6 +38,13 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
+// log(x) for x >= log_eps > 0 (never denormal): lg2.approx * ln 2 without __logf's denormal range fix-up (4 of its 8 instructions)
+__device__ __forceinline__ float fast_log(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.693147182464599609375f;
+}
+
 // ---- asynchronous staging (cp.async): the global loads of frame i+1 are in flight while frame i is
 // transformed, so no half-warp ever waits on a DRAM round trip between its transforms.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -156,15 +163,17 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 // CSPEC: the complex spectrum goes to the workspace row `cs` in the layout K3 consumes (kSpecFloats per frame):
 // float4 (X[k], X[M-k]) at index 16 q + j for k = j + 16 q < 128, and X[128] at floats 512, 513.
 constexpr int kSpecFloats = SE_SPEC_WS_FLOATS;
+// STATS: sacc = the half-warp's (sum x, sum x^2) accumulators in REGISTERS: slot q <-> bin j + 16 q, slot 8 + q <-> bin
+// 256 - (j + 16 q), slot 16 <-> bin 128 (lane 0)
 template <bool POWER, bool PHASE, bool LOGP, bool STATS, bool CSPEC = false>
 __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (&zm)[8], const float2 (&twn)[8], int j,
-                                           const StftArgs& a, long long o, float2* __restrict__ acc,
+                                           const StftArgs& a, long long o, float2 (&sacc)[17],
                                            float* __restrict__ cs = nullptr) {
     float* pw = POWER ? a.power + o : nullptr;
     float* lg = LOGP ? a.logp + o : nullptr;
     float* ph = PHASE ? a.phase + o : nullptr;
-    auto stat = [&](int k, float x) {
-        if (STATS) acc[k] = pfma(make_float2(x, x), make_float2(1.0f, x), acc[k]);
+    auto stat = [&](int slot, float x) {
+        if (STATS) sacc[slot] = pfma(make_float2(x, x), make_float2(1.0f, x), sacc[slot]);
     };
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -175,10 +184,10 @@ __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (
         const float pa = xa.x * xa.x + xa.y * xa.y, pb = xb.x * xb.x + xb.y * xb.y;
         if (POWER) { pw[k] = pa; pw[M - k] = pb; }
         float la = 0.f, lb = 0.f;
-        if (LOGP) { la = __logf(pa + a.log_eps); lb = __logf(pb + a.log_eps); lg[k] = la; lg[M - k] = lb; }
+        if (LOGP) { la = fast_log(pa + a.log_eps); lb = fast_log(pb + a.log_eps); lg[k] = la; lg[M - k] = lb; }
         if (PHASE) { ph[k] = atan2f(k == 0 ? 0.0f : xa.y, xa.x); ph[M - k] = atan2f(k == 0 ? 0.0f : xb.y, xb.x); }
-        stat(k, LOGP ? la : pa);
-        stat(M - k, LOGP ? lb : pb);
+        stat(q, LOGP ? la : pa);
+        stat(8 + q, LOGP ? lb : pb);
     }
     if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
         const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
@@ -186,9 +195,9 @@ __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (
         const float p = x.x * x.x + x.y * x.y;
         float l = 0.f;
         if (POWER) pw[128] = p;
-        if (LOGP) { l = __logf(p + a.log_eps); lg[128] = l; }
+        if (LOGP) { l = fast_log(p + a.log_eps); lg[128] = l; }
         if (PHASE) ph[128] = atan2f(x.y, x.x);
-        stat(128, LOGP ? l : p);
+        stat(16, LOGP ? l : p);
     }
 }
 
@@ -228,37 +237,58 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
         fft256<-1>(v, xbuf, j, tw, hmask);
         float2 zm[8];
         fetch_mirror(v, lane, zm);
-        emit_frame<POWER, PHASE, LOGP, false>(v, zm, twn, j, a, (long long)gg * a.spec_stride, nullptr);
+        float2 no_stats[17];
+        emit_frame<POWER, PHASE, LOGP, false>(v, zm, twn, j, a, (long long)gg * a.spec_stride, no_stats);
         __syncwarp(hmask);                                          // stage[buf] is free for the prefetch after next
     }
 }
 
 // hop = 256 (= N/2): every half-warp owns a RUN of consecutive frames of one utterance (F / rpu frames, the first F mod rpu
-// runs one more) and keeps two 256-sample slots: frame f reads (first, second) = (slot p, slot p^1), and
-// as soon as the frame is in registers the dead first slot receives the second half of frame f+1 (cp.async), which has a
-// whole transform to land behind.  No block-level barrier in the frame loop.
+// runs one more).  The kernel is bound by shared-memory wavefronts and the fp32 pipe in equal parts (tools/micro/fft_loop.cu:
+// the transform alone is 62 SM-cycles, its transpose 34 of them), so everything except the transpose stays out of shared
+// memory: the frame's raw samples live in REGISTERS -- lane j holds the pairs m = j + 16 r -- as two half-frame buffers;
+// frame f reads (first, second) = (A, B), and as soon as it is windowed the dead first buffer receives the second half of
+// frame f+1 straight from global memory (coalesced 8-byte loads, a whole transform to land behind); the next frame reads
+// (B, A).  The window (pre-scaled by 1/2) and the CMVN accumulators are per-lane registers too.  No block-level barrier in
+// the frame loop.
 // STATS: the sum and the sum of squares per (utterance, bin) of the feature written (log-power if LOGP, else power) -- the
-// CMVN statistics of the mask head (model.py:30) -- are accumulated in the half-warp's private shared-memory row (fp32 over
-// the few frames of a run), combined over the CTA's half-warps in double precision after ONE barrier at the end, and added
-// to stat_sums with one double atomicAdd pair per (CTA, utterance, bin).
+// CMVN statistics of the mask head (model.py:30) -- are accumulated in registers (fp32 over the few frames of a run), parked
+// in the half-warp's shared-memory row at the end, combined over the CTA's half-warps in double precision after ONE barrier,
+// and added to stat_sums with one double atomicAdd pair per (CTA, utterance, bin).
 constexpr int kAccFloat2 = M + 2;                                         // bins 0..256, padded to a 16-byte multiple
-constexpr int kHwBytes1 = M * 8 + 2 * H * 4 + kAccFloat2 * 8;             // transpose buffer | two sample slots | accumulators
-constexpr size_t kSmem1Run = (size_t)(kWarps1 * 2) * kHwBytes1 + M * 8 + (kWarps1 * 2) * 4;
+constexpr int kHwBytes1 = M * 8 + kAccFloat2 * 8;                         // transpose buffer | accumulators
+constexpr size_t kSmem1Run = (size_t)(kWarps1 * 2) * kHwBytes1 + (kWarps1 * 2) * 4;
 
 struct StftRunPlan { int runs_per_utt; long long total_runs; };
 
+// buf[r] = samples (2m, 2m+1), m = j + 16 r, r < 8, of the H samples starting at original coordinate t0 (reflect outside [0, T))
+__device__ __forceinline__ void load_half_regs(float2 (&buf)[8], const float* __restrict__ row, int T, int t0, int j) {
+    const float* src = row + t0;
+    if ((t0 >= 0) && (t0 + H <= T) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0)) {
+        const float2* s2 = reinterpret_cast<const float2*>(src) + j;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) buf[r] = __ldg(s2 + 16 * r);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int ta = t0 + 2 * (j + 16 * r), tb = ta + 1;
+            ta = ta < 0 ? -ta : ta; ta = ta >= T ? 2 * (T - 1) - ta : ta;
+            tb = tb < 0 ? -tb : tb; tb = tb >= T ? 2 * (T - 1) - tb : tb;
+            buf[r] = make_float2(__ldg(row + ta), __ldg(row + tb));
+        }
+    }
+}
+
 template <bool POWER, bool PHASE, bool LOGP, bool STATS, bool CSPEC = false>
-__global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, StftRunPlan plan) {
+__global__ void __launch_bounds__(kThreads1, 1) stft512_run_kernel(StftArgs a, StftRunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem1[];
     secommon::TraceScope trace(a.trace, 1);
     const int lane = threadIdx.x & 31, j = lane & 15;
     const int hw = (threadIdx.x >> 4);
     unsigned char* mine = smem1 + (size_t)hw * kHwBytes1;
     float2* xbuf = reinterpret_cast<float2*>(mine);
-    float* slot = reinterpret_cast<float*>(mine + M * 8);
-    float2* acc = reinterpret_cast<float2*>(mine + M * 8 + 2 * H * 4);
-    float2* s_win2 = reinterpret_cast<float2*>(smem1 + (size_t)(kWarps1 * 2) * kHwBytes1);
-    int* s_utt = reinterpret_cast<int*>(s_win2 + M);                  // utterance of every half-warp's run (-1: none)
+    float2* acc = reinterpret_cast<float2*>(mine + M * 8);
+    int* s_utt = reinterpret_cast<int*>(smem1 + (size_t)(kWarps1 * 2) * kHwBytes1);   // utterance of every half-warp's run (-1: none)
     const unsigned hmask = half_mask(lane);
     const long long unit = (long long)blockIdx.x * (kThreads1 / 16) + hw;
     const bool active = unit < plan.total_runs;
@@ -266,6 +296,7 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
     // the first frame's samples come from HBM: put those loads in flight before anything else (tables, accumulators)
     int fa = 0, fb = 0;
     const float* row = a.wav;
+    float2 A[8], B[8];
     if (active) {
         const int ri = (int)(unit - (long long)u * plan.runs_per_utt);
         // the first (F mod rpu) runs are one frame longer; rpu is even, so the two half-warps of a warp (runs 2k, 2k+1 of
@@ -274,45 +305,61 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_run_kernel(StftArgs a, S
         fa = ri * base_len + min(ri, rem_runs);
         fb = fa + base_len + (ri < rem_runs ? 1 : 0);
         row = a.wav + (long long)u * a.utt_stride;
-        stage_half(slot, row, a.T, (fa - 1) * H, j);
-        stage_half(slot + H, row, a.T, fa * H, j);
-        cp_async_commit();
+        load_half_regs(A, row, a.T, (fa - 1) * H, j);
+        load_half_regs(B, row, a.T, fa * H, j);
     }
-    for (int i = threadIdx.x; i < M; i += kThreads1) s_win2[i] = make_float2(0.5f * a.tab.window[2 * i], 0.5f * a.tab.window[2 * i + 1]);
+    float2 wlo[8], whi[8];                                            // window pairs of this lane, pre-scaled by 1/2
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const float2 w0 = __ldg(reinterpret_cast<const float2*>(a.tab.window) + j + 16 * r);
+        const float2 w1 = __ldg(reinterpret_cast<const float2*>(a.tab.window) + j + 16 * r + 128);
+        wlo[r] = make_float2(0.5f * w0.x, 0.5f * w0.y);
+        whi[r] = make_float2(0.5f * w1.x, 0.5f * w1.y);
+    }
     float2 tw[15], twn[8];
     load_lane_constants(j, a.tab.twM, a.tab.twN, tw, twn);
-    if (STATS) {
-        for (int i = j; i < kAccFloat2; i += 16) acc[i] = make_float2(0.0f, 0.0f);
-        if (j == 0) s_utt[hw] = u;
-    }
-    __syncthreads();
+    float2 sacc[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) sacc[i] = make_float2(0.0f, 0.0f);
+    if (STATS && j == 0) s_utt[hw] = u;
     griddep_launch();                                   // a dependent kernel may start its prologue (it waits for our completion)
     if (threadIdx.x == 0) trace.mark(17);
     if (active) {
         const int F = a.n_frames;
-        int p = 0;
-#pragma unroll 1
-        for (int f = fa; f < fb; ++f, p ^= 1) {
-            cp_async_wait<0>();
-            __syncwarp(hmask);
+        // one frame: window (first, second) into v, refill `first` with the second half of frame f + 1, transform, write
+        auto frame = [&](float2 (&first)[8], float2 (&second)[8], int f) {
             float2 v[16];
-            frame_from_slots(slot + p * H, slot + (p ^ 1) * H, j, s_win2, v);
-            __syncwarp(hmask);
-            if (f + 1 < fb) stage_half(slot + p * H, row, a.T, (f + 1) * H, j);   // second half of frame f+1 -> the dead first slot
-            cp_async_commit();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                v[r] = pmul(first[r], wlo[r]);
+                v[r + 8] = pmul(second[r], whi[r]);
+            }
+            if (f + 1 < fb) load_half_regs(first, row, a.T, (f + 1) * H, j);
             fft256<-1>(v, xbuf, j, tw, hmask);
             float2 zm[8];
             fetch_mirror(v, lane, zm);
-            emit_frame<POWER, PHASE, LOGP, STATS, CSPEC>(v, zm, twn, j, a, ((long long)u * F + f) * a.spec_stride, acc,
+            emit_frame<POWER, PHASE, LOGP, STATS, CSPEC>(v, zm, twn, j, a, ((long long)u * F + f) * a.spec_stride, sacc,
                                                          CSPEC ? a.cspec + ((long long)u * F + f) * kSpecFloats : nullptr);
+        };
+#pragma unroll 1
+        for (int f = fa; f < fb; f += 2) {
+            frame(A, B, f);
+            if (f + 1 < fb) frame(B, A, f + 1);
         }
     }
     if (threadIdx.x == 0) trace.mark(18);
     if (STATS) {
+        // park the register accumulators in the half-warp's row: bin k at acc[k]
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            acc[j + 16 * q] = sacc[q];
+            acc[M - j - 16 * q] = sacc[8 + q];
+        }
+        if (j == 0) acc[128] = sacc[16];
         __syncthreads();                                            // every half-warp's accumulators are final
         if (threadIdx.x == 0) trace.mark(19);
         // thread t owns bin t (thread 0 also bin 256); the CTA's runs are consecutive, so utterances are non-decreasing
-        const float2* base = reinterpret_cast<const float2*>(smem1 + M * 8 + 2 * H * 4);
+        const float2* base = reinterpret_cast<const float2*>(smem1 + M * 8);
         constexpr int kStride = kHwBytes1 / 8;
         for (int bin = threadIdx.x; bin <= M; bin += kThreads1) {
             double s1 = 0.0, s2 = 0.0;
@@ -726,7 +773,7 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
     const int per_it = kThreads1 / 16;
     if (a.hop == H) {
         // runs: one balanced wave of 2 CTAs per SM when the batch is small, runs of about 32 frames otherwise
-        const long long slots = 2LL * num_sms() * per_it;
+        const long long slots = 1LL * num_sms() * per_it;       // one 8-warp CTA per SM (register-resident frames)
         long long rpu;
         if (total <= slots * 32) {
             rpu = slots / a.n_utt;
