@@ -361,8 +361,8 @@ SE_HD void mask_istft_tile(Exec& ex, const MaskIstftArgs& a, int utt, int tile, 
             float2 ya, yb;
             if (a.mask_is_power) {            // polar(sqrt(power), phase(X)); phase(0) = 0
                 const float qa = xa.x * xa.x + xa.y * xa.y, qb = xb.x * xb.x + xb.y * xb.y;
-                ya = qa > 0.0f ? cscale(xa, sqrtf(ga / qa)) : make_float2(sqrtf(ga), 0.0f);
-                yb = qb > 0.0f ? cscale(xb, sqrtf(gb / qb)) : make_float2(sqrtf(gb), 0.0f);
+                ya = qa > 0.0f ? cscale(xa, sqrtf(ga) / sqrtf(qa)) : make_float2(sqrtf(ga), 0.0f);
+                yb = qb > 0.0f ? cscale(xb, sqrtf(gb) / sqrtf(qb)) : make_float2(sqrtf(gb), 0.0f);
             } else {
                 ya = cscale(xa, sqrtf(ga));
                 yb = cscale(xb, sqrtf(gb));
