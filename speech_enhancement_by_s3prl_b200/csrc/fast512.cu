@@ -255,9 +255,15 @@ __global__ void __launch_bounds__(kThreads1, 2) stft512_kernel(StftArgs a, long 
 // CMVN statistics of the mask head (model.py:30) -- are accumulated in registers (fp32 over the few frames of a run), parked
 // in the half-warp's shared-memory row at the end, combined over the CTA's half-warps in double precision after ONE barrier,
 // and added to stat_sums with one double atomicAdd pair per (CTA, utterance, bin).
+#ifndef SE_K1_WARPS
+#define SE_K1_WARPS 2
+#endif
+// small CTAs (2 warps, four per SM at 255 registers per thread): with two steps in flight the other step's kernels get SMs
+// back in finer grains (8-warp CTAs: +1.4 us per step; the kernel alone is the same 13.9 us either way)
+constexpr int kWarpsRun = SE_K1_WARPS, kThreadsRun = kWarpsRun * 32;
 constexpr int kAccFloat2 = M + 2;                                         // bins 0..256, padded to a 16-byte multiple
 constexpr int kHwBytes1 = M * 8 + kAccFloat2 * 8;                         // transpose buffer | accumulators
-constexpr size_t kSmem1Run = (size_t)(kWarps1 * 2) * kHwBytes1 + (kWarps1 * 2) * 4;
+constexpr size_t kSmem1Run = (size_t)(kWarpsRun * 2) * kHwBytes1 + (kWarpsRun * 2) * 4;
 
 struct StftRunPlan { int runs_per_utt; long long total_runs; };
 
@@ -280,7 +286,7 @@ __device__ __forceinline__ void load_half_regs(float2 (&buf)[8], const float* __
 }
 
 template <bool POWER, bool PHASE, bool LOGP, bool STATS, bool CSPEC = false>
-__global__ void __launch_bounds__(kThreads1, 1) stft512_run_kernel(StftArgs a, StftRunPlan plan) {
+__global__ void __launch_bounds__(kThreadsRun, 256 / kThreadsRun) stft512_run_kernel(StftArgs a, StftRunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem1[];
     secommon::TraceScope trace(a.trace, 1);
     const int lane = threadIdx.x & 31, j = lane & 15;
@@ -288,9 +294,9 @@ __global__ void __launch_bounds__(kThreads1, 1) stft512_run_kernel(StftArgs a, S
     unsigned char* mine = smem1 + (size_t)hw * kHwBytes1;
     float2* xbuf = reinterpret_cast<float2*>(mine);
     float2* acc = reinterpret_cast<float2*>(mine + M * 8);
-    int* s_utt = reinterpret_cast<int*>(smem1 + (size_t)(kWarps1 * 2) * kHwBytes1);   // utterance of every half-warp's run (-1: none)
+    int* s_utt = reinterpret_cast<int*>(smem1 + (size_t)(kWarpsRun * 2) * kHwBytes1);   // utterance of every half-warp's run (-1: none)
     const unsigned hmask = half_mask(lane);
-    const long long unit = (long long)blockIdx.x * (kThreads1 / 16) + hw;
+    const long long unit = (long long)blockIdx.x * (kThreadsRun / 16) + hw;
     const bool active = unit < plan.total_runs;
     const int u = active ? (int)(unit / plan.runs_per_utt) : -1;
     // the first frame's samples come from HBM: put those loads in flight before anything else (tables, accumulators)
@@ -361,10 +367,10 @@ __global__ void __launch_bounds__(kThreads1, 1) stft512_run_kernel(StftArgs a, S
         // thread t owns bin t (thread 0 also bin 256); the CTA's runs are consecutive, so utterances are non-decreasing
         const float2* base = reinterpret_cast<const float2*>(smem1 + M * 8);
         constexpr int kStride = kHwBytes1 / 8;
-        for (int bin = threadIdx.x; bin <= M; bin += kThreads1) {
+        for (int bin = threadIdx.x; bin <= M; bin += kThreadsRun) {
             double s1 = 0.0, s2 = 0.0;
             int cur = -1;
-            for (int h = 0; h < kThreads1 / 16; ++h) {
+            for (int h = 0; h < kThreadsRun / 16; ++h) {
                 const int uh = s_utt[h];
                 if (uh < 0) break;
                 if (uh != cur) {
@@ -409,7 +415,10 @@ __global__ void __launch_bounds__(kThreads1, 1) stft512_run_kernel(StftArgs a, S
 // The three transforms run through ONE copy of the FFT code inside a non-unrolled pass loop.
 // cp.async groups are committed in the fixed order N(oisy) M(ask) C(lean) once per frame (empty groups at the
 // end of a run), so "all but the two most recent groups" is exactly the data the next consumer needs.
-constexpr int kWarps3 = 4, kThreads3 = kWarps3 * 32;
+#ifndef SE_K3_WARPS
+#define SE_K3_WARPS 4
+#endif
+constexpr int kWarps3 = SE_K3_WARPS, kThreads3 = kWarps3 * 32;
 
 // Run partition of one utterance's `bpu` output blocks into `rpu` runs: base = bpu / rpu blocks each, `rem` = bpu mod rpu
 // runs get one more.  Runs come in pairs (2k, 2k+1) -- the two half-warps of a warp -- and both runs of a pair have the
@@ -465,7 +474,7 @@ __device__ __forceinline__ void mask_merge(float2 xa, float2 xb, float ga, float
 // CS: the noisy spectrum comes from K1's workspace (a.cspec) instead of being recomputed from the waveform -- one transform
 // less per frame.  cp.async groups are then [spectrum row + mask row], [clean] per frame.
 template <bool CS, bool PM = false>
-__global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
+__global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem3[];
     secommon::TraceScope trace(a.trace, 3);
     float2* s_win2 = reinterpret_cast<float2*>(smem3 + (size_t)(kWarps3 * 2) * kHwBytes3);
@@ -770,10 +779,10 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
     if (total > 0x7fffff00LL) return secommon::fail(SE_ERR_BAD_ARG, "too many frames (%lld)", total);
     const int sel = (a.power ? 1 : 0) | (a.phase ? 2 : 0) | (a.logp ? 4 : 0);
     if (sel == 0) return SE_OK;                                  // nothing requested
-    const int per_it = kThreads1 / 16;
     if (a.hop == H) {
+        const int per_it = kThreadsRun / 16;
         // runs: one balanced wave of 2 CTAs per SM when the batch is small, runs of about 32 frames otherwise
-        const long long slots = 1LL * num_sms() * per_it;       // one 8-warp CTA per SM (register-resident frames)
+        const long long slots = (256LL / kThreadsRun) * num_sms() * per_it;   // 8 warps per SM (255 registers per thread)
         long long rpu;
         if (total <= slots * 32) {
             rpu = slots / a.n_utt;
@@ -786,8 +795,8 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
         plan.total_runs = (long long)a.n_utt * rpu;
         const long long grid = (plan.total_runs + per_it - 1) / per_it;
         if (grid > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "grid too large");
-#define SE_RUN(P, Q, L, S) stft512_run_kernel<P, Q, L, S><<<(unsigned)grid, kThreads1, kSmem1Run, st>>>(a, plan)
-#define SE_RUN_CS(P, Q, L) stft512_run_kernel<P, Q, L, true, true><<<(unsigned)grid, kThreads1, kSmem1Run, st>>>(a, plan)
+#define SE_RUN(P, Q, L, S) stft512_run_kernel<P, Q, L, S><<<(unsigned)grid, kThreadsRun, kSmem1Run, st>>>(a, plan)
+#define SE_RUN_CS(P, Q, L) stft512_run_kernel<P, Q, L, true, true><<<(unsigned)grid, kThreadsRun, kSmem1Run, st>>>(a, plan)
         if (a.stat_sums) {
             // statistics of the ONE feature written: log-power (sel 4) or power (sel 1)
             if (sel == 4) { if (a.cspec) SE_RUN_CS(false, false, true); else SE_RUN(false, false, true, true); }
@@ -811,6 +820,7 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
         return secommon::check_launch("stft512_run_kernel");
     }
     if (a.stat_sums || a.cspec) return secommon::fail(SE_ERR_UNSUPPORTED, "fused statistics / spectrum workspace need hop = 256");
+    const int per_it = kThreads1 / 16;
     const long long want = (total + per_it - 1) / per_it;
     const long long cap = 2LL * num_sms();
     const unsigned grid = (unsigned)(want < cap ? want : cap);
@@ -833,7 +843,7 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     // wave covers the GPU -- but at least 4 blocks per run (the halo frame costs 2/3 of a frame).  Large batches: runs of
     // about 32 blocks, many waves.
     const int blocks_per_utt = a.n_frames - 1;
-    const long long slots = (long long)SE_K3_MIN_BLOCKS * num_sms() * (kThreads3 / 16);
+    const long long slots = (long long)(SE_K3_MIN_BLOCKS * 4 / kWarps3) * num_sms() * (kThreads3 / 16);
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("SE_B200_RUN_LEN"); forced = e ? atoi(e) : 0; }
     RunPlan plan;
