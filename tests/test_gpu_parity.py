@@ -613,7 +613,8 @@ def test_bench_configuration_matches_oracle_at_full_size(se, bench_case, mode):
         res = pipe.drain()
         assert len(res) == 3
         for r in res[1:]:                                                   # every slot of the pipeline gives the same answer
-            assert torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1])
+            # (equal up to the order of the double-precision atomics that combine the per-run sums)
+            assert (r[0] - res[0][0]).abs().max().item() < 1e-5 and (r[1] - res[0][1]).abs().max().item() < 1e-5
         sisdr, loss = res[0][1], res[0][0].mean().item()
         out = None
     np.testing.assert_allclose(sisdr.numpy(), ref["sisdr"].numpy(), atol=SISDR_TOL_DB)
@@ -814,7 +815,9 @@ def test_spectrum_workspace_path_equals_recompute_path(se, T, B, logp):
     ws = torch.full((B, F, ops.SPEC_WS_FLOATS), float("nan"), device="cuda")
     feats_ws, sums_ws = ops.stft_features(wavs, 0, 512, 256, mine._frame_window, logpower=logp, spec_ws=ws)
     feats, sums = ops.stft_features(wavs, 0, 512, 256, mine._frame_window, logpower=logp)
-    assert torch.equal(feats_ws[..., :257], feats[..., :257]) and torch.equal(sums_ws[:, :257], sums[:, :257])
+    assert torch.equal(feats_ws[..., :257], feats[..., :257])
+    # (the sums are combined across CTAs with double-precision atomics: the order, hence the last bit, varies between launches)
+    np.testing.assert_allclose(sums_ws[:, :257].cpu().numpy(), sums[:, :257].cpu().numpy(), rtol=1e-12, atol=1e-12)
     # the workspace holds torch.stft's spectrum (layout of include/se_b200.h)
     ref = torch.stft(wavs[:, 0], 512, 256, 512, window=mine._frame_window, center=True, pad_mode="reflect",
                      return_complex=True).transpose(1, 2)                      # (B, F, 257)
