@@ -5,6 +5,7 @@ Tolerances (BASELINE.json north_star): spectra within 1e-4 relative in fp32; rec
 waveforms within 0.01 dB SI-SDR.  "Relative" for a power spectrum is taken against the
 largest bin of the utterance (bins 120 dB below it hold rounding noise in the oracle too).
 """
+import ctypes
 import os
 
 import numpy as np
@@ -111,6 +112,33 @@ def test_abi_error_codes_on_device(se):
         ops.stft(x, 0, 512, 256, torch.hann_window(512).cuda())         # T <= n_fft/2, as torch.stft refuses
     with pytest.raises(RuntimeError, match="n_fft"):
         ops.stft(torch.zeros(1, 1, 2000, device="cuda"), 0, 384, 128, torch.hann_window(384).cuda())
+    # entry points of the training / sampling rows: integer codes through the raw C ABI, text through se_last_error
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    buf = torch.zeros(4096, device="cuda")
+    dbl = torch.zeros(64, device="cuda", dtype=torch.float64)
+    p = buf.data_ptr()
+    assert lib.se_sisdr_mask_fwd(None, 0, p, 3, p, 8, None, 1, 4, 8, 1e-10, dbl.data_ptr(), None, st) == -1   # ld_inp < K
+    assert "stride" in _lib.last_error()
+    assert lib.se_sisdr_mask_bwd(None, 0, p, 8, p, 8, None, 1, 4, 8, 1e-10, dbl.data_ptr(), None, p, 8, st) == -1   # grad_out null
+    assert lib.se_head_grad_embeddings_workspace(2, 16, 257, 257) == 0                    # fewer than 32 frames per utterance
+    assert lib.se_linear_head_bwd_tc_workspace(2, 64, 300, 257) == 0                       # D_in beyond the B tile
+    rc = lib.se_head_grad_embeddings(p, 257, None, None, None, 257, 1e-6, p, p, 257, 2, 16, 257, 257, 2, p, 4096, p, st)
+    assert rc == -2 and "range" in _lib.last_error()                                      # SE_ERR_UNSUPPORTED
+    ptrs = (ctypes.c_void_p * 9)(*([p] * 9))
+    sizes = (ctypes.c_int64 * 9)(*([4] * 9))
+    ints = torch.zeros(2, device="cuda", dtype=torch.int32)
+    for n in (0, 9):
+        assert lib.se_adam_clip_step(ptrs, ptrs, ptrs, ptrs, sizes, n, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, dbl.data_ptr(),
+                                     ints.data_ptr(), st) == -1
+    assert lib.se_match_scores(p, 0, p, 1, 8, 1e-12, dbl.data_ptr(), p, p, st) == -1
+    assert lib.se_stft_features_ws(p, 1, 2000, 2000, 400, 160, p, 1e-10, 1, p, 204, dbl.data_ptr(), 204, p, 0, st) == -2
+    noisy, out = torch.randn(2000, device="cuda"), torch.empty(2000, device="cuda")
+    power, win = torch.rand(8, 257, device="cuda"), torch.hann_window(512, device="cuda")
+    assert lib.se_mask_istft_ex(noisy.data_ptr(), None, 2000, power.data_ptr(), 257, None, 1, 2000, 512, 256, win.data_ptr(),
+                                out.data_ptr(), 2000, 2000, None, 4, st) == 0                # SE_FLAG_MASK_IS_POWER runs
+    assert torch.isfinite(out).all()
+    torch.cuda.synchronize()
 
 
 # ------------------------------------------------------------------------------ iSTFT
