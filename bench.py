@@ -356,6 +356,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dominant],
                 "kernel_ms": {k: round(v, 5) for k, v in kernel_ms.items()},
+                "note": "K1/K3 are bound by the fp32 pipe + shared-memory wavefronts, not HBM (DESIGN.md 4.1: 22 M fp32-pipe cycles "
+                        "and 19 M issue slots per K3 launch = ~48 % / ~50 % busy; DRAM 10-24 %)",
                 "step_algorithmic_bytes": int(audio_s_per_step * 16 * SR * (1 + K / HOP)),
                 "step_frac_of_hbm_peak": (audio_s_per_step * 16 * SR * (1 + K / HOP)) / (ms_total / args.steps * 1e-3) / 1e9 / peak}
 
