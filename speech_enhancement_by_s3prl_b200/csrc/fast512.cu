@@ -443,6 +443,11 @@ __host__ __device__ __forceinline__ void run_bounds(int ri, int bpu, int rpu, in
 
 struct RunPlan { int blocks_per_utt; int runs_per_utt; long long total_runs; };   // run ri: bpu/rpu blocks, the first bpu%rpu runs one more
 
+// SE_K3_RESIDENT (experiment): CTAs per SM the kernel is ALLOWED to occupy (shared memory padded to enforce it), while the
+// register cap stays that of SE_K3_MIN_BLOCKS -- leaves registers / shared memory for another stream's kernels
+#ifndef SE_K3_RESIDENT
+#define SE_K3_RESIDENT SE_K3_MIN_BLOCKS
+#endif
 #ifndef SE_K3_MIN_BLOCKS
 #define SE_K3_MIN_BLOCKS 3
 #endif
@@ -767,9 +772,10 @@ int prepare512() {
     SE_OPT((stft512_run_kernel<true, false, true, true>), kSmem1Run);
     SE_OPT((stft512_run_kernel<true, false, false, true, true>), kSmem1Run);
     SE_OPT((stft512_run_kernel<false, false, true, true, true>), kSmem1Run);
-    SE_OPT(mask_istft512_kernel<false>, kSmem3);
-    SE_OPT(mask_istft512_kernel<true>, kSmem3);
-    SE_OPT((mask_istft512_kernel<false, true>), kSmem3);
+    constexpr size_t kSmem3Max = kSmem3 > 100 * 1024 ? kSmem3 : 100 * 1024;     // room for the SE_K3_RESIDENT padding
+    SE_OPT(mask_istft512_kernel<false>, kSmem3Max);
+    SE_OPT(mask_istft512_kernel<true>, kSmem3Max);
+    SE_OPT((mask_istft512_kernel<false, true>), kSmem3Max);
 #undef SE_OPT
     return SE_OK;
 }
@@ -843,7 +849,7 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     // wave covers the GPU -- but at least 4 blocks per run (the halo frame costs 2/3 of a frame).  Large batches: runs of
     // about 32 blocks, many waves.
     const int blocks_per_utt = a.n_frames - 1;
-    const long long slots = (long long)(SE_K3_MIN_BLOCKS * 4 / kWarps3) * num_sms() * (kThreads3 / 16);
+    const long long slots = (long long)(SE_K3_RESIDENT * 4 / kWarps3) * num_sms() * (kThreads3 / 16);
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("SE_B200_RUN_LEN"); forced = e ? atoi(e) : 0; }
     RunPlan plan;
@@ -866,6 +872,10 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads3);
     cfg.dynamicSmemBytes = kSmem3;
+    if (SE_K3_RESIDENT < SE_K3_MIN_BLOCKS) {                       // pad so that RESIDENT + 1 CTAs do not fit in 227 KB
+        const size_t pad_to = (size_t)(227 * 1024) / (SE_K3_RESIDENT * 4 / kWarps3 + 1) + 1024;
+        if (cfg.dynamicSmemBytes < pad_to) cfg.dynamicSmemBytes = pad_to;
+    }
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // prologue overlaps the upstream kernel's tail
