@@ -133,11 +133,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float activate(float z, int act) {
-    if (act == SE_ACT_RELU) return z > 0.f ? z : 0.f;
-    if (act == SE_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-z));
-    return z;
-}
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

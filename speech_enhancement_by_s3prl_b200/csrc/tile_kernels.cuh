@@ -236,7 +236,7 @@ template <int N> SE_HD float ola_sample(const float2* z, const float* win, int p
 // ------------------------------------------------------------------ inverse STFT tile (power, phase)
 template <int N, class Exec>
 SE_HD void istft_tile(Exec& ex, const IstftArgs& a, int utt, int tile, unsigned char* smem_raw) {
-    constexpr int M = N / 2, K = M + 1, G = Cfg<N>::G;
+    constexpr int M = N / 2, K = M + 1;
     constexpr int PAD = Padded<M>::SIZE;
     using P = Plan<M>;
     Smem<N> s(smem_raw, 0);
