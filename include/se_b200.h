@@ -263,8 +263,10 @@ int se_match_scores(const float* query, int64_t n_query, const float* key, int64
 /* ---- gradient clipping + Adam on the head's parameters (runner.py:463-466: clip_grad_norm_ then optimizer.step) -------
  * params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors (<= 8) device pointers, numels their sizes.  Semantics of
  * torch.nn.utils.clip_grad_norm_(max_norm) (skipped if max_norm <= 0; the scaled gradient is written back) followed by
- * torch.optim.Adam.step (L2 weight_decay, no amsgrad).  ws_acc: 1 double, ws_state: 2 ints (steps taken, internal), both
- * zero before the first call and owned by the caller; the step count advances on the device (CUDA-graph replayable). */
+ * torch.optim.Adam.step (L2 weight_decay, no amsgrad).  A NaN / inf gradient norm skips the update (runner.py:467-470):
+ * parameters, moments and the step count keep their values and the skipped-step counter advances.  ws_acc: 1 double,
+ * ws_state: 3 ints (steps taken, internal, steps skipped), all zero before the first call and owned by the caller; the
+ * counts advance on the device (CUDA-graph replayable). */
 int se_adam_clip_step(float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                       const int64_t* numels, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
                       float max_norm, double* ws_acc, int* ws_state, void* stream);

@@ -89,9 +89,8 @@ def load():
             if path == _build.LIB_PATH and _build.is_stale():
                 try:
                     path = _build.build_library()
-                except Exception as exc:           # no nvcc and no prebuilt library
-                    if not os.path.exists(path):
-                        raise RuntimeError(f"libse_b200.so is missing and cannot be built: {exc}") from exc
+                except Exception as exc:           # a stale library may not match _SIGNATURES: never load it silently
+                    raise RuntimeError(f"libse_b200.so is missing or older than csrc/ and cannot be rebuilt: {exc}") from exc
             lib = ctypes.CDLL(path)
             for name, argtypes in _SIGNATURES.items():
                 fn = getattr(lib, name)            # AttributeError if the symbol is not exported

@@ -739,16 +739,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
 
 namespace sefast {
 
-int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int num_sms() { return secommon::device_sms(); }
 
 // opt the kernels into their dynamic shared-memory sizes (called once per device from se_prepare / first use)
 int prepare512() {

@@ -399,16 +399,7 @@ __global__ void head_grad_pack_kernel(const float* __restrict__ partials, int m_
     }
 }
 
-int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int num_sms() { return secommon::device_sms(); }
 
 struct Geometry { int m_tiles, simt_rows, m_rows, splits; long long rows_per_split; };
 
@@ -507,10 +498,9 @@ static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const f
     a.n_tail = a.b_rows - a.n_main;
     a.partials = ws_partials;
     a.m_rows = g.m_rows; a.m_tiles = g.m_tiles; a.simt_rows = g.simt_rows;
-    static bool opted = false;
-    if (!opted) {
+    static unsigned long long opted = 0;                       // per device: cudaFuncSetAttribute is not process-wide
+    if (secommon::first_use_on_device(opted)) {
         SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        opted = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     linear_head_bwd_tc_kernel<<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kThreads, kSmemBytes, st>>>(a);

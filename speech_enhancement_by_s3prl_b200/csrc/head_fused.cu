@@ -448,16 +448,7 @@ int make_map(CUtensorMap* map, const float* base, long long cols, long long rows
     return SE_OK;
 }
 
-int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int num_sms() { return secommon::device_sms(); }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -513,10 +504,9 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     int rc = make_map(&tmA, x, D_in, a.R, ldx, a.tile_rows);
     if (rc != SE_OK) return rc;
     if ((rc = make_map(&tmW, W, D_in, D_out, ldw, a.w_box_rows)) != SE_OK) return rc;
-    static bool opted = false;
-    if (!opted) {
+    static unsigned long long opted = 0;                       // per device: cudaFuncSetAttribute is not process-wide
+    if (secommon::first_use_on_device(opted)) {
         SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        opted = true;
     }
     cudaLaunchConfig_t cfg{};
     unsigned tiles = (unsigned)((a.R + a.tile_rows - 1) / a.tile_rows);

@@ -335,10 +335,9 @@ int launch_linear_head_tc(const float* x, long long ldx, const float* mean, cons
     if (a.stages < 1) return fail(SE_ERR_UNSUPPORTED, "head tile does not fit in shared memory (Dout=%d)", Dout);
     const size_t ring = (size_t)a.stages * stage_bytes;
     const size_t smem = (ring > staging ? ring : staging) + fixed;
-    static bool opted = false;
-    if (!opted) {
+    static unsigned long long opted = 0;                       // per device: cudaFuncSetAttribute is not process-wide
+    if (secommon::first_use_on_device(opted)) {
         SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        opted = true;
     }
     dim3 grid((unsigned)((R + BM - 1) / BM), (unsigned)chunks);
     linear_head_tc_kernel<<<grid, kThreads, smem, st>>>(a);

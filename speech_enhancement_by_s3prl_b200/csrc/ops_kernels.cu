@@ -257,7 +257,7 @@ struct AdamArgs {
     int count;
     float lr, beta1, beta2, eps, weight_decay, max_norm;   // max_norm <= 0: no clipping
     double* acc;       // [1] sum of squared gradients of this step (zeroed by the update kernel's last CTA)
-    int* state;        // [0] steps taken, [1] CTAs of the update kernel that have finished
+    int* state;        // [0] steps taken, [1] CTAs of the update kernel that have finished, [2] steps skipped (NaN / inf norm)
 };
 
 __global__ void __launch_bounds__(256) adam_norm_kernel(const AdamArgs a) {
@@ -272,13 +272,19 @@ __global__ void __launch_bounds__(256) adam_norm_kernel(const AdamArgs a) {
 
 __global__ void __launch_bounds__(256) adam_update_kernel(const AdamArgs a) {
     const int step = a.state[0] + 1;                                        // torch.optim.Adam: bias corrections use the new count
+    const double sumsq = *a.acc;
+    // runner.py:467-470: a NaN / inf gradient norm skips optimizer.step() -- parameters, moments and the step count stay as
+    // they are (the gradients too: the runner zeroes them next).  The norm is always accumulated so that the guard also holds
+    // without clipping.
+    const bool finite = sumsq == sumsq && sumsq <= 3.0e38;
     float clip = 1.0f;
     if (a.max_norm > 0.0f) {
-        const float total = (float)sqrt(*a.acc);
+        const float total = (float)sqrt(sumsq);
         clip = fminf(a.max_norm / (total + 1e-6f), 1.0f);                   // torch.nn.utils.clip_grad_norm_
     }
     const double bc1 = 1.0 - pow((double)a.beta1, (double)step), bc2 = 1.0 - pow((double)a.beta2, (double)step);
     const float step_size = (float)(a.lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    if (finite)
     for (int t = 0; t < a.count; ++t)
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n[t]; i += (long long)gridDim.x * blockDim.x) {
             float g = a.g[t][i] * clip;
@@ -297,7 +303,8 @@ __global__ void __launch_bounds__(256) adam_update_kernel(const AdamArgs a) {
         if (atomicAdd(a.state + 1, 1) == (int)gridDim.x - 1) {              // every CTA has read acc and the step count
             *a.acc = 0.0;
             a.state[1] = 0;
-            a.state[0] = step;
+            if (finite) a.state[0] = step;
+            else a.state[2] += 1;                                           // skipped steps (ClipAdam.steps_skipped)
         }
     }
 }
@@ -947,7 +954,7 @@ int se_adam_clip_step(float* const* params, float* const* grads, float* const* e
     cudaStream_t st = (cudaStream_t)stream;
     long long blocks = (total + 4 * 256 - 1) / (4 * 256);
     if (blocks > 592) blocks = 592;
-    if (max_norm > 0.0f) {
+    {   // the norm is needed for clipping AND for the NaN / inf guard of runner.py:467-470
         adam_norm_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
         int rc = secommon::check_launch("adam_norm_kernel");
         if (rc != SE_OK) return rc;

@@ -43,6 +43,30 @@ inline int pdl_mask() {
     return m;
 }
 
+// Per-device one-time setup (cudaFuncSetAttribute is per device): true the first time it is called on the current device
+// for the given flag word (one static word per kernel family).
+inline bool first_use_on_device(unsigned long long& seen) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ULL << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
+// SM count of the current device (cached per device)
+inline int device_sms() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& v = sms[dev & 63];
+    if (v == 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+    }
+    return v;
+}
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));

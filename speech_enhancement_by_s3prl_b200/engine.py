@@ -89,17 +89,28 @@ class EnhancementEngine:
             gain, sisdr, loss = ops.finalize_metrics(sums, lengths, T, wav=wav, target_db=None)
         return {"loss_per_utt": loss, "sisdr": sisdr, "wav_predicted": wav, "gain": gain, "mask": mask[..., :K]}
 
-    def _padded_weight(self):
-        """16-byte-row copy of the head weight, refreshed when the parameter changes (optimizer step / load_state_dict)."""
+    def _padded_weight(self, force=False):
+        """16-byte-row (and, for the tensor cores, TF32-rounded) copy of the head weight.
+
+        ONE persistent buffer per (shape, device): captured graphs bake its address in, so it is refreshed IN PLACE --
+        eagerly here when the parameter's version changed (optimizer.step / load_state_dict), and by kernels inside the
+        captured training step after every update (``force``; graph replays never bump ``_version``)."""
         w = self.head.linear.weight
-        key = (w.data_ptr(), w._version, str(w.device))
-        if getattr(self, "_wpad_key", None) != key:
+        Dout, Din = w.shape
+        buf = getattr(self, "_wpad", None)
+        if buf is None or buf.device != w.device or buf.shape != (Dout, ops.round4(Din)):
+            buf = self._wpad = torch.zeros(Dout, ops.round4(Din), device=w.device, dtype=torch.float32)
+            self._wpad_key = None
+            self._graphs = {}                    # graphs captured against another buffer are void
+        key = (w.data_ptr(), w._version)
+        if force or self._wpad_key != key:
             with torch.no_grad():
-                self._wpad = ops.pad_weight(w.detach())
-                if self.precision == 1:
-                    self._wpad = ops.round_tf32(self._wpad)         # the tensor cores read TF32: round to nearest once
+                buf[:, :Din].copy_(w.detach())
+                if self.precision == 1:          # the tensor cores read TF32: round to nearest once (cvt.rna)
+                    bits = buf.view(torch.int32)
+                    bits.add_(0x1000).bitwise_and_(~0x1FFF)
             self._wpad_key = key
-        return self._wpad
+        return buf
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def capture_bound(self, lengths, wavs):
@@ -136,6 +147,7 @@ class EnhancementEngine:
         """Same result as eval_step through the cached graph (inputs are copied into its static buffers)."""
         B, C, T = wavs.shape
         st = self.capture(B, C, T, wavs.device)
+        self._padded_weight()                                       # in-place refresh if the parameters changed since capture
         st["lengths"].copy_(lengths, non_blocking=True)
         st["wavs"].copy_(wavs, non_blocking=True)
         st["graph"].replay()
@@ -194,8 +206,7 @@ class EnhancementEngine:
                                                      want_logpower=self.log_features, log_eps=self.pre.eps, stat_sums=stat_sums)
             feats = logp if self.log_features else linear_inp
             linear_tar = ops.stft_padded(wavs, self.ch_tar, self.n_fft, self.hop, window, logpower=False)
-            self._wpad_key = None                   # the weights change every step (and a captured step must re-derive them)
-            wpad = self._padded_weight()
+            wpad = self._padded_weight()            # current: refreshed in place after every update (_clip_and_step)
             stats = stat_sums if head.cmvn else None
             offset = ops.linear_head_tma(feats, K, wpad, head.linear.bias, head.activation, stats, head.eps)
             frames = lengths // self.hop + 1
@@ -212,14 +223,21 @@ class EnhancementEngine:
         return loss
 
     def _clip_and_step(self, optimizer, grad_clip):
-        """runner.py:463-466; two launches with se_b200.ClipAdam, torch's kernels with any other optimizer."""
+        """runner.py:463-470; two launches with se_b200.ClipAdam (NaN / inf norms skipped on the device), torch's kernels
+        with any other optimizer (the guard is then the runner's host-side check, which cannot run under graph capture)."""
         from .optim import ClipAdam
         if isinstance(optimizer, ClipAdam):
             optimizer.clip_and_step(grad_clip)
-            return
-        if grad_clip is not None:
-            torch.nn.utils.clip_grad_norm_(list(self.head.parameters()), grad_clip)
-        optimizer.step()
+        else:
+            params = list(self.head.parameters())
+            if grad_clip is not None:
+                grad_norm = torch.nn.utils.clip_grad_norm_(params, grad_clip)
+            else:
+                grad_norm = torch.linalg.vector_norm(torch.stack([p.grad.norm() for p in params if p.grad is not None]))
+            if torch.cuda.is_current_stream_capturing() or bool(torch.isfinite(grad_norm)):
+                optimizer.step()
+        # the padded / TF32 copy the kernels read follows the parameters inside the same (possibly captured) step
+        self._padded_weight(force=True)
 
     def train_step(self, lengths, wavs, objective, optimizer=None, grad_clip=None):
         """runner.py:431-471 on the kernels: preprocessor tensors -> head -> criterion -> backward
@@ -336,6 +354,7 @@ class HostPipeline:
         self._next = (self._next + 1) % len(self.slots)
         if st["busy"]:
             self._collect(st)
+        self.engine._padded_weight()                                # in-place refresh if the parameters changed since capture
         lib = _lib.load()
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(st["done"])              # previous use of this slot's inputs has finished

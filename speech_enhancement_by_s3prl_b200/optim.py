@@ -4,7 +4,8 @@ The reference clips with ``torch.nn.utils.clip_grad_norm_`` and steps a torch / 
 (runner.py:114-115, 463-466): about fifteen small launches for two small tensors, which is most of a
 training step once forward and backward are fused.  ``ClipAdam`` keeps ``torch.optim.Adam``'s update
 rule (L2 ``weight_decay``, bias correction, no amsgrad) and state names, and adds
-``clip_and_step(max_norm)``; all of its state is on the device, so the step replays from a CUDA graph.
+``clip_and_step(max_norm)``; all of its state is on the device, so the step replays from a CUDA graph.  A step whose
+gradient norm is NaN / inf is skipped on the device, as the runner does on the host (runner.py:467-470).
 """
 import ctypes
 
@@ -34,7 +35,7 @@ class ClipAdam(torch.optim.Optimizer):
                 st["exp_avg_sq"] = torch.zeros_like(p)
         ws = group.get("_ws")
         if ws is None or ws[0].device != ps[0].device:
-            ws = (torch.zeros(1, device=ps[0].device, dtype=torch.float64), torch.zeros(2, device=ps[0].device, dtype=torch.int32))
+            ws = (torch.zeros(1, device=ps[0].device, dtype=torch.float64), torch.zeros(3, device=ps[0].device, dtype=torch.int32))
             group["_ws"] = ws
         return ps, ws
 
@@ -66,6 +67,10 @@ class ClipAdam(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         self.clip_and_step(None)
         return loss
+
+    def steps_skipped(self):
+        """Steps whose gradient norm was NaN / inf and that therefore left the parameters untouched (runner.py:467-470)."""
+        return [int(g["_ws"][1][2].item()) if g.get("_ws") is not None else 0 for g in self.param_groups]
 
     def steps_taken(self):
         """Device-side step counts, one per parameter group (synchronises)."""

@@ -1011,6 +1011,72 @@ def test_train_step_graph_with_clip_adam(se):
     assert (finals[0][1] - finals[1][1]).abs().max().item() < 2e-3       # 8 Adam steps of lr 1e-3: updates of ~8e-3
 
 
+def test_eval_after_graph_training_uses_current_weights(se):
+    """the padded / TF32 weight copy the kernels read is ONE buffer refreshed in place, so evaluation --
+    eager, through a cached graph captured BEFORE training, and through the host pipeline -- sees the weights that
+    train_step_graph replays produced (which never bump the parameter's version)."""
+    _, mine = make_pair(se, 512)
+    lengths, wavs = synth(4, 16000, seed=77)
+    lengths, wavs = lengths.cuda(), wavs.cuda()
+    torch.manual_seed(9)
+    head = se.LinearResidual(input_size=257, output_size=257, precision=1).cuda()
+    eng = se.EnhancementEngine(mine, head, log_features=True, precision=1)
+    before = eng.eval_step_graph(lengths, wavs)["sisdr"].clone()          # eval graph captured with the initial weights
+    pipe = eng.host_pipeline(4, 3, 16000, depth=1)
+    opt = se.ClipAdam(head.parameters(), lr=5e-3)
+    for _ in range(12):
+        eng.train_step_graph(lengths, wavs, se.SISDR(), opt, 1.0)
+    torch.cuda.synchronize()
+    fresh_head = se.LinearResidual(input_size=257, output_size=257, precision=1).cuda()
+    fresh_head.load_state_dict(head.state_dict())
+    want = se.EnhancementEngine(mine, fresh_head, log_features=True, precision=1).eval_step(lengths, wavs)["sisdr"]
+    assert (want - before).abs().max().item() > 0.05                     # training moved the metric: the check has teeth
+    got_eager = eng.eval_step(lengths, wavs)["sisdr"]
+    got_graph = eng.eval_step_graph(lengths, wavs)["sisdr"]
+    pipe.submit(lengths.cpu().pin_memory(), wavs.cpu().pin_memory())
+    got_pipe = pipe.drain()[0][1].cuda()
+    for got in (got_eager, got_graph, got_pipe):
+        assert (got - want).abs().max().item() < 1e-4
+    # ... and after an eager update with a torch optimizer (version bump path)
+    opt2 = torch.optim.SGD(head.parameters(), lr=0.5)
+    eng.train_step(lengths, wavs, se.SISDR(), opt2, 1.0)
+    fresh_head.load_state_dict(head.state_dict())
+    want2 = se.EnhancementEngine(mine, fresh_head, log_features=True, precision=1).eval_step(lengths, wavs)["sisdr"]
+    assert (eng.eval_step_graph(lengths, wavs)["sisdr"] - want2).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_clip_adam_skips_nan_and_inf_gradient_norms(se, bad):
+    """runner.py:467-470: a NaN / inf gradient norm skips optimizer.step(); the parameters and moments survive the batch."""
+    torch.manual_seed(1)
+    p = torch.nn.Parameter(torch.randn(33, 7).cuda())
+    q = torch.nn.Parameter(torch.randn(5).cuda())
+    opt = se.ClipAdam([p, q], lr=1e-2)
+    p.grad, q.grad = torch.randn_like(p), torch.randn_like(q)
+    opt.clip_and_step(1.0)
+    snap = [t.detach().clone() for t in (p, q, opt.state[p]["exp_avg"], opt.state[p]["exp_avg_sq"])]
+    p.grad, q.grad = torch.randn_like(p), torch.randn_like(q)
+    p.grad[3, 2] = bad
+    for max_norm in (1.0, None):                                         # the guard also holds without clipping
+        opt.clip_and_step(max_norm)
+    torch.cuda.synchronize()
+    for a, b in zip(snap, (p, q, opt.state[p]["exp_avg"], opt.state[p]["exp_avg_sq"])):
+        assert torch.equal(a, b.detach())
+    assert opt.steps_taken() == [1] and opt.steps_skipped() == [2]
+    p.grad, q.grad = torch.randn_like(p), torch.randn_like(q)            # the next healthy batch trains again
+    opt.clip_and_step(1.0)
+    assert opt.steps_taken() == [2] and torch.isfinite(p).all() and not torch.equal(snap[0], p.detach())
+    # generic optimizers: the engine keeps the runner's host-side check
+    _, mine = make_pair(se, 512)
+    head = se.LinearResidual(input_size=257, output_size=257).cuda()
+    eng = se.EnhancementEngine(mine, head)
+    w0 = head.linear.weight.detach().clone()
+    for prm in head.parameters():
+        prm.grad = torch.full_like(prm, bad)
+    eng._clip_and_step(torch.optim.SGD(head.parameters(), lr=0.1), 1.0)
+    assert torch.equal(w0, head.linear.weight.detach())
+
+
 # ------------------------------------------------------------------------------ active sampling: gradient embeddings + matching
 def test_matching_matches_reference_formula(se):
     g = torch.Generator().manual_seed(9)
