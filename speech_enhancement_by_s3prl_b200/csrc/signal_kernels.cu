@@ -16,6 +16,11 @@ namespace sefast {
 int prepare512();
 int launch_stft512(const StftArgs& a, cudaStream_t st);
 int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st);
+// fastgeo.cu: n_fft 1024 / hop 256 and n_fft 400 / hop 160
+bool geo_supported(int n_fft, int hop);
+int prepare_geo_kernels(int n_fft);
+int launch_stft_run(const StftArgs& a, int n_fft, cudaStream_t st);
+int launch_mask_istft_run(const MaskIstftArgs& a, int n_fft, cudaStream_t st);
 }
 
 namespace {
@@ -81,9 +86,9 @@ int get_tables(int n_fft, DeviceTables* out) {
         int rc = SE_OK;
         switch (n_fft) {
             case 256: rc = opt_in_smem<256>(); break;
-            case 400: rc = opt_in_smem<400>(); break;
+            case 400: rc = opt_in_smem<400>(); if (rc == SE_OK) rc = sefast::prepare_geo_kernels(400); break;
             case 512: rc = opt_in_smem<512>(); if (rc == SE_OK) rc = sefast::prepare512(); break;
-            case 1024: rc = opt_in_smem<1024>(); break;
+            case 1024: rc = opt_in_smem<1024>(); if (rc == SE_OK) rc = sefast::prepare_geo_kernels(1024); break;
             case 2048: rc = opt_in_smem<2048>(); break;
         }
         if (rc != SE_OK) return rc;
@@ -195,6 +200,7 @@ int se_stft_strided(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t
     a.power = power; a.phase = phase; a.logp = logpower; a.log_eps = log_eps; a.spec_stride = spec_stride;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_fft == 512 && !g_force_generic) return sefast::launch_stft512(a, st);
+    if (sefast::geo_supported(n_fft, hop) && !g_force_generic) return sefast::launch_stft_run(a, n_fft, st);
     SE_DISPATCH_NFFT(n_fft, launch_stft, a, st)
 }
 
@@ -230,7 +236,8 @@ static int stft_features_impl(const float* wav, int64_t n_utt, int64_t utt_strid
     if (rc != SE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (!(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(stat_sums, 0, sizeof(double) * 2 * ld_stats * n_utt, st));
-    if (n_fft == 512 && hop == 256 && !g_force_generic) {
+    const bool geo = sefast::geo_supported(n_fft, hop) && !spec_ws;
+    if (((n_fft == 512 && hop == 256) || geo) && !g_force_generic) {
         DeviceTables t;
         if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
         StftArgs a{};
@@ -240,7 +247,7 @@ static int stft_features_impl(const float* wav, int64_t n_utt, int64_t utt_strid
         a.power = take_log ? nullptr : feat; a.logp = take_log ? feat : nullptr; a.log_eps = log_eps; a.spec_stride = feat_stride;
         a.stat_sums = stat_sums; a.ld_stats = ld_stats; a.cspec = spec_ws;
         a.trace = secommon::trace_ptr();
-        return sefast::launch_stft512(a, st);
+        return geo ? sefast::launch_stft_run(a, n_fft, st) : sefast::launch_stft512(a, st);
     }
     // other n_fft: generic STFT, then one pass over the features for the sums
     rc = se_stft_strided(wav, n_utt, utt_stride, T, n_fft, hop, window, log_eps, take_log ? nullptr : feat, nullptr,
@@ -258,7 +265,8 @@ int se_stft_features2(const float* wav, int64_t n_utt, int64_t utt_stride, int64
     if (rc != SE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (!(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(stat_sums, 0, sizeof(double) * 2 * ld_stats * n_utt, st));
-    if (n_fft == 512 && hop == 256 && !g_force_generic) {
+    const bool geo = sefast::geo_supported(n_fft, hop);
+    if (((n_fft == 512 && hop == 256) || geo) && !g_force_generic) {
         DeviceTables t;
         if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
         StftArgs a{};
@@ -268,7 +276,7 @@ int se_stft_features2(const float* wav, int64_t n_utt, int64_t utt_stride, int64
         a.power = power; a.logp = logpower; a.log_eps = log_eps; a.spec_stride = spec_stride;
         a.stat_sums = stat_sums; a.ld_stats = ld_stats;
         a.trace = secommon::trace_ptr();
-        return sefast::launch_stft512(a, st);
+        return geo ? sefast::launch_stft_run(a, n_fft, st) : sefast::launch_stft512(a, st);
     }
     rc = se_stft_strided(wav, n_utt, utt_stride, T, n_fft, hop, window, log_eps, power, nullptr, logpower, spec_stride, stream);
     if (rc != SE_OK) return rc;
@@ -353,6 +361,7 @@ static int mask_istft_impl(const float* noisy, const float* spec_ws, const float
     cudaStream_t st = (cudaStream_t)stream;
     if (sums && !(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * SE_NSUMS * n_utt, st));
     if (n_fft == 512 && hop == 256 && a.n_frames >= 2 && !g_force_generic) return sefast::launch_mask_istft512(a, st);
+    if (sefast::geo_supported(n_fft, hop) && a.n_frames >= 6 && !g_force_generic) return sefast::launch_mask_istft_run(a, n_fft, st);
     SE_DISPATCH_NFFT(n_fft, launch_mask_istft, a, st)
 }
 

@@ -487,6 +487,77 @@ def test_fast512_mask_istft_equals_generic_path(se, T, B):
     assert none is None and (wav_n - wav_s).abs().max().item() < 2e-6
 
 
+GEO = {1024: (513, 64, 16, 256), 400: (201, 25, 10, 160)}
+
+
+@pytest.mark.parametrize("n_fft,T", [(1024, 16000), (1024, 16001), (1024, 12345), (1024, 1500), (1024, 64000), (400, 16000),
+                                     (400, 16001), (400, 7777), (400, 350), (400, 64000)])
+def test_fast_geometries_stft_equals_generic_path(se, n_fft, T):
+    """Register-resident n_fft 1024 / hop 256 and n_fft 400 / hop 160 STFT (fastgeo.cu) against the generic tile path and
+    the oracle: odd T (unaligned rows: element-wise reflect loads), runs shorter than the halo, several utterances."""
+    from speech_enhancement_by_s3prl_b200 import _lib
+    n_freq, win_ms, hop_ms, hop = GEO[n_fft]
+    mine = se.OnlinePreprocessor(win_ms=win_ms, hop_ms=hop_ms, n_freq=n_freq).cuda()
+    ora = OraclePre(win_ms=win_ms, hop_ms=hop_ms, n_freq=n_freq)
+    _, wavs = synth(3, T, seed=T + n_fft)
+    c = mine.get_feat_config
+    cfgs = [c("linear", 0), c("phase", 0), c("linear", 1, log=True), c("linear", 2)]
+    lib = _lib.load()
+    fast = [t.cpu() for t in mine(wavs.cuda(), cfgs)]
+    try:
+        lib.se_set_option(0, 1)
+        slow = [t.cpu() for t in mine(wavs.cuda(), cfgs)]
+    finally:
+        lib.se_set_option(0, 0)
+    ref = ora(wavs, cfgs)
+    assert fast[0].shape == ref[0].shape == (3, T // hop + 1, n_freq)
+    assert rel_to_max(fast[0], slow[0]) < 2e-6 and rel_to_max(fast[3], slow[3]) < 2e-6
+    assert rel_to_max(fast[0], ref[0]) < SPEC_RTOL
+    loud = slow[2] > slow[2].amax() - 7.0                                          # log-power of bins within 30 dB of the largest one
+    assert (fast[2] - slow[2]).abs()[loud].max() < 2e-3
+    strong = ref[0] > 1e-5 * ref[0].amax()
+    dphi = torch.angle(torch.polar(torch.ones_like(ref[1]), fast[1] - ref[1]))
+    assert dphi[strong].abs().max() < 2e-3
+
+
+@pytest.mark.parametrize("n_fft,T,B", [(1024, 16000, 3), (1024, 16001, 2), (1024, 9999, 3), (1024, 2100, 2), (1024, 64000, 5),
+                                       (1024, 160000, 2), (400, 16000, 3), (400, 16001, 2), (400, 9999, 3), (400, 1100, 2),
+                                       (400, 64000, 5), (400, 160000, 2)])
+def test_fast_geometries_mask_istft_equals_generic_path(se, n_fft, T, B):
+    """Fused mask -> iSTFT of fastgeo.cu (overlap-add carry in registers, 2-4 frames per sample, emit windows, virtual
+    flush frames, edge envelopes) against the generic tile path: waveform, all six sums, ragged lengths, power mode."""
+    from speech_enhancement_by_s3prl_b200 import _lib, ops
+    n_freq, win_ms, hop_ms, hop = GEO[n_fft]
+    mine = se.OnlinePreprocessor(win_ms=win_ms, hop_ms=hop_ms, n_freq=n_freq).cuda()
+    lengths = torch.LongTensor([T, max(300, T - 777), T // 2 + 3, T, T // 3 + 1][:B])
+    lengths, wavs = synth(B, T, seed=T + 5, lengths=lengths)
+    g = torch.Generator().manual_seed(4)
+    mask = torch.rand(B, T // hop + 1, n_freq, generator=g).cuda()
+    lib = _lib.load()
+    args = (wavs.cuda(), 0, 1, mask, lengths.cuda(), n_fft, hop, mine._frame_window)
+    wav_f, sums_f = ops.mask_istft(*args, pad_to=T)
+    pw_f, _ = ops.mask_istft(*args, pad_to=T, mask_is_power=True)
+    try:
+        lib.se_set_option(0, 1)
+        wav_s, sums_s = ops.mask_istft(*args, pad_to=T)
+        pw_s, _ = ops.mask_istft(*args, pad_to=T, mask_is_power=True)
+    finally:
+        lib.se_set_option(0, 0)
+    assert wav_f.shape == wav_s.shape == (B, T)
+    assert (wav_f - wav_s).abs().max().item() < 3e-6
+    # power mode gives every bin the magnitude sqrt(mask), also bins whose noisy phase is rounding noise: looser bound
+    assert (pw_f - pw_s).abs().max().item() < 2e-4 * pw_s.abs().max().item()
+    np.testing.assert_allclose(sums_f.cpu().numpy(), sums_s.cpu().numpy(), rtol=3e-5, atol=1e-9)
+    # padded mask rows (the fused step's layout), and no clean / sums / lengths
+    LD = (n_freq + 3) // 4 * 4
+    mask_p = torch.zeros(B, T // hop + 1, LD, device="cuda")
+    mask_p[..., :n_freq] = mask
+    wav_p, sums_p = ops.mask_istft(wavs.cuda(), 0, 1, mask_p, lengths.cuda(), n_fft, hop, mine._frame_window, pad_to=T, mask_padded=True)
+    assert torch.equal(wav_p, wav_f)
+    wav_n, none = ops.mask_istft(wavs.cuda(), 0, None, mask, None, n_fft, hop, mine._frame_window, pad_to=T, want_sums=False)
+    assert none is None and (wav_n - wav_s).abs().max().item() < 3e-6
+
+
 # ------------------------------------------------------------------------------ tensor-core head (tcgen05, TF32)
 @pytest.mark.parametrize("B,F,Din,Dout,act,cmvn", [(3, 101, 257, 257, "Sigmoid", True), (2, 300, 201, 201, "ReLU", False),
                                                    (1, 77, 513, 513, "Sigmoid", True), (2, 128, 120, 201, "Identity", True),
@@ -529,7 +600,9 @@ def test_eval_step_with_tensor_core_head_keeps_sisdr_parity(se, golden_dir):
 
 # ------------------------------------------------------------------------------ fused step: K1 with CMVN sums, TMA head
 @pytest.mark.parametrize("n_fft,B,T,logp", [(512, 3, 16000, True), (512, 5, 9999, True), (512, 2, 64000, False),
-                                            (512, 64, 4096, True), (400, 2, 16000, True)])
+                                            (512, 64, 4096, True), (400, 2, 16000, True), (400, 5, 9999, False),
+                                            (400, 64, 4000, True), (1024, 3, 16000, True), (1024, 2, 9999, False),
+                                            (1024, 64, 8192, True)])
 def test_stft_features_and_cmvn_sums(se, n_fft, B, T, logp):
     from speech_enhancement_by_s3prl_b200 import ops
     _, mine = make_pair(se, n_fft)
