@@ -13,6 +13,9 @@
 //                        sums, round to TF32), later run the epilogue
 //   * warp 8 (one lane)  tcgen05.mma kind::tf32, fp32 accumulators in tensor memory: columns
 //                        [0,256) by one N=256 instruction, the remaining <= 16 by a second one
+//   * more than 272 output columns (n_fft 1024: 513 -> 528): blockIdx.y splits the columns into slabs of
+//                        <= 272 (272 + 256); each CTA streams the same A tile (the second read comes from L2)
+//                        and its own slab of weight rows, and stores its slab of every output row
 //   * epilogue           tcgen05.ld -> +bias -> activation -> row-major staging tile in shared
 //                        memory (reusing the A tile) -> ONE bulk async store per 32-row quadrant:
 //                        with ld_out == padded row length the CTA's output is contiguous in HBM
@@ -26,13 +29,13 @@ using secommon::fail;
 
 namespace {
 
-constexpr int BM = 128, BK = 32, kMaxKB = 9, kStages = 4;
+constexpr int BM = 128, BK = 32, kMaxKB = 17, kStages = 4;
 constexpr int kWorkWarps = 8, kWorkThreads = kWorkWarps * 32, kThreads = kWorkThreads + 64;   // + MMA warp + TMA warp
 constexpr int kATileBytes = BM * BK * 4;                       // 16 KB: one 32-float k-block of the A tile
 constexpr int kMaxWRows = 272;
 constexpr int kWTileBytes = kMaxWRows * BK * 4;                // 34 816: the same k-block of all weight rows
 constexpr int kStageBytes = kATileBytes + kWTileBytes;         // 51 200 (multiple of 1024: SWIZZLE_128B atoms stay aligned)
-constexpr int kStatLd = kMaxKB * BK;                           // 288
+constexpr int kStatLd = kMaxKB * BK;                           // 544: features per utterance (n_fft 1024: 513)
 constexpr int kOffRing = 0;
 constexpr int kOffScale = kOffRing + kStages * kStageBytes;    // 204 800
 constexpr int kOffShift = kOffScale + 2 * kStatLd * 4;
@@ -147,9 +150,10 @@ struct Head2Args {
     float* out;
     long long ld_out;
     int tile_rows;             // rows per CTA: multiple of 8, <= 128, <= n_frames (a tile touches <= 2 utterances)
-    int kblocks;               // ceil(Din / 32) <= 9
-    int w_rows;                // Dout rounded up to 16, <= 272
-    int n_main, n_tail;        // MMA column split: [0, n_main) and [n_main, n_main + n_tail)
+    int kblocks;               // ceil(Din / 32) <= 17
+    int w_rows;                // Dout rounded up to 16, <= 544
+    int cta_cols;              // output columns (weight rows) per CTA slab: multiple of 16, <= 272; slab = blockIdx.y
+    int row_bulk;              // column slabs: one bulk store per output row (16-byte aligned rows and slabs)
     int w_box_rows, w_boxes;   // weight tensor-map box rows and boxes per k-block
     int cluster;               // CTAs per cluster (1 or 2): with 2, each CTA loads one weight box and multicasts it to both
     int sld;                   // floats per row of the staging tile
@@ -173,7 +177,10 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r0 = (long long)blockIdx.x * a.tile_rows;
-    const uint32_t w_bytes = (uint32_t)a.w_rows * BK * 4;
+    const int col0 = (int)blockIdx.y * a.cta_cols;                       // this CTA's slab of output columns
+    const int ncols = a.w_rows - col0 < a.cta_cols ? a.w_rows - col0 : a.cta_cols;
+    const int n_main = ncols > 256 ? 256 : ncols, n_tail = ncols - n_main;   // MMA column split: [0, n_main) and [n_main, ncols)
+    const uint32_t w_bytes = (uint32_t)(a.w_box_rows * a.w_boxes) * BK * 4;  // whole boxes land (rows past Dout read as zero)
 
     if (threadIdx.x == 0) {
         if (sbase & 1023) __trap();
@@ -208,10 +215,10 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const uint32_t dst = sbase + kOffRing + s * kStageBytes + kATileBytes;
                 if (a.cluster > 1) {                                       // my box, delivered to both CTAs (the peer sends the other one)
                     const int b = (int)crank;
-                    tma_load_2d_mc(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, b * a.w_box_rows, bar_full + 8 * s, cmask);
+                    tma_load_2d_mc(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, col0 + b * a.w_box_rows, bar_full + 8 * s, cmask);
                 } else {
                     for (int b = 0; b < a.w_boxes; ++b)
-                        tma_load_2d(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, b * a.w_box_rows, bar_full + 8 * s);
+                        tma_load_2d(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, col0 + b * a.w_box_rows, bar_full + 8 * s);
                 }
             };
             auto load_a = [&](int kb, int s) {
@@ -235,7 +242,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else if (warp == kWorkWarps) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc_main = make_idesc(a.n_main), idesc_tail = make_idesc(a.n_tail > 0 ? a.n_tail : 16);
+            const uint32_t idesc_main = make_idesc(n_main), idesc_tail = make_idesc(n_tail > 0 ? n_tail : 16);
             for (int kb = 0; kb < a.kblocks; ++kb) {
                 const int s = kb % kStages;
                 mbar_wait(bar_norm + 8 * s, (kb / kStages) & 1);
@@ -247,8 +254,8 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int kk = 0; kk < ksteps; ++kk) {
                     const uint64_t ad = make_desc(a_addr + kk * 32);
                     umma_tf32(tmem_base, ad, make_desc(b_addr + kk * 32), idesc_main, (kb | kk) ? 1u : 0u);
-                    if (a.n_tail > 0)
-                        umma_tf32(tmem_base + (uint32_t)a.n_main, ad, make_desc(b_addr + a.n_main * BK * 4 + kk * 32), idesc_tail,
+                    if (n_tail > 0)
+                        umma_tf32(tmem_base + (uint32_t)n_main, ad, make_desc(b_addr + n_main * BK * 4 + kk * 32), idesc_tail,
                                   (kb | kk) ? 1u : 0u);
                 }
                 if (a.cluster > 1) umma_commit_mc(bar_empty + 8 * s, cmask);
@@ -296,7 +303,8 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         {
             const float bscale = a.act == SE_ACT_SIGMOID ? -1.4426950408889634f : 1.0f;     // see the epilogue
-            for (int i = t; i < kStatLd; i += kWorkThreads) s_bias[i] = (a.bias && i < a.Dout) ? bscale * __ldg(a.bias + i) : 0.f;
+            for (int i = t; i < 288; i += kWorkThreads)                      // local column i = output column col0 + i
+                s_bias[i] = (a.bias && col0 + i < a.Dout) ? bscale * __ldg(a.bias + col0 + i) : 0.f;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
         if (t == 0) trace.mark(12);
@@ -336,7 +344,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         float* stage = reinterpret_cast<float*>(smem + kOffRing);           // every stage has been consumed: reuse the ring
         const int quad = warp & 3, half = warp >> 2;
         const int row = quad * 32 + lane;
-        const int ncol16 = a.w_rows / 16;
+        const int ncol16 = ncols / 16;
         const int c_lo = 16 * (half == 0 ? 0 : ncol16 / 2), c_hi = 16 * (half == 0 ? ncol16 / 2 : ncol16);
         float* srow = stage + (long long)row * a.sld;
         // two 16-column chunks in flight: the tensor-memory load of chunk c+1 overlaps the activation of chunk c
@@ -392,9 +400,19 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         int rows_valid = (int)rows_left - quad * 32;
         rows_valid = rows_valid > 32 ? 32 : rows_valid;
         if (rows_valid > 0) {
-            float* gdst = a.out + (r0 + quad * 32) * a.ld_out;
+            float* gdst = a.out + (r0 + quad * 32) * a.ld_out + col0;
             const float* ssrc = stage + (long long)quad * 32 * a.sld;
-            if (a.bulk_out) {
+            if (a.row_bulk) {
+                // column slab: the CTA's part of an output row is contiguous, one bulk store per row (lane = row of the quadrant)
+                int nout = (int)a.ld_out - col0;
+                nout = nout > ncols ? ncols : nout;
+                if (half == 0 && lane < rows_valid) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(gdst + (long long)lane * a.ld_out), "r"(smem_u32(ssrc + (long long)lane * a.sld)), "r"((uint32_t)(nout * 4)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+            } else if (a.bulk_out) {
                 if (half == 0 && lane == 0) {
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  ::"l"(gdst), "r"(smem_u32(ssrc)), "r"((uint32_t)(rows_valid * a.sld * 4)) : "memory");
@@ -403,7 +421,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
             } else {
                 for (int r = half; r < rows_valid; r += 2)
-                    for (int c = lane; c < a.Dout; c += 32) gdst[(long long)r * a.ld_out + c] = ssrc[(long long)r * a.sld + c];
+                    for (int c = lane; c < ncols && col0 + c < a.Dout; c += 32) gdst[(long long)r * a.ld_out + c] = ssrc[(long long)r * a.sld + c];
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -459,9 +477,10 @@ extern "C" {
 int se_linear_head_fused_supported(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int64_t ldx, int64_t ldw,
                                    int64_t ld_out) {
     if (n_utt <= 0 || n_frames < 8 || D_in <= 0 || D_out <= 0) return 0;
-    if (D_in > kMaxKB * BK || D_out > kMaxWRows) return 0;
+    if (D_in > kMaxKB * BK || D_out > 2 * kMaxWRows) return 0;
     if (ldx % 4 || ldw % 4 || ldx < D_in || ldw < D_in || ld_out < D_out) return 0;
     const int64_t dout4 = (D_out + 3) / 4 * 4;
+    if (D_out > kMaxWRows) return (ld_out % 4 == 0 && ld_out >= dout4) ? 1 : 0;                 // column slabs: 16-byte aligned row parts
     if ((ld_out == dout4 ? ld_out : dout4 + 4) * 4 * BM > kStages * kStageBytes) return 0;      // staging tile must fit in the ring
     return 1;
 }
@@ -482,24 +501,30 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     a.trace = secommon::trace_ptr();
     a.inv_n = 1.0 / (double)n_frames;
     a.inv_nm1 = 1.0 / (double)(n_frames - 1);
-    long long rows = (a.R + num_sms() - 1) / num_sms();                     // one tile per SM when the batch is small
+    a.kblocks = (int)((D_in + BK - 1) / BK);
+    a.w_rows = (int)((D_out + 15) / 16 * 16);
+    const int n_split = (a.w_rows + kMaxWRows - 1) / kMaxWRows;              // column slabs (blockIdx.y)
+    a.cta_cols = ((a.w_rows + n_split - 1) / n_split + 15) / 16 * 16;
+    // rows per tile: the fewest waves of (tiles x slabs) CTAs over the SMs, then tiles as even as the waves allow
+    const long long min_tiles = (a.R + BM - 1) / BM;
+    const long long waves = (min_tiles * n_split + num_sms() - 1) / num_sms();
+    const long long want_tiles = waves * num_sms() / n_split;
+    long long rows = (a.R + want_tiles - 1) / want_tiles;
     rows = (rows + 7) / 8 * 8;
     if (rows > BM) rows = BM;
     if (rows > n_frames) rows = n_frames / 8 * 8;                           // a tile may touch at most two utterances
     a.tile_rows = (int)rows;
-    a.kblocks = (int)((D_in + BK - 1) / BK);
-    a.w_rows = (int)((D_out + 15) / 16 * 16);
-    a.n_main = a.w_rows > 256 ? 256 : a.w_rows;
-    a.n_tail = a.w_rows - a.n_main;
     static int want_cluster = -1;
     // default 1: halving the weight L2 traffic gave no measured gain (the TF32 MMA rate bounds the main loop)
     if (want_cluster < 0) { const char* e = getenv("SE_B200_HEAD_CLUSTER"); want_cluster = e ? atoi(e) : 1; }
-    a.cluster = want_cluster >= 2 ? 2 : 1;
-    a.w_boxes = (a.w_rows > 256 || a.cluster == 2) ? 2 : 1;           // w_rows is a multiple of 16: both boxes are whole 8-row atoms
-    a.w_box_rows = a.w_rows / a.w_boxes;
+    a.cluster = (want_cluster >= 2 && n_split == 1) ? 2 : 1;
+    a.w_boxes = (a.cta_cols > 256 || a.cluster == 2) ? 2 : 1;         // cta_cols is a multiple of 16: both boxes are whole 8-row atoms
+    a.w_box_rows = a.cta_cols / a.w_boxes;
     const int dout4 = (int)((D_out + 3) / 4 * 4);
-    a.bulk_out = (ld_out == dout4 && aligned16(offset_out)) ? 1 : 0;
-    a.sld = a.bulk_out ? (int)ld_out : dout4 + 4;
+    a.row_bulk = (n_split > 1 && aligned16(offset_out)) ? 1 : 0;
+    a.bulk_out = (n_split == 1 && ld_out == dout4 && aligned16(offset_out)) ? 1 : 0;
+    a.sld = n_split > 1 ? a.cta_cols + 4 : (a.bulk_out ? (int)ld_out : dout4 + 4);
+    if (n_split > 1 && !a.row_bulk) return fail(SE_ERR_UNSUPPORTED, "fused head: column slabs need a 16-byte aligned output");
     CUtensorMap tmA, tmW;
     int rc = make_map(&tmA, x, D_in, a.R, ldx, a.tile_rows);
     if (rc != SE_OK) return rc;
@@ -511,7 +536,7 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     cudaLaunchConfig_t cfg{};
     unsigned tiles = (unsigned)((a.R + a.tile_rows - 1) / a.tile_rows);
     if (a.cluster == 2) tiles = (tiles + 1) & ~1u;                       // an idle tile (all rows out of range) completes the last pair
-    cfg.gridDim = dim3(tiles);
+    cfg.gridDim = dim3(tiles, (unsigned)n_split);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = (cudaStream_t)stream;
