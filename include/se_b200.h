@@ -142,6 +142,12 @@ int se_mask_istft_ws(const float* spec_ws, const float* clean, int64_t utt_strid
 int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_utt, int64_t T,
                         float target_db_or_nan, float* wav, int64_t wav_stride, int64_t width,
                         float* gain, float* sisdr_wave, float* loss_spec, void* stream);
+/* Same, and metric_acc[0..2] (doubles, caller-owned, never zeroed here) += [sum_u loss_spec, sum_u sisdr_wave, n_utt]:
+ * the running sums an evaluation pass averages at its end (runner.py:602; objective.py:100) stay on the device, so
+ * a pass over many batches -- and the one all-reduce of a data-parallel pass -- needs no host read per batch. */
+int se_finalize_metrics_acc(const double* sums, const int64_t* lengths, int64_t n_utt, int64_t T,
+                            float target_db_or_nan, float* wav, int64_t wav_stride, int64_t width,
+                            float* gain, float* sisdr_wave, float* loss_spec, double* metric_acc, void* stream);
 
 /* ---- K4a: spectral SI-SDR objective (objective.py:86-100) -------------------------
  * fwd: per-utterance sums (n_utt x 3 doubles: st, tt, ss; overwritten) over frames

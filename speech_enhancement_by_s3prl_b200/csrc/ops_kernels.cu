@@ -37,7 +37,8 @@ __device__ __forceinline__ double sisdr_from_sums(double st, double tt, double s
 __global__ void finalize_metrics_kernel(const double* __restrict__ sums, const long long* __restrict__ lengths,
                                         int T, double level_or_neg, float* __restrict__ wav, long long wav_stride,
                                         int width, float* __restrict__ gain_out, float* __restrict__ sisdr_wave,
-                                        float* __restrict__ loss_spec, int chunks, unsigned long long* trace_buf) {
+                                        float* __restrict__ loss_spec, double* __restrict__ metric_acc, int chunks,
+                                        unsigned long long* trace_buf) {
     secommon::TraceScope trace(trace_buf, 4);
     asm volatile("griddepcontrol.wait;" ::: "memory");                   // sums and wav come from the upstream kernel
     const int u = blockIdx.x / chunks, chunk = blockIdx.x - u * chunks;
@@ -62,8 +63,15 @@ __global__ void finalize_metrics_kernel(const double* __restrict__ sums, const l
     const double gain = sqrt(level / (mean_yy + eps_mean));
     if (chunk == 0 && threadIdx.x == 0) {
         if (gain_out) gain_out[u] = (float)gain;
-        if (sisdr_wave) sisdr_wave[u] = (float)sisdr_from_sums(gain * s[SE_SUM_YC], s[SE_SUM_CC], gain * gain * s[SE_SUM_YY], 1e-10);
-        if (loss_spec) loss_spec[u] = (float)(-sisdr_from_sums(s[SE_SUM_SPEC_ST], s[SE_SUM_SPEC_TT], s[SE_SUM_SPEC_SS], 1e-10));
+        const float sd = (float)sisdr_from_sums(gain * s[SE_SUM_YC], s[SE_SUM_CC], gain * gain * s[SE_SUM_YY], 1e-10);
+        const float ls = (float)(-sisdr_from_sums(s[SE_SUM_SPEC_ST], s[SE_SUM_SPEC_TT], s[SE_SUM_SPEC_SS], 1e-10));
+        if (sisdr_wave) sisdr_wave[u] = sd;
+        if (loss_spec) loss_spec[u] = ls;
+        if (metric_acc) {                                               // running sums of an evaluation pass (runner.py:602)
+            atomicAdd(metric_acc, (double)ls);
+            atomicAdd(metric_acc + 1, (double)sd);
+            atomicAdd(metric_acc + 2, 1.0);
+        }
     }
     if (!wav) { trace.finish(); return; }
     const float g = (float)gain;
@@ -848,6 +856,13 @@ extern "C" {
 int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_utt, int64_t T, float target_db_or_nan,
                         float* wav, int64_t wav_stride, int64_t width, float* gain, float* sisdr_wave, float* loss_spec,
                         void* stream) {
+    return se_finalize_metrics_acc(sums, lengths, n_utt, T, target_db_or_nan, wav, wav_stride, width, gain, sisdr_wave, loss_spec,
+                                   nullptr, stream);
+}
+
+int se_finalize_metrics_acc(const double* sums, const int64_t* lengths, int64_t n_utt, int64_t T, float target_db_or_nan,
+                            float* wav, int64_t wav_stride, int64_t width, float* gain, float* sisdr_wave, float* loss_spec,
+                            double* metric_acc, void* stream) {
     SE_REQUIRE(sums && n_utt > 0, "sums must not be null");
     // two CTAs per SM in one wave: the launch ramp of ~1000 small CTAs costs more than the scaling itself
     int chunks = 1;
@@ -866,7 +881,8 @@ int se_finalize_metrics(const double* sums, const int64_t* lengths, int64_t n_ut
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, finalize_metrics_kernel, sums, (const long long*)lengths, (int)T, level, wav,
-                                     (long long)wav_stride, (int)width, gain, sisdr_wave, loss_spec, chunks, secommon::trace_ptr()));
+                                     (long long)wav_stride, (int)width, gain, sisdr_wave, loss_spec, metric_acc, chunks,
+                                     secommon::trace_ptr()));
     return secommon::check_launch("finalize_metrics_kernel");
 }
 

@@ -56,6 +56,14 @@ def global_means(per_utt_loss, per_utt_metric):
     return (vec[0] / vec[2]), (vec[1] / vec[2]), int(vec[2].item())
 
 
+def means_from_acc(metric_acc):
+    """Global (mean loss, mean metric, utterances) from the device-side running sums [sum loss, sum metric, n] that
+    ``se_finalize_metrics_acc`` keeps over an evaluation pass: ONE all-reduce of three doubles on the current stream and
+    no host synchronisation -- the returned values are device tensors."""
+    vec = reduce_sums(metric_acc.clone())
+    return vec[0] / vec[2], vec[1] / vec[2], vec[2]
+
+
 def global_l1(acc2):
     """objective.L1 under DP: all-reduce numerator AND element count before dividing (objective.py:113-116)."""
     acc2 = reduce_sums(acc2.clone())

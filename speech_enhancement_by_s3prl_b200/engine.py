@@ -40,9 +40,11 @@ class EnhancementEngine:
         self.launches_per_step = 5          # library kernels per eval_step (set by eval_step: 4 on the fused path)
 
     # ------------------------------------------------------------------ device-resident step
-    def eval_step(self, lengths, wavs, want_spec_loss=True):
+    def eval_step(self, lengths, wavs, want_spec_loss=True, metric_acc=None):
         """lengths (B,) int64, wavs (B, C, T) fp32, both on the GPU.
-        Returns dict(loss_per_utt (B,), sisdr (B,), wav_predicted (B, T), gain (B,))."""
+        Returns dict(loss_per_utt (B,), sisdr (B,), wav_predicted (B, T), gain (B,)).
+        metric_acc: float64 (3,) device tensor += [sum loss, sum SI-SDR, utterances] (the running sums of an evaluation
+        pass, runner.py:587-602; ``dp.means_from_acc`` turns them into the global means with one all-reduce)."""
         B, C, T = wavs.shape
         dev = wavs.device
         window = self.pre._frame_window
@@ -86,7 +88,7 @@ class EnhancementEngine:
                                               head.eps, precision=self.precision)
                 wav, sums = ops.mask_istft(wavs, self.ch_inp, self.ch_tar, mask, lengths, self.n_fft, self.hop, window,
                                            pad_to=T, want_sums=True, want_spec=want_spec_loss, mask_padded=True)
-            gain, sisdr, loss = ops.finalize_metrics(sums, lengths, T, wav=wav, target_db=None)
+            gain, sisdr, loss = ops.finalize_metrics(sums, lengths, T, wav=wav, target_db=None, metric_acc=metric_acc)
         return {"loss_per_utt": loss, "sisdr": sisdr, "wav_predicted": wav, "gain": gain, "mask": mask[..., :K]}
 
     def _padded_weight(self, force=False):
@@ -113,9 +115,10 @@ class EnhancementEngine:
         return buf
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
-    def capture_bound(self, lengths, wavs):
+    def capture_bound(self, lengths, wavs, metric_acc=None):
         """Capture eval_step into a CUDA graph that reads the GIVEN device tensors in place
-        (no staging copy).  Returns dict(graph=, lengths=, wavs=, loss_per_utt=, sisdr=, wav_predicted=, ...)."""
+        (no staging copy).  Returns dict(graph=, lengths=, wavs=, loss_per_utt=, sisdr=, wav_predicted=, ...).
+        metric_acc: see eval_step (every replay adds the batch's sums to it)."""
         device = wavs.device
         ops.prepare(self.n_fft)
         if self.pre._frame_window.device != device:
@@ -124,12 +127,12 @@ class EnhancementEngine:
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(2):                                   # warm up allocator + lazy init outside capture
-                self.eval_step(lengths, wavs)
+                self.eval_step(lengths, wavs)                    # (no metric_acc: warm-up batches are not part of a pass)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.eval_step(lengths, wavs)
+            out = self.eval_step(lengths, wavs, metric_acc=metric_acc)
         static = {"lengths": lengths, "wavs": wavs, "graph": graph}
         static.update(out)
         return static
@@ -262,11 +265,10 @@ class EnhancementEngine:
         return loss
 
 
-    def train_step_graph(self, lengths, wavs, objective, optimizer, grad_clip=None):
-        """``train_step`` replayed from a CUDA graph: forward, backward, gradient all-reduce, clipping and the optimizer
-        update of one batch shape are captured once (the eager step is launch-bound: ~40 small launches).  The optimizer
-        must be capturable (e.g. ``torch.optim.Adam(..., capturable=True)``).  Returns the loss tensor of the static step
-        (valid until the next call)."""
+    def capture_train(self, lengths, wavs, objective, optimizer, grad_clip=None):
+        """Capture the training step of one batch shape -- forward, backward, gradient all-reduce (NCCL under DP), clipping
+        and the optimizer update -- into a CUDA graph with its own static input buffers; cached per (shape, objective,
+        optimizer).  Returns dict(graph=, lengths=, wavs=, loss=): fill the inputs, ``graph.replay()``, read ``loss``."""
         B, C, T = wavs.shape
         key = ("train", B, C, T, id(objective), id(optimizer), grad_clip)
         st = self._graphs.get(key)
@@ -287,6 +289,13 @@ class EnhancementEngine:
                 st["loss"] = self._train_body(st["lengths"], st["wavs"], objective, optimizer, grad_clip)
             st["graph"] = graph
             self._graphs[key] = st
+        return st
+
+    def train_step_graph(self, lengths, wavs, objective, optimizer, grad_clip=None):
+        """``train_step`` replayed from a CUDA graph (the eager step is launch-bound: ~40 small launches).  The optimizer
+        must be capturable (``se_b200.ClipAdam``, or e.g. ``torch.optim.Adam(..., capturable=True)``).  Returns the loss
+        tensor of the static step (valid until the next call)."""
+        st = self.capture_train(lengths, wavs, objective, optimizer, grad_clip)
         st["lengths"].copy_(lengths, non_blocking=True)
         st["wavs"].copy_(wavs, non_blocking=True)
         st["graph"].replay()

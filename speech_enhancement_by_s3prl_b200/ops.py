@@ -347,8 +347,10 @@ def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, 
     return out, (sums if want_sums else None)
 
 
-def finalize_metrics(sums, lengths, T, wav=None, target_db=None, want_gain=True, want_sisdr=True, want_loss=True):
-    """Gain / waveform SI-SDR / spectral-SISDR terms from the sums of mask_istft; scales wav in place."""
+def finalize_metrics(sums, lengths, T, wav=None, target_db=None, want_gain=True, want_sisdr=True, want_loss=True,
+                     metric_acc=None):
+    """Gain / waveform SI-SDR / spectral-SISDR terms from the sums of mask_istft; scales wav in place.
+    metric_acc: float64 (3,) running [sum loss, sum SI-SDR, utterances] of an evaluation pass, updated on the device."""
     B = sums.shape[0]
     dev = sums.device
     with torch.cuda.device(dev):
@@ -356,10 +358,12 @@ def finalize_metrics(sums, lengths, T, wav=None, target_db=None, want_gain=True,
         sisdr = torch.empty(B, device=dev) if want_sisdr else None
         loss = torch.empty(B, device=dev) if want_loss else None
         tdb = float("nan") if target_db is None else float(target_db)
-        rc = _lib.load().se_finalize_metrics(sums.data_ptr(), _p(lengths), B, int(T), tdb, _p(wav),
-                                             0 if wav is None else wav.stride(0), 0 if wav is None else wav.shape[1],
-                                             _p(gain), _p(sisdr), _p(loss), _stream())
-        _lib.check(rc, "se_finalize_metrics")
+        if metric_acc is not None:
+            assert metric_acc.dtype == torch.float64 and metric_acc.numel() >= 3 and metric_acc.is_contiguous()
+        rc = _lib.load().se_finalize_metrics_acc(sums.data_ptr(), _p(lengths), B, int(T), tdb, _p(wav),
+                                                 0 if wav is None else wav.stride(0), 0 if wav is None else wav.shape[1],
+                                                 _p(gain), _p(sisdr), _p(loss), _p(metric_acc), _stream())
+        _lib.check(rc, "se_finalize_metrics_acc")
     return gain, sisdr, loss
 
 
