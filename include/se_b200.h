@@ -325,6 +325,15 @@ int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const 
 int se_mel(const float* power, int64_t n_rows, int64_t K, const float* fb, int64_t n_mels, int take_log, float eps,
            float* out, int64_t out_row_stride, void* stream);
 int se_delta(float* x, int64_t n_utt, int64_t n_frames, int64_t D, int order, void* stream);
+/* The mel feature configs in ONE launch (pretrain_sample.yaml:54-59 "mel, log, delta 1, cmvn"; pseudo_noise.yaml:10-15
+ * "mel, log, delta 2"): out (n_utt, n_frames, ld_out) columns [0, (order+1) n_mels) = [mel | delta | delta-delta] of
+ * log?(power fb (+eps)), deltas as se_delta (order <= 2, n_mels <= 64).  stat_sums (n_utt, (order+1) n_mels, 2) doubles or
+ * NULL: zeroed here, then [sum_f x, sum_f x^2] per column -- what se_cmvn_apply_sums turns into the CMVN
+ * x = (x - mean) / (unbiased std + eps) in place. */
+int se_mel_features(const float* power, int64_t ld_power, int64_t n_utt, int64_t n_frames, int64_t K, const float* fb,
+                    int64_t n_mels, int take_log, float eps, int order, float* out, int64_t ld_out, double* stat_sums,
+                    void* stream);
+int se_cmvn_apply_sums(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const double* sums, float eps, void* stream);
 int se_cmvn_apply(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const float* mean, const float* std,
                   float eps, void* stream);
 
@@ -343,6 +352,11 @@ int se_mix_batch(const float* speech, int64_t speech_stride, const int64_t* spee
  * d_wavs (B, n_ch, T) with one strided async copy (the path consumes the noisy and clean channels
  * only; the scaled-noise channel never crosses PCIe). */
 int se_h2d_channels(const float* h_wavs, int64_t B, int64_t C, int64_t T, int64_t n_ch, float* d_wavs, void* stream);
+/* The same for 16-bit PCM host batches (what the corpora's wav files hold: dataset.py:96-103 reads them into floats on the
+ * host): channels [0, n_ch) of h_pcm (B, C, T) int16 cross PCIe as 2 bytes per sample into the staging buffer
+ * d_pcm (B, n_ch, T) int16, and one kernel widens them to d_wavs (B, n_ch, T) fp32 = sample / 32768 (exact). */
+int se_h2d_channels_pcm16(const int16_t* h_pcm, int64_t B, int64_t C, int64_t T, int64_t n_ch, int16_t* d_pcm, float* d_wavs,
+                          void* stream);
 
 #ifdef __cplusplus
 }

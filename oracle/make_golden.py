@@ -10,6 +10,11 @@ TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.
   ``Runner.evaluate()`` (runner.py:521-622) driven over a 3-batch synthetic
   dataset with the restated preprocessor, the reference ``LinearResidual`` and
   the reference ``SISDR`` criterion.
+* ``recurrent_heads_ref.npz`` -- the reference's ``model.LSTM`` and ``model.Residual`` (model.py:37-91) at small sizes:
+  state dicts, inputs, outputs and the gradients of a scalar loss w.r.t. EVERY parameter (the LSTM below the
+  projection included), so the drop-in heads' projection + multiply / exp -- forward, weight gradient and the input
+  gradient that reaches the LSTM -- are pinned by the reference itself.
+  (``python -m oracle.make_golden recurrent`` regenerates this file alone.)
 * ``preprocessor_oracle.npz`` -- outputs of ``oracle/preprocessor.py``
   (torch.stft / torch.istft based) for small inputs; guards against drift of the
   oracle itself across torch versions (this one is NOT a reference output).
@@ -173,6 +178,35 @@ def make_runner_evaluate(ref):
     return out
 
 
+def make_recurrent_heads(ref):
+    """model.LSTM (log_predicted -> exp) and model.Residual (offset * linears), uni- and bidirectional, with CMVN."""
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    B, Fr, Din, Dh, K = 3, 17, 9, 12, 9
+    feats = torch.randn(B, Fr, Din, generator=g)
+    linears = torch.rand(B, Fr, K, generator=g) * 2.0
+    out.update(feats=_np(feats), linears=_np(linears))
+    cases = {"lstm_uni": ("LSTM", dict(bidirectional=False, activation="Identity")),
+             "lstm_bi": ("LSTM", dict(bidirectional=True, activation="Identity")),
+             "res_uni": ("Residual", dict(bidirectional=False, activation="Sigmoid", cmvn=False)),
+             "res_bi_cmvn": ("Residual", dict(bidirectional=True, activation="Sigmoid", cmvn=True)),
+             "res_relu": ("Residual", dict(bidirectional=False, activation="ReLU", cmvn=True))}
+    for tag, (cls, kw) in cases.items():
+        torch.manual_seed(1337)
+        head = getattr(ref["model"], cls)(input_size=Din, output_size=K, hidden_size=Dh, num_layers=2, **kw)
+        predicted, res = head(features=feats, linears=linears)
+        loss = (predicted * torch.linspace(0.5, 1.5, K)).pow(2).mean() + 0.1 * predicted.mean()
+        loss.backward()
+        out[f"{tag}_predicted"] = _np(predicted)
+        for k, v in res.items():
+            out[f"{tag}_{k}"] = _np(v)
+        out[f"{tag}_loss"] = _np(loss)
+        for name, p in head.named_parameters():
+            out[f"{tag}_param_{name}"] = _np(p)
+            out[f"{tag}_grad_{name}"] = _np(p.grad)
+    return out
+
+
 def make_preprocessor_oracle():
     g = torch.Generator().manual_seed(2024)
     out = {}
@@ -193,9 +227,13 @@ def make_preprocessor_oracle():
 
 
 def main():
+    import sys
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
     ref = ref_loader.load()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "recurrent_heads_ref.npz"), **make_recurrent_heads(ref))
+    if "recurrent" in sys.argv[1:]:
+        return
     np.savez_compressed(os.path.join(GOLDEN_DIR, "signal_path_ref.npz"), **make_signal_path(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "runner_evaluate_ref.npz"), **make_runner_evaluate(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "preprocessor_oracle.npz"), **make_preprocessor_oracle())

@@ -163,3 +163,21 @@ def eval_step(preprocessor, head, lengths, wavs, objective="SISDR"):
     return {"loss": loss, "sisdr": torch.tensor(scores), "wav_predicted": wav_predicted,
             "predicted": predicted, "offset": offset, "linear_inp": linear_inp,
             "linear_tar": linear_tar, "phase_inp": phase_inp, "feats_down": feats_down}
+
+
+def recurrent_head(kind, state, features, linears, bidirectional=False, activation="Identity", cmvn=False, eps=1e-6):
+    """model.py:37-60 (``LSTM``: log_predicted = act(Linear(lstm(x))), predicted = exp) and model.py:63-91 (``Residual``:
+    offset = act(Linear([cmvn](lstm(x)))), predicted = linears * offset) from a reference state dict
+    (keys ``lstm.*`` and ``scaling_layer.0.{weight,bias}``)."""
+    hidden = state["lstm.weight_hh_l0"].shape[1]
+    layers = 1 + max(int(k.split("_l")[1].split("_")[0]) for k in state if k.startswith("lstm.weight_ih_l"))
+    lstm = torch.nn.LSTM(input_size=features.shape[-1], hidden_size=hidden, num_layers=layers, batch_first=True,
+                         bidirectional=bidirectional)
+    lstm.load_state_dict({k[5:]: v for k, v in state.items() if k.startswith("lstm.")})
+    h, _ = lstm(features)
+    if kind == "Residual" and cmvn:
+        h = (h - h.mean(dim=1, keepdim=True)) / (h.std(dim=1, keepdim=True) + eps)
+    out = getattr(torch.nn, activation)()(torch.nn.functional.linear(h, state["scaling_layer.0.weight"], state["scaling_layer.0.bias"]))
+    if kind == "LSTM":
+        return out.exp(), {"log_predicted": out}
+    return linears * out, {"offset": out}

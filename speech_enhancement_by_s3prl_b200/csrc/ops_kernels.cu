@@ -1143,6 +1143,129 @@ int se_cmvn_apply(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const fl
     return secommon::check_launch("cmvn_apply_kernel");
 }
 
+// ------------------------------------------------------------------ K1b fused: mel -> log -> deltas -> CMVN sums, final layout
+// One CTA = kMfTile consecutive frames of one utterance.  The mel(-log) rows of the tile and of 2 * order halo frames on
+// either side (frame indices clamped to the utterance: compute_deltas pads by replication) are computed once into shared
+// memory, the recursive 5-tap regression deltas are taken there, and the finished (order + 1) * n_mels columns are written
+// straight into the output row -- one launch instead of se_mel + order x se_delta (+ se_cmvn_stats).  With stat_sums the
+// per-(utterance, column) sum and sum of squares accumulate in double for the CMVN that follows (se_cmvn_apply_sums).
+constexpr int kMfTile = 32, kMfMaxOrder = 2, kMfMaxMels = 64;
+__global__ void __launch_bounds__(256) mel_features_kernel(const float* __restrict__ power, long long ld_power, int n_frames, int K,
+                                                           const float* __restrict__ fb, int n_mels, int take_log, float eps, int order,
+                                                           float* __restrict__ out, long long ld_out, double* __restrict__ stat_sums,
+                                                           int tiles) {
+    __shared__ float s_m[kMfMaxOrder + 1][kMfTile + 4 * kMfMaxOrder][kMfMaxMels];
+    __shared__ float s_red[2][8][kMfMaxMels];
+    const int u = blockIdx.x / tiles, tile = blockIdx.x - u * tiles;
+    const int f0 = tile * kMfTile;
+    const int nf = min(kMfTile, n_frames - f0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* prow = power + (long long)u * n_frames * ld_power;
+    // level 0: mel rows of frames f0 - 2 order .. f0 + nf + 2 order - 1 (clamped)
+    const int w0 = nf + 4 * order;
+    for (int i = warp; i < w0; i += 8) {
+        int f = f0 - 2 * order + i;
+        f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
+        const float* p = prow + (long long)f * ld_power;
+        const int ma = lane, mb = 32 + lane;
+        float acc_a = 0.f, acc_b = 0.f;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const float pv = (k0 + lane < K) ? p[k0 + lane] : 0.f;
+            const int kn = min(32, K - k0);
+            for (int j = 0; j < kn; ++j) {
+                const float pk = __shfl_sync(0xffffffffu, pv, j);
+                const float* frow = fb + (long long)(k0 + j) * n_mels;
+                if (ma < n_mels) acc_a = fmaf(pk, frow[ma], acc_a);
+                if (mb < n_mels) acc_b = fmaf(pk, frow[mb], acc_b);
+            }
+        }
+        if (ma < n_mels) s_m[0][i][ma] = take_log ? logf(acc_a + eps) : acc_a;
+        if (mb < n_mels) s_m[0][i][mb] = take_log ? logf(acc_b + eps) : acc_b;
+    }
+    __syncthreads();
+    // level o: deltas of level o - 1 on frames f0 - 2 (order - o) .. ; position i of level o is frame f0 - 2 (order - o) + i
+    for (int o = 1; o <= order; ++o) {
+        const int wo = nf + 4 * (order - o);
+        for (int idx = threadIdx.x; idx < wo * n_mels; idx += blockDim.x) {
+            const int i = idx / n_mels, m = idx - i * n_mels;
+            int f = f0 - 2 * (order - o) + i;
+            f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
+            // frame f +- k (clamped) sits at position clamp(f + k) - (f0 - 2 (order - o + 1)) of level o - 1
+            const int base = f0 - 2 * (order - o + 1);
+            auto at = [&](int t) { t = t < 0 ? 0 : (t >= n_frames ? n_frames - 1 : t); return s_m[o - 1][t - base][m]; };
+            s_m[o][i][m] = (-2.0f * at(f - 2) - at(f - 1) + at(f + 1) + 2.0f * at(f + 2)) / 10.0f;
+        }
+        __syncthreads();
+    }
+    // output rows + CMVN sums: thread = (frame lane r, column m); level o's own frames start at position 2 (order - o)
+    const int cols = (order + 1) * n_mels;
+    for (int c0 = 0; c0 < cols; c0 += kMfMaxMels) {
+        const int m = threadIdx.x & (kMfMaxMels - 1), r0 = threadIdx.x / kMfMaxMels;          // 4 frame lanes x 64 columns
+        const int c = c0 + m;
+        float s1 = 0.f, s2 = 0.f;
+        if (m < kMfMaxMels && c < cols) {
+            const int o = c / n_mels, mm = c - o * n_mels;
+            for (int r = r0; r < nf; r += 256 / kMfMaxMels) {
+                const float v = s_m[o][2 * (order - o) + r][mm];
+                out[((long long)u * n_frames + f0 + r) * ld_out + c] = v;
+                s1 += v; s2 += v * v;
+            }
+        }
+        if (stat_sums) {
+            s_red[0][r0][m] = s1;
+            s_red[1][r0][m] = s2;
+            __syncthreads();
+            if (threadIdx.x < kMfMaxMels && c0 + (int)threadIdx.x < cols) {
+                double a = 0.0, b = 0.0;
+                for (int r = 0; r < 256 / kMfMaxMels; ++r) { a += (double)s_red[0][r][threadIdx.x]; b += (double)s_red[1][r][threadIdx.x]; }
+                double* dst = stat_sums + ((long long)u * cols + c0 + threadIdx.x) * 2;
+                atomicAdd(dst, a);
+                atomicAdd(dst + 1, b);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// x = (x - mean) / (std + eps) in place with mean / unbiased std from the (n_utt, D, 2) double sums [sum x, sum x^2]
+__global__ void cmvn_apply_sums_kernel(float* __restrict__ x, long long n_frames, int D, const double* __restrict__ sums, float eps,
+                                       long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / D;
+        const int d = (int)(i - row * D);
+        const long long u = row / n_frames;
+        const double s1 = sums[(u * D + d) * 2], s2 = sums[(u * D + d) * 2 + 1];
+        const double n = (double)n_frames, mean = s1 / n;
+        const double var = (s2 - s1 * mean) / (n - 1.0);
+        x[i] = (x[i] - (float)mean) / ((float)sqrt(var > 0.0 ? var : 0.0) + eps);
+    }
+}
+
+int se_mel_features(const float* power, int64_t ld_power, int64_t n_utt, int64_t n_frames, int64_t K, const float* fb,
+                    int64_t n_mels, int take_log, float eps, int order, float* out, int64_t ld_out, double* stat_sums,
+                    void* stream) {
+    SE_REQUIRE(power && fb && out && n_utt > 0 && n_frames > 0 && K > 0, "bad argument");
+    SE_REQUIRE(n_mels > 0 && n_mels <= kMfMaxMels && order >= 0 && order <= kMfMaxOrder, "n_mels=%lld (<= %d) / order=%d (<= %d) out of range",
+               (long long)n_mels, kMfMaxMels, order, kMfMaxOrder);
+    SE_REQUIRE(ld_power >= K && ld_out >= (order + 1) * n_mels, "row stride smaller than the row");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stat_sums) SE_CUDA_CHECK(cudaMemsetAsync(stat_sums, 0, sizeof(double) * 2 * (order + 1) * n_mels * n_utt, st));
+    const int tiles = (int)((n_frames + kMfTile - 1) / kMfTile);
+    const long long blocks = n_utt * tiles;
+    SE_REQUIRE(blocks <= 0x7fffffffLL, "grid too large");
+    mel_features_kernel<<<(unsigned)blocks, 256, 0, st>>>(power, ld_power, (int)n_frames, (int)K, fb, (int)n_mels, take_log, eps, order, out,
+                                                          ld_out, stat_sums, tiles);
+    return secommon::check_launch("mel_features_kernel");
+}
+
+int se_cmvn_apply_sums(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const double* sums, float eps, void* stream) {
+    SE_REQUIRE(x && sums && n_utt > 0 && n_frames > 1 && D > 0, "bad argument");
+    const long long total = n_utt * n_frames * D;
+    const unsigned blocks = (unsigned)std::min<long long>((total + kThreads - 1) / kThreads, 148LL * 16);
+    cmvn_apply_sums_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(x, n_frames, (int)D, sums, eps, total);
+    return secommon::check_launch("cmvn_apply_sums_kernel");
+}
+
 int se_mel(const float* power, int64_t n_rows, int64_t K, const float* fb, int64_t n_mels, int take_log, float eps,
            float* out, int64_t out_row_stride, void* stream) {
     SE_REQUIRE(power && fb && out && n_rows > 0 && K > 0 && n_mels > 0 && out_row_stride >= n_mels, "bad argument");

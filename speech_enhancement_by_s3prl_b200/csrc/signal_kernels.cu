@@ -365,6 +365,33 @@ static int mask_istft_impl(const float* noisy, const float* spec_ws, const float
     SE_DISPATCH_NFFT(n_fft, launch_mask_istft, a, st)
 }
 
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const short4* __restrict__ src, float4* __restrict__ dst, long long n4,
+                                                             const short* __restrict__ src1, float* __restrict__ dst1, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float s = 1.0f / 32768.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const short4 v = src[i];
+        dst[i] = make_float4(s * (float)v.x, s * (float)v.y, s * (float)v.z, s * (float)v.w);
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst1[i] = s * (float)src1[i];
+}
+
+int se_h2d_channels_pcm16(const int16_t* h_pcm, int64_t B, int64_t C, int64_t T, int64_t n_ch, int16_t* d_pcm, float* d_wavs,
+                          void* stream) {
+    SE_REQUIRE(h_pcm && d_pcm && d_wavs && B > 0 && T > 0 && n_ch > 0 && n_ch <= C, "bad argument");
+    SE_REQUIRE((reinterpret_cast<uintptr_t>(d_pcm) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_wavs) & 15) == 0, "unaligned device buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_CHECK(cudaMemcpy2DAsync(d_pcm, (size_t)(n_ch * T) * sizeof(int16_t), h_pcm, (size_t)(C * T) * sizeof(int16_t),
+                                    (size_t)(n_ch * T) * sizeof(int16_t), (size_t)B, cudaMemcpyHostToDevice, st));
+    const long long n = (long long)B * n_ch * T, n4 = n / 4;
+    long long blocks = (n4 + 256 * 8 - 1) / (256 * 8);
+    const long long cap = 4LL * secommon::device_sms();
+    blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+    pcm16_to_float_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const short4*>(d_pcm), reinterpret_cast<float4*>(d_wavs), n4,
+                                                            d_pcm, d_wavs, n);
+    return secommon::check_launch("pcm16_to_float_kernel");
+}
+
 int se_h2d_channels(const float* h_wavs, int64_t B, int64_t C, int64_t T, int64_t n_ch, float* d_wavs, void* stream) {
     SE_REQUIRE(h_wavs && d_wavs && B > 0 && T > 0 && n_ch > 0 && n_ch <= C, "bad argument");
     SE_CUDA_CHECK(cudaMemcpy2DAsync(d_wavs, (size_t)(n_ch * T) * sizeof(float), h_wavs, (size_t)(C * T) * sizeof(float),

@@ -165,11 +165,13 @@ class EnhancementEngine:
         loss, sisdr = pipe.drain()[0]
         return float(loss.mean()), float(sisdr.mean()), pipe.slots[0]["wav_predicted"]
 
-    def host_pipeline(self, B, C, T, depth=2, device=None):
-        key = ("pipe", B, C, T, depth)
+    def host_pipeline(self, B, C, T, depth=2, device=None, pcm16=False, want_wav=False):
+        """Host-facing evaluation loop for (B, C, T) batches; see HostPipeline.  pcm16: the host batches are int16 PCM
+        (half the PCIe bytes; widened on the device); want_wav: the enhanced waveforms come back to pinned host memory."""
+        key = ("pipe", B, C, T, depth, bool(pcm16), bool(want_wav))
         if key not in self._graphs:
             device = device or torch.device("cuda", torch.cuda.current_device())
-            self._graphs[key] = HostPipeline(self, B, C, T, depth, device)
+            self._graphs[key] = HostPipeline(self, B, C, T, depth, device, pcm16=pcm16, want_wav=want_wav)
         return self._graphs[key]
 
     # ------------------------------------------------------------------ training step (head fwd + bwd)
@@ -327,26 +329,37 @@ class HostPipeline:
     ``submit`` enqueues, on a copy stream, the H2D of the noisy and clean channels (one strided
     cudaMemcpy2DAsync; the scaled-noise channel is never used by the path and never crosses PCIe)
     and of the lengths; the compute stream then replays the slot's graph and copies the 2*B result
-    floats back.  With depth 2 the copy of batch i+1 overlaps the kernels of batch i."""
+    floats back.  With depth 2 the copy of batch i+1 overlaps the kernels of batch i.
+
+    ``pcm16``: the host batches are int16 PCM (the sample format of the corpora's wav files): 2 bytes per sample
+    cross PCIe and one kernel widens them to the fp32 the path computes in (sample / 32768, exact).
+    ``want_wav``: every step also copies the level-matched enhanced waveforms (B, T) fp32 back to pinned host memory
+    (``drain`` then returns (loss_per_utt, sisdr, wav) triples) -- what an "enhance these files" caller needs;
+    ``Runner.evaluate()`` itself only needs the metrics."""
 
     N_CH = 2
 
-    def __init__(self, engine, B, C, T, depth, device):
+    def __init__(self, engine, B, C, T, depth, device, pcm16=False, want_wav=False):
         assert engine.ch_inp in (0, 1) and engine.ch_tar in (0, 1), "pipeline ships channels 0 and 1 only"
         self.engine, self.shape, self.device = engine, (B, C, T), device
+        self.pcm16, self.want_wav = bool(pcm16), bool(want_wav)
         self.copy_stream = torch.cuda.Stream(device=device)
         self.compute_stream = torch.cuda.Stream(device=device)
         self.slots = []
         self.pending = []
-        self.h2d_bytes = B * self.N_CH * T * 4 + B * 8
-        self.d2h_bytes = 2 * B * 4
-        self.launches_per_step = 5
+        self.h2d_bytes = B * self.N_CH * T * (2 if pcm16 else 4) + B * 8
+        self.d2h_bytes = 2 * B * 4 + (B * T * 4 if want_wav else 0)
+        self.launches_per_step = 5 + (1 if pcm16 else 0)
         with torch.cuda.stream(self.compute_stream):
             for _ in range(depth):
                 lengths = torch.full((B,), T, dtype=torch.int64, device=device)
                 wavs = torch.zeros(B, self.N_CH, T, device=device).normal_(0, 0.05)
                 st = engine.capture_bound(lengths, wavs)
                 st["result_host"] = torch.empty(2, B).pin_memory()
+                if self.pcm16:
+                    st["pcm"] = torch.empty(B, self.N_CH, T, device=device, dtype=torch.int16)
+                if self.want_wav:
+                    st["wav_host"] = torch.empty(B, T).pin_memory()
                 st["copied"] = torch.cuda.Event()
                 st["done"] = torch.cuda.Event()
                 st["busy"] = False
@@ -358,7 +371,10 @@ class HostPipeline:
         if self._results is None:
             self._results = []
         B, C, T = self.shape
-        assert tuple(wavs_cpu.shape) == (B, C, T) and wavs_cpu.dtype == torch.float32 and wavs_cpu.is_contiguous()
+        want_dtype = torch.int16 if self.pcm16 else torch.float32
+        if tuple(wavs_cpu.shape) != (B, C, T) or wavs_cpu.dtype != want_dtype or not wavs_cpu.is_contiguous():
+            raise RuntimeError(f"HostPipeline.submit: expected a contiguous {want_dtype} batch of shape {(B, C, T)}, "
+                               f"got {wavs_cpu.dtype} {tuple(wavs_cpu.shape)}")
         st = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
         if st["busy"]:
@@ -367,8 +383,13 @@ class HostPipeline:
         lib = _lib.load()
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(st["done"])              # previous use of this slot's inputs has finished
-            rc = lib.se_h2d_channels(wavs_cpu.data_ptr(), B, C, T, self.N_CH, st["wavs"].data_ptr(), self.copy_stream.cuda_stream)
-            _lib.check(rc, "se_h2d_channels")
+            if self.pcm16:
+                rc = lib.se_h2d_channels_pcm16(wavs_cpu.data_ptr(), B, C, T, self.N_CH, st["pcm"].data_ptr(), st["wavs"].data_ptr(),
+                                               self.copy_stream.cuda_stream)
+                _lib.check(rc, "se_h2d_channels_pcm16")
+            else:
+                rc = lib.se_h2d_channels(wavs_cpu.data_ptr(), B, C, T, self.N_CH, st["wavs"].data_ptr(), self.copy_stream.cuda_stream)
+                _lib.check(rc, "se_h2d_channels")
             st["lengths"].copy_(lengths_cpu, non_blocking=True)
             st["copied"].record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):
@@ -376,6 +397,8 @@ class HostPipeline:
             st["graph"].replay()
             st["result_host"][0].copy_(st["loss_per_utt"], non_blocking=True)
             st["result_host"][1].copy_(st["sisdr"], non_blocking=True)
+            if self.want_wav:
+                st["wav_host"].copy_(st["wav_predicted"][:, :T], non_blocking=True)
             st["done"].record(self.compute_stream)
         st["busy"] = True
         self.pending.append(st)
@@ -384,13 +407,13 @@ class HostPipeline:
         st["done"].synchronize()
         st["busy"] = False
         res = st["result_host"].clone()
-        self._results.append((res[0], res[1]))
+        self._results.append((res[0], res[1], st["wav_host"].clone()) if self.want_wav else (res[0], res[1]))
         self.pending.remove(st)
 
     _results = None
 
     def drain(self):
-        """Wait for everything submitted; returns [(loss_per_utt, sisdr), ...] in submission order."""
+        """Wait for everything submitted; returns [(loss_per_utt, sisdr[, wav]), ...] in submission order."""
         if self._results is None:
             self._results = []
         for st in list(self.pending):

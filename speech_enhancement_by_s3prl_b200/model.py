@@ -71,12 +71,9 @@ def _init_lstm_like(module):
 
 
 def _project(hidden, lin, activation, precision):
-    """Projection after the recurrent body.  The head kernel produces weight/bias gradients
-    only (its input never needs one on the named path); while the LSTM is being trained its
-    output does, so that case goes through torch's linear."""
-    if hidden.requires_grad:
-        return getattr(nn, activation)()(torch.nn.functional.linear(hidden, lin.weight, lin.bias))
-    return ops.linear_head(hidden, lin.weight, lin.bias, activation, precision=precision)
+    """Projection after the recurrent body: the library head, forward and backward (weight, bias and -- while the LSTM
+    trains -- input gradients all come from the head kernels)."""
+    return ops.linear_head(hidden.contiguous(), lin.weight, lin.bias, activation, precision=precision)
 
 
 class LSTM(nn.Module):

@@ -474,6 +474,26 @@ def mel(power, fb, take_log, eps, out=None, out_cols=None):
     return out
 
 
+def mel_features(power, fb, take_log, eps, order=0, cmvn=False, cmvn_eps=None):
+    """K1b in one launch (two with CMVN): power (B, F, K) x fb (K, n_mels) -> (B, F, (order + 1) * n_mels) =
+    [mel | delta | delta-delta] of log?(mel + eps), optionally CMVN-normalised over time."""
+    power, fb = _c(power, "power"), _c(fb, "fb")
+    B, F, K = power.shape
+    n_mels = fb.shape[1]
+    D = (int(order) + 1) * n_mels
+    lib = _lib.load()
+    with torch.cuda.device(power.device):
+        out = torch.empty(B, F, D, device=power.device)
+        sums = torch.empty(B, D, 2, device=power.device, dtype=torch.float64) if cmvn else None
+        rc = lib.se_mel_features(power.data_ptr(), K, B, F, K, fb.data_ptr(), n_mels, int(bool(take_log)), float(eps), int(order),
+                                 out.data_ptr(), D, _p(sums), _stream())
+        _lib.check(rc, "se_mel_features")
+        if cmvn:
+            rc = lib.se_cmvn_apply_sums(out.data_ptr(), B, F, D, sums.data_ptr(), float(eps if cmvn_eps is None else cmvn_eps), _stream())
+            _lib.check(rc, "se_cmvn_apply_sums")
+    return out
+
+
 def delta_(x, D, order):
     """x (B, F, (order+1)*D): fill column blocks 1..order with recursive regression deltas of block 0."""
     B, F, W = x.shape
@@ -731,15 +751,32 @@ def _head_setup(ctx, inputs, output):
 
 def _head_backward(ctx, grad_out):
     x, mean, std, weight, offset = ctx.saved_tensors
-    gw, gb = torch.ops.se_b200.linear_head_bwd(x, mean, std, ctx.cmvn_eps, weight, offset, grad_out, ctx.act, ctx.precision)
-    return None, None, None, None, gw, (gb if ctx.has_bias else None), None, None
+    gw = gb = None
+    if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+        gw, gb = torch.ops.se_b200.linear_head_bwd(x, mean, std, ctx.cmvn_eps, weight, offset, grad_out, ctx.act, ctx.precision)
+    gx = None
+    if ctx.needs_input_grad[0]:
+        # the recurrent heads train the LSTM below the projection (model.py:57-60, 85-91): d loss / d x = (grad_out * act'(z)) W,
+        # the same projection kernel run on the transposed weight.  (With the CMVN inside the op, x would also reach the
+        # output through mean / std: the named path never differentiates that, so it is refused rather than approximated.)
+        if mean is not None:
+            raise RuntimeError("se_b200: linear_head with fused CMVN has no gradient w.r.t. its input (normalise in autograd instead)")
+        if ctx.act == ACT["Sigmoid"]:
+            gz = grad_out * offset * (1.0 - offset)
+        elif ctx.act == ACT["ReLU"]:
+            gz = grad_out * (offset > 0).to(grad_out.dtype)
+        else:
+            gz = grad_out
+        gx = torch.ops.se_b200.linear_head(gz.contiguous(), None, None, 0.0, weight.t().contiguous(), None, ACT["Identity"], ctx.precision)
+    return gx, None, None, None, gw, (gb if ctx.has_bias else None), None, None
 
 
 _linear_head.register_autograd(_head_backward, setup_context=_head_setup)
 
 
 def linear_head(x, weight, bias, activation="Sigmoid", mean=None, std=None, cmvn_eps=1e-6, precision=0):
-    """act(cmvn(x) W^T + b): x (B, F, Din) -> (B, F, Dout); gradients flow to weight and bias."""
+    """act(cmvn(x) W^T + b): x (B, F, Din) -> (B, F, Dout); gradients flow to weight and bias, and -- without the fused
+    CMVN -- to x (the projection after a trainable recurrent body)."""
     return torch.ops.se_b200.linear_head(x, mean, std, float(cmvn_eps), weight, bias, ACT[activation], int(precision))
 
 

@@ -130,6 +130,10 @@ class OnlinePreprocessor(nn.Module):
             ft, ch = cfg["feat_type"], int(cfg.get("channel", 0))
             log, delta, cmvn = bool(cfg.get("log", False)), int(cfg.get("delta", 0)), bool(cfg.get("cmvn", False))
             sp = spectra[ch]
+            if ft == "mel" and delta <= 2 and self._n_mels <= 64:
+                # K1b fused: mel -> log -> deltas (-> CMVN) in one launch (two with CMVN), final layout
+                outs.append(ops.mel_features(sp["power"], melfb, log, self.eps, order=delta, cmvn=cmvn).to(home))
+                continue
             if ft == "mel":
                 feat = ops.mel(sp["power"], melfb, log, self.eps, out_cols=(delta + 1) * self._n_mels)
                 base = self._n_mels

@@ -67,6 +67,49 @@ def _batched_ok(head, criterion, features):
     return _lib.load().se_head_grad_embeddings_workspace(B, F, Din, head.linear.weight.shape[0]) > 0
 
 
+def _projection_of(head):
+    """(nn.Linear, activation, input transform) of a head whose LAST layer emits the log-spectrum the L1 objective reads
+    (objective.py:109-117): ``LSTM`` (model.py:57-60: log_predicted = scaling_layer(lstm(x))) or a bare ``Linear``."""
+    if type(head) is model.LSTM:
+        return head.scaling_layer[0], head.activation, (lambda x: head.lstm(x)[0])
+    if type(head) is model.Linear:
+        return head.linear, head.activation, (lambda x: x)
+    return None
+
+
+def _batched_l1_ok(head, criterion, features, projection_only):
+    if type(criterion) is not objective.L1:
+        return False
+    proj = _projection_of(head)
+    if proj is None or (type(head) is model.LSTM and not projection_only):
+        return False                                     # gradients of the recurrent layers need one BPTT per utterance
+    B, F, _ = features.shape
+    return _lib.load().se_head_grad_embeddings_workspace(B, F, proj[0].weight.shape[1], proj[0].weight.shape[0]) > 0
+
+
+@torch.no_grad()
+def scoring_batched_l1(head, criterion, features, linear_tar, stft_lengths, mean=False):
+    """Gradient embeddings of the projection layer under objective.L1 (sampler.py:72-110 with the objective run_active.sh
+    names) without a Python loop: log_predicted = act(W h + b) from the head kernel, d L1 / d log_predicted = sign(log_predicted -
+    log(linear_tar + eps)) on the valid frames from the objective's backward kernel (ONE launch for the batch), and the
+    split-K weight-gradient kernel with one split per utterance.  Row u is the gradient of the L1 of utterance u ALONE (a
+    mean over ITS valid elements, what the reference's loop computes); mean=True: gradient of the L1 of the whole batch
+    (a mean over ALL valid elements).  Rows are [grad_W.view(-1), grad_b] of the projection."""
+    lin, act, body = _projection_of(head)
+    x = ops._c(body(features), "features")
+    B, F, _ = x.shape
+    K = lin.weight.shape[0]
+    log_pred = ops.linear_head(x, lin.weight, lin.bias, act, precision=head.precision)
+    tar = ops._c(linear_tar, "linear_tar")
+    frames = ops._c(stft_lengths, "stft_lengths", torch.int64)
+    sign = torch.ops.se_b200.l1_logspec_bwd(log_pred, tar, frames, float(criterion.eps), 1.0, torch.ones(1, device=x.device))
+    grads = head_grad_embeddings(x, log_pred, sign, act)                      # per-utterance SUMS of sign * d log_pred / d theta
+    count = (frames.clamp(max=F) * K).to(grads.dtype)
+    if mean:
+        return grads.sum(dim=0, keepdim=True) / count.sum()
+    return grads / count.unsqueeze(1)
+
+
 @torch.no_grad()
 def scoring_batched(head, criterion, features, linear_inp, linear_tar, stft_lengths, mean=False):
     """Gradient embeddings of a Linear / LinearResidual head under objective.SISDR without a Python loop.
@@ -99,10 +142,14 @@ def scoring_batched(head, criterion, features, linear_inp, linear_tar, stft_leng
     return grads.mean(dim=0, keepdim=True) if mean else grads
 
 
-def scoring_loop(head, criterion, features, linear_inp, linear_tar, stft_lengths, mean=False):
+def scoring_loop(head, criterion, features, linear_inp, linear_tar, stft_lengths, mean=False, projection_only=False):
     """The reference's loop (sampler.py:77-110) on the drop-in modules: one backward per utterance."""
     predicted, results = head(features=features, linears=linear_inp)
     extra = {k: v for k, v in results.items()}
+    if type(head) is model.Linear and "log_predicted" not in extra:
+        extra["log_predicted"] = predicted               # a bare projection used as the log-spectrum predictor (L1)
+    proj = _projection_of(head) if projection_only else None
+    keep = None if proj is None else {id(p) for p in proj[0].parameters()}
     idx = [slice(None)] if mean else [slice(u, u + 1) for u in range(predicted.shape[0])]
     grads = []
     for sl in idx:
@@ -111,18 +158,22 @@ def scoring_loop(head, criterion, features, linear_inp, linear_tar, stft_lengths
                             stft_lengths=stft_lengths[sl], **kw)
         head.zero_grad()
         loss.backward(retain_graph=True)
-        grads.append(torch.cat([p.grad.reshape(-1) for _, p in head.named_parameters() if p.grad is not None]).detach())
+        grads.append(torch.cat([p.grad.reshape(-1) for _, p in head.named_parameters()
+                                if p.grad is not None and (keep is None or id(p) in keep)]).detach())
         head.zero_grad()
     return torch.stack(grads, dim=0)
 
 
-def scoring(preprocessor, head, criterion, lengths, wavs, mean=False, feat_log=True):
+def scoring(preprocessor, head, criterion, lengths, wavs, mean=False, feat_log=True, projection_only=False):
     """sampler.py:59-110 for ``--from_rawfeature``: (B, 3, T) batch -> (B, n_params) gradient embeddings
-    ((1, n_params) with mean=True)."""
+    ((1, n_params) with mean=True).  projection_only: score with the gradients of the head's last (projection) layer only --
+    for the recurrent ``LSTM`` head that is the part the library computes in one pass; all parameters go through the loop."""
     c = preprocessor.get_feat_config
     ch_i, ch_t = int(getattr(preprocessor, "channel_inp", 0)), int(getattr(preprocessor, "channel_tar", 1))
     feats, linear_inp, linear_tar = preprocessor(wavs, [c("linear", ch_i, log=feat_log), c("linear", ch_i), c("linear", ch_t)])
     frames = lengths.to(feats.device) // preprocessor._win_args["hop_length"] + 1
     if _batched_ok(head, criterion, feats):
         return scoring_batched(head, criterion, feats, linear_inp, linear_tar, frames, mean=mean)
-    return scoring_loop(head, criterion, feats, linear_inp, linear_tar, frames, mean=mean)
+    if _batched_l1_ok(head, criterion, feats, projection_only):
+        return scoring_batched_l1(head, criterion, feats, linear_tar, frames, mean=mean)
+    return scoring_loop(head, criterion, feats, linear_inp, linear_tar, frames, mean=mean, projection_only=projection_only)

@@ -302,26 +302,51 @@ def test_head_forward_backward_match_torch_fp32(se, D, act, cmvn):
 
 
 # ------------------------------------------------------------------------------ features (K1b)
-@pytest.mark.parametrize("n_fft", [400, 512])
+def _floor_mask(ref_feat, base, order, floor_nats=16.0):
+    """Elements of a log feature (B, F, (order+1) * base) whose value -- and, for the delta columns, every one of the five
+    taps (and the taps of those taps) it is made of -- lies within `floor_nats` (16 nats = 70 dB) of the largest value."""
+    logs = ref_feat[..., :base]
+    ok = logs > logs.amax() - floor_nats
+    cols = [ok]
+    for _ in range(order):
+        prev = cols[-1].float()
+        pad = torch.nn.functional.pad(prev.transpose(1, 2), (2, 2), mode="replicate")
+        cols.append((torch.nn.functional.avg_pool1d(pad, 5, stride=1).transpose(1, 2) > 0.999))
+    return torch.cat(cols, dim=-1)
+
+
+@pytest.mark.parametrize("n_fft", [400, 512, 1024])
 def test_mel_delta_cmvn_features_match_oracle(se, n_fft):
+    """Feature configs of pretrain_sample.yaml:54-65 / pseudo_noise.yaml:10-15 through the fused K1b kernel (mel -> log ->
+    deltas -> CMVN sums in one launch) and the generic log / delta / CMVN kernels: MAXIMUM error against the oracle over all
+    elements above a stated floor (70 dB below the largest value: below it the logarithm of a near-cancelled bin is
+    rounding noise in the oracle as well); the floor must leave > 99 % of the elements in."""
     ora, mine = make_pair(se, n_fft)
-    _, wavs = synth(2, 12000, seed=21)
+    _, wavs = synth(3, 12000, seed=21)
     c = ora.get_feat_config
-    # log / CMVN features on the channels that have a noise floor (0 = noisy, 2 = noise): the clean test
-    # tone has bins 120 dB below its peak whose logarithm is rounding noise in the oracle as well
+    # log / CMVN features on the channels that have a noise floor (0 = noisy, 2 = noise)
     cfgs = [c("mel", 0, log=True, delta=2), c("mel", 2, log=True, delta=1, cmvn=True), c("linear", 0, log=True, delta=1),
-            c("linear", 2, log=True, cmvn=True), c("mel", 1)]
+            c("linear", 2, log=True, cmvn=True), c("mel", 1), c("mel", 0, log=True), c("mel", 2, delta=1)]
     ref = ora(wavs, cfgs)
     got = [g.cpu() for g in mine(wavs.cuda(), cfgs)]
-    assert got[0].shape[-1] == 120 and got[1].shape[-1] == 80
-    for r, g_, tol in zip(ref, got, (2e-3, 5e-3, 2e-2, 2e-2, None)):
+    K = n_fft // 2 + 1
+    assert got[0].shape[-1] == 120 and got[1].shape[-1] == 80 and got[2].shape[-1] == 2 * K
+    for r, g_ in zip(ref, got):
         assert r.shape == g_.shape
-        if tol is None:
-            assert rel_to_max(g_, r) < SPEC_RTOL
-        else:
-            # log features: compare where the bin is not 90 dB below the peak (log amplifies rounding noise there)
-            assert (g_ - r).abs().median() < 2e-4
-            assert torch.quantile((g_ - r).abs().flatten()[:1000000], 0.999) < tol
+    # (feature, base width, delta order, max abs error): log-mel sums 5-40 positive bins, log-linear is one bin
+    for idx, base, order, tol in ((0, 40, 2, 5e-4), (5, 40, 0, 5e-4), (2, K, 1, 2e-3)):
+        mask = _floor_mask(ref[idx], base, order)
+        assert mask.float().mean().item() > 0.99
+        assert (got[idx] - ref[idx]).abs()[mask].max().item() < tol
+    # CMVN over time (unbiased std + eps): the normalised values are O(1); mask from the un-normalised log feature
+    un = ora(wavs, [c("mel", 2, log=True, delta=1), c("linear", 2, log=True)])
+    for idx, base, order, src, tol in ((1, 40, 1, un[0], 2e-3), (3, K, 0, un[1], 5e-3)):
+        mask = _floor_mask(src, base, order)
+        assert mask.float().mean().item() > 0.99
+        assert (got[idx] - ref[idx]).abs()[mask].max().item() < tol
+        assert got[idx].mean(1).abs().max().item() < 1e-3                    # zero mean over time per (utterance, column)
+    assert rel_to_max(got[4], ref[4]) < SPEC_RTOL                             # mel energies (no log): relative to the largest band
+    assert rel_to_max(got[6], ref[6]) < SPEC_RTOL
 
 
 def test_no_wav_call_and_cpu_inputs(se):
@@ -438,6 +463,53 @@ def test_train_step_gradients_match_oracle(se):
     gw = head.linear.weight.grad.cpu()
     assert torch.nn.functional.cosine_similarity(gw.flatten(), w.grad.flatten(), dim=0).item() > 0.9999
     np.testing.assert_allclose(gw.numpy(), w.grad.numpy(), rtol=5e-2, atol=2e-3 * w.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_pseudo_noise_config_end_to_end_matches_oracle_autograd(se, precision):
+    """BASELINE configs[2] (config/pseudo_noise.yaml: n_fft 400 / hop 160, baseline feature mel + log + delta 2 = 120-d):
+    preprocessor -> LinearResidual(120 -> 201) -> SISDR, and the projection-as-log-spectrum route Linear(120 -> 201,
+    Identity) -> L1, forward and backward, against the oracle preprocessor + torch autograd on the same ragged batch."""
+    ora, mine = make_pair(se, 400)
+    B, T = 4, 8000
+    lengths = torch.LongTensor([8000, 6000, 4321, 7999])
+    lengths, wavs = synth(B, T, seed=12, lengths=lengths)
+    c = ora.get_feat_config
+    cfgs = [c("mel", 0, log=True, delta=2), c("linear", 0), c("linear", 1)]
+    feats_r, lin_i_r, lin_t_r = ora(wavs, cfgs)
+    feats, lin_i, lin_t = mine(wavs.cuda(), cfgs)
+    assert feats.shape == (B, T // 160 + 1, 120)
+    masks = sp.length_masks(sp.stft_lengths(lengths, 160))
+    frames = (lengths // 160 + 1).cuda()
+    # ---- LinearResidual + SISDR (runner.py:453-459 with --downstream LinearResidual --objective SISDR)
+    torch.manual_seed(5)
+    head = se.LinearResidual(input_size=120, output_size=201, precision=precision).cuda()
+    w = head.linear.weight.detach().cpu().clone().requires_grad_(True)
+    b = head.linear.bias.detach().cpu().clone().requires_grad_(True)
+    pred_r, _ = sp.linear_residual_head(feats_r, lin_i_r, w, b)
+    ref_loss, _ = sp.sisdr_spectral(pred_r, lin_t_r, masks)
+    ref_loss.backward()
+    predicted, extra = head(features=feats, linears=lin_i)
+    loss, _ = se.SISDR()(predicted=predicted, linear_tar=lin_t, stft_lengths=frames, **extra)
+    loss.backward()
+    assert loss.item() == pytest.approx(ref_loss.item(), abs=2e-3 if precision == 0 else 5e-3)
+    for got, want in ((head.linear.weight.grad.cpu(), w.grad), (head.linear.bias.grad.cpu(), b.grad)):
+        assert torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item() > 0.9995
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=5e-2, atol=(2e-3 if precision == 0 else 1e-2) * want.abs().max().item())
+    # ---- Linear (Identity) as log-spectrum predictor + L1 (objective.py:109-117)
+    torch.manual_seed(6)
+    lin = se.Linear(120, 201, activation="Identity", precision=precision).cuda()
+    w2 = lin.linear.weight.detach().cpu().clone().requires_grad_(True)
+    b2 = lin.linear.bias.detach().cpu().clone().requires_grad_(True)
+    ref_l1 = sp.l1_logspectral(sp.linear_head(feats_r, w2, b2, "Identity"), lin_t_r, masks)
+    ref_l1.backward()
+    log_pred, _ = lin(features=feats)
+    l1, _ = se.L1()(log_predicted=log_pred, linear_tar=lin_t, stft_lengths=frames)
+    l1.backward()
+    assert l1.item() == pytest.approx(ref_l1.item(), rel=2e-4 if precision == 0 else 2e-3)
+    for got, want in ((lin.linear.weight.grad.cpu(), w2.grad), (lin.linear.bias.grad.cpu(), b2.grad)):
+        assert torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item() > 0.999
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=5e-2, atol=(2e-3 if precision == 0 else 2e-2) * want.abs().max().item())
 
 
 # ------------------------------------------------------------------------------ fast paths vs generic tile kernels
@@ -670,6 +742,42 @@ def test_round_tf32_matches_cvt_rna(se):
     assert ((r - w).abs() <= w.abs() * 2.0 ** -11 * 1.0001).all()
 
 
+# ------------------------------------------------------------------------------ recurrent heads (a7): projection + multiply / exp
+RECURRENT = {"lstm_uni": ("LSTM", dict(bidirectional=False, activation="Identity")),
+             "lstm_bi": ("LSTM", dict(bidirectional=True, activation="Identity")),
+             "res_uni": ("Residual", dict(bidirectional=False, activation="Sigmoid", cmvn=False)),
+             "res_bi_cmvn": ("Residual", dict(bidirectional=True, activation="Sigmoid", cmvn=True)),
+             "res_relu": ("Residual", dict(bidirectional=False, activation="ReLU", cmvn=True))}
+
+
+@pytest.mark.parametrize("tag", sorted(RECURRENT))
+@pytest.mark.parametrize("precision", [0, 1])
+def test_recurrent_heads_match_reference_golden(se, golden_dir, tag, precision):
+    """model.py:37-91 -- LSTM / Residual with the REFERENCE's state dict: outputs, and the gradients of every parameter
+    (the projection's from the head kernels' wgrad, the LSTM's through the head kernels' input gradient), against what
+    the reference's own classes produced (oracle/make_golden.py::make_recurrent_heads)."""
+    gold = np.load(os.path.join(golden_dir, "recurrent_heads_ref.npz"))
+    cls, kw = RECURRENT[tag]
+    head = getattr(se, cls)(input_size=9, output_size=9, hidden_size=12, num_layers=2, precision=precision, **kw).cuda()
+    state = {k[len(tag) + 7:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith(f"{tag}_param_")}
+    head.load_state_dict(state)                                             # same parameter names as the reference (strict)
+    feats, linears = torch.from_numpy(gold["feats"]).cuda(), torch.from_numpy(gold["linears"]).cuda()
+    tol = 2e-5 if precision == 0 else 3e-3                                  # precision 1: TF32 operands in the projection
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):        # the cuDNN LSTM body in fp32: the bounds test the projection
+        predicted, res = head(features=feats, linears=linears)
+        assert (predicted.cpu() - torch.from_numpy(gold[f"{tag}_predicted"])).abs().max().item() < tol * 5
+        for k, v in res.items():
+            assert (v.detach().cpu() - torch.from_numpy(gold[f"{tag}_{k}"])).abs().max().item() < tol
+        loss = (predicted * torch.linspace(0.5, 1.5, 9, device="cuda")).pow(2).mean() + 0.1 * predicted.mean()
+        assert loss.item() == pytest.approx(float(gold[f"{tag}_loss"]), rel=tol * 10)
+        loss.backward()
+    for name, p in head.named_parameters():
+        want = torch.from_numpy(gold[f"{tag}_grad_{name}"])
+        assert p.grad is not None, name
+        scale = max(want.abs().max().item(), 1e-4)
+        assert (p.grad.cpu() - want).abs().max().item() < (2e-4 if precision == 0 else 2e-2) * scale, name
+
+
 # ------------------------------------------------------------------------------ the bench configuration at full size
 @pytest.fixture(scope="module")
 def bench_case(se):
@@ -726,6 +834,33 @@ def test_bench_configuration_matches_oracle_at_full_size(se, bench_case, mode):
         for b in (0, 1, 31, 63):
             n = int(lengths[b])
             assert sisdr_db(out["wav_predicted"][b, :n].cpu(), ref["wav_predicted"][b, :n]) > 40.0
+
+
+def test_host_pipeline_pcm16_input_and_waveform_output(se, bench_case):
+    """int16 PCM host batches (2 bytes per sample over PCIe, widened on the device: exact) give what the fp32 pipeline gives
+    on the dequantised batch, and want_wav returns the level-matched enhanced waveforms the device step produced."""
+    bc = bench_case
+    eng = se.EnhancementEngine(bc["mine"], bc["head"], log_features=True, precision=1)
+    lengths = bc["lengths"]
+    pcm = (bc["wavs"] * 32768.0).round().clamp_(-32768, 32767).to(torch.int16)
+    deq = pcm.to(torch.float32) / 32768.0
+    assert (deq - bc["wavs"]).abs().max().item() <= 0.5 / 32768 + 1e-9
+    pipe16 = eng.host_pipeline(64, 3, 64000, depth=2, pcm16=True, want_wav=True)
+    pipe32 = eng.host_pipeline(64, 3, 64000, depth=2)
+    assert pipe16.h2d_bytes == 64 * 2 * 64000 * 2 + 64 * 8 and pipe16.d2h_bytes == 2 * 64 * 4 + 64 * 64000 * 4
+    lp = lengths.clone().pin_memory()
+    for _ in range(2):
+        pipe16.submit(lp, pcm.clone().pin_memory())
+        pipe32.submit(lp, deq.clone().pin_memory())
+    r16, r32 = pipe16.drain(), pipe32.drain()
+    assert len(r16) == 2 and len(r16[0]) == 3 and len(r32[0]) == 2
+    for a, b in zip(r16, r32):
+        assert (a[0] - b[0]).abs().max().item() < 1e-5 and (a[1] - b[1]).abs().max().item() < 1e-5
+    np.testing.assert_allclose(r16[0][1].numpy(), bc["ref"]["sisdr"].numpy(), atol=0.05)          # 16-bit quantisation of the inputs
+    out = eng.eval_step(lengths.cuda(), deq.cuda())
+    assert (r16[1][2] - out["wav_predicted"].cpu()).abs().max().item() < 1e-6
+    with pytest.raises(RuntimeError):
+        pipe16.submit(lp, deq.clone().pin_memory())                                                # fp32 batch into the int16 pipeline
 
 
 def test_fused_step_properties_at_full_size(se, bench_case):
@@ -1222,6 +1357,53 @@ def test_scoring_batched_equals_per_utterance_loop(se, n_fft, cmvn, act):
 
 
 # ------------------------------------------------------------------------------ pseudo-wave generation (runner.py:266-305)
+@pytest.mark.parametrize("kind", ["Linear", "LSTM"])
+def test_scoring_l1_batched_equals_loop_and_oracle(se, kind):
+    """BASELINE configs[4] names the L1 spectral objective (run_active.sh: --downstream LSTM with the L1-trained checkpoint):
+    per-utterance gradient embeddings of the projection layer in one pass against the reference's loop of backward calls
+    (sampler.py:77-110) on the drop-in modules, and against the CPU oracle's autograd for one utterance."""
+    from speech_enhancement_by_s3prl_b200 import sampler_ops
+    ora, mine = make_pair(se, 400)
+    K, B, T = 201, 5, 12000
+    lengths, wavs = synth(B, T, seed=77, lengths=torch.LongTensor([12000, 9000, 12000, 5000, 11111]))
+    torch.manual_seed(4)
+    if kind == "Linear":
+        head = se.Linear(K, K, activation="Identity").cuda()
+    else:
+        head = se.LSTM(input_size=K, output_size=K, hidden_size=64, num_layers=2).cuda()
+    crit = se.L1()
+    c = mine.get_feat_config
+    feats, lin_i, lin_t = mine(wavs.cuda(), [c("linear", 0, log=True), c("linear", 0), c("linear", 1)])
+    frames = lengths.cuda() // 160 + 1
+    assert sampler_ops._batched_l1_ok(head, crit, feats, projection_only=True)
+    assert sampler_ops._batched_l1_ok(head, crit, feats, projection_only=False) == (kind == "Linear")
+    fast = sampler_ops.scoring_batched_l1(head, crit, feats, lin_t, frames)
+    loop = sampler_ops.scoring_loop(head, crit, feats, lin_i, lin_t, frames, projection_only=True)
+    P = (64 if kind == "LSTM" else K) * K + K
+    assert fast.shape == loop.shape == (B, P)
+    for u in range(B):
+        assert (fast[u] - loop[u]).abs().max().item() < 2e-3 * loop[u].abs().max().item()      # TF32 operands in the batched kernel
+        assert torch.nn.functional.cosine_similarity(fast[u], loop[u], dim=0).item() > 0.99999
+    fast_m = sampler_ops.scoring_batched_l1(head, crit, feats, lin_t, frames, mean=True)
+    loop_m = sampler_ops.scoring_loop(head, crit, feats, lin_i, lin_t, frames, mean=True, projection_only=True)
+    assert fast_m.shape == (1, P) and torch.nn.functional.cosine_similarity(fast_m[0], loop_m[0], dim=0).item() > 0.99999
+    top = se.scoring(mine, head, crit, lengths.cuda(), wavs.cuda(), projection_only=True)
+    assert (top - fast).abs().max().item() <= 1e-6 * fast.abs().max().item()
+    if kind == "LSTM":                                  # all parameters (the reference's default): the loop, LSTM layers included
+        full = se.scoring(mine, head, crit, lengths[:2].cuda(), wavs[:2].cuda())
+        assert full.shape == (2, sum(p.numel() for p in head.parameters()))
+    else:                                               # oracle autograd (CPU, fp32) for one utterance
+        w = head.linear.weight.detach().cpu().clone().requires_grad_(True)
+        b = head.linear.bias.detach().cpu().clone().requires_grad_(True)
+        oc = ora.get_feat_config
+        f_o, lt_o = ora(wavs[1:2], [oc("linear", 0, log=True), oc("linear", 1)])
+        masks = sp.length_masks(sp.stft_lengths(lengths[1:2], 160))
+        masks = torch.nn.functional.pad(masks, (0, f_o.shape[1] - masks.shape[1]))
+        sp.l1_logspectral(sp.linear_head(f_o, w, b, "Identity"), lt_o, masks).backward()
+        ref = torch.cat([w.grad.reshape(-1), b.grad.reshape(-1)])
+        assert torch.nn.functional.cosine_similarity(fast[1].cpu(), ref, dim=0).item() > 0.999
+
+
 @pytest.mark.parametrize("n_fft", [512, 400, 1024])
 def test_pseudo_wav_matches_decode_wav_of_the_oracle(se, n_fft):
     """_pseudo_clean / _pseudo_noise: a predicted power spectrum with the noisy phase -> waveform at -25 dB.  The fused path

@@ -156,3 +156,22 @@ def test_no_wav_call_returns_dummy_features():
     c = pre.get_feat_config
     out = pre(feat_list=[c("mel", 0, log=True, delta=1, cmvn=True), c("linear", 1)])
     assert out[0].shape[-1] == 80 and out[1].shape[-1] == 201 and out[0].shape[1] == 16000 // 160 + 1
+
+
+@pytest.mark.parametrize("tag,cls,kw", [("lstm_uni", "LSTM", dict(bidirectional=False)), ("lstm_bi", "LSTM", dict(bidirectional=True)),
+                                        ("res_uni", "Residual", dict(bidirectional=False, activation="Sigmoid", cmvn=False)),
+                                        ("res_bi_cmvn", "Residual", dict(bidirectional=True, activation="Sigmoid", cmvn=True)),
+                                        ("res_relu", "Residual", dict(bidirectional=False, activation="ReLU", cmvn=True))])
+def test_recurrent_head_golden_is_reproducible(golden_dir, tag, cls, kw):
+    """tests/golden/recurrent_heads_ref.npz (outputs of the reference's model.LSTM / model.Residual, model.py:37-91): the
+    restatement in oracle/signal_path.py reproduces outputs and loss from the stored state dict, and the drop-in
+    classes accept that state dict by name (strict) -- the contract the GPU parity test builds on."""
+    import speech_enhancement_by_s3prl_b200 as se
+    gold = np.load(os.path.join(golden_dir, "recurrent_heads_ref.npz"))
+    state = {k[len(tag) + 7:]: T(gold[k]) for k in gold.files if k.startswith(f"{tag}_param_")}
+    predicted, res = sp.recurrent_head(cls, state, T(gold["feats"]), T(gold["linears"]), **kw)
+    np.testing.assert_allclose(predicted.detach().numpy(), gold[f"{tag}_predicted"], rtol=1e-5, atol=1e-6)
+    for k, v in res.items():
+        np.testing.assert_allclose(v.detach().numpy(), gold[f"{tag}_{k}"], rtol=1e-5, atol=1e-6)
+    head = getattr(se, cls)(input_size=9, output_size=9, hidden_size=12, num_layers=2, **kw)
+    head.load_state_dict(state)                                    # strict: same names and shapes as the reference
