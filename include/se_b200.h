@@ -115,23 +115,6 @@ int se_mask_istft_ex(const float* noisy, const float* clean, int64_t utt_stride,
                      const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
                      float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags, void* stream);
 
-/* ---- spectrum workspace between K1 and K3 (n_fft = 512, hop = 256) -------------------
- * The fused step needs the noisy spectrum twice: for the features (K1) and for mask x spectrum -> iSTFT (K3).
- * se_stft_features_ws is se_stft_features that also leaves the complex spectrum of every frame in spec_ws
- * (n_utt, n_frames, SE_SPEC_WS_FLOATS) floats, 16-byte aligned, in the order K3's lanes read it: float4
- * (Re X[k], Im X[k], Re X[256-k], Im X[256-k]) at index 16 (k / 16) + k % 16 for k < 128, X[128] at floats 512, 513.
- * se_mask_istft_ws is se_mask_istft_ex reading that workspace instead of transforming the noisy waveform again
- * (one FFT less per frame; same arithmetic, so the results are identical to se_mask_istft_ex).
- * se_spec_ws_supported: 1 if (n_fft, hop) has this path, else 0 (the entry points then return SE_ERR_UNSUPPORTED). */
-#define SE_SPEC_WS_FLOATS 516
-int se_spec_ws_supported(int n_fft, int hop);
-int se_stft_features_ws(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
-                        float log_eps, int take_log, float* feat, int64_t feat_stride, double* stat_sums, int64_t ld_stats,
-                        float* spec_ws, int flags, void* stream);
-int se_mask_istft_ws(const float* spec_ws, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
-                     const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
-                     float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags, void* stream);
-
 /* ---- K3 epilogue: level normalisation + metrics from the sums --------------------
  * Per utterance: gain so that the masked mean-square of wav matches the clean
  * reference's (target_db_or_nan = NaN; runner.py:570 + utils.py:38-40) or a fixed level

@@ -32,7 +32,6 @@ _SIGNATURES = {
     "se_mask_istft_strided": [c_f, c_f, i64, c_f, i64, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
     "se_mask_istft_ex": [c_f, c_f, i64, c_f, i64, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
     "se_stft_features": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_int, c_f, i64, c_f, i64, c_int, c_f],
-    "se_spec_ws_supported": [c_int, c_int],
     "se_stft_features2": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_f, c_f, i64, c_f, i64, c_int, c_f],
     "se_linear_head_bwd_fused": [c_f, i64, c_f, i64, c_float, c_f, c_f, i64, i64, i64, i64, i64, c_int, c_f, i64, c_f, c_f, c_f],
     "se_adam_clip_step": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_int, c_float, c_float,
@@ -42,8 +41,6 @@ _SIGNATURES = {
     "se_match_scores": [c_f, i64, c_f, i64, i64, c_float, c_f, c_f, c_f, c_f],
     "se_sisdr_mask_fwd": [c_f, i64, c_f, i64, c_f, i64, c_f, i64, i64, i64, c_float, c_f, c_f, c_f],
     "se_sisdr_mask_bwd": [c_f, i64, c_f, i64, c_f, i64, c_f, i64, i64, i64, c_float, c_f, c_f, c_f, i64, c_f],
-    "se_stft_features_ws": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_int, c_f, i64, c_f, i64, c_f, c_int, c_f],
-    "se_mask_istft_ws": [c_f, c_f, i64, c_f, i64, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
     "se_feature_sums": [c_f, i64, i64, i64, i64, c_f, i64, c_f],
     "se_linear_head_fused_supported": [i64, i64, i64, i64, i64, i64, i64],
     "se_linear_head_fused": [c_f, i64, c_f, i64, c_float, c_f, i64, c_f, i64, i64, i64, i64, c_int, c_f, i64, c_f],

@@ -110,15 +110,11 @@ constexpr size_t kSmem1 = (size_t)(kWarps1 * 2) * (M * 8 + 2 * N * 4) + M * 8;
 
 // write the requested outputs of one frame (lane j of a half-warp holds Z[j + 16 q] and the mirrored bins);
 // `acc` (STATS): the half-warp's private (sum x, sum x^2) accumulators in shared memory, updated for the feature written
-// CSPEC: the complex spectrum goes to the workspace row `cs` in the layout K3 consumes (kSpecFloats per frame):
-// float4 (X[k], X[M-k]) at index 16 q + j for k = j + 16 q < 128, and X[128] at floats 512, 513.
-constexpr int kSpecFloats = SE_SPEC_WS_FLOATS;
 // STATS: sacc = the half-warp's (sum x, sum x^2) accumulators in REGISTERS: slot q <-> bin j + 16 q, slot 8 + q <-> bin
 // 256 - (j + 16 q), slot 16 <-> bin 128 (lane 0)
-template <bool POWER, bool PHASE, bool LOGP, bool STATS, bool CSPEC = false>
+template <bool POWER, bool PHASE, bool LOGP, bool STATS>
 __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (&zm)[8], const float2 (&twn)[8], int j,
-                                           const StftArgs& a, long long o, float2 (&sacc)[17],
-                                           float* __restrict__ cs = nullptr) {
+                                           const StftArgs& a, long long o, float2 (&sacc)[17]) {
     float* pw = POWER ? a.power + o : nullptr;
     float* lg = LOGP ? a.logp + o : nullptr;
     float* ph = PHASE ? a.phase + o : nullptr;
@@ -130,7 +126,6 @@ __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (
         const int k = j + 16 * q;
         float2 xa, xb;
         split_pair(v[q], zm[q], twn[q], xa, xb);
-        if (CSPEC) reinterpret_cast<float4*>(cs)[16 * q + j] = make_float4(xa.x, xa.y, xb.x, xb.y);
         const float pa = xa.x * xa.x + xa.y * xa.y, pb = xb.x * xb.x + xb.y * xb.y;
         if (POWER) { pw[k] = pa; pw[M - k] = pb; }
         float la = 0.f, lb = 0.f;
@@ -141,7 +136,6 @@ __device__ __forceinline__ void emit_frame(const float2 (&v)[16], const float2 (
     }
     if (j == 0) {                                               // k = 128 pairs with itself: X = 2 conj(Z[128])
         const float2 x = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
-        if (CSPEC) reinterpret_cast<float2*>(cs)[256] = x;
         const float p = x.x * x.x + x.y * x.y;
         float l = 0.f;
         if (POWER) pw[128] = p;
@@ -235,7 +229,7 @@ __device__ __forceinline__ void load_half_regs(float2 (&buf)[8], const float* __
     }
 }
 
-template <bool POWER, bool PHASE, bool LOGP, bool STATS, bool CSPEC = false>
+template <bool POWER, bool PHASE, bool LOGP, bool STATS>
 __global__ void __launch_bounds__(kThreadsRun, 256 / kThreadsRun) stft512_run_kernel(StftArgs a, StftRunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem1[];
     secommon::TraceScope trace(a.trace, 1);
@@ -294,8 +288,7 @@ __global__ void __launch_bounds__(kThreadsRun, 256 / kThreadsRun) stft512_run_ke
             fft256<-1>(v, xbuf, j, tw, hmask);
             float2 zm[8];
             fetch_mirror(v, lane, zm);
-            emit_frame<POWER, PHASE, LOGP, STATS, CSPEC>(v, zm, twn, j, a, ((long long)u * F + f) * a.spec_stride, sacc,
-                                                         CSPEC ? a.cspec + ((long long)u * F + f) * kSpecFloats : nullptr);
+            emit_frame<POWER, PHASE, LOGP, STATS>(v, zm, twn, j, a, ((long long)u * F + f) * a.spec_stride, sacc);
         };
 #pragma unroll 1
         for (int f = fa; f < fb; f += 2) {
@@ -393,30 +386,23 @@ __host__ __device__ __forceinline__ void run_bounds(int ri, int bpu, int rpu, in
 
 struct RunPlan { int blocks_per_utt; int runs_per_utt; long long total_runs; };   // run ri: bpu/rpu blocks, the first bpu%rpu runs one more
 
-// SE_K3_RESIDENT (experiment): CTAs per SM the kernel is ALLOWED to occupy (shared memory padded to enforce it), while the
-// register cap stays that of SE_K3_MIN_BLOCKS -- leaves registers / shared memory for another stream's kernels
-#ifndef SE_K3_RESIDENT
-#define SE_K3_RESIDENT SE_K3_MIN_BLOCKS
-#endif
 #ifndef SE_K3_MIN_BLOCKS
 #define SE_K3_MIN_BLOCKS 3
 #endif
 constexpr int kMaskFloats3 = 272;
-// per half-warp: transpose buffer | noisy slots 2 x 256 (CS: one spectrum row of K1's workspace) | clean slots 2 x 256 | mask row
-constexpr int kNoisyBytes3 = kSpecFloats * 4 > 2 * H * 4 ? kSpecFloats * 4 : 2 * H * 4;
+// per half-warp: transpose buffer | noisy slots 2 x 256 | clean slots 2 x 256 | mask row
+constexpr int kNoisyBytes3 = 2 * H * 4;
 constexpr int kHwBytes3 = M * 8 + kNoisyBytes3 + 2 * H * 4 + kMaskFloats3 * 4;
 constexpr size_t kSmem3 = (size_t)(kWarps3 * 2) * kHwBytes3 + 2 * M * 8;
 static_assert(kHwBytes3 % 16 == 0 && kNoisyBytes3 % 16 == 0, "16-byte aligned cp.async destinations");
 
-// CS: the noisy spectrum comes from K1's workspace (a.cspec) instead of being recomputed from the waveform -- one transform
-// less per frame.  cp.async groups are then [spectrum row + mask row], [clean] per frame.
-template <bool CS, bool PM = false>
+template <bool PM>
 __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mask_istft512_kernel(MaskIstftArgs a, RunPlan plan) {
     extern __shared__ __align__(16) unsigned char smem3[];
     secommon::TraceScope trace(a.trace, 3);
     float2* s_win2 = reinterpret_cast<float2*>(smem3 + (size_t)(kWarps3 * 2) * kHwBytes3);
     float2* s_bw2 = s_win2 + M;
-    if (!CS) {   // the first frame's noisy samples come from HBM and do not depend on the upstream kernel: loads in flight first
+    {   // the first frame's noisy samples come from HBM and do not depend on the upstream kernel: loads in flight first
         const int hw0 = threadIdx.x >> 4, j0 = threadIdx.x & 15;
         const long long unit0 = (long long)blockIdx.x * (kThreads3 / 16) + hw0;
         if (unit0 < plan.total_runs) {
@@ -447,7 +433,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
     griddep_launch();
     unsigned char* mine = smem3 + (size_t)hw * kHwBytes3;
     float2* xbuf = reinterpret_cast<float2*>(mine);
-    float* nb = reinterpret_cast<float*>(mine + M * 8);            // noisy slots (CS: spectrum row)
+    float* nb = reinterpret_cast<float*>(mine + M * 8);            // noisy slots
     float* cb = reinterpret_cast<float*>(mine + M * 8 + kNoisyBytes3);   // clean slots
     float* mb = cb + 2 * H;                                        // mask row
     const long long unit = (long long)blockIdx.x * (kThreads3 / 16) + hw;
@@ -480,14 +466,6 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
     // are inputs of the step, so their first loads are issued before waiting for the upstream kernel (the mask's producer).
     const int f0 = b0 - 1;                                        // (its noisy samples were requested at the top: group N)
     griddep_wait();                                               // the mask (and the zeroed sums) come from upstream kernels
-    const float* srow0 = CS ? a.cspec + (long long)u * F * kSpecFloats : nullptr;
-    auto stage_spec = [&](int f) {                                // one workspace row: 129 x 16 bytes
-        const float* src = srow0 + (long long)f * kSpecFloats;
-#pragma unroll
-        for (int c = 0; c < 9; ++c)
-            if (j + 16 * c < kSpecFloats / 4) cp_async16(nb + 4 * (j + 16 * c), src + 4 * (j + 16 * c));
-    };
-    if (CS) stage_spec(f0);
     stage_row(mb, mrow0 + (long long)f0 * a.mask_stride, M + 1, j, mask_padded);
     cp_async_commit();
     if (need_clean) {
@@ -506,35 +484,9 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
 #pragma unroll
         for (int q = 0; q < 8; ++q) { ra[q] = 0.0f; rb[q] = 0.0f; }
         float2 v[16];
-        if (CS) {
-            // pass 0 without a transform: X[k], X[M-k] from the staged workspace row
-            cp_async_wait<1>();                                     // spectrum + mask rows of frame f have landed
-            __syncwarp(hmask);
-            float2 ca[8], cbv[8];
-            const float4* s4 = reinterpret_cast<const float4*>(nb);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 x = s4[16 * q + j];
-                mask_merge<PM>(make_float2(x.x, x.y), make_float2(x.z, x.w), mb[j + 16 * q], mb[M - j - 16 * q], twn[q], own,
-                           ra[q], rb[q], ca[q], cbv[q]);
-            }
-            const float g128 = mb[128];
-            const float2 x128 = reinterpret_cast<const float2*>(nb)[256];
-            if (own) r128 = fmaxf(PM ? g128 : g128 * (x128.x * x128.x + x128.y * x128.y), 0.0f);
-            __syncwarp(hmask);
-            if (more) {
-                stage_spec(f + 1);
-                stage_row(mb, mrow0 + (long long)(f + 1) * a.mask_stride, M + 1, j, mask_padded);
-            }
-            cp_async_commit();
-            float2 y128;
-            if (PM) { y128 = apply_gain<true>(x128, g128); y128.x *= 2.0f; y128.y *= 2.0f; }
-            else { const float s128 = 2.0f * fast_sqrt(g128); y128 = make_float2(s128 * x128.x, s128 * x128.y); }
-            scatter_mirror(ca, cbv, y128, lane, v);
-        }
 #pragma unroll 1
-        for (int pass = CS ? 1 : 0; pass < (own ? 3 : 2); ++pass) {
-            if (!CS && pass == 0) {
+        for (int pass = 0; pass < (own ? 3 : 2); ++pass) {
+            if (pass == 0) {
                 cp_async_wait<2>();                                 // N(f) has landed
                 __syncwarp(hmask);
                 frame_from_slots(nb + p * H, nb + (p ^ 1) * H, j, s_win2, v);
@@ -545,7 +497,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
                 frame_from_slots(cb + p * H, cb + (p ^ 1) * H, j, s_win2, v);        // C(f) landed before pass 1's overlap-add
             }
             fft256<-1>(v, xbuf, j, tw, hmask);
-            if (!CS && pass == 0) {
+            if (pass == 0) {
                 float2 zm[8];
                 fetch_mirror(v, lane, zm);
                 cp_async_wait<2>();                                 // M(f) has landed
@@ -570,7 +522,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
                 scatter_mirror(ca, cbv, y128, lane, v);
             } else if (pass == 1) {
                 // v[q] = conj(z[m]), z[m] = (x[2m], x[2m+1]) unnormalised, m = j + 16 q; signs and scales are in s_bw2
-                if (CS) cp_async_wait<1>(); else cp_async_wait<2>();   // C(f) has landed
+                cp_async_wait<2>();                                 // C(f) has landed
                 __syncwarp(hmask);
                 if (!halo) {
                     const int t0 = (f - 1) * H;
@@ -693,12 +645,8 @@ int prepare512() {
     SE_OPT((stft512_run_kernel<true, false, false, true>), kSmem1Run);
     SE_OPT((stft512_run_kernel<false, false, true, true>), kSmem1Run);
     SE_OPT((stft512_run_kernel<true, false, true, true>), kSmem1Run);
-    SE_OPT((stft512_run_kernel<true, false, false, true, true>), kSmem1Run);
-    SE_OPT((stft512_run_kernel<false, false, true, true, true>), kSmem1Run);
-    constexpr size_t kSmem3Max = kSmem3 > 100 * 1024 ? kSmem3 : 100 * 1024;     // room for the SE_K3_RESIDENT padding
-    SE_OPT(mask_istft512_kernel<false>, kSmem3Max);
-    SE_OPT(mask_istft512_kernel<true>, kSmem3Max);
-    SE_OPT((mask_istft512_kernel<false, true>), kSmem3Max);
+    SE_OPT(mask_istft512_kernel<false>, kSmem3);
+    SE_OPT(mask_istft512_kernel<true>, kSmem3);
 #undef SE_OPT
     return SE_OK;
 }
@@ -725,15 +673,13 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
         const long long grid = (plan.total_runs + per_it - 1) / per_it;
         if (grid > 0x7fffffffLL) return secommon::fail(SE_ERR_BAD_ARG, "grid too large");
 #define SE_RUN(P, Q, L, S) stft512_run_kernel<P, Q, L, S><<<(unsigned)grid, kThreadsRun, kSmem1Run, st>>>(a, plan)
-#define SE_RUN_CS(P, Q, L) stft512_run_kernel<P, Q, L, true, true><<<(unsigned)grid, kThreadsRun, kSmem1Run, st>>>(a, plan)
         if (a.stat_sums) {
             // statistics of the ONE feature written: log-power (sel 4) or power (sel 1)
-            if (sel == 4) { if (a.cspec) SE_RUN_CS(false, false, true); else SE_RUN(false, false, true, true); }
-            else if (sel == 1) { if (a.cspec) SE_RUN_CS(true, false, false); else SE_RUN(true, false, false, true); }
-            else if (sel == 5 && !a.cspec) SE_RUN(true, false, true, true);        // power + log-power, statistics of log-power
+            if (sel == 4) SE_RUN(false, false, true, true);
+            else if (sel == 1) SE_RUN(true, false, false, true);
+            else if (sel == 5) SE_RUN(true, false, true, true);                      // power + log-power, statistics of log-power
             else return secommon::fail(SE_ERR_BAD_ARG, "statistics need power and / or logpower (no phase)");
         } else {
-            if (a.cspec) return secommon::fail(SE_ERR_UNSUPPORTED, "the spectrum workspace is written by the statistics variants only");
             switch (sel) {
                 case 1: SE_RUN(true, false, false, false); break;
                 case 2: SE_RUN(false, true, false, false); break;
@@ -745,10 +691,9 @@ int launch_stft512(const StftArgs& a, cudaStream_t st) {
             }
         }
 #undef SE_RUN
-#undef SE_RUN_CS
         return secommon::check_launch("stft512_run_kernel");
     }
-    if (a.stat_sums || a.cspec) return secommon::fail(SE_ERR_UNSUPPORTED, "fused statistics / spectrum workspace need hop = 256");
+    if (a.stat_sums) return secommon::fail(SE_ERR_UNSUPPORTED, "fused statistics need hop = 256");
     const int per_it = kThreads1 / 16;
     const long long want = (total + per_it - 1) / per_it;
     const long long cap = 2LL * num_sms();
@@ -772,7 +717,7 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     // wave covers the GPU -- but at least 4 blocks per run (the halo frame costs 2/3 of a frame).  Large batches: runs of
     // about 32 blocks, many waves.
     const int blocks_per_utt = a.n_frames - 1;
-    const long long slots = (long long)(SE_K3_RESIDENT * 4 / kWarps3) * num_sms() * (kThreads3 / 16);
+    const long long slots = (long long)(SE_K3_MIN_BLOCKS * 4 / kWarps3) * num_sms() * (kThreads3 / 16);
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("SE_B200_RUN_LEN"); forced = e ? atoi(e) : 0; }
     RunPlan plan;
@@ -795,19 +740,13 @@ int launch_mask_istft512(const MaskIstftArgs& a, cudaStream_t st) {
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads3);
     cfg.dynamicSmemBytes = kSmem3;
-    if (SE_K3_RESIDENT < SE_K3_MIN_BLOCKS) {                       // pad so that RESIDENT + 1 CTAs do not fit in 227 KB
-        const size_t pad_to = (size_t)(227 * 1024) / (SE_K3_RESIDENT * 4 / kWarps3 + 1) + 1024;
-        if (cfg.dynamicSmemBytes < pad_to) cfg.dynamicSmemBytes = pad_to;
-    }
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // prologue overlaps the upstream kernel's tail
     attr[0].val.programmaticStreamSerializationAllowed = (secommon::pdl_mask() & 2) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (a.mask_is_power && a.cspec) return secommon::fail(SE_ERR_UNSUPPORTED, "power mode reads the waveform, not the spectrum workspace");
-    if (a.mask_is_power) SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<false, true>, a, plan));
-    else if (a.cspec) SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<true>, a, plan));
+    if (a.mask_is_power) SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<true>, a, plan));
     else SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mask_istft512_kernel<false>, a, plan));
     return secommon::check_launch("mask_istft512_kernel");
 }

@@ -77,22 +77,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
-// same load, delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in cta_mask
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -121,10 +105,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {     // arrive on `bar` of every CTA in cta_mask
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -155,7 +135,6 @@ struct Head2Args {
     int cta_cols;              // output columns (weight rows) per CTA slab: multiple of 16, <= 272; slab = blockIdx.y
     int row_bulk;              // column slabs: one bulk store per output row (16-byte aligned rows and slabs)
     int w_box_rows, w_boxes;   // weight tensor-map box rows and boxes per k-block
-    int cluster;               // CTAs per cluster (1 or 2): with 2, each CTA loads one weight box and multicasts it to both
     int sld;                   // floats per row of the staging tile
     int bulk_out;              // staging rows == output rows and 16-byte aligned: one bulk store per quadrant
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
@@ -187,7 +166,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_norm + 8 * s, kWorkWarps);
-            mbar_init(bar_empty + 8 * s, (uint32_t)a.cluster);          // every CTA of the cluster reads the multicast weight tile
+            mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -199,9 +178,6 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (a.cluster > 1) cluster_sync_all();              // the peer's mbarriers exist before anything is multicast to them
-    const uint16_t cmask = (uint16_t)((1u << a.cluster) - 1);
-    const uint32_t crank = a.cluster > 1 ? cluster_ctarank() : 0;
     const uint32_t tmem_base = *tmem_slot;
     griddep_launch();                                   // the next kernel may start its own prologue
     if (threadIdx.x == 0) trace.mark(11);
@@ -213,13 +189,8 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t a_bytes = (uint32_t)a.tile_rows * BK * 4;
             auto load_w = [&](int kb, int s) {
                 const uint32_t dst = sbase + kOffRing + s * kStageBytes + kATileBytes;
-                if (a.cluster > 1) {                                       // my box, delivered to both CTAs (the peer sends the other one)
-                    const int b = (int)crank;
-                    tma_load_2d_mc(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, col0 + b * a.w_box_rows, bar_full + 8 * s, cmask);
-                } else {
-                    for (int b = 0; b < a.w_boxes; ++b)
-                        tma_load_2d(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, col0 + b * a.w_box_rows, bar_full + 8 * s);
-                }
+                for (int b = 0; b < a.w_boxes; ++b)
+                    tma_load_2d(dst + b * a.w_box_rows * BK * 4, &tmW, kb * BK, col0 + b * a.w_box_rows, bar_full + 8 * s);
             };
             auto load_a = [&](int kb, int s) {
                 tma_load_2d(sbase + kOffRing + s * kStageBytes, &tmA, kb * BK, (int)r0, bar_full + 8 * s);
@@ -258,8 +229,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         umma_tf32(tmem_base + (uint32_t)n_main, ad, make_desc(b_addr + n_main * BK * 4 + kk * 32), idesc_tail,
                                   (kb | kk) ? 1u : 0u);
                 }
-                if (a.cluster > 1) umma_commit_mc(bar_empty + 8 * s, cmask);
-                else umma_commit(bar_empty + 8 * s);
+                umma_commit(bar_empty + 8 * s);
             }
             umma_commit(bar_accum);
         }
@@ -427,7 +397,6 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
-    if (a.cluster > 1) cluster_sync_all();              // the peer may still signal my barriers until its MMAs have retired
     trace.finish();
     if (warp == kWorkWarps) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -514,11 +483,7 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     if (rows > BM) rows = BM;
     if (rows > n_frames) rows = n_frames / 8 * 8;                           // a tile may touch at most two utterances
     a.tile_rows = (int)rows;
-    static int want_cluster = -1;
-    // default 1: halving the weight L2 traffic gave no measured gain (the TF32 MMA rate bounds the main loop)
-    if (want_cluster < 0) { const char* e = getenv("SE_B200_HEAD_CLUSTER"); want_cluster = e ? atoi(e) : 1; }
-    a.cluster = (want_cluster >= 2 && n_split == 1) ? 2 : 1;
-    a.w_boxes = (a.cta_cols > 256 || a.cluster == 2) ? 2 : 1;         // cta_cols is a multiple of 16: both boxes are whole 8-row atoms
+    a.w_boxes = a.cta_cols > 256 ? 2 : 1;                              // cta_cols is a multiple of 16: both boxes are whole 8-row atoms
     a.w_box_rows = a.cta_cols / a.w_boxes;
     const int dout4 = (int)((D_out + 3) / 4 * 4);
     a.row_bulk = (n_split > 1 && aligned16(offset_out)) ? 1 : 0;
@@ -535,20 +500,15 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     }
     cudaLaunchConfig_t cfg{};
     unsigned tiles = (unsigned)((a.R + a.tile_rows - 1) / a.tile_rows);
-    if (a.cluster == 2) tiles = (tiles + 1) & ~1u;                       // an idle tile (all rows out of range) completes the last pair
     cfg.gridDim = dim3(tiles, (unsigned)n_split);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = (secommon::pdl_mask() & 1) ? 1 : 0;
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 2;
-    attr[1].val.clusterDim.y = 1;
-    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = a.cluster == 2 ? 2 : 1;
+    cfg.numAttrs = 1;
     SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, linear_head_fused_kernel, tmA, tmW, a));
     return secommon::check_launch("linear_head_fused_kernel");
 }

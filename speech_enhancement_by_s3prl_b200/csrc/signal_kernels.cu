@@ -204,39 +204,27 @@ int se_stft_strided(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t
     SE_DISPATCH_NFFT(n_fft, launch_stft, a, st)
 }
 
-int se_spec_ws_supported(int n_fft, int hop) { return (n_fft == 512 && hop == 256 && !g_force_generic) ? 1 : 0; }
-
 static int stft_features_impl(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
                               float log_eps, int take_log, float* feat, int64_t feat_stride, double* stat_sums, int64_t ld_stats,
-                              float* spec_ws, int flags, void* stream);
+                              int flags, void* stream);
 
 int se_stft_features(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
                      float log_eps, int take_log, float* feat, int64_t feat_stride, double* stat_sums, int64_t ld_stats,
                      int flags, void* stream) {
     return stft_features_impl(wav, n_utt, utt_stride, T, n_fft, hop, window, log_eps, take_log, feat, feat_stride, stat_sums,
-                              ld_stats, nullptr, flags, stream);
-}
-
-int se_stft_features_ws(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
-                        float log_eps, int take_log, float* feat, int64_t feat_stride, double* stat_sums, int64_t ld_stats,
-                        float* spec_ws, int flags, void* stream) {
-    SE_REQUIRE(spec_ws && (reinterpret_cast<uintptr_t>(spec_ws) & 15) == 0, "spec_ws must be a 16-byte aligned pointer");
-    if (!se_spec_ws_supported(n_fft, hop))
-        return fail(SE_ERR_UNSUPPORTED, "spectrum workspace: n_fft=%d hop=%d is not 512/256", n_fft, hop);
-    return stft_features_impl(wav, n_utt, utt_stride, T, n_fft, hop, window, log_eps, take_log, feat, feat_stride, stat_sums,
-                              ld_stats, spec_ws, flags, stream);
+                              ld_stats, flags, stream);
 }
 
 static int stft_features_impl(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t T, int n_fft, int hop, const float* window,
                               float log_eps, int take_log, float* feat, int64_t feat_stride, double* stat_sums, int64_t ld_stats,
-                              float* spec_ws, int flags, void* stream) {
+                              int flags, void* stream) {
     SE_REQUIRE(wav && window && feat && stat_sums, "null pointer");
     SE_REQUIRE(feat_stride >= n_fft / 2 + 1 && ld_stats >= n_fft / 2 + 1, "feat_stride / ld_stats smaller than K");
     int rc = check_geometry(n_utt, T, n_fft, hop);
     if (rc != SE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (!(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(stat_sums, 0, sizeof(double) * 2 * ld_stats * n_utt, st));
-    const bool geo = sefast::geo_supported(n_fft, hop) && !spec_ws;
+    const bool geo = sefast::geo_supported(n_fft, hop);
     if (((n_fft == 512 && hop == 256) || geo) && !g_force_generic) {
         DeviceTables t;
         if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
@@ -245,7 +233,7 @@ static int stft_features_impl(const float* wav, int64_t n_utt, int64_t utt_strid
         a.n_frames = (int)(T / hop) + 1;
         a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
         a.power = take_log ? nullptr : feat; a.logp = take_log ? feat : nullptr; a.log_eps = log_eps; a.spec_stride = feat_stride;
-        a.stat_sums = stat_sums; a.ld_stats = ld_stats; a.cspec = spec_ws;
+        a.stat_sums = stat_sums; a.ld_stats = ld_stats;
         a.trace = secommon::trace_ptr();
         return geo ? sefast::launch_stft_run(a, n_fft, st) : sefast::launch_stft512(a, st);
     }
@@ -314,42 +302,18 @@ int se_mask_istft_strided(const float* noisy, const float* clean, int64_t utt_st
                             pad_to, sums, want_spec ? SE_FLAG_WANT_SPEC : 0, stream);
 }
 
-static int mask_istft_impl(const float* noisy, const float* spec_ws, const float* clean, int64_t utt_stride, const float* mask,
-                           int64_t mask_stride, const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop,
-                           const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags,
-                           void* stream);
-
 int se_mask_istft_ex(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
                      const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
                      float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags, void* stream) {
-    SE_REQUIRE(noisy, "null pointer");
-    return mask_istft_impl(noisy, nullptr, clean, utt_stride, mask, mask_stride, lengths, n_utt, T, n_fft, hop, window, wav_out,
-                           out_stride, pad_to, sums, flags, stream);
-}
-
-int se_mask_istft_ws(const float* spec_ws, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
-                     const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
-                     float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags, void* stream) {
-    SE_REQUIRE(spec_ws && (reinterpret_cast<uintptr_t>(spec_ws) & 15) == 0, "spec_ws must be a 16-byte aligned pointer");
-    if (!se_spec_ws_supported(n_fft, hop) || T / hop + 1 < 2)
-        return fail(SE_ERR_UNSUPPORTED, "spectrum workspace: n_fft=%d hop=%d is not 512/256", n_fft, hop);
-    return mask_istft_impl(nullptr, spec_ws, clean, utt_stride, mask, mask_stride, lengths, n_utt, T, n_fft, hop, window, wav_out,
-                           out_stride, pad_to, sums, flags, stream);
-}
-
-static int mask_istft_impl(const float* noisy, const float* spec_ws, const float* clean, int64_t utt_stride, const float* mask,
-                           int64_t mask_stride, const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop,
-                           const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags,
-                           void* stream) {
     const int want_spec = (flags & SE_FLAG_WANT_SPEC) ? 1 : 0;
-    SE_REQUIRE((noisy || spec_ws) && mask && window && wav_out, "null pointer");
+    SE_REQUIRE(noisy && mask && window && wav_out, "null pointer");
     SE_REQUIRE(mask_stride >= n_fft / 2 + 1, "mask_stride=%lld smaller than K", (long long)mask_stride);
     int rc = check_geometry(n_utt, T, n_fft, hop);
     if (rc != SE_OK) return rc;
     DeviceTables t;
     if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
     MaskIstftArgs a{};
-    a.noisy = noisy; a.cspec = spec_ws; a.clean = clean; a.utt_stride = utt_stride; a.mask = mask;
+    a.noisy = noisy; a.clean = clean; a.utt_stride = utt_stride; a.mask = mask;
     a.lengths = reinterpret_cast<const long long*>(lengths);
     a.n_utt = (int)n_utt; a.T = (int)T; a.hop = hop; a.n_frames = (int)(T / hop) + 1;
     a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;

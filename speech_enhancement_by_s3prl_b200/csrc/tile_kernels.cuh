@@ -44,7 +44,6 @@ struct StftArgs {
     double* stat_sums;         // (n_utt, ld_stats, 2) += [sum x, sum x^2] over frames of the feature written, or null
     long long ld_stats;
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
-    float* cspec;              // (n_utt, n_frames, SE_SPEC_WS_FLOATS) complex-spectrum workspace for K3, or null (512/256 only)
 };
 
 struct IstftArgs {
@@ -77,7 +76,6 @@ struct MaskIstftArgs {
     int want_spec;             // also accumulate the spectral SI-SDR sums (needs clean)
     long long mask_stride;     // floats between consecutive frames of mask (>= K)
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
-    const float* cspec;        // spectrum workspace written by K1 (then `noisy` is not read), or null (512/256 only)
     int mask_is_power;         // `mask` holds the TARGET power spectrum: output = iSTFT(sqrt(mask) e^{i phase(noisy)}) (runner.py:266-281)
 };
 

@@ -33,9 +33,6 @@ class EnhancementEngine:
         self.ch_inp = int(getattr(preprocessor, "channel_inp", 0))
         self.ch_tar = int(getattr(preprocessor, "channel_tar", 1))
         self._graphs = {}
-        # K1 -> K3 spectrum workspace (512/256): one transform less in K3, but K1 writes / K3 reads 2 KB more per frame.
-        # Measured on B200: K3 41 -> 37 us, K1 17.6 -> 21.6 us, and slower once the batch outgrows L2 -- off by default.
-        self.use_spec_ws = os.environ.get("SE_B200_SPEC_WS", "0") == "1"
         self.fused_training = os.environ.get("SE_B200_FUSED_TRAIN", "1") != "0"  # train_step without autograd (see fused_training_supported)
         self.launches_per_step = 5          # library kernels per eval_step (set by eval_step: 4 on the fused path)
 
@@ -67,18 +64,13 @@ class EnhancementEngine:
                 ws = torch.zeros(B * (2 * LD + ops.NSUMS), device=dev, dtype=torch.float64)
                 stat_sums = ws[:B * 2 * LD].view(B, LD, 2)
                 sums = ws[B * 2 * LD:].view(B, ops.NSUMS)
-                # optional: K1 leaves the noisy spectrum in a workspace (n_fft 512 / hop 256) so that K3 does not
-                # transform the noisy frames a second time (see use_spec_ws)
-                spec_ws = None
-                if self.use_spec_ws and ops.spec_ws_supported(self.n_fft, self.hop):
-                    spec_ws = torch.empty(B, F, ops.SPEC_WS_FLOATS, device=dev, dtype=torch.float32)
                 feats, _ = ops.stft_features(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=self.log_features,
-                                             log_eps=self.pre.eps, stat_sums=stat_sums, spec_ws=spec_ws)
+                                             log_eps=self.pre.eps, stat_sums=stat_sums)
                 mask = ops.linear_head_tma(feats, K, wpad, head.linear.bias, head.activation,
                                              stat_sums if head.cmvn else None, head.eps)
                 wav, sums = ops.mask_istft(wavs, self.ch_inp, self.ch_tar, mask, lengths, self.n_fft, self.hop, window,
                                            pad_to=T, want_sums=True, want_spec=want_spec_loss, mask_padded=True, sums=sums,
-                                           sums_zeroed=True, spec_ws=spec_ws)
+                                           sums_zeroed=True)
             else:
                 feats = ops.stft_padded(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=self.log_features, log_eps=self.pre.eps)
                 mean = std = None

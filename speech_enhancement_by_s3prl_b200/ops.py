@@ -105,19 +105,10 @@ def stft_padded(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10)
 FLAG_WANT_SPEC, FLAG_SUMS_ZEROED, FLAG_MASK_IS_POWER = 1, 2, 4
 
 
-SPEC_WS_FLOATS = 516
-
-
-def spec_ws_supported(n_fft, hop):
-    """True if K1 can leave the complex spectrum in a workspace for K3 (se_stft_features_ws / se_mask_istft_ws)."""
-    return bool(_lib.load().se_spec_ws_supported(int(n_fft), int(hop)))
-
-
-def stft_features(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10, stat_sums=None, spec_ws=None):
+def stft_features(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10, stat_sums=None):
     """Fused-step K1: ONE feature tensor (B, F, round4(K)) -- log-power or power -- plus the CMVN sums
     (B, round4(K), 2) float64 = [sum_f x, sum_f x^2].  If ``stat_sums`` is given it must already be zero
-    (the caller zeroed its workspace once for the whole step); otherwise it is allocated and zeroed here.
-    ``spec_ws`` (B, F, SPEC_WS_FLOATS) fp32: also receives the complex spectrum in K3's layout (n_fft 512 / hop 256)."""
+    (the caller zeroed its workspace once for the whole step); otherwise it is allocated and zeroed here."""
     wavs = _chk(wavs, "wavs")
     B, C, T = wavs.shape
     F, K = T // hop + 1, n_fft // 2 + 1
@@ -130,13 +121,6 @@ def stft_features(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-1
             stat_sums = torch.empty(B, LD, 2, device=wavs.device, dtype=torch.float64)
             flags = 0
         assert stat_sums.shape == (B, LD, 2) and stat_sums.dtype == torch.float64 and stat_sums.is_contiguous()
-        if spec_ws is not None:
-            assert spec_ws.shape == (B, F, SPEC_WS_FLOATS) and spec_ws.dtype == torch.float32 and spec_ws.is_contiguous()
-            rc = _lib.load().se_stft_features_ws(wavs.data_ptr() + 4 * int(channel) * T, B, C * T, T, n_fft, hop,
-                                                 window.data_ptr(), float(log_eps), int(bool(logpower)), out.data_ptr(), LD,
-                                                 stat_sums.data_ptr(), LD, spec_ws.data_ptr(), flags, _stream())
-            _lib.check(rc, "se_stft_features_ws")
-            return out, stat_sums
         rc = _lib.load().se_stft_features(wavs.data_ptr() + 4 * int(channel) * T, B, C * T, T, n_fft, hop, window.data_ptr(),
                                           float(log_eps), int(bool(logpower)), out.data_ptr(), LD, stat_sums.data_ptr(), LD,
                                           flags, _stream())
@@ -311,9 +295,8 @@ def istft(power, phase, n_fft, hop, window, pad_to=0):
 
 
 def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, want_sums=True, want_spec=True,
-               out=None, sums=None, mask_padded=False, sums_zeroed=False, spec_ws=None, mask_is_power=False):
-    """Fused ``istft(linear_inp * mask, phase_inp)`` straight from the noisy waveform -- or, with ``spec_ws`` (the
-    workspace stft_features filled for the same wavs / ch_inp), from the spectrum K1 already computed.
+               out=None, sums=None, mask_padded=False, sums_zeroed=False, mask_is_power=False):
+    """Fused ``istft(linear_inp * mask, phase_inp)`` straight from the noisy waveform.
 
     wavs (B, C, T); mask (B, F, K); lengths (B,) int64 or None.  Returns (wav (B, width), sums (B, 6) float64|None)."""
     wavs, mask, window = _chk(wavs, "wavs"), _c(mask, "mask"), _c(window, "window")
@@ -333,13 +316,6 @@ def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, 
         clean = None if ch_tar is None else wavs.data_ptr() + 4 * int(ch_tar) * T
         flags = (FLAG_WANT_SPEC if want_spec else 0) | (FLAG_SUMS_ZEROED if sums_zeroed else 0)
         flags |= FLAG_MASK_IS_POWER if mask_is_power else 0     # `mask` = target power; output keeps the noisy phase
-        if spec_ws is not None:
-            assert spec_ws.shape == (B, F, SPEC_WS_FLOATS) and spec_ws.dtype == torch.float32 and spec_ws.is_contiguous()
-            rc = _lib.load().se_mask_istft_ws(spec_ws.data_ptr(), clean, C * T, mask.data_ptr(), mask_stride, _p(lengths), B, T,
-                                              n_fft, hop, window.data_ptr(), out.data_ptr(), out.stride(0), int(pad_to),
-                                              _p(sums) if want_sums else None, flags, _stream())
-            _lib.check(rc, "se_mask_istft_ws")
-            return out, (sums if want_sums else None)
         rc = _lib.load().se_mask_istft_ex(wavs.data_ptr() + 4 * int(ch_inp) * T, clean, C * T, mask.data_ptr(), mask_stride,
                                           _p(lengths), B, T, n_fft, hop, window.data_ptr(), out.data_ptr(), out.stride(0),
                                           int(pad_to), _p(sums) if want_sums else None, flags, _stream())

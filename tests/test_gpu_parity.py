@@ -132,7 +132,6 @@ def test_abi_error_codes_on_device(se):
         assert lib.se_adam_clip_step(ptrs, ptrs, ptrs, ptrs, sizes, n, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, dbl.data_ptr(),
                                      ints.data_ptr(), st) == -1
     assert lib.se_match_scores(p, 0, p, 1, 8, 1e-12, dbl.data_ptr(), p, p, st) == -1
-    assert lib.se_stft_features_ws(p, 1, 2000, 2000, 400, 160, p, 1e-10, 1, p, 204, dbl.data_ptr(), 204, p, 0, st) == -2
     noisy, out = torch.randn(2000, device="cuda"), torch.empty(2000, device="cuda")
     power, win = torch.rand(8, 257, device="cuda"), torch.hann_window(512, device="cuda")
     assert lib.se_mask_istft_ex(noisy.data_ptr(), None, 2000, power.data_ptr(), 257, None, 1, 2000, 512, 256, win.data_ptr(),
@@ -762,7 +761,7 @@ def test_recurrent_heads_match_reference_golden(se, golden_dir, tag, precision):
     state = {k[len(tag) + 7:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith(f"{tag}_param_")}
     head.load_state_dict(state)                                             # same parameter names as the reference (strict)
     feats, linears = torch.from_numpy(gold["feats"]).cuda(), torch.from_numpy(gold["linears"]).cuda()
-    tol = 2e-5 if precision == 0 else 3e-3                                  # precision 1: TF32 operands in the projection
+    tol = 1e-4 if precision == 0 else 3e-3                                  # values are O(1); precision 1: TF32 operands in the projection
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):        # the cuDNN LSTM body in fp32: the bounds test the projection
         predicted, res = head(features=feats, linears=linears)
         assert (predicted.cpu() - torch.from_numpy(gold[f"{tag}_predicted"])).abs().max().item() < tol * 5
@@ -1036,65 +1035,6 @@ def test_tensor_core_head_trains_like_fp32_head(se):
 
 
 # ------------------------------------------------------------------------------ K1 -> K3 spectrum workspace (512/256)
-@pytest.mark.parametrize("T,B,logp", [(16000, 3, True), (16001, 2, True), (9999, 3, False), (1100, 2, True), (64000, 5, True),
-                                      (300, 1, True)])
-def test_spectrum_workspace_path_equals_recompute_path(se, T, B, logp):
-    """se_stft_features_ws + se_mask_istft_ws against se_stft_features + se_mask_istft_ex (which transforms the noisy
-    frames again) and against torch.stft: same arithmetic, so waveform and sums agree to rounding of the summation order."""
-    from speech_enhancement_by_s3prl_b200 import ops
-    assert ops.spec_ws_supported(512, 256) and not ops.spec_ws_supported(400, 160) and not ops.spec_ws_supported(512, 128)
-    mine = se.OnlinePreprocessor(win_ms=32, hop_ms=16, n_freq=257).cuda()
-    lengths = torch.LongTensor([T, max(300, T - 777), T // 2 + 3, T, T // 3 + 1][:B])
-    lengths, wavs = synth(B, T, seed=T + 9, lengths=lengths)
-    wavs, lengths = wavs.cuda(), lengths.cuda()
-    F = T // 256 + 1
-    g = torch.Generator().manual_seed(T)
-    mask = torch.rand(B, F, 257, generator=g).cuda()
-    ws = torch.full((B, F, ops.SPEC_WS_FLOATS), float("nan"), device="cuda")
-    feats_ws, sums_ws = ops.stft_features(wavs, 0, 512, 256, mine._frame_window, logpower=logp, spec_ws=ws)
-    feats, sums = ops.stft_features(wavs, 0, 512, 256, mine._frame_window, logpower=logp)
-    assert torch.equal(feats_ws[..., :257], feats[..., :257])
-    # (the sums are combined across CTAs with double-precision atomics: the order, hence the last bit, varies between launches)
-    np.testing.assert_allclose(sums_ws[:, :257].cpu().numpy(), sums[:, :257].cpu().numpy(), rtol=1e-12, atol=1e-12)
-    # the workspace holds torch.stft's spectrum (layout of include/se_b200.h)
-    ref = torch.stft(wavs[:, 0], 512, 256, 512, window=mine._frame_window, center=True, pad_mode="reflect",
-                     return_complex=True).transpose(1, 2)                      # (B, F, 257)
-    pairs = ws[..., :512].view(B, F, 8, 16, 4)
-    lo = torch.complex(pairs[..., 0], pairs[..., 1]).reshape(B, F, 128)        # k = 16 q + j
-    hi = torch.complex(pairs[..., 2], pairs[..., 3]).reshape(B, F, 128)        # 256 - k
-    got = torch.cat([lo, torch.complex(ws[..., 512], ws[..., 513])[..., None], hi.flip(-1)], -1)
-    scale = ref.abs().amax(dim=(-1, -2), keepdim=True)
-    assert ((got - ref).abs() / scale).max().item() < 1e-5
-    args = (wavs, 0, 1, mask, lengths, 512, 256, mine._frame_window)
-    wav_a, s_a = ops.mask_istft(*args, pad_to=T)
-    wav_b, s_b = ops.mask_istft(*args, pad_to=T, spec_ws=ws)
-    assert (wav_a - wav_b).abs().max().item() < 1e-6
-    np.testing.assert_allclose(s_b.cpu().numpy(), s_a.cpu().numpy(), rtol=1e-5, atol=1e-9)
-    wav_c, none = ops.mask_istft(wavs, 0, None, mask, None, 512, 256, mine._frame_window, pad_to=T, want_sums=False, spec_ws=ws)
-    assert none is None and (wav_c - wav_a).abs().max().item() < 1e-6
-    with pytest.raises(RuntimeError):                                          # other geometries have no workspace path
-        pre400 = se.OnlinePreprocessor(win_ms=25, hop_ms=10, n_freq=201).cuda()
-        ops.stft_features(wavs, 0, 400, 160, pre400._frame_window, spec_ws=torch.empty(B, T // 160 + 1, 516, device="cuda"))
-
-
-def test_eval_step_same_with_and_without_spectrum_workspace(se):
-    _, mine = make_pair(se, 512)
-    lengths, wavs = synth(6, 32000, seed=77, lengths=torch.LongTensor([32000, 30001, 16000, 32000, 777, 25600]))
-    lengths, wavs = lengths.cuda(), wavs.cuda()
-    torch.manual_seed(3)
-    head = se.LinearResidual(input_size=257, output_size=257).cuda()
-    outs = []
-    for use in (True, False):
-        eng = se.EnhancementEngine(mine, head, log_features=True, precision=1)
-        eng.use_spec_ws = use
-        outs.append(eng.eval_step(lengths, wavs))
-    a, b = outs
-    assert (a["wav_predicted"] - b["wav_predicted"]).abs().max().item() < 1e-6
-    assert (a["sisdr"] - b["sisdr"]).abs().max().item() < 1e-4
-    assert (a["loss_per_utt"] - b["loss_per_utt"]).abs().max().item() < 1e-4
-
-
-# ------------------------------------------------------------------------------ fused training step (no autograd graph)
 @pytest.mark.parametrize("B,T,ragged", [(4, 16000, False), (6, 32000, True), (64, 64000, False)])
 def test_fused_training_step_matches_autograd_path(se, B, T, ragged):
     """K1(power + log-power + sums) -> TMA head -> SISDR on offset * linear_inp -> its backward -> split-K weight gradient
