@@ -223,7 +223,9 @@ template <class Geo> struct Sz {
     static constexpr int MROW = (K + 16 * (K >> 7) + 3) / 4 * 4;    // skewed mask row (bins 128 apart land 16 banks apart)
     static constexpr int TAB_BYTES = (2 * M * 8 + 127) / 128 * 128; // s_win2 | s_bw2
 };
-__device__ __forceinline__ int mpos(int k) { return k + ((k >> 7) << 4); }
+// position of bin k in the staged mask row.  Geo1024: the two halves of a warp read bins 128 apart in the same instruction, so
+// every 128 bins are skewed by 16 floats (16 banks); Geo400: plain.
+template <class Geo> __device__ __forceinline__ int mpos(int k) { return Geo::G == 32 ? k + ((k >> 7) << 4) : k; }
 
 // stage one block of Bs floats starting at original coordinate t0 (reflect outside [0, T)); jg = lane in group
 template <class Geo>
@@ -247,9 +249,16 @@ template <class Geo>
 __device__ __forceinline__ void stage_mask_row(float* __restrict__ dst, const float* __restrict__ src, bool padded, int jg) {
     constexpr int K = Sz<Geo>::K, G = Geo::G;
     if (padded && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        for (int c = jg; c < (K + 3) / 4; c += G) cp_async16(dst + mpos(4 * c), src + 4 * c);
+        if (Geo::G == 32) {
+            // chunk c = jg + 32 i holds bins 4 c .. 4 c + 3 = 128 i + 4 jg ..: destination 4 jg + 144 i (immediate offsets)
+#pragma unroll
+            for (int i = 0; i < (K + 3) / 4 / 32; ++i) cp_async16(dst + 4 * jg + 144 * i, src + 4 * jg + 128 * i);
+            if (jg < (K + 3) / 4 % 32) cp_async16(dst + 4 * jg + 144 * ((K + 3) / 4 / 32), src + 4 * jg + 128 * ((K + 3) / 4 / 32));
+        } else {
+            for (int c = jg; c < (K + 3) / 4; c += G) cp_async16(dst + 4 * c, src + 4 * c);
+        }
     } else {
-        for (int k = jg; k < K; k += G) cp_async4(dst + mpos(k), src + k);
+        for (int k = jg; k < K; k += G) cp_async4(dst + mpos<Geo>(k), src + k);
     }
 }
 // v[r] = (x[2m], x[2m+1]) * win2[m], m = tidx + G r, from the ring (block 0 of the frame in ring slot `slot0`)
@@ -521,6 +530,10 @@ __global__ void __launch_bounds__(K3Cfg<Geo>::WARPS * 32, K3Cfg<Geo>::MIN_BLOCKS
     const bool mask_padded = (a.mask_stride & 3) == 0;
     const float* mrow0 = a.mask + (long long)u * F * a.mask_stride;
     const int tidx = core.tidx;
+    // Geo1024: bins k = k0 + 16 q and M - k = (M - k0) - 16 q of pairs q >= 1 at constant offsets from two per-lane pointers
+    const int k0 = core.pair_bin(0);
+    const float* mlo = mb + mpos<Geo>(k0 + 16) - 16;
+    const float* mhi = mb + mpos<Geo>(M - k0 - 16) + 16;
     float acc[sekern::NSUMS];
 #pragma unroll
     for (int i = 0; i < sekern::NSUMS; ++i) acc[i] = 0.0f;
@@ -586,9 +599,12 @@ __global__ void __launch_bounds__(K3Cfg<Geo>::WARPS * 32, K3Cfg<Geo>::MIN_BLOCKS
                     const int k = core.pair_bin(q);
                     float2 xa, xb;
                     split_pair(v[q], zm[q], core.twn[q], xa, xb);
-                    mask_merge<PM>(xa, xb, mb[mpos(k)], mb[mpos(M - k)], core.twn[q], own, ra[q], rb[q], ca[q], cbv[q]);
+                    // (Geo1024: q >= 1 keeps k and M - k inside one 128-bin skew block per lane: constant offsets from mlo / mhi)
+                    const float ga = (Geo::G == 32 && q > 0) ? mlo[16 * q] : mb[mpos<Geo>(k)];
+                    const float gb = (Geo::G == 32 && q > 0) ? mhi[-16 * q] : mb[mpos<Geo>(M - k)];
+                    mask_merge<PM>(xa, xb, ga, gb, core.twn[q], own, ra[q], rb[q], ca[q], cbv[q]);
                 }
-                const float gmid = mb[mpos(M / 2)];
+                const float gmid = mb[mpos<Geo>(M / 2)];
                 const float2 xmid = make_float2(2.0f * v[V / 2].x, -2.0f * v[V / 2].y);   // bin M/2 pairs with itself: X = 2 conj(Z[M/2])
                 if (own) rmid = fmaxf(PM ? gmid : gmid * (xmid.x * xmid.x + xmid.y * xmid.y), 0.0f);
                 __syncwarp();

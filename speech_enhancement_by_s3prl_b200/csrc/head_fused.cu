@@ -14,8 +14,9 @@
 //   * warp 8 (one lane)  tcgen05.mma kind::tf32, fp32 accumulators in tensor memory: columns
 //                        [0,256) by one N=256 instruction, the remaining <= 16 by a second one
 //   * more than 272 output columns (n_fft 1024: 513 -> 528): blockIdx.y splits the columns into slabs of
-//                        <= 272 (272 + 256); each CTA streams the same A tile (the second read comes from L2)
-//                        and its own slab of weight rows, and stores its slab of every output row
+//                        <= 256 (3 x 176); each CTA streams the same A tile (re-reads come from L2) and its
+//                        own slab of weight rows, and stores its slab of every output row
+//   * more tiles than SMs: two CTAs per SM (2-stage rings, 256 tensor-memory columns each, direct stores)
 //   * epilogue           tcgen05.ld -> +bias -> activation -> row-major staging tile in shared
 //                        memory (reusing the A tile) -> ONE bulk async store per 32-row quadrant:
 //                        with ld_out == padded row length the CTA's output is contiguous in HBM
@@ -29,23 +30,28 @@ using secommon::fail;
 
 namespace {
 
-constexpr int BM = 128, BK = 32, kMaxKB = 17, kStages = 4;
+constexpr int BM = 128, BK = 32, kMaxKB = 17, kMaxStages = 4;
 constexpr int kWorkWarps = 8, kWorkThreads = kWorkWarps * 32, kThreads = kWorkThreads + 64;   // + MMA warp + TMA warp
 constexpr int kATileBytes = BM * BK * 4;                       // 16 KB: one 32-float k-block of the A tile
 constexpr int kMaxWRows = 272;
 constexpr int kWTileBytes = kMaxWRows * BK * 4;                // 34 816: the same k-block of all weight rows
-constexpr int kStageBytes = kATileBytes + kWTileBytes;         // 51 200 (multiple of 1024: SWIZZLE_128B atoms stay aligned)
+constexpr int kMaxStageBytes = kATileBytes + kWTileBytes;      // 51 200 (multiple of 1024: SWIZZLE_128B atoms stay aligned)
 constexpr int kStatLd = kMaxKB * BK;                           // 544: features per utterance (n_fft 1024: 513)
-constexpr int kOffRing = 0;
-constexpr int kOffScale = kOffRing + kStages * kStageBytes;    // 204 800
+// shared memory: fixed part (CMVN scale / shift of two utterances, bias, mbarriers, TMEM slot) | ring of `stages` stages.
+// Two launch shapes share the kernel: ONE CTA per SM with a 4-stage ring, 512 tensor-memory columns and bulk stores from a
+// staging tile (a single wave of <= 272-column tiles: the headline), or TWO CTAs per SM with 2-stage rings, 256 columns
+// each and direct stores -- when the tiles outnumber the SMs, the second CTA's loads fill the L2 pipe while the first one
+// is in its prologue / epilogue (the kernel is bound by the chip-wide L2 throughput of the weight re-reads).
+constexpr int kOffScale = 0;
 constexpr int kOffShift = kOffScale + 2 * kStatLd * 4;
 constexpr int kOffBias = kOffShift + 2 * kStatLd * 4;
 constexpr int kOffBar = kOffBias + kStatLd * 4;
-constexpr int kNumBars = 3 * kStages + 1;
+constexpr int kNumBars = 3 * kMaxStages + 1;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmem + 16;
+constexpr int kOffRing = (kOffTmem + 16 + 1023) / 1024 * 1024;
+constexpr int kSmemBytes = kOffRing + kMaxStages * kMaxStageBytes;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-static_assert(kStageBytes % 1024 == 0 && kATileBytes % 1024 == 0, "swizzle atom alignment");
+static_assert(kMaxStageBytes % 1024 == 0 && kATileBytes % 1024 == 0, "swizzle atom alignment");
 constexpr unsigned kSpinLimit = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,14 +139,16 @@ struct Head2Args {
     int kblocks;               // ceil(Din / 32) <= 17
     int w_rows;                // Dout rounded up to 16, <= 544
     int cta_cols;              // output columns (weight rows) per CTA slab: multiple of 16, <= 272; slab = blockIdx.y
-    int row_bulk;              // column slabs: one bulk store per output row (16-byte aligned rows and slabs)
     int w_box_rows, w_boxes;   // weight tensor-map box rows and boxes per k-block
     int sld;                   // floats per row of the staging tile
     int bulk_out;              // staging rows == output rows and 16-byte aligned: one bulk store per quadrant
+    int stages, stage_bytes;   // ring depth (2 or 4) and bytes per stage (A k-block + this launch's weight k-block, 1024-aligned)
+    int tmem_cols;             // tensor-memory columns allocated per CTA (256: two CTAs per SM; 512: one)
+    int direct_out;            // epilogue stores registers straight to global memory (no staging tile: 2-stage rings are too small)
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Head2Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     secommon::TraceScope trace(a.trace, 2);
@@ -149,10 +157,11 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     float* s_shift = reinterpret_cast<float*>(smem + kOffShift);
     float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
-    const uint32_t bar_full = sbase + kOffBar;                         // [kStages] TMA landed the stage's A and W k-block
-    const uint32_t bar_norm = bar_full + 8 * kStages;                  // [kStages] A k-block normalised in place
-    const uint32_t bar_empty = bar_norm + 8 * kStages;                 // [kStages] the MMAs have read the stage
-    const uint32_t bar_accum = bar_empty + 8 * kStages;
+    const uint32_t bar_full = sbase + kOffBar;                         // [stages] TMA landed the stage's A and W k-block
+    const uint32_t bar_norm = bar_full + 8 * kMaxStages;               // [stages] A k-block normalised in place
+    const uint32_t bar_empty = bar_norm + 8 * kMaxStages;              // [stages] the MMAs have read the stage
+    const uint32_t bar_accum = bar_empty + 8 * kMaxStages;
+    const int kStages = a.stages, kStageBytes = a.stage_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r0 = (long long)blockIdx.x * a.tile_rows;
@@ -163,7 +172,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     if (threadIdx.x == 0) {
         if (sbase & 1023) __trap();
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_norm + 8 * s, kWorkWarps);
             mbar_init(bar_empty + 8 * s, 1);
@@ -172,7 +181,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWorkWarps) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)a.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -317,6 +326,9 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int ncol16 = ncols / 16;
         const int c_lo = 16 * (half == 0 ? 0 : ncol16 / 2), c_hi = 16 * (half == 0 ? ncol16 / 2 : ncol16);
         float* srow = stage + (long long)row * a.sld;
+        // direct mode: registers -> global memory (row = this lane's frame; 64 contiguous bytes per 16-column chunk)
+        const bool row_ok = row < a.tile_rows && r0 + row < a.R;
+        float* grow = a.out + (r0 + row) * a.ld_out + col0;
         // two 16-column chunks in flight: the tensor-memory load of chunk c+1 overlaps the activation of chunk c
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
         // The activation of a chunk is written stage by stage over all 16 values (all exponentials, then all adds, then
@@ -345,6 +357,22 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
+            if (a.direct_out) {
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const int c = col0 + c0 + j;
+                        if (a.direct_out == 2 && c + 4 <= (int)a.ld_out) {
+                            *reinterpret_cast<float4*>(grow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (c + e < a.Dout) grow[c0 + j + e] = v[j + e];
+                        }
+                    }
+                }
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
                 if (c0 + j < a.sld) *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -362,27 +390,19 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 tmem_ld_wait();
             }
         }
+        if (!a.direct_out) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");        // both warps of the quadrant have staged their columns
+        }
         if (t == 0) trace.mark(16);
         long long rows_left = a.R - r0;
         if (rows_left > a.tile_rows) rows_left = a.tile_rows;
         int rows_valid = (int)rows_left - quad * 32;
         rows_valid = rows_valid > 32 ? 32 : rows_valid;
-        if (rows_valid > 0) {
+        if (rows_valid > 0 && !a.direct_out) {
             float* gdst = a.out + (r0 + quad * 32) * a.ld_out + col0;
             const float* ssrc = stage + (long long)quad * 32 * a.sld;
-            if (a.row_bulk) {
-                // column slab: the CTA's part of an output row is contiguous, one bulk store per row (lane = row of the quadrant)
-                int nout = (int)a.ld_out - col0;
-                nout = nout > ncols ? ncols : nout;
-                if (half == 0 && lane < rows_valid) {
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 ::"l"(gdst + (long long)lane * a.ld_out), "r"(smem_u32(ssrc + (long long)lane * a.sld)), "r"((uint32_t)(nout * 4)) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                }
-            } else if (a.bulk_out) {
+            if (a.bulk_out) {
                 if (half == 0 && lane == 0) {
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  ::"l"(gdst), "r"(smem_u32(ssrc)), "r"((uint32_t)(rows_valid * a.sld * 4)) : "memory");
@@ -400,7 +420,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     trace.finish();
     if (warp == kWorkWarps) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
     }
 }
 
@@ -446,11 +466,11 @@ extern "C" {
 int se_linear_head_fused_supported(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int64_t ldx, int64_t ldw,
                                    int64_t ld_out) {
     if (n_utt <= 0 || n_frames < 8 || D_in <= 0 || D_out <= 0) return 0;
-    if (D_in > kMaxKB * BK || D_out > 2 * kMaxWRows) return 0;
+    if (D_in > kMaxKB * BK || D_out > kMaxKB * BK) return 0;
     if (ldx % 4 || ldw % 4 || ldx < D_in || ldw < D_in || ld_out < D_out) return 0;
     const int64_t dout4 = (D_out + 3) / 4 * 4;
-    if (D_out > kMaxWRows) return (ld_out % 4 == 0 && ld_out >= dout4) ? 1 : 0;                 // column slabs: 16-byte aligned row parts
-    if ((ld_out == dout4 ? ld_out : dout4 + 4) * 4 * BM > kStages * kStageBytes) return 0;      // staging tile must fit in the ring
+    if (D_out > kMaxWRows) return 1;                                                            // column slabs, direct stores
+    if ((ld_out == dout4 ? ld_out : dout4 + 4) * 4 * BM > kMaxStages * kMaxStageBytes) return 0;  // staging tile must fit in the ring
     return 1;
 }
 
@@ -472,12 +492,33 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     a.inv_nm1 = 1.0 / (double)(n_frames - 1);
     a.kblocks = (int)((D_in + BK - 1) / BK);
     a.w_rows = (int)((D_out + 15) / 16 * 16);
-    const int n_split = (a.w_rows + kMaxWRows - 1) / kMaxWRows;              // column slabs (blockIdx.y)
+    const int sms = num_sms();
+    const long long tiles128 = (a.R + BM - 1) / BM;
+    // Launch shape (see the shared-memory comment at the top): ONE CTA per SM with the deep ring (bulk stores from a staging
+    // tile for a single slab, direct stores for the two <= 272-column slabs of K = 513), or TWO CTAs per SM when the slab
+    // fits 256 tensor-memory columns and the tiles outnumber the SMs.
+    // measured on B200 (tools/time_head_fused.py): two CTAs per SM win when no extra slab is needed (K = 201: 25.7 -> 21.0 us
+    // for 64 x 401 rows); splitting 272 columns into 2 x 136 or 528 into 3 x 176 to get there re-reads every A tile once
+    // more and loses (K = 257: 17.5 -> 20.0 us, K = 513: 45.3 -> 52.9 us)
+    const bool dual = a.w_rows <= 256 && tiles128 > sms;
+    int n_split = 1;
+    long long slots = sms;
+    if (dual) {
+        n_split = (a.w_rows + 255) / 256;
+        slots = 2LL * sms;
+        a.stages = 2; a.tmem_cols = 256;
+        a.direct_out = (ld_out % 4 == 0 && aligned16(offset_out)) ? 2 : 1;
+    } else {
+        n_split = (a.w_rows + kMaxWRows - 1) / kMaxWRows;       // <= 2 slabs of <= 272 columns
+        a.stages = kMaxStages; a.tmem_cols = 512;
+        a.direct_out = n_split > 1 ? ((ld_out % 4 == 0 && aligned16(offset_out)) ? 2 : 1) : 0;
+    }
     a.cta_cols = ((a.w_rows + n_split - 1) / n_split + 15) / 16 * 16;
-    // rows per tile: the fewest waves of (tiles x slabs) CTAs over the SMs, then tiles as even as the waves allow
-    const long long min_tiles = (a.R + BM - 1) / BM;
-    const long long waves = (min_tiles * n_split + num_sms() - 1) / num_sms();
-    const long long want_tiles = waves * num_sms() / n_split;
+    a.stage_bytes = kATileBytes + (a.cta_cols * BK * 4 + 1023) / 1024 * 1024;
+    // rows per tile: the fewest waves of (tiles x slabs) CTAs over the resident slots, then tiles as even as the waves allow
+    const long long waves = (tiles128 * n_split + slots - 1) / slots;
+    long long want_tiles = waves * slots / n_split;
+    if (want_tiles < 1) want_tiles = 1;
     long long rows = (a.R + want_tiles - 1) / want_tiles;
     rows = (rows + 7) / 8 * 8;
     if (rows > BM) rows = BM;
@@ -486,10 +527,9 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     a.w_boxes = a.cta_cols > 256 ? 2 : 1;                              // cta_cols is a multiple of 16: both boxes are whole 8-row atoms
     a.w_box_rows = a.cta_cols / a.w_boxes;
     const int dout4 = (int)((D_out + 3) / 4 * 4);
-    a.row_bulk = (n_split > 1 && aligned16(offset_out)) ? 1 : 0;
-    a.bulk_out = (n_split == 1 && ld_out == dout4 && aligned16(offset_out)) ? 1 : 0;
-    a.sld = n_split > 1 ? a.cta_cols + 4 : (a.bulk_out ? (int)ld_out : dout4 + 4);
-    if (n_split > 1 && !a.row_bulk) return fail(SE_ERR_UNSUPPORTED, "fused head: column slabs need a 16-byte aligned output");
+    a.bulk_out = (!a.direct_out && ld_out == dout4 && aligned16(offset_out)) ? 1 : 0;
+    a.sld = a.bulk_out ? (int)ld_out : dout4 + 4;
+    const size_t smem_bytes = (size_t)kOffRing + (size_t)a.stages * a.stage_bytes;
     CUtensorMap tmA, tmW;
     int rc = make_map(&tmA, x, D_in, a.R, ldx, a.tile_rows);
     if (rc != SE_OK) return rc;
@@ -502,7 +542,7 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     unsigned tiles = (unsigned)((a.R + a.tile_rows - 1) / a.tile_rows);
     cfg.gridDim = dim3(tiles, (unsigned)n_split);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
