@@ -194,6 +194,9 @@ class Ctx:
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        # one process per GPU: keep the process and its pinned host batches on the GPU's NUMA node (the e2e feed of 8 ranks)
+        from speech_enhancement_by_s3prl_b200 import dp
+        self.numa_node = dp.bind_to_gpu_numa_node(self.local_rank) if self.world > 1 else None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.align = torch.zeros(1, device=self.dev)
@@ -390,13 +393,32 @@ def bench_training(ctx, se, args):
     # SURVEY 8(d) training path, recompute variant: custom kernels 4 (5 H + D + 3 K) per frame + head forward / backward I/O
     # (forward reads D writes K; backward reads D, offset K, grad K), D = K here
     step_bytes = frames * (4 * (5 * hop + K + 3 * K) + 4 * (K + K) + 4 * 3 * K)
-    return {"workload": f"configs[2]: training step at n_fft={n_fft} hop={hop}, LinearResidual({K}) on log-power + SISDR, fwd + bwd + "
-                        f"gradient all-reduce + clip + Adam in one CUDA graph, {B} utterances of 3-10 s per GPU",
-            "metric": "trained audio-sec/sec (fwd+bwd+update)", "value": t.item() / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-            "steps": steps, "scaling": "weak", "fused_route": bool(fused), "audio_s_per_gpu_step": audio_s,
-            "grad_allreduce": "NCCL all-reduce of the flat head gradient (162 KB) captured inside the step's graph" if ctx.world > 1 else "world size 1",
-            "step_algorithmic_bytes": int(step_bytes), "step_frac_of_hbm_peak": step_bytes / (ms * 1e-3) / 1e9 / ctx.peak,
-            "check": {"loss": float(st["loss"]), "steps_taken": opt.steps_taken()[0], "steps_skipped": opt.steps_skipped()[0]}}
+    out = {"workload": f"configs[2]: training step at n_fft={n_fft} hop={hop}, LinearResidual({K}) on log-power + SISDR, fwd + bwd + "
+                       f"gradient all-reduce + clip + Adam in one CUDA graph, {B} utterances of 3-10 s per GPU",
+           "metric": "trained audio-sec/sec (fwd+bwd+update)", "value": t.item() / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+           "steps": steps, "scaling": "weak", "fused_route": bool(fused), "audio_s_per_gpu_step": audio_s,
+           "grad_allreduce": "NCCL all-reduce of the flat head gradient (162 KB) captured inside the step's graph" if ctx.world > 1 else "world size 1",
+           "step_algorithmic_bytes": int(step_bytes), "step_frac_of_hbm_peak": step_bytes / (ms * 1e-3) / 1e9 / ctx.peak,
+           "check": {"loss": float(st["loss"]), "steps_taken": opt.steps_taken()[0], "steps_skipped": opt.steps_skipped()[0]}}
+    # the same step with the baseline feature of config/pseudo_noise.yaml:10-15 -- mel + log + delta 2 (120-d, fused K1b kernel)
+    # -- into LinearResidual(120 -> K): autograd route through the custom ops, also captured with its all-reduce
+    torch.manual_seed(1337)
+    head2 = se.LinearResidual(input_size=120, output_size=K, precision=1).to(ctx.dev)
+    eng2 = se.EnhancementEngine(pre, head2, precision=1, feat_cfg=pre.get_feat_config("mel", 0, log=True, delta=2))
+    opt2 = se.ClipAdam(head2.parameters(), lr=1e-4)
+    st2 = eng2.capture_train(lengths, wavs, crit, opt2, 1.0)
+    for _ in range(3):
+        st2["graph"].replay()
+
+    def run2():
+        for _ in range(steps):
+            st2["graph"].replay()
+        if ctx.world > 1:
+            ctx.dist.all_reduce(ctx.align)
+    ms2 = ctx.timed(run2) / steps
+    out["mel_log_delta2"] = {"workload": f"mel(40) + log + delta 2 (120-d) -> LinearResidual(120, {K}) + SISDR, autograd route, one CUDA graph",
+                             "value": t.item() / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "loss": float(st2["loss"].detach())}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- configs[4]: scoring
@@ -427,7 +449,28 @@ def bench_scoring(ctx, se, args):
     t = torch.tensor([audio_s], device=ctx.dev, dtype=torch.float64)
     if ctx.world > 1:
         ctx.dist.all_reduce(t)
-    return {"workload": "configs[4]: active-sampling scoring, 12 + 32 utterances of 3-10 s per GPU, n_fft=400 hop=160, per-utterance "
+    # run_active.sh's own combination: --downstream LSTM with the L1-trained checkpoint; the library part is the projection layer
+    torch.manual_seed(1337)
+    lstm = se.LSTM(input_size=201, output_size=201, hidden_size=201, num_layers=3, precision=1).to(ctx.dev)
+    l1 = se.L1()
+
+    def one_l1():
+        g = sampler_ops.scoring(pre, lstm, l1, lengths, wavs, projection_only=True)
+        return g, sampler_ops.matching(g[12:], g[:12])
+    for _ in range(3):
+        g_l1, s_l1 = one_l1()
+
+    def run_l1():
+        for _ in range(steps):
+            one_l1()
+        if ctx.world > 1:
+            ctx.dist.all_reduce(ctx.align)
+    ms_l1 = ctx.timed(run_l1) / steps
+    l1_out = {"workload": "LSTM(3 x 201) head + L1 objective, gradient embeddings of the projection layer (cuDNN LSTM forward included)",
+              "value": t.item() / (ms_l1 * 1e-3), "unit": UNIT, "ms_per_step": ms_l1, "parameters": int(g_l1.shape[1]),
+              "finite": bool(torch.isfinite(g_l1).all())}
+    return {"l1_lstm_projection": l1_out,
+            "workload": "configs[4]: active-sampling scoring, 12 + 32 utterances of 3-10 s per GPU, n_fft=400 hop=160, per-utterance "
                         "gradient embeddings of LinearResidual(201) under the spectral SISDR objective + cosine matching",
             "metric": "scored audio-sec/sec", "value": t.item() / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "scaling": "weak", "parameters": int(grads.shape[1]), "launch": "eager (10 library launches per scoring call)",
@@ -607,7 +650,8 @@ def main():
                            "launch": ("eager" if args.eager else "cuda-graph replay") + f", {args.streams} step(s) in flight (streams)",
                            "l2": f"inputs rotate over {args.ring} distinct device batches ({args.ring * N_UTT * 3 * T * 4 / 1e6:.0f} MB > 126 MB L2); no explicit flush",
                            "parallelism": f"dp{world} (utterance-sharded, no data-path collective; metric sums accumulate on the device, one all-reduce per pass)",
-                           "timing": "ranks aligned by a collective on the stream before the first event; max over ranks"},
+                           "timing": "ranks aligned by a collective on the stream before the first event; max over ranks",
+                           "numa": f"rank 0 bound to NUMA node {ctx.numa_node}" if ctx.numa_node is not None else "no NUMA binding"},
                 "e2e": e2e, "e2e_pcm16": e2e_pcm16, "e2e_wav_out": e2e_wav,
                 "gpu_launches": engine.launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "check": {"mean_sisdr_db": mean_sisdr, "mean_loss": mean_loss,

@@ -455,8 +455,14 @@ __global__ void __launch_bounds__(K1Cfg<Geo>::WARPS * 32, K1Cfg<Geo>::MIN_BLOCKS
 
 // ------------------------------------------------------------------ K3
 template <class Geo> struct K3Cfg;
-template <> struct K3Cfg<Geo1024> { static constexpr int WARPS = 4, MIN_BLOCKS = 2; };
-template <> struct K3Cfg<Geo400>  { static constexpr int WARPS = 4, MIN_BLOCKS = 2; };
+#ifndef SE_GEO_K3_WARPS
+#define SE_GEO_K3_WARPS 4
+#endif
+#ifndef SE_GEO_K3_MINB
+#define SE_GEO_K3_MINB 2
+#endif
+template <> struct K3Cfg<Geo1024> { static constexpr int WARPS = SE_GEO_K3_WARPS, MIN_BLOCKS = SE_GEO_K3_MINB; };
+template <> struct K3Cfg<Geo400>  { static constexpr int WARPS = SE_GEO_K3_WARPS, MIN_BLOCKS = SE_GEO_K3_MINB; };
 template <class Geo> struct K3Sz {
     using S = Sz<Geo>;
     static constexpr int RING_BYTES = S::RB * S::Bs * 4;

@@ -27,6 +27,35 @@ def init_from_env(backend=None):
     return world()
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (and the pinned host buffers it allocates afterwards: first touch) to the CPUs of the NUMA node the
+    GPU hangs off.  With one process per GPU on an 8-GPU box the host-to-device copies of every rank then come from local
+    memory instead of crossing the inter-socket link (round 1: the e2e feed of 8 ranks reached 0.47 of linear).
+    Returns the node number, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(int(device_index))).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                        # 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_bounds(n_utt, rank, world_size):
     """Contiguous split of the batch dimension: rank r owns [lo, hi)."""
     base, rem = divmod(n_utt, world_size)

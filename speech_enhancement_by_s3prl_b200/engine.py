@@ -21,13 +21,17 @@ from . import _lib, dp, ops
 
 
 class EnhancementEngine:
-    def __init__(self, preprocessor, head, log_features=True, precision=0):
+    def __init__(self, preprocessor, head, log_features=True, precision=0, feat_cfg=None):
         """preprocessor: se_b200 OnlinePreprocessor (gives n_fft / hop / window, channel_inp/tar);
-        head: se_b200 LinearResidual on the (log-)power spectrum of the input channel."""
+        head: se_b200 LinearResidual on the (log-)power spectrum of the input channel.
+        feat_cfg: a preprocessor feature config (``get_feat_config``) for the head's input instead of the (log-)power
+        spectrum -- e.g. the baseline feature of config/pseudo_noise.yaml:10-15, mel + log + delta 2 (120-d); the training
+        step then takes the autograd route through the custom ops (the fused routes are for spectrum-in / spectrum-out heads)."""
         self.pre = preprocessor
         self.head = head
         self.log_features = bool(log_features)
         self.precision = precision
+        self.feat_cfg = feat_cfg
         self.n_fft = preprocessor._win_args["n_fft"]
         self.hop = preprocessor._win_args["hop_length"]
         self.ch_inp = int(getattr(preprocessor, "channel_inp", 0))
@@ -171,7 +175,7 @@ class EnhancementEngine:
         """True if train_step can take the fused route: LinearResidual on the (log-)power spectrum with the SISDR
         objective, tensor-core head, shapes inside the TMA head's / the split-K backward's range."""
         from . import model, objective as obj
-        if not self.fused_training or self.precision != 1 or type(objective) is not obj.SISDR:
+        if not self.fused_training or self.precision != 1 or type(objective) is not obj.SISDR or self.feat_cfg is not None:
             return False
         if type(self.head) is not model.LinearResidual:
             return False
@@ -246,7 +250,7 @@ class EnhancementEngine:
             self._clip_and_step(optimizer, grad_clip)
             return loss
         c = self.pre.get_feat_config
-        feat_cfg = c("linear", self.ch_inp, log=self.log_features)
+        feat_cfg = self.feat_cfg or c("linear", self.ch_inp, log=self.log_features)
         feats, linear_inp, linear_tar = self.pre(wavs, [feat_cfg, c("linear", self.ch_inp), c("linear", self.ch_tar)])
         predicted, extra = self.head(features=feats, linears=linear_inp)
         frames = lengths // self.hop + 1
@@ -303,7 +307,7 @@ class EnhancementEngine:
             self._clip_and_step(optimizer, grad_clip)
             return loss
         c = self.pre.get_feat_config
-        feat_cfg = c("linear", self.ch_inp, log=self.log_features)
+        feat_cfg = self.feat_cfg or c("linear", self.ch_inp, log=self.log_features)
         feats, linear_inp, linear_tar = self.pre(wavs, [feat_cfg, c("linear", self.ch_inp), c("linear", self.ch_tar)])
         predicted, extra = self.head(features=feats, linears=linear_inp)
         frames = lengths // self.hop + 1

@@ -511,6 +511,39 @@ def test_pseudo_noise_config_end_to_end_matches_oracle_autograd(se, precision):
         np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=5e-2, atol=(2e-3 if precision == 0 else 2e-2) * want.abs().max().item())
 
 
+def test_engine_training_step_with_a_feature_config(se):
+    """EnhancementEngine(feat_cfg=...): the training step on the pseudo_noise.yaml baseline feature (mel + log + delta 2)
+    equals the hand-written chain on the drop-in modules, eagerly and replayed from a CUDA graph with ClipAdam."""
+    _, mine = make_pair(se, 400)
+    lengths, wavs = synth(4, 8000, seed=3, lengths=torch.LongTensor([8000, 6000, 4321, 7999]))
+    lengths, wavs = lengths.cuda(), wavs.cuda()
+    c = mine.get_feat_config
+    cfg = c("mel", 0, log=True, delta=2)
+    torch.manual_seed(5)
+    head = se.LinearResidual(input_size=120, output_size=201, precision=1).cuda()
+    eng = se.EnhancementEngine(mine, head, precision=1, feat_cfg=cfg)
+    assert not eng.fused_training_supported(se.SISDR(), 4, 8000)
+    loss = eng.train_step(lengths, wavs, se.SISDR())
+    loss.backward()
+    g_eng = head.linear.weight.grad.clone()
+    head.zero_grad()
+    feats, lin_i, lin_t = mine(wavs, [cfg, c("linear", 0), c("linear", 1)])
+    predicted, extra = head(features=feats, linears=lin_i)
+    ref, _ = se.SISDR()(predicted=predicted, linear_tar=lin_t, stft_lengths=lengths // 160 + 1, **extra)
+    ref.backward()
+    assert loss.item() == pytest.approx(ref.item(), abs=1e-6) and torch.equal(g_eng, head.linear.weight.grad)
+    del loss, ref, predicted, extra, feats                  # (eager autograd graphs hold default-stream nodes: drop them before capturing)
+    torch.manual_seed(5)
+    head_g = se.LinearResidual(input_size=120, output_size=201, precision=1).cuda()
+    eng_g = se.EnhancementEngine(mine, head_g, precision=1, feat_cfg=cfg)
+    w0 = head_g.linear.weight.detach().clone()
+    opt = se.ClipAdam(head_g.parameters(), lr=1e-3)
+    for _ in range(5):
+        out = eng_g.train_step_graph(lengths, wavs, se.SISDR(), opt, 1.0)
+    torch.cuda.synchronize()
+    assert opt.steps_taken() == [8] and torch.isfinite(out).all() and not torch.equal(w0, head_g.linear.weight.detach())
+
+
 # ------------------------------------------------------------------------------ fast paths vs generic tile kernels
 @pytest.mark.parametrize("T,hop_ms", [(16000, 16), (16001, 16), (12345, 16), (700, 16), (16000, 10), (9999, 8)])
 def test_fast512_stft_equals_generic_path(se, T, hop_ms):
