@@ -31,7 +31,11 @@ def _worker(rank, world_size, port, ret):
     for p in lin.parameters():
         p.grad = torch.full_like(p, float(rank + 1))
     dp.allreduce_gradients(lin.parameters())
-    ret[rank] = (ml.item(), mm.item(), n, l1.item(), lin.weight.grad[0, 0].item())
+    # running sums of an evaluation pass as se_finalize_metrics_acc keeps them: [sum loss, sum metric, utterances]
+    acc = torch.tensor([float(loss[lo:hi].double().sum()), float(metric[lo:hi].double().sum()), float(hi - lo)], dtype=torch.float64)
+    al, am, an = dp.means_from_acc(acc)
+    assert acc[2].item() == hi - lo                         # the accumulator itself is left untouched
+    ret[rank] = (ml.item(), mm.item(), n, l1.item(), lin.weight.grad[0, 0].item(), al.item(), am.item(), an.item())
     dist.destroy_process_group()
 
 
@@ -46,7 +50,8 @@ def test_two_rank_reductions_match_single_process():
     loss = torch.randn(7, generator=g)
     metric = torch.randn(7, generator=g) * 10
     for r in range(world_size):
-        ml, mm, n, l1, g00 = ret[r]
+        ml, mm, n, l1, g00, al, am, an = ret[r]
+        assert an == 7 and al == pytest.approx(ml, abs=1e-12) and am == pytest.approx(mm, abs=1e-12)
         assert n == 7
         assert ml == pytest.approx(loss.double().mean().item(), abs=1e-12)
         assert mm == pytest.approx(metric.double().mean().item(), abs=1e-12)
