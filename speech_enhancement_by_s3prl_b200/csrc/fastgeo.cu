@@ -794,7 +794,7 @@ template <class Geo> int launch_mask_istft_geo(const MaskIstftArgs& a, cudaStrea
     constexpr int WARPS = K3Cfg<Geo>::WARPS, GROUPS = K3Sz<Geo>::GROUPS;
     // emit windows E_MIN .. F - 1 + NV of every utterance are cut into runs_per_utt near-equal runs.  Small batches: as many
     // runs as there are resident lane groups (one balanced wave), but runs of at least 4 x halo windows (every run recomputes
-    // `halo` frames); large batches: runs of about 32 windows.
+    // `halo` frames); large batches: runs of about 64 windows.
     const int per_utt = a.n_frames - 1 + S::NV - S::E_MIN + 1;
     const long long slots = resident_groups<Geo>(WARPS, K3Cfg<Geo>::MIN_BLOCKS);
     static int forced = -1;
@@ -805,7 +805,7 @@ template <class Geo> int launch_mask_istft_geo(const MaskIstftArgs& a, cudaStrea
         rpu = slots / a.n_utt;
         const long long cap = per_utt / (4 * S::HALO);
         if (rpu > cap) rpu = cap;
-    } else rpu = (per_utt + 31) / 32;
+    } else rpu = (per_utt + 63) / 64;                                 // (every run recomputes `halo` frames: 64 beats 32 by 3 % at 128 x 60 s)
     if (rpu < 1) rpu = 1;
     if (rpu > per_utt) rpu = per_utt;
     GeoRunPlan plan;

@@ -45,7 +45,8 @@ constexpr int kStatLd = kMaxKB * BK;                           // 544: features 
 constexpr int kOffScale = 0;
 constexpr int kOffShift = kOffScale + 2 * kStatLd * 4;
 constexpr int kOffBias = kOffShift + 2 * kStatLd * 4;
-constexpr int kOffBar = kOffBias + kStatLd * 4;
+constexpr int kOffExtra = kOffBias + kStatLd * 4;              // [BM] the "+1" output column of a 256 + 1 slab (SIMT dot products)
+constexpr int kOffBar = kOffExtra + BM * 4;
 constexpr int kNumBars = 3 * kMaxStages + 1;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kOffRing = (kOffTmem + 16 + 1023) / 1024 * 1024;
@@ -145,6 +146,8 @@ struct Head2Args {
     int stages, stage_bytes;   // ring depth (2 or 4) and bytes per stage (A k-block + this launch's weight k-block, 1024-aligned)
     int tmem_cols;             // tensor-memory columns allocated per CTA (256: two CTAs per SM; 512: one)
     int direct_out;            // epilogue stores registers straight to global memory (no staging tile: 2-stage rings are too small)
+    const float* w_extra;      // 256 m + 1 output columns (K = 257, 513) as m slabs of 256 tensor-core columns: the last column's
+    long long ldw;             //   weight row (its dot products run in the CMVN warps while they normalise the A tile), or null
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
 };
 
@@ -156,6 +159,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     float* s_scale = reinterpret_cast<float*>(smem + kOffScale);
     float* s_shift = reinterpret_cast<float*>(smem + kOffShift);
     float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+    float* s_extra = reinterpret_cast<float*>(smem + kOffExtra);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
     const uint32_t bar_full = sbase + kOffBar;                         // [stages] TMA landed the stage's A and W k-block
     const uint32_t bar_norm = bar_full + 8 * kMaxStages;               // [stages] A k-block normalised in place
@@ -288,8 +292,14 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
         if (t == 0) trace.mark(12);
 
+        // the "+1" column (last slab only): every thread owns one 4-float chunk of four rows per k-block
+        const bool has_extra = a.w_extra != nullptr && blockIdx.y == gridDim.y - 1;
+        const int cx = (t & 7) ^ ((t >> 3) & 7);                          // logical chunk of this thread's four rows
+        float dot[4] = {0.f, 0.f, 0.f, 0.f};
         for (int kb = 0; kb < a.kblocks; ++kb) {
             const int s = kb % kStages;
+            float4 wx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_extra && kb * BK + 4 * cx + 4 <= (int)a.ldw) wx = __ldg(reinterpret_cast<const float4*>(a.w_extra + kb * BK + 4 * cx));
             mbar_wait(bar_full + 8 * s, (kb / kStages) & 1);
             if (t == 0 && kb == 0) trace.mark(13);
             float4* tile = reinterpret_cast<float4*>(smem + kOffRing + s * kStageBytes);
@@ -308,11 +318,23 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     v.z = to_tf32(fmaf(v.z, sc.z, sh.z));
                     v.w = to_tf32(fmaf(v.w, sc.w, sh.w));
                     tile[idx] = v;
+                    if (has_extra) dot[i] = fmaf(v.x, wx.x, fmaf(v.y, wx.y, fmaf(v.z, wx.z, fmaf(v.w, wx.w, dot[i]))));
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_norm + 8 * s);
+        }
+        if (has_extra) {                                                   // the 8 lanes that share a row add up their chunks
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float d = dot[i];
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                if ((t & 7) == 0) s_extra[(t >> 3) + 32 * i] = d;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
         }
 
         // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31, column half (w >> 2)
@@ -389,6 +411,15 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 emit(acc1, c0 + 16);
                 tmem_ld_wait();
             }
+        }
+        if (has_extra && half == 0 && row_ok) {                             // column Dout - 1 of this row
+            float z = fmaf(s_extra[row], zscale, (a.bias ? zscale * __ldg(a.bias + a.Dout - 1) : 0.f));
+            if (act == SE_ACT_SIGMOID) {
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(z) : "f"(z));
+                z += 1.0f;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(z) : "f"(z));
+            } else if (act == SE_ACT_RELU) z = fmaxf(z, 0.0f);
+            a.out[(r0 + row) * a.ld_out + a.Dout - 1] = z;
         }
         if (!a.direct_out) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -497,19 +528,28 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     // Launch shape (see the shared-memory comment at the top): ONE CTA per SM with the deep ring (bulk stores from a staging
     // tile for a single slab, direct stores for the two <= 272-column slabs of K = 513), or TWO CTAs per SM when the slab
     // fits 256 tensor-memory columns and the tiles outnumber the SMs.
-    // measured on B200 (tools/time_head_fused.py): two CTAs per SM win when no extra slab is needed (K = 201: 25.7 -> 21.0 us
-    // for 64 x 401 rows); splitting 272 columns into 2 x 136 or 528 into 3 x 176 to get there re-reads every A tile once
-    // more and loses (K = 257: 17.5 -> 20.0 us, K = 513: 45.3 -> 52.9 us)
-    const bool dual = a.w_rows <= 256 && tiles128 > sms;
+    // Two CTAs per SM need slabs of <= 256 tensor-memory columns.  K = 2^k + 1 (257, 513: every power-of-two n_fft) is cut into
+    // slabs of 256 tensor-core columns plus ONE column of SIMT dot products in the CMVN warps, so it gets there without an extra
+    // slab (cutting 272 into 2 x 136 or 528 into 3 x 176 re-reads every A tile once more and loses: measured 17.5 -> 20.0 us
+    // and 45.3 -> 52.9 us, tools/time_head_fused.py).  Used when the tiles of the one-CTA shape outnumber the SMs.
+    const bool plus_one = D_out > 256 && (D_out - 1) % 256 == 0;
+    const int single_split = (a.w_rows + kMaxWRows - 1) / kMaxWRows;
+    const bool fits256 = a.w_rows <= 256 || plus_one;
+    const bool dual = fits256 && tiles128 * single_split > sms;
     int n_split = 1;
     long long slots = sms;
+    a.w_extra = nullptr; a.ldw = ldw;
     if (dual) {
-        n_split = (a.w_rows + 255) / 256;
+        if (plus_one) {
+            n_split = (int)((D_out - 1) / 256);
+            a.w_rows = 256 * n_split;                                       // tensor-core columns; column D_out - 1 is the SIMT one
+            a.w_extra = W + (D_out - 1) * ldw;
+        }
         slots = 2LL * sms;
         a.stages = 2; a.tmem_cols = 256;
         a.direct_out = (ld_out % 4 == 0 && aligned16(offset_out)) ? 2 : 1;
     } else {
-        n_split = (a.w_rows + kMaxWRows - 1) / kMaxWRows;       // <= 2 slabs of <= 272 columns
+        n_split = single_split;                                             // <= 2 slabs of <= 272 columns
         a.stages = kMaxStages; a.tmem_cols = 512;
         a.direct_out = n_split > 1 ? ((ld_out % 4 == 0 && aligned16(offset_out)) ? 2 : 1) : 0;
     }

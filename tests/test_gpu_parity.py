@@ -740,7 +740,9 @@ def test_stft_features_and_cmvn_sums(se, n_fft, B, T, logp):
                                                    (2, 128, 120, 201, "Identity", True), (64, 251, 257, 257, "Sigmoid", True),
                                                    (1, 9, 257, 257, "Sigmoid", True), (700, 40, 129, 129, "Sigmoid", True),
                                                    (2, 77, 513, 513, "Sigmoid", True), (64, 251, 513, 513, "Sigmoid", True),
-                                                   (3, 40, 513, 300, "ReLU", False), (2, 33, 120, 513, "Identity", True)])
+                                                   (3, 40, 513, 300, "ReLU", False), (2, 33, 120, 513, "Identity", True),
+                                                   (96, 251, 257, 257, "Sigmoid", True), (40, 777, 257, 257, "ReLU", True),
+                                                   (30, 1001, 201, 201, "Sigmoid", True), (9, 3751, 513, 513, "Sigmoid", True)])
 def test_tma_head_matches_fp32_head(se, B, F, Din, Dout, act, cmvn):
     from speech_enhancement_by_s3prl_b200 import ops
     g = torch.Generator().manual_seed(Din + F)
