@@ -386,8 +386,11 @@ __host__ __device__ __forceinline__ void run_bounds(int ri, int bpu, int rpu, in
 
 struct RunPlan { int blocks_per_utt; int runs_per_utt; long long total_runs; };   // run ri: bpu/rpu blocks, the first bpu%rpu runs one more
 
+// resident warps per SM = 4 x SE_K3_MIN_BLOCKS.  2 (8 warps, 255-register cap: no spills, runs of 6.8 blocks at 64 x 4 s so the
+// halo frame is 15 % instead of 22 %) beats 3 (12 warps, 168 registers): K3 alone 38.2 vs 41.1 us, two steps in flight 67.2 vs
+// 68.1 us per step (round 2, tools/sweep_lib.sh)
 #ifndef SE_K3_MIN_BLOCKS
-#define SE_K3_MIN_BLOCKS 3
+#define SE_K3_MIN_BLOCKS 2
 #endif
 constexpr int kMaskFloats3 = 272;
 // per half-warp: transpose buffer | noisy slots 2 x 256 | clean slots 2 x 256 | mask row

@@ -151,7 +151,10 @@ struct Head2Args {
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+// DUAL = two CTAs per SM: 2-stage ring of `a.stage_bytes` stages, "+1" SIMT column, direct stores; else one CTA per SM with
+// the 4-stage ring of full-size stages (compile-time constants: this is the headline's shape)
+template <bool DUAL>
+__global__ void __launch_bounds__(kThreads, DUAL ? 2 : 1)
 linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Head2Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     secommon::TraceScope trace(a.trace, 2);
@@ -165,7 +168,8 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t bar_norm = bar_full + 8 * kMaxStages;               // [stages] A k-block normalised in place
     const uint32_t bar_empty = bar_norm + 8 * kMaxStages;              // [stages] the MMAs have read the stage
     const uint32_t bar_accum = bar_empty + 8 * kMaxStages;
-    const int kStages = a.stages, kStageBytes = a.stage_bytes;
+    constexpr int kStages = DUAL ? 2 : kMaxStages;
+    const int kStageBytes = DUAL ? a.stage_bytes : kMaxStageBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r0 = (long long)blockIdx.x * a.tile_rows;
@@ -293,7 +297,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (t == 0) trace.mark(12);
 
         // the "+1" column (last slab only): every thread owns one 4-float chunk of four rows per k-block
-        const bool has_extra = a.w_extra != nullptr && blockIdx.y == gridDim.y - 1;
+        const bool has_extra = DUAL && a.w_extra != nullptr && blockIdx.y == gridDim.y - 1;
         const int cx = (t & 7) ^ ((t >> 3) & 7);                          // logical chunk of this thread's four rows
         float dot[4] = {0.f, 0.f, 0.f, 0.f};
         for (int kb = 0; kb < a.kblocks; ++kb) {
@@ -554,7 +558,7 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
         a.direct_out = n_split > 1 ? ((ld_out % 4 == 0 && aligned16(offset_out)) ? 2 : 1) : 0;
     }
     a.cta_cols = ((a.w_rows + n_split - 1) / n_split + 15) / 16 * 16;
-    a.stage_bytes = kATileBytes + (a.cta_cols * BK * 4 + 1023) / 1024 * 1024;
+    a.stage_bytes = dual ? kATileBytes + (a.cta_cols * BK * 4 + 1023) / 1024 * 1024 : kMaxStageBytes;
     // rows per tile: the fewest waves of (tiles x slabs) CTAs over the resident slots, then tiles as even as the waves allow
     const long long waves = (tiles128 * n_split + slots - 1) / slots;
     long long want_tiles = waves * slots / n_split;
@@ -576,7 +580,8 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     if ((rc = make_map(&tmW, W, D_in, D_out, ldw, a.w_box_rows)) != SE_OK) return rc;
     static unsigned long long opted = 0;                       // per device: cudaFuncSetAttribute is not process-wide
     if (secommon::first_use_on_device(opted)) {
-        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOffRing + 2 * (kATileBytes + 256 * BK * 4)));
     }
     cudaLaunchConfig_t cfg{};
     unsigned tiles = (unsigned)((a.R + a.tile_rows - 1) / a.tile_rows);
@@ -589,7 +594,8 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     attr[0].val.programmaticStreamSerializationAllowed = (secommon::pdl_mask() & 1) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, linear_head_fused_kernel, tmA, tmW, a));
+    if (dual) SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, linear_head_fused_kernel<true>, tmA, tmW, a));
+    else SE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, linear_head_fused_kernel<false>, tmA, tmW, a));
     return secommon::check_launch("linear_head_fused_kernel");
 }
 
