@@ -455,14 +455,22 @@ __global__ void __launch_bounds__(K1Cfg<Geo>::WARPS * 32, K1Cfg<Geo>::MIN_BLOCKS
 
 // ------------------------------------------------------------------ K3
 template <class Geo> struct K3Cfg;
-#ifndef SE_GEO_K3_WARPS
-#define SE_GEO_K3_WARPS 4
+// warps per CTA / CTAs per SM the register cap is set for (8 resident warps per SM either way; the occupancy sweeps of round 2
+// -- 12 warps at a 168-register cap lose 30 % to spills -- are in DESIGN.md 4.2)
+#ifndef SE_GEO1024_K3_WARPS
+#define SE_GEO1024_K3_WARPS 4
 #endif
-#ifndef SE_GEO_K3_MINB
-#define SE_GEO_K3_MINB 2
+#ifndef SE_GEO1024_K3_MINB
+#define SE_GEO1024_K3_MINB 2
 #endif
-template <> struct K3Cfg<Geo1024> { static constexpr int WARPS = SE_GEO_K3_WARPS, MIN_BLOCKS = SE_GEO_K3_MINB; };
-template <> struct K3Cfg<Geo400>  { static constexpr int WARPS = SE_GEO_K3_WARPS, MIN_BLOCKS = SE_GEO_K3_MINB; };
+#ifndef SE_GEO400_K3_WARPS
+#define SE_GEO400_K3_WARPS 8                 // one 8-warp CTA per SM: 103.0 vs 104.7 us per 64 x 4 s step (tools/sweep_lib_configs.sh)
+#endif
+#ifndef SE_GEO400_K3_MINB
+#define SE_GEO400_K3_MINB 1
+#endif
+template <> struct K3Cfg<Geo1024> { static constexpr int WARPS = SE_GEO1024_K3_WARPS, MIN_BLOCKS = SE_GEO1024_K3_MINB; };
+template <> struct K3Cfg<Geo400>  { static constexpr int WARPS = SE_GEO400_K3_WARPS, MIN_BLOCKS = SE_GEO400_K3_MINB; };
 template <class Geo> struct K3Sz {
     using S = Sz<Geo>;
     static constexpr int RING_BYTES = S::RB * S::Bs * 4;
