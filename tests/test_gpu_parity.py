@@ -662,6 +662,42 @@ def test_fast_geometries_mask_istft_equals_generic_path(se, n_fft, T, B):
     assert none is None and (wav_n - wav_s).abs().max().item() < 3e-6
 
 
+@pytest.mark.parametrize("n_fft,B,T", [(1024, 1, 960000), (1024, 200, 1100), (1024, 3, 1281), (1024, 2, 1535), (400, 1, 480000),
+                                       (400, 300, 700), (400, 3, 801), (400, 2, 959), (400, 5, 201)])
+def test_fast_geometries_edge_shapes_match_oracle(se, n_fft, B, T):
+    """Edge shapes of the register-resident kernels against the CPU oracle: one long utterance (60 s / 30 s: thousands of
+    runs per utterance), hundreds of tiny ones (every run shorter than its halo; fewer than six frames falls back to the
+    generic path), T just above n_fft/2 (torch.stft's minimum), first / last samples covered by fewer frames than the interior."""
+    from speech_enhancement_by_s3prl_b200 import ops
+    ora, mine = make_pair(se, n_fft)
+    hop = mine._win_args["hop_length"]
+    K = n_fft // 2 + 1
+    g = torch.Generator().manual_seed(n_fft + B + T)
+    wavs = torch.randn(B, 3, T, generator=g) * 0.05
+    lengths = torch.randint(max(n_fft // 2 + 1, T // 2), T + 1, (B,), generator=g)
+    lengths[0] = T
+    for b, n in enumerate(lengths.tolist()):
+        wavs[b, :, n:] = 0
+    c = ora.get_feat_config
+    lin_r, ph_r = ora(wavs[:4], [c("linear", 0), c("phase", 0)])
+    lin = mine(wavs[:4].cuda(), [c("linear", 0)])[0].cpu()
+    assert lin.shape == lin_r.shape == (min(B, 4), T // hop + 1, K)
+    assert rel_to_max(lin, lin_r) < SPEC_RTOL
+    mask = torch.rand(B, T // hop + 1, K, generator=g)
+    wav, sums = ops.mask_istft(wavs.cuda(), 0, 1, mask.cuda(), lengths.cuda(), n_fft, hop, mine._frame_window, pad_to=T)
+    torch.cuda.synchronize()
+    assert wav.shape == (B, T) and torch.isfinite(wav).all() and torch.isfinite(sums).all()
+    ref = ora.istft(lin_r * mask[:4], ph_r)                                  # (4, hop * (F - 1))
+    n_out = ref.shape[1]
+    assert (wav[:4, :n_out].cpu() - ref).abs().max().item() < 5e-6 * max(1.0, ref.abs().max().item() / 0.05)
+    assert wav[:, n_out:].abs().max().item() == 0.0 if n_out < T else True     # zero-padded to T (runner.py:268)
+    for b in range(min(B, 4)):
+        n = int(lengths[b])
+        y, cl = wav[b, :n].double().cpu(), wavs[b, 1, :n].double()
+        np.testing.assert_allclose(sums[b, :3].cpu().numpy(), [float((y * cl).sum()), float((cl * cl).sum()), float((y * y).sum())],
+                                   rtol=2e-4, atol=1e-7)
+
+
 # ------------------------------------------------------------------------------ tensor-core head (tcgen05, TF32)
 @pytest.mark.parametrize("B,F,Din,Dout,act,cmvn", [(3, 101, 257, 257, "Sigmoid", True), (2, 300, 201, 201, "ReLU", False),
                                                    (1, 77, 513, 513, "Sigmoid", True), (2, 128, 120, 201, "Identity", True),
