@@ -111,6 +111,12 @@ int se_mask_istft_strided(const float* noisy, const float* clean, int64_t utt_st
 #define SE_FLAG_MASK_IS_POWER 4    /* se_mask_istft_ex: `mask` holds a TARGET power spectrum P (e.g. the upstream SpecHead's
                                       output, runner.py:272-281): wav_out = istft(P, phase(STFT(noisy))) = iSTFT(sqrt(P) X / |X|),
                                       sqrt(P) where X = 0 -- _decode_wav on a predicted spectrum without materialising the phase */
+#define SE_FLAG_WS_SELF_CLEAN 8     /* the fused step's workspace is ONE caller-owned block of doubles, zeroed once:
+                                      [ stat_sums (n_utt, round4(K), 2) | sums (n_utt, SE_NSUMS) ].  With this flag (and
+                                      SE_FLAG_SUMS_ZEROED) the step's kernels leave it zeroed for the next replay instead of the
+                                      caller filling it every step: se_stft_features zeroes the `sums` part (consumed by the
+                                      previous step's se_finalize_metrics), se_mask_istft_ex zeroes the stat_sums part (consumed
+                                      by this step's head) -- a captured step then has no fill node at its start */
 int se_mask_istft_ex(const float* noisy, const float* clean, int64_t utt_stride, const float* mask, int64_t mask_stride,
                      const int64_t* lengths, int64_t n_utt, int64_t T, int n_fft, int hop, const float* window,
                      float* wav_out, int64_t out_stride, int64_t pad_to, double* sums, int flags, void* stream);

@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(kThreadsRun, 256 / kThreadsRun) stft512_run_ke
     float2* acc = reinterpret_cast<float2*>(mine + M * 8);
     int* s_utt = reinterpret_cast<int*>(smem1 + (size_t)(kWarpsRun * 2) * kHwBytes1);   // utterance of every half-warp's run (-1: none)
     const unsigned hmask = half_mask(lane);
+    if (a.zero_ptr)                                                   // SE_FLAG_WS_SELF_CLEAN: K3's sums of this step
+        for (long long i = (long long)blockIdx.x * kThreadsRun + threadIdx.x; i < a.zero_count; i += (long long)gridDim.x * kThreadsRun)
+            a.zero_ptr[i] = 0.0;
     const long long unit = (long long)blockIdx.x * (kThreadsRun / 16) + hw;
     const bool active = unit < plan.total_runs;
     const int u = active ? (int)(unit / plan.runs_per_utt) : -1;
@@ -440,7 +443,12 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
     float* cb = reinterpret_cast<float*>(mine + M * 8 + kNoisyBytes3);   // clean slots
     float* mb = cb + 2 * H;                                        // mask row
     const long long unit = (long long)blockIdx.x * (kThreads3 / 16) + hw;
-    if (unit >= plan.total_runs) { griddep_wait(); return; }      // no block-level barrier below (tracing: approximate for ragged CTAs)
+    auto zero_ws = [&]() {                                        // SE_FLAG_WS_SELF_CLEAN: the CMVN sums the head has consumed
+        if (a.zero_ptr)
+            for (long long i = (long long)blockIdx.x * kThreads3 + threadIdx.x; i < a.zero_count; i += (long long)gridDim.x * kThreads3)
+                a.zero_ptr[i] = 0.0;
+    };
+    if (unit >= plan.total_runs) { griddep_wait(); zero_ws(); return; }   // no block-level barrier below (tracing: approximate for ragged CTAs)
     const int u = (int)(unit / plan.runs_per_utt), ri = (int)(unit - (long long)u * plan.runs_per_utt);
     const int F = a.n_frames;
     int b0, run_len;
@@ -469,6 +477,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
     // are inputs of the step, so their first loads are issued before waiting for the upstream kernel (the mask's producer).
     const int f0 = b0 - 1;                                        // (its noisy samples were requested at the top: group N)
     griddep_wait();                                               // the mask (and the zeroed sums) come from upstream kernels
+    zero_ws();
     stage_row(mb, mrow0 + (long long)f0 * a.mask_stride, M + 1, j, mask_padded);
     cp_async_commit();
     if (need_clean) {

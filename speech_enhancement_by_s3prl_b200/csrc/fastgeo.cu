@@ -340,6 +340,9 @@ __global__ void __launch_bounds__(K1Cfg<Geo>::WARPS * 32, K1Cfg<Geo>::MIN_BLOCKS
     const int grp = Core<Geo>::group_of(lane), jg = Core<Geo>::lane_in_group(lane);
     unsigned char* region = smem + S::TAB_BYTES + (size_t)warp * K1Sz<Geo>::WARP_BYTES + (size_t)grp * K1Sz<Geo>::GSTRIDE;
     int* s_utt = reinterpret_cast<int*>(smem + S::TAB_BYTES + (size_t)WARPS * K1Sz<Geo>::WARP_BYTES);
+    if (a.zero_ptr)                                                                 // SE_FLAG_WS_SELF_CLEAN: K3's sums of this step
+        for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < a.zero_count; i += (long long)gridDim.x * THREADS)
+            a.zero_ptr[i] = 0.0;
     Core<Geo> core;
     core.init(lane, region, a.tab);
     float2* acc = reinterpret_cast<float2*>(region + Geo::XBUF);
@@ -557,6 +560,9 @@ __global__ void __launch_bounds__(K3Cfg<Geo>::WARPS * 32, K3Cfg<Geo>::MIN_BLOCKS
     float2 yy2 = make_float2(0.0f, 0.0f), yc2 = yy2, cc2 = yy2, st2 = yy2, tt2 = yy2, ss2 = yy2;
 
     griddep_wait();                                                                 // the mask (and the zeroed sums) come from upstream kernels
+    if (a.zero_ptr)                                                                 // SE_FLAG_WS_SELF_CLEAN: the CMVN sums the head has consumed
+        for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < a.zero_count; i += (long long)gridDim.x * THREADS)
+            a.zero_ptr[i] = 0.0;
     if (my_iters > 0 && need_clean) {
 #pragma unroll
         for (int b = 0; b < Geo::NB; ++b) stage_block<Geo>(cring + b * Bs, crow, a.T, (f_first * Geo::HB + b) * Bs - N / 2, jg);

@@ -235,8 +235,11 @@ static int stft_features_impl(const float* wav, int64_t n_utt, int64_t utt_strid
         a.power = take_log ? nullptr : feat; a.logp = take_log ? feat : nullptr; a.log_eps = log_eps; a.spec_stride = feat_stride;
         a.stat_sums = stat_sums; a.ld_stats = ld_stats;
         a.trace = secommon::trace_ptr();
+        if (flags & SE_FLAG_WS_SELF_CLEAN) { a.zero_ptr = stat_sums + 2 * ld_stats * n_utt; a.zero_count = (long long)SE_NSUMS * n_utt; }
         return geo ? sefast::launch_stft_run(a, n_fft, st) : sefast::launch_stft512(a, st);
     }
+    if (flags & SE_FLAG_WS_SELF_CLEAN)                      // no fast path for this geometry: the same contract by a memset
+        SE_CUDA_CHECK(cudaMemsetAsync(stat_sums + 2 * ld_stats * n_utt, 0, sizeof(double) * SE_NSUMS * n_utt, st));
     // other n_fft: generic STFT, then one pass over the features for the sums
     rc = se_stft_strided(wav, n_utt, utt_stride, T, n_fft, hop, window, log_eps, take_log ? nullptr : feat, nullptr,
                          take_log ? feat : nullptr, feat_stride, stream);
@@ -324,8 +327,12 @@ int se_mask_istft_ex(const float* noisy, const float* clean, int64_t utt_stride,
     SE_REQUIRE(out_stride >= a.out_len && out_stride >= pad_to, "out_stride=%lld too small", (long long)out_stride);
     cudaStream_t st = (cudaStream_t)stream;
     if (sums && !(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * SE_NSUMS * n_utt, st));
+    const long long stat_doubles = 2LL * ((n_fft / 2 + 1 + 3) / 4 * 4) * n_utt;         // (n_utt, round4(K), 2) right before `sums`
+    const bool self_clean = (flags & SE_FLAG_WS_SELF_CLEAN) && sums;
+    if (self_clean) { a.zero_ptr = sums - stat_doubles; a.zero_count = stat_doubles; }
     if (n_fft == 512 && hop == 256 && a.n_frames >= 2 && !g_force_generic) return sefast::launch_mask_istft512(a, st);
     if (sefast::geo_supported(n_fft, hop) && a.n_frames >= 6 && !g_force_generic) return sefast::launch_mask_istft_run(a, n_fft, st);
+    if (self_clean) SE_CUDA_CHECK(cudaMemsetAsync(sums - stat_doubles, 0, sizeof(double) * stat_doubles, st));   // generic path: by a memset
     SE_DISPATCH_NFFT(n_fft, launch_mask_istft, a, st)
 }
 

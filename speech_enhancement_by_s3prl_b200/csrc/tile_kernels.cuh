@@ -44,6 +44,8 @@ struct StftArgs {
     double* stat_sums;         // (n_utt, ld_stats, 2) += [sum x, sum x^2] over frames of the feature written, or null
     long long ld_stats;
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
+    double* zero_ptr;          // SE_FLAG_WS_SELF_CLEAN: doubles this kernel zeroes for the step's next replay (or null)
+    long long zero_count;
 };
 
 struct IstftArgs {
@@ -76,6 +78,8 @@ struct MaskIstftArgs {
     int want_spec;             // also accumulate the spectral SI-SDR sums (needs clean)
     long long mask_stride;     // floats between consecutive frames of mask (>= K)
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
+    double* zero_ptr;          // SE_FLAG_WS_SELF_CLEAN: doubles zeroed after the upstream kernel has completed (or null)
+    long long zero_count;
     int mask_is_power;         // `mask` holds the TARGET power spectrum: output = iSTFT(sqrt(mask) e^{i phase(noisy)}) (runner.py:266-281)
 };
 

@@ -41,11 +41,18 @@ class EnhancementEngine:
         self.launches_per_step = 5          # library kernels per eval_step (set by eval_step: 4 on the fused path)
 
     # ------------------------------------------------------------------ device-resident step
-    def eval_step(self, lengths, wavs, want_spec_loss=True, metric_acc=None):
+    def step_workspace(self, B, device):
+        """Persistent, zeroed workspace of one captured evaluation step: [CMVN sums (B, round4(K), 2) | K3 sums (B, 6)] doubles.
+        The step's kernels leave it zeroed for the next replay (SE_FLAG_WS_SELF_CLEAN), so the graph has no fill node."""
+        LD = ops.round4(self.n_fft // 2 + 1)
+        return torch.zeros(B * (2 * LD + ops.NSUMS), device=device, dtype=torch.float64)
+
+    def eval_step(self, lengths, wavs, want_spec_loss=True, metric_acc=None, ws=None):
         """lengths (B,) int64, wavs (B, C, T) fp32, both on the GPU.
         Returns dict(loss_per_utt (B,), sisdr (B,), wav_predicted (B, T), gain (B,)).
         metric_acc: float64 (3,) device tensor += [sum loss, sum SI-SDR, utterances] (the running sums of an evaluation
-        pass, runner.py:587-602; ``dp.means_from_acc`` turns them into the global means with one all-reduce)."""
+        pass, runner.py:587-602; ``dp.means_from_acc`` turns them into the global means with one all-reduce).
+        ws: a ``step_workspace`` that this call may use and must leave zeroed (captured steps); None = a fresh one per call."""
         B, C, T = wavs.shape
         dev = wavs.device
         window = self.pre._frame_window
@@ -65,16 +72,18 @@ class EnhancementEngine:
                 # K1 (+ CMVN sums) -> K2 (TMA + tcgen05 head) -> K3 -> K3': one zeroed workspace, no other memset, so
                 # the four kernels are chained by programmatic dependent launches
                 self.launches_per_step = 4      # K1, K2, K3, K3' (+ torch's fill of the workspace)
-                ws = torch.zeros(B * (2 * LD + ops.NSUMS), device=dev, dtype=torch.float64)
+                self_clean = ws is not None
+                if ws is None:
+                    ws = torch.zeros(B * (2 * LD + ops.NSUMS), device=dev, dtype=torch.float64)
                 stat_sums = ws[:B * 2 * LD].view(B, LD, 2)
                 sums = ws[B * 2 * LD:].view(B, ops.NSUMS)
                 feats, _ = ops.stft_features(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=self.log_features,
-                                             log_eps=self.pre.eps, stat_sums=stat_sums)
+                                             log_eps=self.pre.eps, stat_sums=stat_sums, self_clean=self_clean)
                 mask = ops.linear_head_tma(feats, K, wpad, head.linear.bias, head.activation,
                                              stat_sums if head.cmvn else None, head.eps)
                 wav, sums = ops.mask_istft(wavs, self.ch_inp, self.ch_tar, mask, lengths, self.n_fft, self.hop, window,
                                            pad_to=T, want_sums=True, want_spec=want_spec_loss, mask_padded=True, sums=sums,
-                                           sums_zeroed=True)
+                                           sums_zeroed=True, self_clean=self_clean)
             else:
                 feats = ops.stft_padded(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=self.log_features, log_eps=self.pre.eps)
                 mean = std = None
@@ -121,15 +130,16 @@ class EnhancementEngine:
             self.pre.to(device)
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
+        ws = self.step_workspace(wavs.shape[0], device)          # zeroed once here; every replay leaves it zeroed
         with torch.cuda.stream(side):
             for _ in range(2):                                   # warm up allocator + lazy init outside capture
-                self.eval_step(lengths, wavs)                    # (no metric_acc: warm-up batches are not part of a pass)
+                self.eval_step(lengths, wavs, ws=ws)             # (no metric_acc: warm-up batches are not part of a pass)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.eval_step(lengths, wavs, metric_acc=metric_acc)
-        static = {"lengths": lengths, "wavs": wavs, "graph": graph}
+            out = self.eval_step(lengths, wavs, metric_acc=metric_acc, ws=ws)
+        static = {"lengths": lengths, "wavs": wavs, "graph": graph, "ws": ws}
         static.update(out)
         return static
 

@@ -102,13 +102,15 @@ def stft_padded(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10)
     return out
 
 
-FLAG_WANT_SPEC, FLAG_SUMS_ZEROED, FLAG_MASK_IS_POWER = 1, 2, 4
+FLAG_WANT_SPEC, FLAG_SUMS_ZEROED, FLAG_MASK_IS_POWER, FLAG_WS_SELF_CLEAN = 1, 2, 4, 8
 
 
-def stft_features(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10, stat_sums=None):
+def stft_features(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-10, stat_sums=None, self_clean=False):
     """Fused-step K1: ONE feature tensor (B, F, round4(K)) -- log-power or power -- plus the CMVN sums
     (B, round4(K), 2) float64 = [sum_f x, sum_f x^2].  If ``stat_sums`` is given it must already be zero
-    (the caller zeroed its workspace once for the whole step); otherwise it is allocated and zeroed here."""
+    (the caller zeroed its workspace once for the whole step); otherwise it is allocated and zeroed here.
+    self_clean: ``stat_sums`` is the head of a persistent step workspace ``[stat_sums | K3 sums]`` (SE_FLAG_WS_SELF_CLEAN):
+    this kernel zeroes the K3 sums that follow it, ``mask_istft(self_clean=True)`` zeroes ``stat_sums`` after the head."""
     wavs = _chk(wavs, "wavs")
     B, C, T = wavs.shape
     F, K = T // hop + 1, n_fft // 2 + 1
@@ -116,8 +118,9 @@ def stft_features(wavs, channel, n_fft, hop, window, logpower=True, log_eps=1e-1
     window = _c(window, "window")
     with torch.cuda.device(wavs.device):
         out = torch.empty(B, F, LD, device=wavs.device, dtype=torch.float32)
-        flags = FLAG_SUMS_ZEROED
+        flags = FLAG_SUMS_ZEROED | (FLAG_WS_SELF_CLEAN if self_clean else 0)
         if stat_sums is None:
+            assert not self_clean
             stat_sums = torch.empty(B, LD, 2, device=wavs.device, dtype=torch.float64)
             flags = 0
         assert stat_sums.shape == (B, LD, 2) and stat_sums.dtype == torch.float64 and stat_sums.is_contiguous()
@@ -295,7 +298,7 @@ def istft(power, phase, n_fft, hop, window, pad_to=0):
 
 
 def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, want_sums=True, want_spec=True,
-               out=None, sums=None, mask_padded=False, sums_zeroed=False, mask_is_power=False):
+               out=None, sums=None, mask_padded=False, sums_zeroed=False, mask_is_power=False, self_clean=False):
     """Fused ``istft(linear_inp * mask, phase_inp)`` straight from the noisy waveform.
 
     wavs (B, C, T); mask (B, F, K); lengths (B,) int64 or None.  Returns (wav (B, width), sums (B, 6) float64|None)."""
@@ -316,6 +319,7 @@ def mask_istft(wavs, ch_inp, ch_tar, mask, lengths, n_fft, hop, window, pad_to, 
         clean = None if ch_tar is None else wavs.data_ptr() + 4 * int(ch_tar) * T
         flags = (FLAG_WANT_SPEC if want_spec else 0) | (FLAG_SUMS_ZEROED if sums_zeroed else 0)
         flags |= FLAG_MASK_IS_POWER if mask_is_power else 0     # `mask` = target power; output keeps the noisy phase
+        flags |= FLAG_WS_SELF_CLEAN if self_clean else 0        # `sums` is the tail of a persistent step workspace (see stft_features)
         rc = _lib.load().se_mask_istft_ex(wavs.data_ptr() + 4 * int(ch_inp) * T, clean, C * T, mask.data_ptr(), mask_stride,
                                           _p(lengths), B, T, n_fft, hop, window.data_ptr(), out.data_ptr(), out.stride(0),
                                           int(pad_to), _p(sums) if want_sums else None, flags, _stream())
