@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kThreads3, SE_K3_MIN_BLOCKS * 4 / kWarps3) mas
     const float* nrow = a.noisy + (long long)u * a.utt_stride;
     const float* crow = a.clean ? a.clean + (long long)u * a.utt_stride : nullptr;
     float* orow = a.wav_out + (long long)u * a.out_stride;
-    const int len = a.lengths ? (int)a.lengths[u] : a.T;
+    const int len = a.lengths ? (int)min((long long)a.T, max(0LL, a.lengths[u])) : a.T;   // (a length beyond the padded row would read past it)
     const int valid_frames = min(F, len / H + 1);                  // runner.py:455
     const bool spec = a.want_spec && crow && a.sums;
     const bool need_clean = crow && a.sums;

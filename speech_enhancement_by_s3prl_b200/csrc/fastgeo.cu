@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(K3Cfg<Geo>::WARPS * 32, K3Cfg<Geo>::MIN_BLOCKS
     const int n_iter = __reduce_max_sync(kFull, my_iters);
     const float* crow = a.clean ? a.clean + (long long)u * a.utt_stride : nullptr;
     float* orow = a.wav_out + (long long)u * a.out_stride;
-    const int len = a.lengths ? (int)a.lengths[active ? u : 0] : a.T;
+    const int len = a.lengths ? (int)min((long long)a.T, max(0LL, a.lengths[active ? u : 0])) : a.T;   // clamped to the padded row
     const int valid_frames = min(F, len / H + 1);                                   // runner.py:455
     const bool spec = a.want_spec && crow && a.sums;
     const bool need_clean = crow && a.sums;

@@ -303,7 +303,8 @@ SE_HD void mask_istft_tile(Exec& ex, const MaskIstftArgs& a, int utt, int tile, 
     float* orow = a.wav_out + (long long)utt * a.out_stride;
     const float* nrow = a.noisy + (long long)utt * a.utt_stride;
     const float* crow = a.clean ? a.clean + (long long)utt * a.utt_stride : nullptr;
-    const int len = a.lengths ? (int)a.lengths[utt] : a.T;
+    const long long len_raw = a.lengths ? a.lengths[utt] : (long long)a.T;
+    const int len = (int)(len_raw < 0 ? 0 : (len_raw > a.T ? a.T : len_raw));          // clamped to the padded row
     int f_lo, f_hi;
     covering_frames(t_lo + N / 2, imin(t_hi, a.out_len) + N / 2, N, a.hop, a.n_frames, f_lo, f_hi);
     const bool spec = a.want_spec && crow && a.sums;

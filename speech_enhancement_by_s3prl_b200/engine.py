@@ -71,7 +71,7 @@ class EnhancementEngine:
             if self.precision == 1 and ops.linear_head_tma_supported(B, F, K, Dout, LD, wpad.shape[1], ops.round4(Dout)):
                 # K1 (+ CMVN sums) -> K2 (TMA + tcgen05 head) -> K3 -> K3': one zeroed workspace, no other memset, so
                 # the four kernels are chained by programmatic dependent launches
-                self.launches_per_step = 4      # K1, K2, K3, K3' (+ torch's fill of the workspace)
+                self.launches_per_step = 4      # K1, K2, K3, K3' (+ torch's fill of the workspace unless `ws` is given)
                 self_clean = ws is not None
                 if ws is None:
                     ws = torch.zeros(B * (2 * LD + ops.NSUMS), device=dev, dtype=torch.float64)
