@@ -401,7 +401,7 @@ def bench_training(ctx, se, args):
            "step_algorithmic_bytes": int(step_bytes), "step_frac_of_hbm_peak": step_bytes / (ms * 1e-3) / 1e9 / ctx.peak,
            "check": {"loss": float(st["loss"]), "steps_taken": opt.steps_taken()[0], "steps_skipped": opt.steps_skipped()[0]}}
     # the same step with the baseline feature of config/pseudo_noise.yaml:10-15 -- mel + log + delta 2 (120-d, fused K1b kernel)
-    # -- into LinearResidual(120 -> K): autograd route through the custom ops, also captured with its all-reduce
+    # -- into LinearResidual(120 -> K): the fused route with the K1b kernel in front of the head, also captured with its all-reduce
     torch.manual_seed(1337)
     head2 = se.LinearResidual(input_size=120, output_size=K, precision=1).to(ctx.dev)
     eng2 = se.EnhancementEngine(pre, head2, precision=1, feat_cfg=pre.get_feat_config("mel", 0, log=True, delta=2))
@@ -416,7 +416,8 @@ def bench_training(ctx, se, args):
         if ctx.world > 1:
             ctx.dist.all_reduce(ctx.align)
     ms2 = ctx.timed(run2) / steps
-    out["mel_log_delta2"] = {"workload": f"mel(40) + log + delta 2 (120-d) -> LinearResidual(120, {K}) + SISDR, autograd route, one CUDA graph",
+    out["mel_log_delta2"] = {"workload": f"mel(40) + log + delta 2 (120-d, fused K1b kernel) -> LinearResidual(120, {K}) + SISDR, "
+                                         f"{'fused route (no autograd graph)' if eng2.fused_training_supported(crit, B, wavs.shape[2]) else 'autograd route'}, one CUDA graph",
                              "value": t.item() / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "loss": float(st2["loss"].detach())}
     return out
 

@@ -318,10 +318,12 @@ int se_delta(float* x, int64_t n_utt, int64_t n_frames, int64_t D, int order, vo
  * "mel, log, delta 2"): out (n_utt, n_frames, ld_out) columns [0, (order+1) n_mels) = [mel | delta | delta-delta] of
  * log?(power fb (+eps)), deltas as se_delta (order <= 2, n_mels <= 64).  stat_sums (n_utt, (order+1) n_mels, 2) doubles or
  * NULL: zeroed here, then [sum_f x, sum_f x^2] per column -- what se_cmvn_apply_sums turns into the CMVN
- * x = (x - mean) / (unbiased std + eps) in place. */
+ * x = (x - mean) / (unbiased std + eps) in place.  fb_ranges (n_mels, 2) int32 device array or NULL: [first bin, last bin + 1)
+ * where filter m is non-zero -- the triangular filters are sparse, so the projection costs ~2 K instead of 40 K
+ * multiply-adds per frame (NULL: dense). */
 int se_mel_features(const float* power, int64_t ld_power, int64_t n_utt, int64_t n_frames, int64_t K, const float* fb,
-                    int64_t n_mels, int take_log, float eps, int order, float* out, int64_t ld_out, double* stat_sums,
-                    void* stream);
+                    const int32_t* fb_ranges, int64_t n_mels, int take_log, float eps, int order, float* out, int64_t ld_out,
+                    double* stat_sums, void* stream);
 int se_cmvn_apply_sums(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const double* sums, float eps, void* stream);
 int se_cmvn_apply(float* x, int64_t n_utt, int64_t n_frames, int64_t D, const float* mean, const float* std,
                   float eps, void* stream);

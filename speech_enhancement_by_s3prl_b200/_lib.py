@@ -65,7 +65,7 @@ _SIGNATURES = {
     "se_linear_head_bwd_tc": [c_f, i64, c_f, c_f, i64, c_float, c_f, c_f, i64, i64, i64, i64, i64, c_int, c_f, i64, c_f, c_f, c_f],
     "se_mel": [c_f, i64, i64, c_f, i64, c_int, c_float, c_f, i64, c_f],
     "se_delta": [c_f, i64, i64, i64, c_int, c_f],
-    "se_mel_features": [c_f, i64, i64, i64, i64, c_f, i64, c_int, c_float, c_int, c_f, i64, c_f, c_f],
+    "se_mel_features": [c_f, i64, i64, i64, i64, c_f, c_f, i64, c_int, c_float, c_int, c_f, i64, c_f, c_f],
     "se_cmvn_apply_sums": [c_f, i64, i64, i64, c_f, c_float, c_f],
     "se_cmvn_apply": [c_f, i64, i64, i64, c_f, c_f, c_float, c_f],
     "se_h2d_channels": [c_f, i64, i64, i64, i64, c_f, c_f],

