@@ -68,7 +68,23 @@ class EnhancementEngine:
             F = T // self.hop + 1
             wpad = self._padded_weight()
             Dout = wpad.shape[0]
-            if self.precision == 1 and ops.linear_head_tma_supported(B, F, K, Dout, LD, wpad.shape[1], ops.round4(Dout)):
+            D = self._mel_feature_dim() if self.feat_cfg is not None else K
+            if self.feat_cfg is not None:
+                # head input = a mel feature config (e.g. pseudo_noise.yaml:10-15) built by the fused K1b kernel from the
+                # power spectrum; the mask still applies to the K bins of the noisy spectrum
+                if D is None or D % 4 or Dout != K or not ops.linear_head_tma_supported(B, F, D, K, D, wpad.shape[1], LD):
+                    raise RuntimeError("EnhancementEngine.eval_step: feat_cfg must be a mel config (log / delta <= 2, no CMVN of its "
+                                       "own) feeding a LinearResidual(D, K) head with the tensor-core path (precision=1)")
+                cfg = self.feat_cfg
+                self.launches_per_step = 7      # K1, K1b, sums (+ its zero fill), K2, K3, K3'
+                power = ops.stft_padded(wavs, self.ch_inp, self.n_fft, self.hop, window, logpower=False)
+                feats = ops.mel_features(power, self.pre._tables(dev)[1], bool(cfg.get("log", False)), self.pre.eps,
+                                         order=int(cfg.get("delta", 0)), K=K)
+                stat_sums = ops.feature_sums(feats, D) if head.cmvn else None
+                mask = ops.linear_head_tma(feats, D, wpad, head.linear.bias, head.activation, stat_sums, head.eps)
+                wav, sums = ops.mask_istft(wavs, self.ch_inp, self.ch_tar, mask, lengths, self.n_fft, self.hop, window,
+                                           pad_to=T, want_sums=True, want_spec=want_spec_loss, mask_padded=True)
+            elif self.precision == 1 and ops.linear_head_tma_supported(B, F, K, Dout, LD, wpad.shape[1], ops.round4(Dout)):
                 # K1 (+ CMVN sums) -> K2 (TMA + tcgen05 head) -> K3 -> K3': one zeroed workspace, no other memset, so
                 # the four kernels are chained by programmatic dependent launches
                 self.launches_per_step = 4      # K1, K2, K3, K3' (+ torch's fill of the workspace unless `ws` is given)

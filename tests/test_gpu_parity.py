@@ -545,6 +545,15 @@ def test_engine_training_step_with_a_feature_config(se):
     for got, want in ((head.linear.weight.grad, g_w), (head.linear.bias.grad, g_b)):
         assert torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item() > 0.99999
         assert (got - want).abs().max().item() < 2e-3 * want.abs().max().item()
+    # evaluation step on the same feature config: the hand-written chain on the drop-in modules gives the same metrics
+    with torch.no_grad():
+        out = eng.eval_step(lengths, wavs)
+        feats, lin_i, ph_i = mine(wavs, [cfg, c("linear", 0), c("phase", 0)])
+        predicted, _ = head(features=feats, linears=lin_i)
+        wav_ref = se.decode_wav(mine, predicted, ph_i, lengths)            # (level differs: SI-SDR is scale-invariant)
+    for b in range(4):
+        n = int(lengths[b])
+        assert abs(sp.sisdr_eval(wav_ref[b, :n].cpu(), wavs[b, 1, :n].cpu()) - out["sisdr"][b].item()) < 0.02
     torch.manual_seed(5)
     head_g = se.LinearResidual(input_size=120, output_size=201, precision=1).cuda()
     eng_g = se.EnhancementEngine(mine, head_g, precision=1, feat_cfg=cfg)
