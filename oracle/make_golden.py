@@ -15,6 +15,10 @@ TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.
   projection included), so the drop-in heads' projection + multiply / exp -- forward, weight gradient and the input
   gradient that reaches the LSTM -- are pinned by the reference itself.
   (``python -m oracle.make_golden recurrent`` regenerates this file alone.)
+* ``scoring_ref.npz`` -- the reference's own ``sampler.scoring()`` (sampler.py:59-110) and ``sampler.matching()``
+  (sampler.py:113-116) driven with the restated preprocessor, the reference ``model.LSTM`` and ``objective.L1`` -- the
+  combination ``run_active.sh`` names -- on a small ragged batch: per-utterance gradient embeddings over ALL parameters,
+  the batch-mean embedding, and the match scores.  (``python -m oracle.make_golden scoring`` regenerates this file alone.)
 * ``preprocessor_oracle.npz`` -- outputs of ``oracle/preprocessor.py``
   (torch.stft / torch.istft based) for small inputs; guards against drift of the
   oracle itself across torch versions (this one is NOT a reference output).
@@ -207,6 +211,35 @@ def make_recurrent_heads(ref):
     return out
 
 
+def make_scoring(ref):
+    """sampler.scoring / matching of the unmodified reference (LSTM head + L1 objective, --from_rawfeature)."""
+    g = torch.Generator().manual_seed(777)
+    pre = OnlinePreprocessor(sample_rate=16000, win_ms=25, hop_ms=10, n_freq=201, n_mels=40, n_mfcc=13)
+    c = pre.get_feat_config
+    pre.feat_list = [c("linear", 0, log=True), c("linear", 0, log=True), c("linear", 0), c("phase", 0), c("linear", 1), c("phase", 1)]
+    pre.channel_inp, pre.channel_tar = 0, 1
+    lengths = torch.LongTensor([3200, 2400, 3200, 1777, 2999])
+    T = int(lengths.max())
+    wavs = torch.zeros(len(lengths), 3, T)
+    for b, n in enumerate(lengths.tolist()):
+        clean = speechlike(n, g) * 0.05
+        noise = torch.randn(n, generator=g) * 0.02
+        wavs[b, 0, :n], wavs[b, 1, :n], wavs[b, 2, :n] = clean + noise, clean, noise
+    torch.manual_seed(1337)
+    head = ref["model"].LSTM(input_size=201, output_size=201, hidden_size=24, num_layers=2, bidirectional=False)
+    crit = ref["objective"].L1()
+    args = Namespace(from_waveform=False, from_rawfeature=True, active_layerid=None)
+    ascending = torch.arange(ref["sampler"].MAX_POSITIONS_LEN)
+    per_utt = ref["sampler"].scoring(args, {}, pre, head, crit, ascending, lengths, wavs)
+    mean = ref["sampler"].scoring(args, {}, pre, head, crit, ascending, lengths, wavs, mean=True)
+    match = ref["sampler"].matching(per_utt[:2], per_utt[2:])
+    out = {"lengths": _np(lengths), "wavs": _np(wavs), "per_utt": _np(per_utt), "mean": _np(mean), "match": _np(match),
+           "param_names": np.array([n for n, _ in head.named_parameters()])}
+    for name, p in head.named_parameters():
+        out[f"param_{name}"] = _np(p)
+    return out
+
+
 def make_preprocessor_oracle():
     g = torch.Generator().manual_seed(2024)
     out = {}
@@ -231,9 +264,13 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
     ref = ref_loader.load()
+    if "scoring" in sys.argv[1:]:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "scoring_ref.npz"), **make_scoring(ref))
+        return
     np.savez_compressed(os.path.join(GOLDEN_DIR, "recurrent_heads_ref.npz"), **make_recurrent_heads(ref))
     if "recurrent" in sys.argv[1:]:
         return
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "scoring_ref.npz"), **make_scoring(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "signal_path_ref.npz"), **make_signal_path(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "runner_evaluate_ref.npz"), **make_runner_evaluate(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "preprocessor_oracle.npz"), **make_preprocessor_oracle())

@@ -1390,6 +1390,38 @@ def test_scoring_batched_equals_per_utterance_loop(se, n_fft, cmvn, act):
 
 
 # ------------------------------------------------------------------------------ pseudo-wave generation (runner.py:266-305)
+def test_scoring_matches_reference_sampler_golden(se, golden_dir):
+    """sampler.py:59-116 pinned by the reference ITSELF: tests/golden/scoring_ref.npz holds what the unmodified
+    ``sampler.scoring`` / ``sampler.matching`` returned for the reference ``model.LSTM`` + ``objective.L1`` (run_active.sh's
+    combination).  The drop-in ``scoring`` (all parameters: the loop, with the projection and its input gradient on the head
+    kernels), the batched projection-only path and ``matching`` must reproduce it."""
+    from speech_enhancement_by_s3prl_b200 import sampler_ops
+    gold = np.load(os.path.join(golden_dir, "scoring_ref.npz"))
+    _, mine = make_pair(se, 400)
+    lengths, wavs = torch.from_numpy(gold["lengths"]).cuda(), torch.from_numpy(gold["wavs"]).cuda()
+    head = se.LSTM(input_size=201, output_size=201, hidden_size=24, num_layers=2).cuda()
+    head.load_state_dict({str(n): torch.from_numpy(gold[f"param_{n}"]) for n in gold["param_names"]})
+    want, want_mean = torch.from_numpy(gold["per_utt"]), torch.from_numpy(gold["mean"])
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):        # the cuDNN LSTM body in fp32
+        got = se.scoring(mine, head, se.L1(), lengths, wavs).cpu()
+        got_mean = se.scoring(mine, head, se.L1(), lengths, wavs, mean=True).cpu()
+        proj = se.scoring(mine, head, se.L1(), lengths, wavs, projection_only=True).cpu()
+    assert got.shape == want.shape and got_mean.shape == want_mean.shape
+    for u in range(want.shape[0]):
+        assert torch.nn.functional.cosine_similarity(got[u], want[u], dim=0).item() > 0.99999
+        assert (got[u] - want[u]).abs().max().item() < 2e-3 * want[u].abs().max().item()
+    assert torch.nn.functional.cosine_similarity(got_mean[0], want_mean[0], dim=0).item() > 0.99999
+    n_proj = 201 * 24 + 201                                                  # scaling_layer.0.{weight, bias} come last
+    assert proj.shape == (want.shape[0], n_proj)
+    for u in range(want.shape[0]):
+        ref_u = want[u, -n_proj:]
+        assert torch.nn.functional.cosine_similarity(proj[u], ref_u, dim=0).item() > 0.99999
+        assert (proj[u] - ref_u).abs().max().item() < 2e-3 * ref_u.abs().max().item()
+    match = se.matching(got[:2].cuda(), got[2:].cuda()).cpu()
+    np.testing.assert_allclose(match.numpy(), gold["match"], atol=2e-4)
+    np.testing.assert_allclose(se.matching(want[:2].cuda(), want[2:].cuda()).cpu().numpy(), gold["match"], atol=1e-5)
+
+
 @pytest.mark.parametrize("kind", ["Linear", "LSTM"])
 def test_scoring_l1_batched_equals_loop_and_oracle(se, kind):
     """BASELINE configs[4] names the L1 spectral objective (run_active.sh: --downstream LSTM with the L1-trained checkpoint):

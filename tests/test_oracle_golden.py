@@ -175,3 +175,23 @@ def test_recurrent_head_golden_is_reproducible(golden_dir, tag, cls, kw):
         np.testing.assert_allclose(v.detach().numpy(), gold[f"{tag}_{k}"], rtol=1e-5, atol=1e-6)
     head = getattr(se, cls)(input_size=9, output_size=9, hidden_size=12, num_layers=2, **kw)
     head.load_state_dict(state)                                    # strict: same names and shapes as the reference
+
+
+def test_scoring_golden_is_self_consistent(golden_dir):
+    """tests/golden/scoring_ref.npz (the reference's own sampler.scoring / matching, LSTM head + L1): the matching formula
+    (sampler.py:113-116) restated in numpy reproduces the stored match scores from the stored gradient embeddings, the
+    batch-mean embedding is the element-count-weighted mean of the per-utterance ones (objective.py:113-116 averages over
+    ALL valid elements), and the parameter layout is the drop-in LSTM's."""
+    import speech_enhancement_by_s3prl_b200 as se
+    g = np.load(os.path.join(golden_dir, "scoring_ref.npz"))
+    per, mean, lengths = g["per_utt"].astype(np.float64), g["mean"].astype(np.float64), g["lengths"]
+    q, k = per[:2], per[2:]
+    qn = q / (np.sqrt((q ** 2).sum(-1, keepdims=True)) + 1e-12)
+    kn = k / (np.sqrt((k ** 2).sum(-1, keepdims=True)) + 1e-12)
+    np.testing.assert_allclose(kn @ qn.mean(0), g["match"], rtol=1e-5, atol=1e-6)
+    frames = lengths // 160 + 1
+    w = frames / frames.sum()
+    np.testing.assert_allclose((per * w[:, None]).sum(0), mean[0], rtol=2e-3, atol=1e-6 * np.abs(mean).max())
+    head = se.LSTM(input_size=201, output_size=201, hidden_size=24, num_layers=2)
+    assert [n for n, _ in head.named_parameters()] == [str(n) for n in g["param_names"]]
+    assert per.shape[1] == sum(p.numel() for p in head.parameters())
