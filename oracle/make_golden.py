@@ -15,6 +15,10 @@ TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.
   projection included), so the drop-in heads' projection + multiply / exp -- forward, weight gradient and the input
   gradient that reaches the LSTM -- are pinned by the reference itself.
   (``python -m oracle.make_golden recurrent`` regenerates this file alone.)
+* ``runner_train_ref.npz`` -- the reference's own ``Runner.train()`` (runner.py:307-518) driven for four optimizer steps
+  (``--optim Adam``, gradient clipping 1.0) over a one-batch synthetic dataset with the restated preprocessor, the reference
+  ``LinearResidual`` and ``SISDR``: the loss of every step and the weights before / after.
+  (``python -m oracle.make_golden train`` regenerates this file alone.)
 * ``scoring_ref.npz`` -- the reference's own ``sampler.scoring()`` (sampler.py:59-110) and ``sampler.matching()``
   (sampler.py:113-116) driven with the restated preprocessor, the reference ``model.LSTM`` and ``objective.L1`` -- the
   combination ``run_active.sh`` names -- on a small ragged batch: per-utterance gradient embeddings over ALL parameters,
@@ -211,6 +215,43 @@ def make_recurrent_heads(ref):
     return out
 
 
+def make_runner_train(ref):
+    """Drive the reference's own Runner.train() (unmodified) for four steps and record losses and weights."""
+    import tempfile
+    pre = OnlinePreprocessor(sample_rate=16000, win_ms=32, hop_ms=16, n_freq=257, n_mels=40, n_mfcc=13)
+    c = pre.get_feat_config
+    pre.feat_list = [c("linear", 0, log=True), c("linear", 0, log=True), c("linear", 0), c("phase", 0), c("linear", 1), c("phase", 1)]
+    pre.channel_inp, pre.channel_tar = 0, 1
+    torch.manual_seed(1337)
+    head = ref["model"].LinearResidual(input_size=257, output_size=257)
+    w0, b0 = head.linear.weight.detach().clone(), head.linear.bias.detach().clone()
+    args = Namespace(gpu=False, objective="SISDR", dropout=None, dropout2=None, optim="Adam", resume=None,
+                     seed=1337, from_waveform=False, from_rawfeature=True, no_metric=False, n_jobs=0,
+                     save_best=None, eval_init=False, sync_sampler=False, sampler_device=None,
+                     active_sampling=False, pseudo_clean=False, pseudo_noise=False)
+    steps = 4
+    config = {"runner": {"gradient_clipping": 1.0, "eval_metrics": ["sisdr"], "learning_rate": 1e-3,
+                         "total_step": steps, "eval_splits": [], "log_step": 1000, "media_step": 1000,
+                         "eval_step": 1000, "save_step": 1000, "max_keep": 1},
+              "objective": {}, "dataloader": {"batch_size": 4, "eval_batch_size": 4}}
+    lengths = [9000, 8333, 8200, 9100]                       # >= 32 frames each: inside the fused training route's range
+    dset = _SynthSet(lengths, seed=11, ref=ref)
+    losses = []
+    with tempfile.TemporaryDirectory() as tmp:
+        runner = ref["runner"].Runner(args, config, pre, torch.nn.Identity(), torch.nn.Identity(), head, tmp)
+        runner.set_model()
+        runner.criterion.register_forward_hook(lambda mod, inp, out: losses.append(float(out[0].detach())))
+        runner.get_dataset = lambda *a, **k: dset            # (instance attribute: the class and its source stay untouched)
+        torch.manual_seed(5)                                 # DataLoader shuffle order (one batch per epoch: order only)
+        runner.train()
+        runner.manager.shutdown()
+    out = {"lengths": np.array(lengths), "losses": np.array(losses), "steps": np.int64(steps), "lr": np.float64(1e-3),
+           "grad_clip": np.float64(1.0), "w0": _np(w0), "b0": _np(b0), "w1": _np(head.linear.weight), "b1": _np(head.linear.bias)}
+    for i, it in enumerate(dset.items):
+        out[f"item{i}"] = _np(it)
+    return out
+
+
 def make_scoring(ref):
     """sampler.scoring / matching of the unmodified reference (LSTM head + L1 objective, --from_rawfeature)."""
     g = torch.Generator().manual_seed(777)
@@ -264,6 +305,9 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
     ref = ref_loader.load()
+    if "train" in sys.argv[1:]:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "runner_train_ref.npz"), **make_runner_train(ref))
+        return
     if "scoring" in sys.argv[1:]:
         np.savez_compressed(os.path.join(GOLDEN_DIR, "scoring_ref.npz"), **make_scoring(ref))
         return
@@ -271,6 +315,7 @@ def main():
     if "recurrent" in sys.argv[1:]:
         return
     np.savez_compressed(os.path.join(GOLDEN_DIR, "scoring_ref.npz"), **make_scoring(ref))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "runner_train_ref.npz"), **make_runner_train(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "signal_path_ref.npz"), **make_signal_path(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "runner_evaluate_ref.npz"), **make_runner_evaluate(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "preprocessor_oracle.npz"), **make_preprocessor_oracle())

@@ -511,6 +511,65 @@ def test_pseudo_noise_config_end_to_end_matches_oracle_autograd(se, precision):
         np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=5e-2, atol=(2e-3 if precision == 0 else 2e-2) * want.abs().max().item())
 
 
+@pytest.mark.parametrize("route", ["autograd-fp32-torch-adam", "fused-tf32-clipadam", "fused-tf32-clipadam-graph"])
+def test_training_steps_match_reference_runner_train(se, golden_dir, route):
+    """runner.py:431-471 pinned by the reference ITSELF: tests/golden/runner_train_ref.npz holds the loss of every step and the
+    final weights of four optimizer steps of the unmodified ``Runner.train()`` (LinearResidual + SISDR, Adam lr 1e-3, clipping
+    1.0).  The engine's training step -- autograd route with torch's Adam, the fused route with ClipAdam, and the fused route
+    replayed from a CUDA graph -- follows the same trajectory."""
+    g = np.load(os.path.join(golden_dir, "runner_train_ref.npz"))
+    items = [torch.from_numpy(g[f"item{i}"]) for i in range(len(g["lengths"]))]
+    lengths, wavs = sp.collate(items)
+    lengths, wavs = lengths.cuda(), wavs.cuda()
+    _, mine = make_pair(se, 512)
+    precision = 0 if route.startswith("autograd") else 1
+    head = se.LinearResidual(input_size=257, output_size=257, precision=precision).cuda()
+    with torch.no_grad():
+        head.linear.weight.copy_(torch.from_numpy(g["w0"]))
+        head.linear.bias.copy_(torch.from_numpy(g["b0"]))
+    eng = se.EnhancementEngine(mine, head, log_features=True, precision=precision)
+    crit, steps, clip = se.SISDR(), int(g["steps"]), float(g["grad_clip"])
+    losses = []
+    if route.startswith("autograd"):
+        opt = torch.optim.Adam(head.parameters(), lr=float(g["lr"]), betas=(0.9, 0.999))
+        for _ in range(steps):
+            losses.append(eng.train_step(lengths, wavs, crit, opt, clip).item())
+    else:
+        opt = se.ClipAdam(head.parameters(), lr=float(g["lr"]), betas=(0.9, 0.999))
+        assert eng.fused_training_supported(crit, wavs.shape[0], wavs.shape[2])
+        if route.endswith("graph"):
+            st = eng.capture_train(lengths, wavs, crit, opt, clip)       # three eager warm-up steps happen in here:
+            with torch.no_grad():                                        # rewind to the golden's starting point
+                head.linear.weight.copy_(torch.from_numpy(g["w0"]))
+                head.linear.bias.copy_(torch.from_numpy(g["b0"]))
+                for p in head.parameters():
+                    opt.state[p]["exp_avg"].zero_()
+                    opt.state[p]["exp_avg_sq"].zero_()
+                opt.param_groups[0]["_ws"][1].zero_()
+            eng._padded_weight(force=True)
+            for _ in range(steps):
+                st["graph"].replay()
+                losses.append(st["loss"].item())
+        else:
+            for _ in range(steps):
+                losses.append(eng.train_step(lengths, wavs, crit, opt, clip).item())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(losses, g["losses"], atol=2e-3 if precision == 0 else 5e-3)
+    dw = head.linear.weight.detach().cpu().numpy() - g["w1"]
+    db = head.linear.bias.detach().cpu().numpy() - g["b1"]
+    moved = np.abs(g["w1"] - g["w0"])
+    print(route, "max |dw|", np.abs(dw).max(), "mean |dw|", np.abs(dw).mean(), "moved max / mean", moved.max(), moved.mean())
+    if precision == 0:
+        assert np.abs(dw).max() < 5e-5 and np.abs(db).max() < 5e-5 and moved.max() > 1e-3
+    else:
+        # TF32 operands in the weight-gradient GEMM: Adam's m / sqrt(v) turns the rounding noise of a near-zero gradient into a
+        # full-size step for that element, so single weights may differ by a step or two while the bulk follows the trajectory
+        assert np.abs(dw).mean() < 0.02 * moved.mean() and np.abs(dw).max() < 0.6 * moved.max()
+        assert np.abs(db).mean() < 0.05 * np.abs(g["b1"] - g["b0"]).mean()
+        update = (head.linear.weight.detach().cpu().numpy() - g["w0"]).ravel()
+        assert np.dot(update, (g["w1"] - g["w0"]).ravel()) / (np.linalg.norm(update) * np.linalg.norm(g["w1"] - g["w0"])) > 0.995
+
+
 def test_engine_training_step_with_a_feature_config(se):
     """EnhancementEngine(feat_cfg=...): the training step on the pseudo_noise.yaml baseline feature (mel + log + delta 2).
     The autograd route equals the hand-written chain on the drop-in modules; the FUSED route (K1b kernel -> sums -> TMA head ->

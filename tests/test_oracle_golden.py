@@ -195,3 +195,31 @@ def test_scoring_golden_is_self_consistent(golden_dir):
     head = se.LSTM(input_size=201, output_size=201, hidden_size=24, num_layers=2)
     assert [n for n, _ in head.named_parameters()] == [str(n) for n in g["param_names"]]
     assert per.shape[1] == sum(p.numel() for p in head.parameters())
+
+
+def test_oracle_training_steps_match_reference_runner_train(golden_dir):
+    """tests/golden/runner_train_ref.npz = four optimizer steps of the reference's own Runner.train() (runner.py:431-471:
+    preprocessor -> LinearResidual -> SISDR -> backward -> clip_grad_norm_(1.0) -> Adam).  The oracle restatement of that
+    step reproduces every loss and the final weights."""
+    g = np.load(os.path.join(golden_dir, "runner_train_ref.npz"))
+    items = [T(g[f"item{i}"]) for i in range(len(g["lengths"]))]
+    lengths, wavs = sp.collate(items)
+    pre = OnlinePreprocessor(sample_rate=16000, win_ms=32, hop_ms=16, n_freq=257)
+    c = pre.get_feat_config
+    w = T(g["w0"]).clone().requires_grad_(True)
+    b = T(g["b0"]).clone().requires_grad_(True)
+    opt = torch.optim.Adam([w, b], lr=float(g["lr"]), betas=(0.9, 0.999))
+    masks = sp.length_masks(sp.stft_lengths(lengths, 256))
+    feats, lin_i, lin_t = pre(wavs, [c("linear", 0, log=True), c("linear", 0), c("linear", 1)])
+    losses = []
+    for _ in range(int(g["steps"])):
+        pred, _ = sp.linear_residual_head(feats, lin_i, w, b)
+        loss, _ = sp.sisdr_spectral(pred, lin_t, masks)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([w, b], float(g["grad_clip"]))
+        opt.step()
+        losses.append(loss.item())
+    np.testing.assert_allclose(losses, g["losses"], atol=2e-4)
+    np.testing.assert_allclose(w.detach().numpy(), g["w1"], atol=2e-5)
+    np.testing.assert_allclose(b.detach().numpy(), g["b1"], atol=2e-5)
