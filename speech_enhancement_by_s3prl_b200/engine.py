@@ -187,13 +187,14 @@ class EnhancementEngine:
         loss, sisdr = pipe.drain()[0]
         return float(loss.mean()), float(sisdr.mean()), pipe.slots[0]["wav_predicted"]
 
-    def host_pipeline(self, B, C, T, depth=2, device=None, pcm16=False, want_wav=False):
+    def host_pipeline(self, B, C, T, depth=2, device=None, pcm16=False, want_wav=False, copy_wav=True):
         """Host-facing evaluation loop for (B, C, T) batches; see HostPipeline.  pcm16: the host batches are int16 PCM
-        (half the PCIe bytes; widened on the device); want_wav: the enhanced waveforms come back to pinned host memory."""
-        key = ("pipe", B, C, T, depth, bool(pcm16), bool(want_wav))
+        (half the PCIe bytes; widened on the device); want_wav: the enhanced waveforms come back to pinned host memory
+        (copy_wav=False: as views of the slot's pinned buffer, valid until that slot is submitted to again)."""
+        key = ("pipe", B, C, T, depth, bool(pcm16), bool(want_wav), bool(copy_wav))
         if key not in self._graphs:
             device = device or torch.device("cuda", torch.cuda.current_device())
-            self._graphs[key] = HostPipeline(self, B, C, T, depth, device, pcm16=pcm16, want_wav=want_wav)
+            self._graphs[key] = HostPipeline(self, B, C, T, depth, device, pcm16=pcm16, want_wav=want_wav, copy_wav=copy_wav)
         return self._graphs[key]
 
     # ------------------------------------------------------------------ training step (head fwd + bwd)
@@ -384,10 +385,10 @@ class HostPipeline:
 
     N_CH = 2
 
-    def __init__(self, engine, B, C, T, depth, device, pcm16=False, want_wav=False):
+    def __init__(self, engine, B, C, T, depth, device, pcm16=False, want_wav=False, copy_wav=True):
         assert engine.ch_inp in (0, 1) and engine.ch_tar in (0, 1), "pipeline ships channels 0 and 1 only"
         self.engine, self.shape, self.device = engine, (B, C, T), device
-        self.pcm16, self.want_wav = bool(pcm16), bool(want_wav)
+        self.pcm16, self.want_wav, self.copy_wav = bool(pcm16), bool(want_wav), bool(copy_wav)
         self.copy_stream = torch.cuda.Stream(device=device)
         self.compute_stream = torch.cuda.Stream(device=device)
         self.slots = []
@@ -452,7 +453,10 @@ class HostPipeline:
         st["done"].synchronize()
         st["busy"] = False
         res = st["result_host"].clone()
-        self._results.append((res[0], res[1], st["wav_host"].clone()) if self.want_wav else (res[0], res[1]))
+        if self.want_wav:                           # (a 16 MB host copy per step unless the caller consumes the slot's buffer in place)
+            self._results.append((res[0], res[1], st["wav_host"].clone() if self.copy_wav else st["wav_host"]))
+        else:
+            self._results.append((res[0], res[1]))
         self.pending.remove(st)
 
     _results = None
