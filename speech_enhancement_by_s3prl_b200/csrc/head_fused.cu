@@ -13,7 +13,7 @@
 //                        sums, round to TF32), later run the epilogue
 //   * warp 8 (one lane)  tcgen05.mma kind::tf32, fp32 accumulators in tensor memory: columns
 //                        [0,256) by one N=256 instruction, the remaining <= 16 by a second one
-//   * more than 272 output columns (n_fft 1024: 513 -> 528): blockIdx.y splits the columns into slabs of
+//   * more than 272 output columns (n_fft 1024: 513 -> 528): blockIdx.x % n_split selects one of the column slabs of
 //                        <= 256 (3 x 176); each CTA streams the same A tile (re-reads come from L2) and its
 //                        own slab of weight rows, and stores its slab of every output row
 //   * more tiles than SMs: two CTAs per SM (2-stage rings, 256 tensor-memory columns each, direct stores)
@@ -139,7 +139,8 @@ struct Head2Args {
     int tile_rows;             // rows per CTA: multiple of 8, <= 128, <= n_frames (a tile touches <= 2 utterances)
     int kblocks;               // ceil(Din / 32) <= 17
     int w_rows;                // Dout rounded up to 16, <= 544
-    int cta_cols;              // output columns (weight rows) per CTA slab: multiple of 16, <= 272; slab = blockIdx.y
+    int cta_cols;              // output columns (weight rows) per CTA slab: multiple of 16, <= 272; slab = blockIdx.x % n_split
+    int n_split;               // column slabs per row tile
     int w_box_rows, w_boxes;   // weight tensor-map box rows and boxes per k-block
     int sld;                   // floats per row of the staging tile
     int bulk_out;              // staging rows == output rows and 16-byte aligned: one bulk store per quadrant
@@ -172,8 +173,10 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int kStageBytes = DUAL ? a.stage_bytes : kMaxStageBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long r0 = (long long)blockIdx.x * a.tile_rows;
-    const int col0 = (int)blockIdx.y * a.cta_cols;                       // this CTA's slab of output columns
+    // slab index fastest: the slabs of one row tile are dispatched together, so the second read of the A tile hits L2
+    const int slab = (int)(blockIdx.x % (unsigned)a.n_split);
+    const long long r0 = (long long)(blockIdx.x / (unsigned)a.n_split) * a.tile_rows;
+    const int col0 = slab * a.cta_cols;                                  // this CTA's slab of output columns
     const int ncols = a.w_rows - col0 < a.cta_cols ? a.w_rows - col0 : a.cta_cols;
     const int n_main = ncols > 256 ? 256 : ncols, n_tail = ncols - n_main;   // MMA column split: [0, n_main) and [n_main, ncols)
     const uint32_t w_bytes = (uint32_t)(a.w_box_rows * a.w_boxes) * BK * 4;  // whole boxes land (rows past Dout read as zero)
@@ -257,6 +260,13 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const long long u0 = r0 / a.n_frames;
         const int split = (int)((u0 + 1) * a.n_frames - r0);              // first tile row of the next utterance
         // per-utterance CMVN scale / shift for the (at most two) utterances of the tile; loads first, then the arithmetic
+        const float bscale = a.act == SE_ACT_SIGMOID ? -1.4426950408889634f : 1.0f;     // see the epilogue
+        float bias_r[2];                                                  // 288 local columns over 256 threads; in flight with the sums
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = t + q * kWorkThreads;
+            bias_r[q] = (i < 288 && a.bias && col0 + i < a.Dout) ? bscale * __ldg(a.bias + col0 + i) : 0.f;
+        }
         {
             constexpr int kPer = (2 * kStatLd + kWorkThreads - 1) / kWorkThreads;
             double2 p[kPer];
@@ -288,16 +298,14 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
             }
         }
-        {
-            const float bscale = a.act == SE_ACT_SIGMOID ? -1.4426950408889634f : 1.0f;     // see the epilogue
-            for (int i = t; i < 288; i += kWorkThreads)                      // local column i = output column col0 + i
-                s_bias[i] = (a.bias && col0 + i < a.Dout) ? bscale * __ldg(a.bias + col0 + i) : 0.f;
-        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)                                         // local column i = output column col0 + i
+            if (t + q * kWorkThreads < 288) s_bias[t + q * kWorkThreads] = bias_r[q];
         asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
         if (t == 0) trace.mark(12);
 
         // the "+1" column (last slab only): every thread owns one 4-float chunk of four rows per k-block
-        const bool has_extra = DUAL && a.w_extra != nullptr && blockIdx.y == gridDim.y - 1;
+        const bool has_extra = DUAL && a.w_extra != nullptr && slab == a.n_split - 1;
         const int cx = (t & 7) ^ ((t >> 3) & 7);                          // logical chunk of this thread's four rows
         float dot[4] = {0.f, 0.f, 0.f, 0.f};
         for (int kb = 0; kb < a.kblocks; ++kb) {
@@ -362,7 +370,11 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // Sigmoid: s_bias holds -log2(e) * bias and z is scaled by -log2(e) in the same FFMA: 1 / (1 + 2^t).
         const int act = a.act;
         const float zscale = act == SE_ACT_SIGMOID ? -1.4426950408889634f : 1.0f;
-        auto emit = [&](const uint32_t (&acc)[16], int c0) {
+        // direct mode, aligned rows: each warp turns its 32 rows x 32 columns around in a private 4 KB scratch of the (consumed)
+        // ring -- lanes own rows on the tensor-memory side, 8 lanes share a row on the store side, so one store instruction writes
+        // four whole 128-byte lines instead of 16 bytes of 32 different rows.  Chunk j of row r sits at r * 8 + (j ^ (r & 7)).
+        float4* sw = reinterpret_cast<float4*>(stage) + warp * 256;
+        auto emit = [&](const uint32_t (&acc)[16], int c0, int cb) {
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -383,18 +395,20 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
+            if (a.direct_out == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    sw[lane * 8 + ((cb + j) ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                return;
+            }
             if (a.direct_out) {
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const int c = col0 + c0 + j;
-                        if (a.direct_out == 2 && c + 4 <= (int)a.ld_out) {
-                            *reinterpret_cast<float4*>(grow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (c + e < a.Dout) grow[c0 + j + e] = v[j + e];
-                        }
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < a.Dout) grow[c0 + j + e] = v[j + e];
                     }
                 }
                 return;
@@ -403,18 +417,42 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int j = 0; j < 16; j += 4)
                 if (c0 + j < a.sld) *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         };
+        auto flush = [&](int c0, int ncol) {                                 // scratch columns [0, ncol) -> output columns col0 + c0 ...
+            __syncwarp();
+            const int c = lane & 7;
+            if (4 * c < ncol) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + (lane >> 3), trow = quad * 32 + r;
+                    if (trow < a.tile_rows && r0 + trow < a.R) {
+                        const float4 x = sw[r * 8 + (c ^ (r & 7))];
+                        float* g = a.out + (r0 + trow) * a.ld_out + col0 + c0 + 4 * c;
+                        const int gc = col0 + c0 + 4 * c;
+                        if (gc + 4 <= (int)a.ld_out) *reinterpret_cast<float4*>(g) = x;
+                        else {
+                            if (gc < a.Dout) g[0] = x.x;
+                            if (gc + 1 < a.Dout) g[1] = x.y;
+                            if (gc + 2 < a.Dout) g[2] = x.z;
+                            if (gc + 3 < a.Dout) g[3] = x.w;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        };
         uint32_t acc0[16], acc1[16];
         tmem_ld16(tbase + (uint32_t)c_lo, acc0);
         tmem_ld_wait();
         for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
             if (c0 + 16 < c_hi) tmem_ld16(tbase + (uint32_t)(c0 + 16), acc1);
-            emit(acc0, c0);
+            emit(acc0, c0, 0);
             tmem_ld_wait();
             if (c0 + 16 < c_hi) {
                 if (c0 + 32 < c_hi) tmem_ld16(tbase + (uint32_t)(c0 + 32), acc0);
-                emit(acc1, c0 + 16);
+                emit(acc1, c0 + 16, 4);
                 tmem_ld_wait();
             }
+            if (a.direct_out == 2) flush(c0, c_hi - c0 < 32 ? c_hi - c0 : 32);
         }
         if (has_extra && half == 0 && row_ok) {                             // column Dout - 1 of this row
             float z = fmaf(s_extra[row], zscale, (a.bias ? zscale * __ldg(a.bias + a.Dout - 1) : 0.f));
@@ -442,7 +480,7 @@ linear_head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  ::"l"(gdst), "r"(smem_u32(ssrc)), "r"((uint32_t)(rows_valid * a.sld * 4)) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging tile has been read; the writes land on their own
                 }
             } else {
                 for (int r = half; r < rows_valid; r += 2)
@@ -585,7 +623,8 @@ int se_linear_head_fused(const float* x, int64_t ldx, const double* stat_sums, i
     }
     cudaLaunchConfig_t cfg{};
     unsigned tiles = (unsigned)((a.R + a.tile_rows - 1) / a.tile_rows);
-    cfg.gridDim = dim3(tiles, (unsigned)n_split);
+    a.n_split = n_split;
+    cfg.gridDim = dim3(tiles * (unsigned)n_split);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = (cudaStream_t)stream;

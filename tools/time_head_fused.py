@@ -25,7 +25,7 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / (4 * n) * 1e3
 
 
-for B, F, D in [(64, 251, 257), (256, 251, 257), (64, 401, 201), (256, 401, 201), (64, 251, 513), (256, 251, 513), (16, 3751, 513)]:
+for B, F, D in [(64, 251, 257), (256, 251, 257), (64, 401, 201), (256, 401, 201), (64, 251, 513), (256, 251, 513), (16, 3751, 513), (128, 3751, 513), (128, 3751, 257)]:
     gen = torch.Generator().manual_seed(0)
     LD = ops.round4(D)
     feats = torch.zeros(B, F, LD)
