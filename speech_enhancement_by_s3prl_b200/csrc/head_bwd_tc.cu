@@ -10,7 +10,7 @@
 //                loads across the warp, one conflict-free STS.128 into the K-major SWIZZLE_128B tile; dZ's activation
 //                derivative and xhat's CMVN are applied here, operands rounded to TF32 (cvt.rna).  Column k = D_in of
 //                the B tile is the constant 1, so grad_b falls out of the GEMM as column D_in of D.
-//   * warp 8     tcgen05.mma kind::tf32 (M = 128, N = 256 + 16), commits stages back to the producers
+//   * warp 0     also issues the tcgen05.mma kind::tf32 (M = 128, N = 256 + 16) of the previous block and commits stages back
 //   * epilogue   tcgen05.ld -> staging tile -> coalesced stores of the CTA's partial into the workspace
 // Output rows that do not fill a 128-row tile are few when D_out = 257 (one row): up to kMaxSimtRows such rows go through a
 // fp32 dot products accumulated by the B-operand producers of the first tile's CTAs (they hold xhat in registers anyway)
@@ -22,7 +22,7 @@ using secommon::fail;
 namespace {
 
 constexpr int BM = 128, BK = 32, kStages = 4;
-constexpr int kProdWarps = 8, kProdThreads = kProdWarps * 32, kThreads = kProdThreads + 32;
+constexpr int kProdWarps = 8, kProdThreads = kProdWarps * 32, kThreads = kProdThreads;   // 8 warps: 2 per scheduler, 255-register cap
 constexpr int kATileBytes = BM * BK * 4;                       // 16 KB
 constexpr int kMaxBRows = 272;
 constexpr int kBTileBytes = kMaxBRows * BK * 4;                // 34 816
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
         mbar_init(bar_accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kProdWarps) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -170,9 +170,32 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < kProdWarps) {
+    {
         // ===================== producers: transpose both operands into K-major tiles =====================
+        // Warp 0 doubles as the MMA issuer: before it starts on block kb it issues the MMAs of block kb - 1 (whose stage the
+        // other warps have filled, or are about to -- they run in step), so the CTA is 8 warps = 2 per scheduler and the
+        // two register sets of the software pipeline below fit without spills.
         const int t = threadIdx.x;
+        const uint32_t idesc_main = make_idesc(a.n_main), idesc_tail = make_idesc(a.n_tail > 0 ? a.n_tail : 16);
+        auto issue_mma = [&](int kb) {
+            const int s = kb % kStages;
+            mbar_wait(bar_full + 8 * s, (kb / kStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a_addr = sbase + kOffRing + s * kStageBytes;
+                const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint64_t ad = make_desc(a_addr + kk * 32);
+                    umma_tf32(tmem_base, ad, make_desc(b_addr + kk * 32), idesc_main, (kb | kk) ? 1u : 0u);
+                    if (a.n_tail > 0)
+                        umma_tf32(tmem_base + (uint32_t)a.n_main, ad, make_desc(b_addr + a.n_main * BK * 4 + kk * 32), idesc_tail,
+                                  (kb | kk) ? 1u : 0u);
+                }
+                umma_commit(bar_empty + 8 * s);
+            }
+            __syncwarp();
+        };
         // leftover output rows [128 m_tiles, +simt_rows): the thread that normalises column k of a block also accumulates
         // sum_r dZ[r, n_left] * xhat[r, k] in fp32 (dZ of the block's 32 rows is shared through s_dz); first-tile CTAs only
         const bool do_left = a.simt_rows > 0 && blockIdx.y == 0;
@@ -180,49 +203,75 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
         float acc_l[kMaxSimtRows], acc_t[kMaxSimtRows];
 #pragma unroll
         for (int i = 0; i < kMaxSimtRows; ++i) { acc_l[i] = 0.0f; acc_t[i] = 0.0f; }
-        for (int kb = 0; kb < nkb; ++kb) {
+        // Software pipeline: the global loads of block kb + 1 are issued BEFORE block kb is transposed into shared memory, so the
+        // load latency of one block hides under the arithmetic / stores of the previous one (two register sets, loop unrolled by 2).
+        struct Regs { float ao[16], ag[16], bv[32], bx[4], dzg, dzo; };
+        const int n = t & (BM - 1), ch = t >> 7;
+        const bool nvalid = n0 + n < a.Dout;
+        const bool kvalid = t < a.b_rows, isx = t < a.Din;
+        const bool has_shared = a.b_rows > kProdThreads && t < 16 * 8 && kProdThreads + (t & 15) < a.b_rows;
+        const int ks = kProdThreads + (t & 15), cs = t >> 4;               // shared-out column / chunk of this thread
+        const bool dz_owner = do_left && t < 32 * a.simt_rows;
+        // Loads are UNCONDITIONAL in a full block (the column index is clamped into the row, out-of-range lanes are zeroed by
+        // selects when the values are consumed): a guarded `ok ? __ldg(p) : 0` per element compiles into a branch with its own
+        // convergence barrier per load, which serialises the 70 loads of a block.
+        const int ncl = nvalid ? n : 0, tcl = isx ? t : 0, kcl = (has_shared && ks < a.Din) ? ks : 0;
+        auto issue = [&](int kb, Regs& R) {
+            const long long r0 = ra + (long long)kb * BK;
+            const float* po = a.offset + r0 * a.ld_off + n0 + ncl;
+            const float* pg = a.grad_offset + r0 * a.ld_off + n0 + ncl;
+            const float* px = a.x + r0 * a.ldx;
+            R.dzg = 0.0f; R.dzo = 0.0f;
+            if (r0 + BK <= rb) {                                           // all 32 rows of the block exist
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {                             // A: chunks c = ch + 2 (e >> 2), rows 4 c + (e & 3)
+                    const int rr = 4 * (ch + 2 * (e >> 2)) + (e & 3);
+                    R.ao[e] = __ldg(po + (long long)rr * a.ld_off);
+                    R.ag[e] = __ldg(pg + (long long)rr * a.ld_off);
+                }
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) R.bv[rr] = __ldg(px + (long long)rr * a.ldx + tcl);       // B: column t, rows 0..31
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) R.bx[jj] = __ldg(px + (long long)(4 * cs + jj) * a.ldx + kcl);   // B: columns 256 ..
+                if (dz_owner) {                                            // dZ of the leftover rows (whole warps)
+                    R.dzg = __ldg(a.grad_offset + (r0 + (t & 31)) * a.ld_off + n_left + (t >> 5));
+                    R.dzo = __ldg(a.offset + (r0 + (t & 31)) * a.ld_off + n_left + (t >> 5));
+                }
+            } else {                                                       // last block of the split: row guards
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int rr = 4 * (ch + 2 * (e >> 2)) + (e & 3);
+                    const bool ok = r0 + rr < rb;
+                    R.ao[e] = ok ? __ldg(po + (long long)rr * a.ld_off) : 0.0f;
+                    R.ag[e] = ok ? __ldg(pg + (long long)rr * a.ld_off) : 0.0f;
+                }
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) R.bv[rr] = r0 + rr < rb ? __ldg(px + (long long)rr * a.ldx + tcl) : 0.0f;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) R.bx[jj] = r0 + 4 * cs + jj < rb ? __ldg(px + (long long)(4 * cs + jj) * a.ldx + kcl) : 0.0f;
+                if (dz_owner && r0 + (t & 31) < rb) {
+                    R.dzg = __ldg(a.grad_offset + (r0 + (t & 31)) * a.ld_off + n_left + (t >> 5));
+                    R.dzo = __ldg(a.offset + (r0 + (t & 31)) * a.ld_off + n_left + (t >> 5));
+                }
+            }
+        };
+        auto process = [&](int kb, const Regs& R) {
             const int s = kb % kStages;
             unsigned char* At = smem + kOffRing + s * kStageBytes;
             unsigned char* Bt = At + kATileBytes;
             const long long r0 = ra + (long long)kb * BK;
-            const bool full = r0 + BK <= rb;                               // all 32 rows of the block exist
-            const int n = t & (BM - 1), ch = t >> 7;
-            const bool nvalid = n0 + n < a.Dout;
-            const bool kvalid = t < a.b_rows, isx = t < a.Din;
-            // ---- every global load of the block is issued before anything is consumed (96 per thread in flight)
-            float ao[32], ag[32], bv[32];
-            {
-                const float* po = a.offset + r0 * a.ld_off + n0 + n;
-                const float* pg = a.grad_offset + r0 * a.ld_off + n0 + n;
-                const float* px = a.x + r0 * a.ldx + (isx ? t : 0);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {                             // A: chunks c = ch + 2 (e >> 2), rows 4 c + (e & 3)
-                    const int rr = 4 * (ch + 2 * (e >> 2)) + (e & 3);
-                    const bool ok = nvalid && (full || r0 + rr < rb);
-                    ao[e] = ok ? __ldg(po + (long long)rr * a.ld_off) : 0.0f;
-                    ag[e] = ok ? __ldg(pg + (long long)rr * a.ld_off) : 0.0f;
-                }
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr) {                          // B: column t, rows 0..31
-                    const bool ok = isx && (full || r0 + rr < rb);
-                    bv[rr] = ok ? __ldg(px + (long long)rr * a.ldx) : 0.0f;
-                }
-            }
-            if (do_left && t < 32 * a.simt_rows) {                         // dZ of the leftover rows for this block
-                const int rr = t & 31, i = t >> 5;
-                float dz = 0.0f;
-                if (full || r0 + rr < rb)
-                    dz = dact(__ldg(a.grad_offset + (r0 + rr) * a.ld_off + n_left + i), __ldg(a.offset + (r0 + rr) * a.ld_off + n_left + i), a.act);
-                s_dz[((kb & 1) * kMaxSimtRows + i) * 32 + rr] = dz;
-            }
+            const bool full = r0 + BK <= rb;
+            if (dz_owner) s_dz[((kb & 1) * kMaxSimtRows + (t >> 5)) * 32 + (t & 31)] = dact(R.dzg, R.dzo, a.act);   // dact(0, 0) = 0
+            if (warp == 0 && kb > 0) issue_mma(kb - 1);
             if (kb >= kStages) mbar_wait(bar_empty + 8 * s, ((kb / kStages) - 1) & 1);   // the MMAs that read this stage are done
-            // ---- A tile: dZ^T
+            // ---- A tile: dZ^T (rows of the tile past D_out: zero)
+            const float nz = nvalid ? 1.0f : 0.0f;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 const int c = ch + 2 * h;
                 *reinterpret_cast<float4*>(At + n * 128 + ((c ^ (n & 7)) << 4)) =
-                    make_float4(to_tf32(dact(ag[4 * h], ao[4 * h], a.act)), to_tf32(dact(ag[4 * h + 1], ao[4 * h + 1], a.act)),
-                                to_tf32(dact(ag[4 * h + 2], ao[4 * h + 2], a.act)), to_tf32(dact(ag[4 * h + 3], ao[4 * h + 3], a.act)));
+                    make_float4(to_tf32(nz * dact(R.ag[4 * h], R.ao[4 * h], a.act)), to_tf32(nz * dact(R.ag[4 * h + 1], R.ao[4 * h + 1], a.act)),
+                                to_tf32(nz * dact(R.ag[4 * h + 2], R.ao[4 * h + 2], a.act)), to_tf32(nz * dact(R.ag[4 * h + 3], R.ao[4 * h + 3], a.act)));
             }
             // ---- B tile: xhat^T with the ones column at k = Din.  thread -> column k = t; the columns 256 .. b_rows - 1 are
             // shared out afterwards as (k = 256 + (t & 15), chunk t >> 4) over the first 128 threads
@@ -242,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
                     for (int jj = 0; jj < 4; ++jj) {
                         const int rr = 4 * c + jj;
                         const float2 st = rr >= bnd ? st1 : st0;
-                        w[jj] = isx ? (bv[rr] - st.x) * st.y : fill;
+                        w[jj] = isx ? (R.bv[rr] - st.x) * st.y : fill;
                         if (!full && r0 + rr >= rb) w[jj] = 0.0f;
                     }
                     *reinterpret_cast<float4*>(Bt + t * 128 + ((c ^ (t & 7)) << 4)) =
@@ -257,36 +306,49 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
                     }
                 }
             }
-            if (a.b_rows > kProdThreads && t < 16 * 8) {
-                const int k = kProdThreads + (t & 15), c = t >> 4;
-                if (k < a.b_rows) {
-                    const bool tx = k < a.Din;
-                    const float2 st0 = s_stats[ul0 * kMaxBRows + k];
-                    const float2 st1 = bnd < BK ? s_stats[(ul0 + 1) * kMaxBRows + k] : st0;
-                    const float fill = k == a.Din ? 1.0f : 0.0f;
-                    float w[4];
+            if (has_shared) {
+                const int k = ks, c = cs;
+                const bool tx = k < a.Din;
+                const float2 st0 = s_stats[ul0 * kMaxBRows + k];
+                const float2 st1 = bnd < BK ? s_stats[(ul0 + 1) * kMaxBRows + k] : st0;
+                const float fill = k == a.Din ? 1.0f : 0.0f;
+                float w[4];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int rr = 4 * c + jj;
-                        const bool ok = full || r0 + rr < rb;
-                        const float2 st = rr >= bnd ? st1 : st0;
-                        w[jj] = !ok ? 0.0f : (tx ? (__ldg(a.x + (r0 + rr) * a.ldx + k) - st.x) * st.y : fill);
-                    }
-                    *reinterpret_cast<float4*>(Bt + k * 128 + ((c ^ (k & 7)) << 4)) =
-                        make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
-                    if (do_left) {
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int rr = 4 * c + jj;
+                    const bool ok = full || r0 + rr < rb;
+                    const float2 st = rr >= bnd ? st1 : st0;
+                    w[jj] = !ok ? 0.0f : (tx ? (R.bx[jj] - st.x) * st.y : fill);
+                }
+                *reinterpret_cast<float4*>(Bt + k * 128 + ((c ^ (k & 7)) << 4)) =
+                    make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
+                if (do_left) {
 #pragma unroll
-                        for (int i = 0; i < kMaxSimtRows; ++i)
-                            if (i < a.simt_rows) {
-                                const float4 d = *reinterpret_cast<const float4*>(dzb + i * 32 + 4 * c);
-                                acc_t[i] += w[0] * d.x + w[1] * d.y + w[2] * d.z + w[3] * d.w;
-                            }
-                    }
+                    for (int i = 0; i < kMaxSimtRows; ++i)
+                        if (i < a.simt_rows) {
+                            const float4 d = *reinterpret_cast<const float4*>(dzb + i * 32 + 4 * c);
+                            acc_t[i] += w[0] * d.x + w[1] * d.y + w[2] * d.z + w[3] * d.w;
+                        }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        };
+        Regs r_even, r_odd;
+        if (nkb > 0) issue(0, r_even);
+        for (int kb = 0; kb < nkb; kb += 2) {
+            if (kb + 1 < nkb) issue(kb + 1, r_odd);
+            process(kb, r_even);
+            if (kb + 1 < nkb) {
+                if (kb + 2 < nkb) issue(kb + 2, r_even);
+                process(kb + 1, r_odd);
+            }
+        }
+        if (warp == 0 && nkb > 0) {
+            issue_mma(nkb - 1);
+            if (lane == 0) umma_commit(bar_accum);
+            __syncwarp();
         }
         if (do_left) {
             // partial rows n_left + i of this split: main columns straight from the registers, the shared-out columns
@@ -334,31 +396,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
         for (int rr = warp; rr < BM; rr += kProdWarps)
             for (int c = lane; c < a.b_rows; c += 32) dst[(long long)rr * kMaxBRows + c] = stage[rr * kStageLd + c];
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else {
-        // ===================== MMA issuer =====================
-        if (lane == 0 && nkb > 0) {
-            const uint32_t idesc_main = make_idesc(a.n_main), idesc_tail = make_idesc(a.n_tail > 0 ? a.n_tail : 16);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait(bar_full + 8 * s, (kb / kStages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = sbase + kOffRing + s * kStageBytes;
-                const uint32_t b_addr = a_addr + kATileBytes;
-#pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {
-                    const uint64_t ad = make_desc(a_addr + kk * 32);
-                    umma_tf32(tmem_base, ad, make_desc(b_addr + kk * 32), idesc_main, (kb | kk) ? 1u : 0u);
-                    if (a.n_tail > 0)
-                        umma_tf32(tmem_base + (uint32_t)a.n_main, ad, make_desc(b_addr + a.n_main * BK * 4 + kk * 32), idesc_tail,
-                                  (kb | kk) ? 1u : 0u);
-                }
-                umma_commit(bar_empty + 8 * s);
-            }
-            umma_commit(bar_accum);
-        }
     }
     __syncthreads();
-    if (warp == kProdWarps) {
+    if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
