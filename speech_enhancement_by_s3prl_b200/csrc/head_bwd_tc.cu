@@ -15,6 +15,8 @@
 // Output rows that do not fill a 128-row tile are few when D_out = 257 (one row): up to kMaxSimtRows such rows go through a
 // fp32 dot products accumulated by the B-operand producers of the first tile's CTAs (they hold xhat in registers anyway)
 // instead of a third tensor-core tile that would transpose the whole B operand again for one useful row.  A second kernel sums the partials over the splits into grad_W / grad_b.
+#include <cuda.h>
+#include <cstdlib>
 #include "se_common.cuh"
 
 using secommon::fail;
@@ -404,6 +406,281 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TMA variant (aligned operands: row strides multiples of 4 floats, 16-byte aligned bases, at most one leftover output row).
+// Both operands are row-major in r, the reduction index -- which is exactly the MN-MAJOR shared-memory layout of tcgen05
+// (M / N contiguous, K strided): a TMA box of 32 rows x 32 floats with SWIZZLE_128B_ATOM_32B is one MN-major atom column (4-row K
+// groups 512 B apart, 32-element M / N groups one box = 4096 B apart).  So nothing is transposed: TMA lands grad_offset,
+// offset and x as they lie in HBM, the worker warps rewrite the tiles IN PLACE (dZ = grad * act'(offset), xhat = x * scale +
+// shift with scale = 0 / shift = 1 in the ones column, TF32 rounding) with 128-bit shared-memory accesses, and the MMAs read
+// them with the transpose bits of the instruction descriptor set.  Per 32-row block a CTA pulls 16 + 16 + <= 36 KB through
+// TMA instead of ~70 scalar loads per thread (the LSU path could not keep enough bytes in flight: 4 us per block).
+constexpr int kTStages = 3;
+constexpr int kTBox = 32 * 32 * 4;                              // one TMA box: 32 rows x 128 B
+constexpr int kTMaxXBoxes = 9;                                  // 288 columns >= 272
+constexpr int kTOffG = 0, kTOffO = 4 * kTBox, kTOffX = 8 * kTBox;
+constexpr int kTStageBytes = (8 + kTMaxXBoxes) * kTBox;         // 69 632
+constexpr int kTStatLd = kTMaxXBoxes * 32;                      // 288
+constexpr int kTOffScale = kTStages * kTStageBytes;             // [kMaxUtt][288]
+constexpr int kTOffShift = kTOffScale + kMaxUtt * kTStatLd * 4;
+constexpr int kTOffBar = kTOffShift + kMaxUtt * kTStatLd * 4;
+constexpr int kTNumBars = 3 * kTStages + 1;                     // full, norm, empty per stage + accum
+constexpr int kTOffTmem = kTOffBar + kTNumBars * 8;
+constexpr int kTSmemBytes = kTOffTmem + 16;
+constexpr int kTWorkWarps = 8, kTWorkThreads = kTWorkWarps * 32, kTThreads = kTWorkThreads + 64;   // + MMA warp + TMA warp
+static_assert(kTSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(BM * kStageLd * 4 <= kTStages * kTStageBytes && 32 * kTStatLd * 4 <= kTStages * kTStageBytes, "staging tiles fit in the ring");
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// MN-major TF32 operands have ONE legal shared-memory layout: the 128-byte swizzle with 32-byte atoms (layout type 1; TMA's
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B = 32 consecutive M / N elements, the 32-byte unit index XORed with
+// (row & 3), K groups of FOUR rows 512 B apart (stride offset), 32-element M / N groups one box = 4096 B apart (leading offset).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(kTBox >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) {        // as make_idesc, A and B MN-major (transpose bits 15, 16)
+    return make_idesc(n) | (1u << 15) | (1u << 16);
+}
+
+__global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmG,
+                                                                            const __grid_constant__ CUtensorMap tmO,
+                                                                            const __grid_constant__ CUtensorMap tmX, const BwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    float* s_scale = reinterpret_cast<float*>(smem + kTOffScale);
+    float* s_shift = reinterpret_cast<float*>(smem + kTOffShift);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kTOffTmem);
+    const uint32_t bar_full = sbase + kTOffBar, bar_norm = bar_full + 8 * kTStages, bar_empty = bar_norm + 8 * kTStages,
+                   bar_accum = bar_empty + 8 * kTStages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, n0 = blockIdx.y * BM;
+    const long long ra = (long long)split * a.rows_per_split;
+    const long long rb = ra + a.rows_per_split < a.R ? ra + a.rows_per_split : a.R;
+    const int nkb = rb > ra ? (int)((rb - ra + BK - 1) / BK) : 0;
+    const int nbx = (a.b_rows + 31) / 32;                              // x boxes per block
+
+    if (threadIdx.x == 0) {
+        if (sbase & 1023) __trap();
+        for (int s = 0; s < kTStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_norm + 8 * s, kTWorkWarps);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kTWorkWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // xhat = x * scale + shift for the (at most kMaxUtt) utterances of this CTA's rows: scale = 1 / (std + eps), shift = -mean * scale;
+    // column Din: scale 0, shift 1 (the ones column that makes grad_b column Din of D); columns past it: 0, 0
+    const long long u_first = ra / a.n_frames;
+    for (int i = threadIdx.x; i < kMaxUtt * kTStatLd; i += kTThreads) {
+        const int ul = i / kTStatLd, k = i - ul * kTStatLd;
+        const long long u = u_first + ul;
+        float sc = k < a.Din ? 1.0f : 0.0f, sh = k == a.Din ? 1.0f : 0.0f;
+        if (k < a.Din && u * a.n_frames < a.R) {
+            if (a.mean) {
+                sc = 1.0f / (__ldg(a.stdv + u * a.ld_stats + k) + a.cmvn_eps);
+                sh = -__ldg(a.mean + u * a.ld_stats + k) * sc;
+            } else if (a.sums) {                                       // same arithmetic as the fused forward head (head_fused.cu)
+                const double2 p = *reinterpret_cast<const double2*>(a.sums + (u * a.ld_stats + k) * 2);
+                const double mean = p.x * a.inv_n;
+                const float var = (float)((p.y - p.x * mean) * a.inv_nm1);
+                sc = __fdividef(1.0f, sqrtf(fmaxf(var, 0.0f)) + a.cmvn_eps);
+                sh = -(float)mean * sc;
+            }
+        }
+        s_scale[i] = sc;
+        s_shift[i] = sh;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == kTWorkWarps + 1) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)(8 + nbx) * kTBox;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kTStages;
+                if (kb >= kTStages) mbar_wait(bar_empty + 8 * s, ((kb / kTStages) - 1) & 1);
+                const uint32_t st = sbase + s * kTStageBytes, bar = bar_full + 8 * s;
+                const int r0 = (int)(ra + (long long)kb * BK);
+                mbar_expect_tx(bar, tx);
+                for (int m = 0; m < 4; ++m) {
+                    tma_load_2d(st + kTOffG + m * kTBox, &tmG, n0 + 32 * m, r0, bar);
+                    tma_load_2d(st + kTOffO + m * kTBox, &tmO, n0 + 32 * m, r0, bar);
+                }
+                for (int j = 0; j < nbx; ++j) tma_load_2d(st + kTOffX + j * kTBox, &tmX, 32 * j, r0, bar);
+            }
+        }
+    } else if (warp == kTWorkWarps) {
+        // ===================== MMA issuer =====================
+        if (lane == 0 && nkb > 0) {
+            const uint32_t idesc_main = make_idesc_mn(a.n_main), idesc_tail = make_idesc_mn(a.n_tail > 0 ? a.n_tail : 16);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kTStages;
+                mbar_wait(bar_norm + 8 * s, (kb / kTStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = sbase + s * kTStageBytes + kTOffG, b_addr = sbase + s * kTStageBytes + kTOffX;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {                    // 8 rows of r per instruction = one 1024-byte K group
+                    const uint64_t ad = make_desc_mn(a_addr + kk * 1024);
+                    umma_tf32(tmem_base, ad, make_desc_mn(b_addr + kk * 1024), idesc_main, (kb | kk) ? 1u : 0u);
+                    if (a.n_tail > 0)
+                        umma_tf32(tmem_base + (uint32_t)a.n_main, ad, make_desc_mn(b_addr + (a.n_main / 32) * kTBox + kk * 1024),
+                                  idesc_tail, (kb | kk) ? 1u : 0u);
+                }
+                umma_commit(bar_empty + 8 * s);
+            }
+            umma_commit(bar_accum);
+        }
+    } else {
+        // ===================== workers: rewrite the landed tiles in place, then the epilogue =====================
+        const int t = threadIdx.x;
+        const int row = t >> 3, pc = t & 7, lc = pc ^ ((row & 3) << 1);    // this thread's row of every box, physical / logical 16-byte chunk
+        const bool do_left = a.simt_rows > 0 && blockIdx.y == 0;           // leftover output row n_left (at most one here)
+        const int n_left = a.m_tiles * BM;
+        float4 acc_l[kTMaxXBoxes];
+#pragma unroll
+        for (int j = 0; j < kTMaxXBoxes; ++j) acc_l[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kTStages;
+            const long long r0 = ra + (long long)kb * BK;
+            float dzl = 0.0f;
+            if (do_left && r0 + row < rb)                                  // in flight while the stage lands
+                dzl = dact(__ldg(a.grad_offset + (r0 + row) * a.ld_off + n_left), __ldg(a.offset + (r0 + row) * a.ld_off + n_left), a.act);
+            const long long uq = r0 / a.n_frames;
+            const int bnd = (int)((uq + 1) * a.n_frames - r0);             // rows of the block before the next utterance (n_frames >= 32)
+            const int so = ((int)(uq - u_first) + (row >= bnd ? 1 : 0)) * kTStatLd + 4 * lc;
+            mbar_wait(bar_full + 8 * s, (kb / kTStages) & 1);
+            float4* G = reinterpret_cast<float4*>(smem + s * kTStageBytes + kTOffG);
+            const float4* O = reinterpret_cast<const float4*>(smem + s * kTStageBytes + kTOffO);
+            float4* X = reinterpret_cast<float4*>(smem + s * kTStageBytes + kTOffX);
+#pragma unroll
+            const float live = r0 + row < rb ? 1.0f : 0.0f;                // rows past the split (the next utterance's, per-utterance mode)
+            for (int m = 0; m < 4; ++m) {                                  // dZ = grad * act'(offset); rows past R / columns past D_out landed as 0
+                const float4 g = G[t + 256 * m], o = O[t + 256 * m];
+                G[t + 256 * m] = make_float4(to_tf32(live * dact(g.x, o.x, a.act)), to_tf32(live * dact(g.y, o.y, a.act)),
+                                             to_tf32(live * dact(g.z, o.z, a.act)), to_tf32(live * dact(g.w, o.w, a.act)));
+            }
+#pragma unroll
+            for (int j = 0; j < kTMaxXBoxes; ++j) {
+                if (j < nbx) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + so + 32 * j);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + so + 32 * j);
+                    float4 v = X[t + 256 * j];
+                    v.x = to_tf32(fmaf(v.x, sc.x, sh.x));
+                    v.y = to_tf32(fmaf(v.y, sc.y, sh.y));
+                    v.z = to_tf32(fmaf(v.z, sc.z, sh.z));
+                    v.w = to_tf32(fmaf(v.w, sc.w, sh.w));
+                    if (r0 + row >= rb) v = make_float4(0.f, 0.f, 0.f, 0.f);   // (only the ones column matters: dZ of these rows is 0)
+                    X[t + 256 * j] = v;
+                    if (do_left) {
+                        acc_l[j].x = fmaf(v.x, dzl, acc_l[j].x);
+                        acc_l[j].y = fmaf(v.y, dzl, acc_l[j].y);
+                        acc_l[j].z = fmaf(v.z, dzl, acc_l[j].z);
+                        acc_l[j].w = fmaf(v.w, dzl, acc_l[j].w);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_norm + 8 * s);
+        }
+        if (nkb > 0) {
+            mbar_wait(bar_accum, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        float* stage = reinterpret_cast<float*>(smem);                       // every stage has been consumed: reuse the ring
+        if (do_left) {
+            // partial row n_left of this split: column sums over the 32 rows of the per-thread accumulators
+#pragma unroll
+            for (int j = 0; j < kTMaxXBoxes; ++j)
+                if (j < nbx) *reinterpret_cast<float4*>(stage + row * kTStatLd + 32 * j + 4 * lc) = acc_l[j];
+            asm volatile("bar.sync 1, %0;" ::"n"(kTWorkThreads) : "memory");
+            float* dst = a.partials + ((long long)split * a.m_rows + n_left) * kMaxBRows;
+            for (int k = t; k < a.b_rows; k += kTWorkThreads) {
+                float sum = 0.0f;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) sum += stage[r * kTStatLd + k];
+                dst[k] = sum;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTWorkThreads) : "memory");
+        }
+        // ---- epilogue: the CTA's partial D -> workspace
+        const int quad = warp & 3, half = warp >> 2;
+        const int trow = quad * 32 + lane;
+        const int ncol16 = a.b_rows / 16;
+        const int c_lo = 16 * (half == 0 ? 0 : ncol16 / 2), c_hi = 16 * (half == 0 ? ncol16 / 2 : ncol16);
+        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            uint32_t acc[16];
+            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4)
+                *reinterpret_cast<float4*>(stage + trow * kStageLd + c0 + jj) =
+                    nkb > 0 ? make_float4(__uint_as_float(acc[jj]), __uint_as_float(acc[jj + 1]), __uint_as_float(acc[jj + 2]),
+                                          __uint_as_float(acc[jj + 3]))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTWorkThreads) : "memory");
+        float* dst = a.partials + ((long long)split * a.m_rows + n0) * kMaxBRows;
+        for (int rr = warp; rr < BM; rr += kTWorkWarps)
+            for (int c = lane; c < a.b_rows; c += 32) dst[(long long)rr * kMaxBRows + c] = stage[rr * kStageLd + c];
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == kTWorkWarps) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: `cols` x `rows` elements, `ld` floats between rows, box = 32 floats x 32 rows, SWIZZLE_128B_ATOM_32B; elements
+// outside [0, cols) x [0, rows) read as zero
+bool make_map32(CUtensorMap* map, const float* base, long long cols, long long rows, long long ld) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // grad_W[n, k] = sum_s partials[s, n, k], grad_b[n] = sum_s partials[s, n, Din]
 __global__ void head_bwd_reduce_kernel(const float* __restrict__ partials, int splits, int m_rows, int Din, int Dout,
                                        float* __restrict__ grad_W, float* __restrict__ grad_b) {
@@ -543,8 +820,24 @@ static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const f
         SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
     cudaStream_t st = (cudaStream_t)stream;
-    linear_head_bwd_tc_kernel<<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kThreads, kSmemBytes, st>>>(a);
-    int rc = secommon::check_launch("linear_head_bwd_tc_kernel");
+    // aligned operands (the engine's padded tensors): the TMA / MN-major kernel; anything else: the transposing producers
+    const bool aligned = ldx % 4 == 0 && ld_off % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(offset) |
+                                                               reinterpret_cast<uintptr_t>(grad_offset)) & 15) == 0;
+    CUtensorMap tmG, tmO, tmX;
+    static int force_old = -1;
+    if (force_old < 0) { const char* e = getenv("SE_B200_BWD_OLD"); force_old = e && atoi(e) ? 1 : 0; }
+    int rc;
+    if (!force_old && aligned && g.simt_rows <= 1 && a.R < 0x7fffffffLL && make_map32(&tmG, grad_offset, D_out, a.R, ld_off) &&
+        make_map32(&tmO, offset, D_out, a.R, ld_off) && make_map32(&tmX, x, D_in, a.R, ldx)) {
+        static unsigned long long opted_t = 0;
+        if (secommon::first_use_on_device(opted_t))
+            SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes));
+        linear_head_bwd_tma_kernel<<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kTThreads, kTSmemBytes, st>>>(tmG, tmO, tmX, a);
+        rc = secommon::check_launch("linear_head_bwd_tma_kernel");
+    } else {
+        linear_head_bwd_tc_kernel<<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kThreads, kSmemBytes, st>>>(a);
+        rc = secommon::check_launch("linear_head_bwd_tc_kernel");
+    }
     if (rc != SE_OK) return rc;
     const long long total = D_out * (D_in + 1);
     if (per_utt_out) {
