@@ -238,6 +238,14 @@ int se_sisdr_mask_fwd(const float* offset, int64_t ld_off, const float* linear_i
 int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar,
                       int64_t ld_tar, const int64_t* stft_len, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
                       const double* sums3, const float* grad_out, float* grad_offset, int64_t ld_g, void* stream);
+/* se_sisdr_mask_step: the objective's part of one training step (runner.py:455-460) in three launches: the sums, the
+ * per-utterance losses + their batch mean (objective.py:100; loss_mean: 1 float, loss_per_utt may be NULL) and
+ * grad_offset = d loss_mean / d offset.  lengths: frame counts (len_hop = 0) or SAMPLE lengths with len_hop = hop, in which
+ * case frames = length / hop + 1 is taken in the kernels (runner.py:455).  sums_zeroed != 0: sums3 is already zero. */
+int se_sisdr_mask_step(const float* offset, int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar,
+                       int64_t ld_tar, const int64_t* lengths, int64_t len_hop, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
+                       double* sums3, int sums_zeroed, float* loss_per_utt, float* loss_mean, float* grad_offset, int64_t ld_g,
+                       void* stream);
 
 /* ---- active sampling (sampler.py:59-120, driven by runner.py:383-411) ----------------------------------------------------
  * se_head_grad_embeddings: per-UTTERANCE gradients of the head -- row u of grads_out (n_utt, D_out*D_in + D_out) is
@@ -265,6 +273,14 @@ int se_match_scores(const float* query, int64_t n_query, const float* key, int64
 int se_adam_clip_step(float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                       const int64_t* numels, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
                       float max_norm, double* ws_acc, int* ws_state, void* stream);
+/* se_adam_clip_step_mirror: the same step; additionally tensor t (viewed as rows of mirror_cols[t] elements) is written to
+ * mirrors[t] with mirror_lds[t] floats between rows (mirrors NULL or mirrors[t] NULL: none) -- the 16-byte-row copy of the
+ * head weight that the TMA / tensor-core head reads, rounded to TF32 (nearest, ties away) if mirror_tf32 != 0 -- so the copy
+ * follows the parameters inside the same launch (skipped steps leave both untouched). */
+int se_adam_clip_step_mirror(float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                             const int64_t* numels, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             float max_norm, float* const* mirrors, const int64_t* mirror_cols, const int64_t* mirror_lds,
+                             int mirror_tf32, double* ws_acc, int* ws_state, void* stream);
 
 /* ---- K1 + K2 of the fused evaluation step ------------------------------------------
  * se_stft_features: STFT of one channel -> ONE feature tensor feat (n_utt, n_frames, feat_stride): power (take_log = 0)

@@ -36,6 +36,10 @@ _SIGNATURES = {
     "se_linear_head_bwd_fused": [c_f, i64, c_f, i64, c_float, c_f, c_f, i64, i64, i64, i64, i64, c_int, c_f, i64, c_f, c_f, c_f],
     "se_adam_clip_step": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_int, c_float, c_float,
                           c_float, c_float, c_float, c_float, c_f, c_f, c_f],
+    "se_adam_clip_step_mirror": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_int, c_float,
+                                 c_float, c_float, c_float, c_float, c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_int,
+                                 c_f, c_f, c_f],
+    "se_sisdr_mask_step": [c_f, i64, c_f, i64, c_f, i64, c_f, i64, i64, i64, i64, c_float, c_f, c_int, c_f, c_f, c_f, i64, c_f],
     "se_head_grad_embeddings_workspace": [i64, i64, i64, i64],
     "se_head_grad_embeddings": [c_f, i64, c_f, c_f, c_f, i64, c_float, c_f, c_f, i64, i64, i64, i64, i64, c_int, c_f, i64, c_f, c_f],
     "se_match_scores": [c_f, i64, c_f, i64, i64, c_float, c_f, c_f, c_f, c_f],

@@ -120,6 +120,26 @@ __global__ void sisdr_spec_finish_kernel(const double* __restrict__ sums3, int n
     if (u < n_utt) loss[u] = (float)(-sisdr_from_sums(sums3[3 * u], sums3[3 * u + 1], sums3[3 * u + 2], (double)eps));
 }
 
+// one block: per-utterance losses and their batch mean (objective.py:100) in one launch
+__global__ void __launch_bounds__(256) sisdr_finish_mean_kernel(const double* __restrict__ sums3, int n_utt, float eps,
+                                                                float* __restrict__ loss, float* __restrict__ loss_mean) {
+    __shared__ double part[8];
+    double acc = 0.0;
+    for (int u = threadIdx.x; u < n_utt; u += blockDim.x) {
+        const float l = (float)(-sisdr_from_sums(sums3[3 * u], sums3[3 * u + 1], sums3[3 * u + 2], (double)eps));
+        if (loss) loss[u] = l;
+        acc += (double)l;
+    }
+    acc = secommon::warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+        *loss_mean = (float)(t / (double)n_utt);
+    }
+}
+
 __global__ void sisdr_spec_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar,
                                       const long long* __restrict__ stft_len, int n_utt, int n_frames, int K, float eps_f,
                                       const double* __restrict__ sums3, const float* __restrict__ grad_out,
@@ -175,12 +195,20 @@ struct SisdrMaskArgs {
     int n_utt, n_frames, K, chunks;
     double* sums3;
     float eps; const float* grad_out; float* grad_offset; long long ld_g;   // backward only
+    int len_hop;             // > 0: stft_len holds SAMPLE lengths, frames = len / len_hop + 1 (runner.py:455)
+    float grad_uniform;      // grad_out == nullptr: every utterance's upstream gradient (1 / B for the batch-mean loss)
 };
+
+__device__ __forceinline__ int mask_valid_frames(const SisdrMaskArgs& a, int u) {
+    long long v = a.n_frames;
+    if (a.stft_len) v = a.len_hop > 0 ? a.stft_len[u] / a.len_hop + 1 : a.stft_len[u];
+    return (int)min((long long)a.n_frames, v);
+}
 
 template <int V>
 __global__ void __launch_bounds__(256) sisdr_mask_sums_kernel(const SisdrMaskArgs a) {
     const int u = blockIdx.x / a.chunks, chunk = blockIdx.x - u * a.chunks;
-    const int valid = (int)min((long long)a.n_frames, a.stft_len ? a.stft_len[u] : (long long)a.n_frames);
+    const int valid = mask_valid_frames(a, u);
     const int KV = (a.K + V - 1) / V;
     const int per = (valid + a.chunks - 1) / a.chunks;
     const int f_lo = chunk * per, f_hi = min(valid, f_lo + per);
@@ -210,7 +238,7 @@ __global__ void __launch_bounds__(256) sisdr_mask_sums_kernel(const SisdrMaskArg
 template <int V>
 __global__ void __launch_bounds__(256) sisdr_mask_bwd_kernel(const SisdrMaskArgs a) {
     const int u = blockIdx.x / a.chunks, chunk = blockIdx.x - u * a.chunks;
-    const int valid = (int)min((long long)a.n_frames, a.stft_len ? a.stft_len[u] : (long long)a.n_frames);
+    const int valid = mask_valid_frames(a, u);
     const int KV = (int)(a.ld_g / V) < (a.K + V - 1) / V ? (a.K + V - 1) / V : (int)(a.ld_g / V);   // whole rows of grad_offset
     const int per = (a.n_frames + a.chunks - 1) / a.chunks;
     const int f_lo = chunk * per, f_hi = min(a.n_frames, f_lo + per);
@@ -223,7 +251,7 @@ __global__ void __launch_bounds__(256) sisdr_mask_bwd_kernel(const SisdrMaskArgs
     const double kappa = -10.0 / (log(10.0) * (R + eps) * D * D);        // see sisdr_spec_bwd_kernel
     const double ca = 2.0 * al * tt / (tt + eps);
     const double cd = 2.0 * (al * tt - st) / (tt + eps) - 2.0 * al;
-    const double go = (double)a.grad_out[u];
+    const double go = a.grad_out ? (double)a.grad_out[u] : (double)a.grad_uniform;
     const float c_t = (float)(go * kappa * (ca * D - A * cd));
     const float c_s = (float)(go * kappa * (-2.0 * A));
     const long long row0 = (long long)u * a.n_frames;
@@ -264,6 +292,7 @@ struct AdamArgs {
     long long n[kAdamMaxTensors];
     int count;
     float lr, beta1, beta2, eps, weight_decay, max_norm;   // max_norm <= 0: no clipping
+    float* mir[kAdamMaxTensors]; int mir_cols[kAdamMaxTensors]; long long mir_ld[kAdamMaxTensors]; int mir_tf32;   // optional row-padded copies
     double* acc;       // [1] sum of squared gradients of this step (zeroed by the update kernel's last CTA)
     int* state;        // [0] steps taken, [1] CTAs of the update kernel that have finished, [2] steps skipped (NaN / inf norm)
 };
@@ -303,7 +332,15 @@ __global__ void __launch_bounds__(256) adam_update_kernel(const AdamArgs a) {
             const float v = a.beta2 * a.v[t][i] + (1.0f - a.beta2) * g * g;
             a.m[t][i] = m;
             a.v[t][i] = v;
-            a.p[t][i] = p - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+            const float pn = p - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+            a.p[t][i] = pn;
+            if (a.mir[t]) {                                                 // the row-padded (TF32-rounded) copy the head kernels read
+                const long long row = i / a.mir_cols[t];
+                const int col = (int)(i - row * a.mir_cols[t]);
+                float w = pn;
+                if (a.mir_tf32) w = __int_as_float((__float_as_int(pn) + 0x1000) & ~0x1FFF);   // nearest, ties away (cvt.rna.tf32)
+                a.mir[t][row * a.mir_ld[t] + col] = w;
+            }
         }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -953,10 +990,47 @@ int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_i
     return secommon::check_launch("sisdr_mask_bwd_kernel");
 }
 
+int se_sisdr_mask_step(const float* offset, int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar,
+                       int64_t ld_tar, const int64_t* lengths, int64_t len_hop, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
+                       double* sums3, int sums_zeroed, float* loss_per_utt, float* loss_mean, float* grad_offset, int64_t ld_g,
+                       void* stream) {
+    SE_REQUIRE(linear_inp && linear_tar && sums3 && loss_mean && grad_offset && n_utt > 0 && n_frames > 0 && K > 0, "bad argument");
+    SE_REQUIRE(ld_inp >= K && ld_tar >= K && ld_g >= K && (!offset || ld_off >= K), "row stride smaller than K");
+    SE_REQUIRE(len_hop >= 0 && len_hop < (1LL << 30), "len_hop=%lld out of range", (long long)len_hop);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!sums_zeroed) SE_CUDA_CHECK(cudaMemsetAsync(sums3, 0, sizeof(double) * 3 * n_utt, st));
+    SisdrMaskArgs a{};
+    a.offset = offset; a.inp = linear_inp; a.tar = linear_tar; a.ld_off = ld_off; a.ld_inp = ld_inp; a.ld_tar = ld_tar;
+    a.stft_len = (const long long*)lengths; a.len_hop = (int)len_hop; a.n_utt = (int)n_utt; a.n_frames = (int)n_frames; a.K = (int)K;
+    a.chunks = pick_chunks(n_utt, n_frames * K, 2048); a.sums3 = sums3; a.eps = eps;
+    a.grad_out = nullptr; a.grad_uniform = 1.0f / (float)n_utt; a.grad_offset = grad_offset; a.ld_g = ld_g;
+    const long long need = (K + 3) / 4 * 4;
+    const bool v4 = vec4_ok(offset, ld_off) && vec4_ok(linear_inp, ld_inp) && vec4_ok(linear_tar, ld_tar) && vec4_ok(grad_offset, ld_g) &&
+                    ld_inp >= need && ld_tar >= need && ld_g >= need && (!offset || ld_off >= need);
+    if (v4) sisdr_mask_sums_kernel<4><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
+    else sisdr_mask_sums_kernel<1><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
+    int rc = secommon::check_launch("sisdr_mask_sums_kernel");
+    if (rc != SE_OK) return rc;
+    sisdr_finish_mean_kernel<<<1, 256, 0, st>>>(sums3, (int)n_utt, eps, loss_per_utt, loss_mean);
+    if ((rc = secommon::check_launch("sisdr_finish_mean_kernel")) != SE_OK) return rc;
+    if (v4) sisdr_mask_bwd_kernel<4><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
+    else sisdr_mask_bwd_kernel<1><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
+    return secommon::check_launch("sisdr_mask_bwd_kernel");
+}
+
 int se_adam_clip_step(float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                       const int64_t* numels, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
                       float max_norm, double* ws_acc, int* ws_state, void* stream) {
+    return se_adam_clip_step_mirror(params, grads, exp_avg, exp_avg_sq, numels, n_tensors, lr, beta1, beta2, eps, weight_decay, max_norm,
+                                    nullptr, nullptr, nullptr, 0, ws_acc, ws_state, stream);
+}
+
+int se_adam_clip_step_mirror(float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                             const int64_t* numels, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             float max_norm, float* const* mirrors, const int64_t* mirror_cols, const int64_t* mirror_lds,
+                             int mirror_tf32, double* ws_acc, int* ws_state, void* stream) {
     SE_REQUIRE(params && grads && exp_avg && exp_avg_sq && numels && ws_acc && ws_state, "null pointer");
+    SE_REQUIRE(!mirrors || (mirror_cols && mirror_lds), "mirrors need their column counts and row strides");
     SE_REQUIRE(n_tensors > 0 && n_tensors <= kAdamMaxTensors, "n_tensors=%d must be in [1, %d]", n_tensors, kAdamMaxTensors);
     AdamArgs a{};
     long long total = 0;
@@ -964,7 +1038,13 @@ int se_adam_clip_step(float* const* params, float* const* grads, float* const* e
         SE_REQUIRE(params[t] && grads[t] && exp_avg[t] && exp_avg_sq[t] && numels[t] > 0, "tensor %d: null pointer or empty", t);
         a.p[t] = params[t]; a.g[t] = grads[t]; a.m[t] = exp_avg[t]; a.v[t] = exp_avg_sq[t]; a.n[t] = numels[t];
         total += numels[t];
+        if (mirrors && mirrors[t]) {
+            SE_REQUIRE(mirror_cols[t] > 0 && mirror_cols[t] < (1LL << 31) && numels[t] % mirror_cols[t] == 0 && mirror_lds[t] >= mirror_cols[t],
+                       "tensor %d: mirror shape does not match", t);
+            a.mir[t] = mirrors[t]; a.mir_cols[t] = (int)mirror_cols[t]; a.mir_ld[t] = mirror_lds[t];
+        }
     }
+    a.mir_tf32 = mirror_tf32;
     a.count = n_tensors; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
     a.acc = ws_acc; a.state = ws_state;
     cudaStream_t st = (cudaStream_t)stream;

@@ -20,6 +20,11 @@ import torch
 from . import _lib, dp, ops
 
 
+def _c64(lengths):
+    """contiguous int64 lengths (what the kernels read)"""
+    return lengths if lengths.dtype == torch.int64 and lengths.is_contiguous() else lengths.to(torch.int64).contiguous()
+
+
 class EnhancementEngine:
     def __init__(self, preprocessor, head, log_features=True, precision=0, feat_cfg=None):
         """preprocessor: se_b200 OnlinePreprocessor (gives n_fft / hop / window, channel_inp/tar);
@@ -260,11 +265,9 @@ class EnhancementEngine:
             wpad = self._padded_weight()            # current: refreshed in place after every update (_clip_and_step)
             stats = stat_sums if head.cmvn else None
             offset = ops.linear_head_tma(feats, D, wpad, head.linear.bias, head.activation, stats, head.eps)
-            frames = lengths // self.hop + 1
-            loss_u, sums3 = ops.sisdr_mask_fwd(offset, linear_inp, linear_tar, frames, K, objective.eps, sums3=sums3)
-            loss = loss_u.mean()
-            grad_out = torch.full((B,), 1.0 / B, device=dev)
-            grad_offset = ops.sisdr_mask_bwd(offset, linear_inp, linear_tar, frames, K, sums3, grad_out, objective.eps)
+            # frames = lengths // hop + 1, the batch-mean loss and d loss / d offset inside three launches
+            loss, _, grad_offset, _ = ops.sisdr_mask_step(offset, linear_inp, linear_tar, _c64(lengths), self.hop, K, objective.eps,
+                                                           sums3=sums3, sums_zeroed=True)
             gw, gb = ops.linear_head_bwd_fused(feats, D, stats, head.eps, offset, grad_offset, K, head.activation)
             for p, g in ((head.linear.weight, gw), (head.linear.bias, gb)):
                 if p.grad is None:
@@ -278,7 +281,12 @@ class EnhancementEngine:
         with any other optimizer (the guard is then the runner's host-side check, which cannot run under graph capture)."""
         from .optim import ClipAdam
         if isinstance(optimizer, ClipAdam):
-            optimizer.clip_and_step(grad_clip)
+            # the update kernel also writes the padded / TF32 copy the head kernels read (one persistent buffer, see _padded_weight)
+            w = self.head.linear.weight
+            buf = self._padded_weight()
+            optimizer.clip_and_step(grad_clip, mirrors={w: buf}, mirror_tf32=self.precision == 1)
+            self._wpad_key = (w.data_ptr(), w._version)
+            return
         else:
             params = list(self.head.parameters())
             if grad_clip is not None:

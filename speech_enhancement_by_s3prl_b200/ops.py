@@ -181,6 +181,26 @@ def linear_head_bwd_fused(x, D_in, stat_sums, cmvn_eps, offset, grad_offset, D_o
     return gw, gb
 
 
+def sisdr_mask_step(offset, linear_inp, linear_tar, lengths, hop, K, eps=1e-10, sums3=None, sums_zeroed=False):
+    """The objective's part of a training step on (B, F, LD) row-padded tensors in three launches: objective.SISDR of
+    predicted = offset * linear_inp (mean over the batch, objective.py:100) and d loss / d offset.  ``lengths``: SAMPLE lengths
+    (int64, device), frames = lengths // hop + 1 is taken inside the kernels (runner.py:455).
+    Returns (loss (0-dim), loss_per_utt (B,), grad_offset (B, F, LDo), sums3)."""
+    B, F, LDi = linear_inp.shape
+    dev = linear_inp.device
+    with torch.cuda.device(dev):
+        if sums3 is None:
+            sums3, sums_zeroed = torch.zeros(B, 3, device=dev, dtype=torch.float64), True
+        out = torch.empty(B + 1, device=dev)
+        grad = torch.empty_like(offset)
+        rc = _lib.load().se_sisdr_mask_step(offset.data_ptr(), offset.shape[2], linear_inp.data_ptr(), LDi, linear_tar.data_ptr(),
+                                            linear_tar.shape[2], lengths.data_ptr(), int(hop), B, F, int(K), float(eps), sums3.data_ptr(),
+                                            1 if sums_zeroed else 0, out.data_ptr(), out[B:].data_ptr(), grad.data_ptr(),
+                                            grad.shape[2], _stream())
+        _lib.check(rc, "se_sisdr_mask_step")
+    return out[B], out[:B], grad, sums3
+
+
 def sisdr_mask_fwd(offset, linear_inp, linear_tar, stft_lengths, K, eps=1e-10, sums3=None):
     """objective.SISDR of predicted = offset * linear_inp on (B, F, LD) row-padded tensors (offset None: predicted =
     linear_inp).  Returns (loss_per_utt (B,), sums3 (B, 3) float64 for the backward)."""

@@ -40,8 +40,11 @@ class ClipAdam(torch.optim.Optimizer):
         return ps, ws
 
     @torch.no_grad()
-    def clip_and_step(self, max_norm=None):
-        """``clip_grad_norm_(params, max_norm)`` (skipped for None / <= 0) followed by ``Adam.step()``, per parameter group."""
+    def clip_and_step(self, max_norm=None, mirrors=None, mirror_tf32=False):
+        """``clip_grad_norm_(params, max_norm)`` (skipped for None / <= 0) followed by ``Adam.step()``, per parameter group.
+        mirrors: {parameter: (rows, LD) fp32 buffer} -- the update kernel also writes the new value of a 2-D parameter
+        (rows, cols <= LD) into its row-padded buffer, rounded to TF32 if ``mirror_tf32`` (the copy the TMA / tensor-core head
+        reads: it follows the parameters inside the same launch instead of three more)."""
         lib = _lib.load()
         for group in self.param_groups:
             ps, ws = self._group_state(group)
@@ -50,15 +53,28 @@ class ClipAdam(torch.optim.Optimizer):
             n = len(ps)
             arr = ctypes.c_void_p * n
             sizes = (ctypes.c_int64 * n)(*[p.numel() for p in ps])
+            mir = [None] * n
+            if mirrors:
+                for i, p in enumerate(ps):
+                    buf = next((b for q, b in mirrors.items() if q is p), None)
+                    if buf is not None:
+                        if p.dim() != 2 or buf.dim() != 2 or buf.shape[0] != p.shape[0] or buf.shape[1] < p.shape[1] or \
+                                buf.dtype != torch.float32 or buf.device != p.device or buf.stride(1) != 1:
+                            raise RuntimeError("ClipAdam: a mirror must be a (rows, LD >= cols) fp32 buffer on the parameter's device")
+                        mir[i] = buf
+            cols = (ctypes.c_int64 * n)(*[(p.shape[1] if mir[i] is not None else 0) for i, p in enumerate(ps)])
+            lds = (ctypes.c_int64 * n)(*[(mir[i].stride(0) if mir[i] is not None else 0) for i in range(n)])
             with torch.cuda.device(ps[0].device):
-                rc = lib.se_adam_clip_step(arr(*[p.data_ptr() for p in ps]), arr(*[p.grad.data_ptr() for p in ps]),
-                                           arr(*[self.state[p]["exp_avg"].data_ptr() for p in ps]),
-                                           arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps]), sizes, n,
-                                           float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
-                                           float(group["eps"]), float(group["weight_decay"]),
-                                           float(max_norm) if max_norm is not None else 0.0, ws[0].data_ptr(), ws[1].data_ptr(),
-                                           torch.cuda.current_stream().cuda_stream)
-            _lib.check(rc, "se_adam_clip_step")
+                rc = lib.se_adam_clip_step_mirror(arr(*[p.data_ptr() for p in ps]), arr(*[p.grad.data_ptr() for p in ps]),
+                                                  arr(*[self.state[p]["exp_avg"].data_ptr() for p in ps]),
+                                                  arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps]), sizes, n,
+                                                  float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
+                                                  float(group["eps"]), float(group["weight_decay"]),
+                                                  float(max_norm) if max_norm is not None else 0.0,
+                                                  arr(*[(b.data_ptr() if b is not None else None) for b in mir]), cols, lds,
+                                                  1 if mirror_tf32 else 0, ws[0].data_ptr(), ws[1].data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "se_adam_clip_step_mirror")
             for p in ps:                            # the kernel wrote through raw pointers: let version-keyed caches see it
                 torch.autograd.graph.increment_version(p)
                 torch.autograd.graph.increment_version(p.grad)

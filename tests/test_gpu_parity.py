@@ -1257,6 +1257,13 @@ def test_sisdr_mask_kernels_match_unfused_objective(se):
         assert (gr[1, 60:] == 0).all() and (gr[2, 1:] == 0).all()
         loss_p, _ = ops.sisdr_mask_fwd(None, pad(off * inp), pad(tar), frames, K)   # offset = None: predicted given
         np.testing.assert_allclose(loss_p.cpu().numpy(), loss_ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
+        # the training step's three-launch form: frames = lengths // hop + 1 in the kernels, batch-mean loss, uniform 1 / B gradient
+        hop = 160
+        lens = (frames - 1) * hop + torch.LongTensor([0, 159, 7, 80, 1]).cuda()
+        l_mean, l_u, g_step, _ = ops.sisdr_mask_step(pad(off), pad(inp), pad(tar), lens, hop, K)
+        assert l_mean.dim() == 0 and abs(l_mean.item() - loss_ref.mean().item()) < 1e-5
+        np.testing.assert_allclose(l_u.cpu().numpy(), loss.cpu().numpy(), rtol=0, atol=0)
+        assert torch.equal(g_step, gr)
 
 
 # ------------------------------------------------------------------------------ clip + Adam in two launches
@@ -1281,6 +1288,20 @@ def test_clip_adam_matches_torch_clip_and_adam(se, max_norm, wd):
             assert (p.grad - q.grad).abs().max().item() <= 1e-6 * max(1.0, p.grad.abs().max().item())
             assert (p - q).abs().max().item() < 2e-6
     assert o_new.steps_taken() == [5]
+    # mirrors: the update kernel keeps a row-padded, TF32-rounded copy of a 2-D parameter current (what the head kernels read)
+    from speech_enhancement_by_s3prl_b200 import ops
+    buf = torch.full((257, 260), 7.0, device="cuda")
+    for q, gr in zip(p_new, grads):
+        q.grad = gr.clone()
+    o_new.clip_and_step(max_norm, mirrors={p_new[0]: buf}, mirror_tf32=True)
+    assert torch.equal(buf[:, :257], ops.round_tf32(p_new[0].detach())) and (buf[:, 257:] == 7.0).all()
+    buf32 = torch.zeros(257, 260, device="cuda")
+    for q, gr in zip(p_new, grads):
+        q.grad = gr.clone()
+    o_new.clip_and_step(max_norm, mirrors={p_new[0]: buf32})
+    assert torch.equal(buf32[:, :257], p_new[0].detach())
+    with pytest.raises(RuntimeError):
+        o_new.clip_and_step(max_norm, mirrors={p_new[1]: buf32})              # a 1-D parameter has no row-padded copy
     with pytest.raises(RuntimeError):
         cpu_p = torch.nn.Parameter(torch.zeros(3))
         cpu_p.grad = torch.ones(3)
