@@ -29,7 +29,7 @@ constexpr int kATileBytes = BM * BK * 4;                       // 16 KB
 constexpr int kMaxBRows = 272;
 constexpr int kBTileBytes = kMaxBRows * BK * 4;                // 34 816
 constexpr int kStageBytes = kATileBytes + kBTileBytes;         // 51 200
-constexpr int kMaxUtt = 4;                                     // utterances one CTA's row range may touch
+constexpr int kMaxUtt = 8;                                     // utterances one CTA's row range may touch
 constexpr int kMaxSimtRows = 4;                                // leftover output rows handled without the tensor cores
 constexpr int kOffRing = 0;
 constexpr int kOffStats = kOffRing + kStages * kStageBytes;    // [kMaxUtt][272] (mean, 1/(std+eps))
@@ -737,9 +737,14 @@ bool plan(long long R, long long n_frames, long long Din, long long Dout, Geomet
     if (splits < 1) splits = 1;
     long long rows = (R + splits - 1) / splits;
     rows = (rows + BK - 1) / BK * BK;
+    // a split may touch at most kMaxUtt utterances (their CMVN constants are staged in shared memory): large batches of short
+    // utterances get more splits than one wave of CTAs instead of longer row ranges
+    const long long max_rows = (kMaxUtt - 2) * n_frames / BK * BK;
+    if (rows > max_rows) rows = max_rows;
     g->rows_per_split = rows;
-    g->splits = (int)((R + rows - 1) / rows);
-    // a split may touch at most kMaxUtt utterances (their CMVN constants are staged in shared memory)
+    const long long n_splits = (R + rows - 1) / rows;
+    if (n_splits > 65535) return false;
+    g->splits = (int)n_splits;
     return (rows + n_frames - 1) / n_frames + 1 <= kMaxUtt;
 }
 

@@ -1169,6 +1169,46 @@ def test_tensor_core_head_backward_matches_torch(se, B, F, Din, Dout, act, cmvn)
     assert (gb1.double() - gb_ref).abs().max().item() < 2e-3 * sb
 
 
+@pytest.mark.parametrize("B,F,Din,Dout,act,cmvn", [(3, 101, 257, 257, "Sigmoid", True), (64, 251, 257, 257, "Sigmoid", True),
+                                                   (48, 1001, 201, 201, "Sigmoid", True), (256, 251, 257, 257, "ReLU", True),
+                                                   (300, 40, 129, 129, "Sigmoid", True), (5, 64, 120, 201, "Identity", False),
+                                                   (2, 33, 256, 256, "Sigmoid", True), (7, 95, 201, 128, "Sigmoid", True)])
+def test_tma_head_backward_on_padded_operands_matches_torch(se, B, F, Din, Dout, act, cmvn):
+    """se_linear_head_bwd_fused on the engine's row-padded tensors (16-byte rows: the TMA / MN-major tcgen05 kernel; NaN in the
+    padding columns must not leak) against torch in float64 -- including batches that need more splits than one wave of CTAs."""
+    from speech_enhancement_by_s3prl_b200 import ops
+    assert ops.linear_head_bwd_fused_supported(B, F, Din, Dout)
+    g = torch.Generator().manual_seed(Din + F + B)
+    LDx, LDo = ops.round4(Din), ops.round4(Dout)
+    feats = torch.full((B, F, LDx), float("nan"))
+    feats[..., :Din] = torch.randn(B, F, Din, generator=g) * 2 - 3
+    offset = torch.full((B, F, LDo), float("nan"))
+    offset[..., :Dout] = torch.rand(B, F, Dout, generator=g)
+    if act == "ReLU":
+        offset[..., :Dout] = (offset[..., :Dout] - 0.3).clamp_min(0.0)
+    grad = torch.full((B, F, LDo), float("nan"))
+    grad[..., :Dout] = torch.randn(B, F, Dout, generator=g)
+    feats, offset, grad = feats.cuda(), offset.cuda(), grad.cuda()
+    sums = ops.feature_sums(feats, Din) if cmvn else None
+    gw, gb = ops.linear_head_bwd_fused(feats, Din, sums, 1e-6, offset, grad, Dout, act)
+    torch.cuda.synchronize()
+    xh = feats[..., :Din].double()
+    if cmvn:
+        xh = (xh - xh.mean(1, keepdim=True)) / (xh.std(1, keepdim=True) + 1e-6)
+    o, dz = offset[..., :Dout].double(), grad[..., :Dout].double()
+    if act == "Sigmoid":
+        dz = dz * o * (1 - o)
+    elif act == "ReLU":
+        dz = dz * (o > 0).double()
+    gw_ref = torch.einsum("bfn,bfk->nk", dz, xh)
+    gb_ref = dz.sum((0, 1))
+    sw, sb = gw_ref.abs().max().item(), gb_ref.abs().max().item()
+    assert gw.shape == (Dout, Din) and torch.isfinite(gw).all() and torch.isfinite(gb).all()
+    assert (gw.double() - gw_ref).abs().max().item() < 2e-3 * sw
+    assert (gw.double() - gw_ref).abs().mean().item() < 2e-4 * sw
+    assert (gb.double() - gb_ref).abs().max().item() < 2e-3 * sb
+
+
 def test_tensor_core_head_trains_like_fp32_head(se):
     """End to end through autograd: a few Adam steps with the tensor-core forward + backward track the fp32 head's loss."""
     _, mine = make_pair(se, 512)
