@@ -228,6 +228,19 @@ int se_linear_head_bwd_fused(const float* x, int64_t ldx, const double* stat_sum
                              int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats, float* grad_W,
                              float* grad_b, void* stream);
 
+/* se_linear_head_bwd_sisdr: se_linear_head_bwd_fused with the backward of objective.SISDR on predicted = offset * linear_inp
+ * (objective.py:86-100 after model.py:33) folded in: d loss / d offset is rebuilt per element from offset, linear_inp, linear_tar and
+ * the per-utterance sums3 of se_sisdr_mask_fwd / _step (same arithmetic as se_sisdr_mask_bwd with grad_out = 1 / n_utt), so grad_offset
+ * is never written or read.  lengths / len_hop as in se_sisdr_mask_step.  Operands must be 16-byte aligned with row strides that are
+ * multiples of 4 floats (se_linear_head_bwd_sisdr_supported; otherwise SE_ERR_UNSUPPORTED: use se_sisdr_mask_bwd + _bwd_fused). */
+int se_linear_head_bwd_sisdr_supported(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int64_t ldx, int64_t ld_off,
+                                       int64_t ld_inp, int64_t ld_tar);
+int se_linear_head_bwd_sisdr(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps, const float* offset,
+                             int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar, int64_t ld_tar,
+                             const int64_t* lengths, int64_t len_hop, const double* sums3, float loss_eps, int64_t n_utt, int64_t n_frames,
+                             int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats, float* grad_W, float* grad_b,
+                             void* stream);
+
 /* ---- spectral SI-SDR objective on predicted = offset * linear_inp (objective.py:86-100 after model.py:33) ----------------
  * Same sums / loss as se_sisdr_spec_fwd without materialising `predicted`; rows of the three tensors are ld_* floats apart
  * (float4 loads when every ld is a multiple of 4 and the pointers are 16-byte aligned).  offset NULL: predicted = linear_inp.
@@ -241,7 +254,8 @@ int se_sisdr_mask_bwd(const float* offset, int64_t ld_off, const float* linear_i
 /* se_sisdr_mask_step: the objective's part of one training step (runner.py:455-460) in three launches: the sums, the
  * per-utterance losses + their batch mean (objective.py:100; loss_mean: 1 float, loss_per_utt may be NULL) and
  * grad_offset = d loss_mean / d offset.  lengths: frame counts (len_hop = 0) or SAMPLE lengths with len_hop = hop, in which
- * case frames = length / hop + 1 is taken in the kernels (runner.py:455).  sums_zeroed != 0: sums3 is already zero. */
+ * case frames = length / hop + 1 is taken in the kernels (runner.py:455).  sums_zeroed != 0: sums3 is already zero.  grad_offset NULL:
+ * the backward launch is skipped (se_linear_head_bwd_sisdr rebuilds the gradient inside the weight-gradient kernel). */
 int se_sisdr_mask_step(const float* offset, int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar,
                        int64_t ld_tar, const int64_t* lengths, int64_t len_hop, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
                        double* sums3, int sums_zeroed, float* loss_per_utt, float* loss_mean, float* grad_offset, int64_t ld_g,

@@ -115,6 +115,9 @@ struct BwdArgs {
     int n_main, n_tail;
     float* partials;               // (splits, m_rows, 272)
     int m_rows;                    // m_tiles * 128 + simt_rows
+    // LOSS kernel: grad_offset is not read; d loss / d offset of objective.SISDR on predicted = offset * linear_inp is rebuilt per element
+    const float* inp; const float* tar; long long ld_inp, ld_tar;
+    const double* sums3; const long long* lengths; int len_hop; float loss_eps; float grad_uniform; const float* grad_out;
     int m_tiles, simt_rows;        // tensor-core tiles; leftover rows [128 m_tiles, 128 m_tiles + simt_rows) done by SIMT CTAs
 };
 
@@ -426,7 +429,11 @@ constexpr int kTOffShift = kTOffScale + kMaxUtt * kTStatLd * 4;
 constexpr int kTOffBar = kTOffShift + kMaxUtt * kTStatLd * 4;
 constexpr int kTNumBars = 3 * kTStages + 1;                     // full, norm, empty per stage + accum
 constexpr int kTOffTmem = kTOffBar + kTNumBars * 8;
-constexpr int kTSmemBytes = kTOffTmem + 16;
+constexpr int kTOffCoef = kTOffTmem + 16;                       // LOSS: [kMaxUtt] (c_t, c_s) + [kMaxUtt] valid frames
+constexpr int kTSmemBytes = kTOffCoef + kMaxUtt * 12;
+// LOSS variant (the SISDR objective's backward folded in): stages of inp | offset | tar | x = 12 + 9 boxes, two of them
+constexpr int kLStages = 2, kLOffT = 8 * kTBox, kLOffX = 12 * kTBox, kLStageBytes = (12 + kTMaxXBoxes) * kTBox;
+static_assert(kLStages * kLStageBytes <= kTStages * kTStageBytes && BM * kStageLd * 4 <= kLStages * kLStageBytes, "LOSS ring inside the plain ring");
 constexpr int kTWorkWarps = 8, kTWorkThreads = kTWorkWarps * 32, kTThreads = kTWorkThreads + 64;   // + MMA warp + TMA warp
 static_assert(kTSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(BM * kStageLd * 4 <= kTStages * kTStageBytes && 32 * kTStatLd * 4 <= kTStages * kTStageBytes, "staging tiles fit in the ring");
@@ -456,9 +463,34 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int n) {        // as make_ide
     return make_idesc(n) | (1u << 15) | (1u << 16);
 }
 
+// d loss_u / d predicted coefficients of objective.SISDR (the arithmetic of sisdr_mask_bwd_kernel in ops_kernels.cu)
+__device__ __forceinline__ float2 sisdr_coef(const double* sums3, double eps, double go) {
+    const double st = sums3[0], tt = sums3[1], ss = sums3[2];
+    const double al = st / (tt + eps);
+    const double A = al * al * tt;
+    const double D = al * al * tt - 2.0 * al * st + ss + eps;
+    const double R = A / D;
+    const double kappa = -10.0 / (log(10.0) * (R + eps) * D * D);
+    const double ca = 2.0 * al * tt / (tt + eps);
+    const double cd = 2.0 * (al * tt - st) / (tt + eps) - 2.0 * al;
+    return make_float2((float)(go * kappa * (ca * D - A * cd)), (float)(go * kappa * (-2.0 * A)));
+}
+// grad_offset of one element: predicted = o * x, target power t (sisdr_mask_bwd_kernel)
+__device__ __forceinline__ float sisdr_grad(float o, float x, float t, float2 c) {
+    const float pi = o * x, tp = fmaxf(t, 0.0f);
+    const float rs = rsqrtf(fmaxf(pi, 1e-37f));                              // one MUFU each instead of sqrt + divide
+    const float ti = tp * rsqrtf(fmaxf(tp, 1e-37f));
+    const float g = (c.x * ti + c.y * (pi * rs)) * (0.5f * rs) * x;
+    return pi > 0.0f ? g : 0.0f;
+}
+
+template <bool LOSS>
 __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmG,
                                                                             const __grid_constant__ CUtensorMap tmO,
-                                                                            const __grid_constant__ CUtensorMap tmX, const BwdArgs a) {
+                                                                            const __grid_constant__ CUtensorMap tmX,
+                                                                            const __grid_constant__ CUtensorMap tmT, const BwdArgs a) {
+    constexpr int STAGES = LOSS ? kLStages : kTStages, STAGE_BYTES = LOSS ? kLStageBytes : kTStageBytes;
+    constexpr int OFF_X = LOSS ? kLOffX : kTOffX;
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     float* s_scale = reinterpret_cast<float*>(smem + kTOffScale);
@@ -466,6 +498,8 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kTOffTmem);
     const uint32_t bar_full = sbase + kTOffBar, bar_norm = bar_full + 8 * kTStages, bar_empty = bar_norm + 8 * kTStages,
                    bar_accum = bar_empty + 8 * kTStages;
+    float2* s_coef = reinterpret_cast<float2*>(smem + kTOffCoef);
+    int* s_valid = reinterpret_cast<int*>(smem + kTOffCoef + kMaxUtt * 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, n0 = blockIdx.y * BM;
     const long long ra = (long long)split * a.rows_per_split;
@@ -475,7 +509,7 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
 
     if (threadIdx.x == 0) {
         if (sbase & 1023) __trap();
-        for (int s = 0; s < kTStages; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_norm + 8 * s, kTWorkWarps);
             mbar_init(bar_empty + 8 * s, 1);
@@ -509,6 +543,19 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
         s_scale[i] = sc;
         s_shift[i] = sh;
     }
+    if (LOSS && threadIdx.x < kMaxUtt) {
+        const long long u = u_first + threadIdx.x;
+        float2 c = make_float2(0.f, 0.f);
+        int valid = 0;
+        if (u * a.n_frames < a.R) {
+            c = sisdr_coef(a.sums3 + 3 * u, (double)a.loss_eps, a.grad_out ? (double)a.grad_out[u] : (double)a.grad_uniform);
+            long long v = a.n_frames;
+            if (a.lengths) v = a.len_hop > 0 ? a.lengths[u] / a.len_hop + 1 : a.lengths[u];
+            valid = (int)(v < a.n_frames ? v : a.n_frames);
+        }
+        s_coef[threadIdx.x] = c;
+        s_valid[threadIdx.x] = valid;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -517,18 +564,19 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
     if (warp == kTWorkWarps + 1) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)(8 + nbx) * kTBox;
+            const uint32_t tx = (uint32_t)((LOSS ? 12 : 8) + nbx) * kTBox;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kTStages;
-                if (kb >= kTStages) mbar_wait(bar_empty + 8 * s, ((kb / kTStages) - 1) & 1);
-                const uint32_t st = sbase + s * kTStageBytes, bar = bar_full + 8 * s;
+                const int s = kb % STAGES;
+                if (kb >= STAGES) mbar_wait(bar_empty + 8 * s, ((kb / STAGES) - 1) & 1);
+                const uint32_t st = sbase + s * STAGE_BYTES, bar = bar_full + 8 * s;
                 const int r0 = (int)(ra + (long long)kb * BK);
                 mbar_expect_tx(bar, tx);
                 for (int m = 0; m < 4; ++m) {
-                    tma_load_2d(st + kTOffG + m * kTBox, &tmG, n0 + 32 * m, r0, bar);
+                    tma_load_2d(st + kTOffG + m * kTBox, &tmG, n0 + 32 * m, r0, bar);       // grad_offset, or linear_inp (LOSS)
                     tma_load_2d(st + kTOffO + m * kTBox, &tmO, n0 + 32 * m, r0, bar);
+                    if (LOSS) tma_load_2d(st + kLOffT + m * kTBox, &tmT, n0 + 32 * m, r0, bar);
                 }
-                for (int j = 0; j < nbx; ++j) tma_load_2d(st + kTOffX + j * kTBox, &tmX, 32 * j, r0, bar);
+                for (int j = 0; j < nbx; ++j) tma_load_2d(st + OFF_X + j * kTBox, &tmX, 32 * j, r0, bar);
             }
         }
     } else if (warp == kTWorkWarps) {
@@ -536,10 +584,10 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
         if (lane == 0 && nkb > 0) {
             const uint32_t idesc_main = make_idesc_mn(a.n_main), idesc_tail = make_idesc_mn(a.n_tail > 0 ? a.n_tail : 16);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kTStages;
-                mbar_wait(bar_norm + 8 * s, (kb / kTStages) & 1);
+                const int s = kb % STAGES;
+                mbar_wait(bar_norm + 8 * s, (kb / STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = sbase + s * kTStageBytes + kTOffG, b_addr = sbase + s * kTStageBytes + kTOffX;
+                const uint32_t a_addr = sbase + s * STAGE_BYTES + kTOffG, b_addr = sbase + s * STAGE_BYTES + OFF_X;
 #pragma unroll
                 for (int kk = 0; kk < BK / 8; ++kk) {                    // 8 rows of r per instruction = one 1024-byte K group
                     const uint64_t ad = make_desc_mn(a_addr + kk * 1024);
@@ -562,22 +610,40 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
 #pragma unroll
         for (int j = 0; j < kTMaxXBoxes; ++j) acc_l[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % kTStages;
+            const int s = kb % STAGES;
             const long long r0 = ra + (long long)kb * BK;
-            float dzl = 0.0f;
-            if (do_left && r0 + row < rb)                                  // in flight while the stage lands
-                dzl = dact(__ldg(a.grad_offset + (r0 + row) * a.ld_off + n_left), __ldg(a.offset + (r0 + row) * a.ld_off + n_left), a.act);
             const long long uq = r0 / a.n_frames;
             const int bnd = (int)((uq + 1) * a.n_frames - r0);             // rows of the block before the next utterance (n_frames >= 32)
-            const int so = ((int)(uq - u_first) + (row >= bnd ? 1 : 0)) * kTStatLd + 4 * lc;
-            mbar_wait(bar_full + 8 * s, (kb / kTStages) & 1);
-            float4* G = reinterpret_cast<float4*>(smem + s * kTStageBytes + kTOffG);
-            const float4* O = reinterpret_cast<const float4*>(smem + s * kTStageBytes + kTOffO);
-            float4* X = reinterpret_cast<float4*>(smem + s * kTStageBytes + kTOffX);
+            const int ui = (int)(uq - u_first) + (row >= bnd ? 1 : 0);     // this row's utterance (index into the staged constants)
+            const int so = ui * kTStatLd + 4 * lc;
+            float live = r0 + row < rb ? 1.0f : 0.0f;                      // rows past the split (the next utterance's, per-utterance mode)
+            float2 coef = make_float2(0.f, 0.f);
+            if (LOSS) {                                                    // padded frames of the utterance carry no loss
+                const int fr = (int)(r0 + row - (u_first + ui) * a.n_frames);
+                if (fr >= s_valid[ui]) live = 0.0f;
+                coef = s_coef[ui];
+            }
+            float dzl = 0.0f;
+            if (do_left && live != 0.0f) {                                 // in flight while the stage lands
+                const float ol = __ldg(a.offset + (r0 + row) * a.ld_off + n_left);
+                const float gl = LOSS ? sisdr_grad(ol, __ldg(a.inp + (r0 + row) * a.ld_inp + n_left), __ldg(a.tar + (r0 + row) * a.ld_tar + n_left), coef)
+                                      : __ldg(a.grad_offset + (r0 + row) * a.ld_off + n_left);
+                dzl = dact(gl, ol, a.act);
+            }
+            mbar_wait(bar_full + 8 * s, (kb / STAGES) & 1);
+            float4* G = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + kTOffG);
+            const float4* O = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + kTOffO);
+            const float4* Tt = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + kLOffT);
+            float4* X = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + OFF_X);
 #pragma unroll
-            const float live = r0 + row < rb ? 1.0f : 0.0f;                // rows past the split (the next utterance's, per-utterance mode)
             for (int m = 0; m < 4; ++m) {                                  // dZ = grad * act'(offset); rows past R / columns past D_out landed as 0
-                const float4 g = G[t + 256 * m], o = O[t + 256 * m];
+                float4 g = G[t + 256 * m];
+                const float4 o = O[t + 256 * m];
+                if (LOSS) {                                                // G holds linear_inp: rebuild d loss / d offset first
+                    const float4 tt = Tt[t + 256 * m];
+                    g = make_float4(sisdr_grad(o.x, g.x, tt.x, coef), sisdr_grad(o.y, g.y, tt.y, coef), sisdr_grad(o.z, g.z, tt.z, coef),
+                                    sisdr_grad(o.w, g.w, tt.w, coef));
+                }
                 G[t + 256 * m] = make_float4(to_tf32(live * dact(g.x, o.x, a.act)), to_tf32(live * dact(g.y, o.y, a.act)),
                                              to_tf32(live * dact(g.z, o.z, a.act)), to_tf32(live * dact(g.w, o.w, a.act)));
             }
@@ -758,10 +824,14 @@ int64_t se_linear_head_bwd_tc_workspace(int64_t n_utt, int64_t n_frames, int64_t
     return (int64_t)g.splits * g.m_rows * kMaxBRows;
 }
 
+struct LossArgs {          // the SISDR objective's backward folded into the weight gradient (TMA kernel only)
+    const float* inp; int64_t ld_inp; const float* tar; int64_t ld_tar; const double* sums3; const int64_t* lengths; int64_t len_hop;
+    float eps, grad_uniform; const float* grad_out;
+};
 static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums, int64_t ld_stats,
                          float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt,
                          int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats,
-                         float* grad_W, float* grad_b, void* stream, float* per_utt_out = nullptr);
+                         float* grad_W, float* grad_b, void* stream, float* per_utt_out = nullptr, const LossArgs* loss = nullptr);
 
 int se_linear_head_bwd_tc(const float* x, int64_t ldx, const float* mean, const float* std, int64_t ld_stats, float cmvn_eps,
                           const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt, int64_t n_frames,
@@ -797,11 +867,31 @@ int se_head_grad_embeddings(const float* x, int64_t ldx, const float* mean, cons
                          act, ws, ws_floats, nullptr, nullptr, stream, grads_out);
 }
 
+int se_linear_head_bwd_sisdr_supported(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int64_t ldx, int64_t ld_off,
+                                       int64_t ld_inp, int64_t ld_tar) {
+    Geometry g;
+    if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g)) return 0;
+    return (g.simt_rows <= 1 && ldx % 4 == 0 && ld_off % 4 == 0 && ld_inp % 4 == 0 && ld_tar % 4 == 0 && n_utt * n_frames < 0x7fffffffLL) ? 1 : 0;
+}
+
+int se_linear_head_bwd_sisdr(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps, const float* offset,
+                             int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar, int64_t ld_tar,
+                             const int64_t* lengths, int64_t len_hop, const double* sums3, float loss_eps, int64_t n_utt, int64_t n_frames,
+                             int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats, float* grad_W, float* grad_b,
+                             void* stream) {
+    SE_REQUIRE(linear_inp && linear_tar && sums3 && grad_W, "null pointer");
+    SE_REQUIRE(ld_inp >= D_out && ld_tar >= D_out && len_hop >= 0 && len_hop < (1LL << 30), "bad stride / hop");
+    SE_REQUIRE(!stat_sums || n_frames >= 2, "CMVN statistics need at least two frames");
+    LossArgs l{linear_inp, ld_inp, linear_tar, ld_tar, sums3, lengths, len_hop, loss_eps, 1.0f / (float)n_utt, nullptr};
+    return head_bwd_impl(x, ldx, nullptr, nullptr, stat_sums, ld_stats, cmvn_eps, offset, nullptr, ld_off, n_utt, n_frames, D_in, D_out, act,
+                         ws_partials, ws_floats, grad_W, grad_b, stream, nullptr, &l);
+}
+
 static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums, int64_t ld_stats,
                          float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt,
                          int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats,
-                         float* grad_W, float* grad_b, void* stream, float* per_utt_out) {
-    SE_REQUIRE(x && offset && grad_offset && ws_partials && (grad_W || per_utt_out) && n_utt > 0 && n_frames > 0, "bad argument");
+                         float* grad_W, float* grad_b, void* stream, float* per_utt_out, const LossArgs* loss) {
+    SE_REQUIRE(x && offset && (grad_offset || loss) && ws_partials && (grad_W || per_utt_out) && n_utt > 0 && n_frames > 0, "bad argument");
     SE_REQUIRE(ldx >= D_in && ld_off >= D_out && ((!mean && !stat_sums) || ld_stats >= D_in), "row stride smaller than the row");
     SE_REQUIRE(act >= SE_ACT_IDENTITY && act <= SE_ACT_SIGMOID, "unknown activation %d", act);
     Geometry g;
@@ -826,18 +916,35 @@ static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const f
     }
     cudaStream_t st = (cudaStream_t)stream;
     // aligned operands (the engine's padded tensors): the TMA / MN-major kernel; anything else: the transposing producers
-    const bool aligned = ldx % 4 == 0 && ld_off % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(offset) |
-                                                               reinterpret_cast<uintptr_t>(grad_offset)) & 15) == 0;
-    CUtensorMap tmG, tmO, tmX;
+    const float* gsrc = loss ? loss->inp : grad_offset;
+    const int64_t ld_g = loss ? loss->ld_inp : ld_off;
+    bool aligned = ldx % 4 == 0 && ld_off % 4 == 0 && ld_g % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(offset) | reinterpret_cast<uintptr_t>(gsrc)) & 15) == 0;
+    if (loss) aligned = aligned && loss->ld_tar % 4 == 0 && (reinterpret_cast<uintptr_t>(loss->tar) & 15) == 0;
+    CUtensorMap tmG, tmO, tmX, tmT;
     static int force_old = -1;
     if (force_old < 0) { const char* e = getenv("SE_B200_BWD_OLD"); force_old = e && atoi(e) ? 1 : 0; }
     int rc;
-    if (!force_old && aligned && g.simt_rows <= 1 && a.R < 0x7fffffffLL && make_map32(&tmG, grad_offset, D_out, a.R, ld_off) &&
-        make_map32(&tmO, offset, D_out, a.R, ld_off) && make_map32(&tmX, x, D_in, a.R, ldx)) {
-        static unsigned long long opted_t = 0;
-        if (secommon::first_use_on_device(opted_t))
-            SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes));
-        linear_head_bwd_tma_kernel<<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kTThreads, kTSmemBytes, st>>>(tmG, tmO, tmX, a);
+    const bool tma_ok = aligned && g.simt_rows <= 1 && a.R < 0x7fffffffLL && make_map32(&tmG, gsrc, D_out, a.R, ld_g) &&
+                        make_map32(&tmO, offset, D_out, a.R, ld_off) && make_map32(&tmX, x, D_in, a.R, ldx) &&
+                        (!loss || make_map32(&tmT, loss->tar, D_out, a.R, loss->ld_tar));
+    if (loss) {
+        if (!tma_ok) return fail(SE_ERR_UNSUPPORTED, "head backward with the objective folded in: operands must be 16-byte aligned with row "
+                                                     "strides that are multiples of 4 floats");
+        a.inp = loss->inp; a.ld_inp = loss->ld_inp; a.tar = loss->tar; a.ld_tar = loss->ld_tar; a.sums3 = loss->sums3;
+        a.lengths = (const long long*)loss->lengths; a.len_hop = (int)loss->len_hop; a.loss_eps = loss->eps;
+        a.grad_uniform = loss->grad_uniform; a.grad_out = loss->grad_out;
+    }
+    static unsigned long long opted_t = 0;
+    if (tma_ok && !force_old && secommon::first_use_on_device(opted_t)) {
+        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes));
+        SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes));
+    }
+    if (loss) {
+        linear_head_bwd_tma_kernel<true><<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kTThreads, kTSmemBytes, st>>>(tmG, tmO, tmX, tmT, a);
+        rc = secommon::check_launch("linear_head_bwd_tma_kernel<loss>");
+    } else if (!force_old && tma_ok) {
+        linear_head_bwd_tma_kernel<false><<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kTThreads, kTSmemBytes, st>>>(tmG, tmO, tmX, tmX, a);
         rc = secommon::check_launch("linear_head_bwd_tma_kernel");
     } else {
         linear_head_bwd_tc_kernel<<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kThreads, kSmemBytes, st>>>(a);

@@ -994,8 +994,8 @@ int se_sisdr_mask_step(const float* offset, int64_t ld_off, const float* linear_
                        int64_t ld_tar, const int64_t* lengths, int64_t len_hop, int64_t n_utt, int64_t n_frames, int64_t K, float eps,
                        double* sums3, int sums_zeroed, float* loss_per_utt, float* loss_mean, float* grad_offset, int64_t ld_g,
                        void* stream) {
-    SE_REQUIRE(linear_inp && linear_tar && sums3 && loss_mean && grad_offset && n_utt > 0 && n_frames > 0 && K > 0, "bad argument");
-    SE_REQUIRE(ld_inp >= K && ld_tar >= K && ld_g >= K && (!offset || ld_off >= K), "row stride smaller than K");
+    SE_REQUIRE(linear_inp && linear_tar && sums3 && loss_mean && n_utt > 0 && n_frames > 0 && K > 0, "bad argument");
+    SE_REQUIRE(ld_inp >= K && ld_tar >= K && (!grad_offset || ld_g >= K) && (!offset || ld_off >= K), "row stride smaller than K");
     SE_REQUIRE(len_hop >= 0 && len_hop < (1LL << 30), "len_hop=%lld out of range", (long long)len_hop);
     cudaStream_t st = (cudaStream_t)stream;
     if (!sums_zeroed) SE_CUDA_CHECK(cudaMemsetAsync(sums3, 0, sizeof(double) * 3 * n_utt, st));
@@ -1005,14 +1005,14 @@ int se_sisdr_mask_step(const float* offset, int64_t ld_off, const float* linear_
     a.chunks = pick_chunks(n_utt, n_frames * K, 2048); a.sums3 = sums3; a.eps = eps;
     a.grad_out = nullptr; a.grad_uniform = 1.0f / (float)n_utt; a.grad_offset = grad_offset; a.ld_g = ld_g;
     const long long need = (K + 3) / 4 * 4;
-    const bool v4 = vec4_ok(offset, ld_off) && vec4_ok(linear_inp, ld_inp) && vec4_ok(linear_tar, ld_tar) && vec4_ok(grad_offset, ld_g) &&
-                    ld_inp >= need && ld_tar >= need && ld_g >= need && (!offset || ld_off >= need);
+    const bool v4 = vec4_ok(offset, ld_off) && vec4_ok(linear_inp, ld_inp) && vec4_ok(linear_tar, ld_tar) && ld_inp >= need && ld_tar >= need &&
+                    (!offset || ld_off >= need) && (!grad_offset || (vec4_ok(grad_offset, ld_g) && ld_g >= need));
     if (v4) sisdr_mask_sums_kernel<4><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
     else sisdr_mask_sums_kernel<1><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
     int rc = secommon::check_launch("sisdr_mask_sums_kernel");
     if (rc != SE_OK) return rc;
     sisdr_finish_mean_kernel<<<1, 256, 0, st>>>(sums3, (int)n_utt, eps, loss_per_utt, loss_mean);
-    if ((rc = secommon::check_launch("sisdr_finish_mean_kernel")) != SE_OK) return rc;
+    if ((rc = secommon::check_launch("sisdr_finish_mean_kernel")) != SE_OK || !grad_offset) return rc;
     if (v4) sisdr_mask_bwd_kernel<4><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
     else sisdr_mask_bwd_kernel<1><<<(unsigned)(n_utt * a.chunks), 256, 0, st>>>(a);
     return secommon::check_launch("sisdr_mask_bwd_kernel");

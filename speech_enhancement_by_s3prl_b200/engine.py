@@ -266,9 +266,16 @@ class EnhancementEngine:
             stats = stat_sums if head.cmvn else None
             offset = ops.linear_head_tma(feats, D, wpad, head.linear.bias, head.activation, stats, head.eps)
             # frames = lengths // hop + 1, the batch-mean loss and d loss / d offset inside three launches
-            loss, _, grad_offset, _ = ops.sisdr_mask_step(offset, linear_inp, linear_tar, _c64(lengths), self.hop, K, objective.eps,
-                                                           sums3=sums3, sums_zeroed=True)
-            gw, gb = ops.linear_head_bwd_fused(feats, D, stats, head.eps, offset, grad_offset, K, head.activation)
+            lens = _c64(lengths)
+            fold = ops.linear_head_bwd_sisdr_supported(B, feats.shape[1], D, K, feats.shape[2], offset.shape[2], linear_inp.shape[2],
+                                                       linear_tar.shape[2])
+            loss, _, grad_offset, _ = ops.sisdr_mask_step(offset, linear_inp, linear_tar, lens, self.hop, K, objective.eps,
+                                                           sums3=sums3, sums_zeroed=True, want_grad=not fold)
+            if fold:            # the objective's backward runs inside the weight-gradient kernel: no grad_offset tensor
+                gw, gb = ops.linear_head_bwd_sisdr(feats, D, stats, head.eps, offset, linear_inp, linear_tar, lens, self.hop, sums3, K,
+                                                   head.activation, objective.eps)
+            else:
+                gw, gb = ops.linear_head_bwd_fused(feats, D, stats, head.eps, offset, grad_offset, K, head.activation)
             for p, g in ((head.linear.weight, gw), (head.linear.bias, gb)):
                 if p.grad is None:
                     p.grad = g

@@ -181,22 +181,49 @@ def linear_head_bwd_fused(x, D_in, stat_sums, cmvn_eps, offset, grad_offset, D_o
     return gw, gb
 
 
-def sisdr_mask_step(offset, linear_inp, linear_tar, lengths, hop, K, eps=1e-10, sums3=None, sums_zeroed=False):
+def linear_head_bwd_sisdr_supported(B, F, D_in, D_out, ldx, ld_off, ld_inp, ld_tar):
+    return bool(_lib.load().se_linear_head_bwd_sisdr_supported(B, F, int(D_in), int(D_out), ldx, ld_off, ld_inp, ld_tar))
+
+
+def linear_head_bwd_sisdr(x, D_in, stat_sums, cmvn_eps, offset, linear_inp, linear_tar, lengths, hop, sums3, D_out, activation, loss_eps=1e-10):
+    """Weight / bias gradients of the batch-mean objective.SISDR loss on predicted = offset * linear_inp through the TMA head's
+    backward with the objective's own backward folded in (no grad_offset tensor): x (B, F, LDx), offset / linear_inp / linear_tar
+    (B, F, LD*) row-padded, sums3 (B, 3) from ``sisdr_mask_step``, lengths = SAMPLE lengths with ``hop`` (frame counts if hop = 0).
+    Returns (grad_W (D_out, D_in), grad_b (D_out,))."""
+    B, F, LDx = x.shape
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        ws_floats = lib.se_linear_head_bwd_tc_workspace(B, F, int(D_in), int(D_out))
+        if ws_floats <= 0:
+            raise RuntimeError(f"se_linear_head_bwd_sisdr: shape (B={B}, F={F}, D_in={D_in}, D_out={D_out}) is not supported")
+        ws = torch.empty(ws_floats, device=x.device)
+        gw = torch.empty(D_out, D_in, device=x.device)
+        gb = torch.empty(D_out, device=x.device)
+        rc = lib.se_linear_head_bwd_sisdr(x.data_ptr(), LDx, _p(stat_sums), 0 if stat_sums is None else stat_sums.shape[1], float(cmvn_eps),
+                                          offset.data_ptr(), offset.shape[2], linear_inp.data_ptr(), linear_inp.shape[2],
+                                          linear_tar.data_ptr(), linear_tar.shape[2], lengths.data_ptr(), int(hop), sums3.data_ptr(),
+                                          float(loss_eps), B, F, int(D_in), int(D_out), ACT[activation], ws.data_ptr(), ws_floats,
+                                          gw.data_ptr(), gb.data_ptr(), _stream())
+        _lib.check(rc, "se_linear_head_bwd_sisdr")
+    return gw, gb
+
+
+def sisdr_mask_step(offset, linear_inp, linear_tar, lengths, hop, K, eps=1e-10, sums3=None, sums_zeroed=False, want_grad=True):
     """The objective's part of a training step on (B, F, LD) row-padded tensors in three launches: objective.SISDR of
     predicted = offset * linear_inp (mean over the batch, objective.py:100) and d loss / d offset.  ``lengths``: SAMPLE lengths
     (int64, device), frames = lengths // hop + 1 is taken inside the kernels (runner.py:455).
-    Returns (loss (0-dim), loss_per_utt (B,), grad_offset (B, F, LDo), sums3)."""
+    Returns (loss (0-dim), loss_per_utt (B,), grad_offset (B, F, LDo) or None (want_grad=False: sums and losses only), sums3)."""
     B, F, LDi = linear_inp.shape
     dev = linear_inp.device
     with torch.cuda.device(dev):
         if sums3 is None:
             sums3, sums_zeroed = torch.zeros(B, 3, device=dev, dtype=torch.float64), True
         out = torch.empty(B + 1, device=dev)
-        grad = torch.empty_like(offset)
+        grad = torch.empty_like(offset) if want_grad else None
         rc = _lib.load().se_sisdr_mask_step(offset.data_ptr(), offset.shape[2], linear_inp.data_ptr(), LDi, linear_tar.data_ptr(),
                                             linear_tar.shape[2], lengths.data_ptr(), int(hop), B, F, int(K), float(eps), sums3.data_ptr(),
-                                            1 if sums_zeroed else 0, out.data_ptr(), out[B:].data_ptr(), grad.data_ptr(),
-                                            grad.shape[2], _stream())
+                                            1 if sums_zeroed else 0, out.data_ptr(), out[B:].data_ptr(), _p(grad),
+                                            0 if grad is None else grad.shape[2], _stream())
         _lib.check(rc, "se_sisdr_mask_step")
     return out[B], out[:B], grad, sums3
 

@@ -1209,6 +1209,62 @@ def test_tma_head_backward_on_padded_operands_matches_torch(se, B, F, Din, Dout,
     assert (gb.double() - gb_ref).abs().max().item() < 2e-3 * sb
 
 
+@pytest.mark.parametrize("B,F,D,act,cmvn,hop", [(4, 101, 257, "Sigmoid", True, 256), (48, 300, 201, "Sigmoid", True, 160),
+                                                (5, 64, 129, "ReLU", False, 0), (130, 40, 257, "Sigmoid", True, 128)])
+def test_head_backward_with_the_objective_folded_in(se, B, F, D, act, cmvn, hop):
+    """se_linear_head_bwd_sisdr (d loss / d offset rebuilt inside the TMA weight-gradient kernel) equals se_sisdr_mask_bwd followed by
+    se_linear_head_bwd_fused on the same operands -- ragged lengths, padded frames, sample lengths or frame counts."""
+    from speech_enhancement_by_s3prl_b200 import ops
+    g = torch.Generator().manual_seed(B + F + D)
+    LD = ops.round4(D)
+    pad = lambda x: torch.nn.functional.pad(x, (0, LD - D), value=float("nan")).contiguous().cuda()
+    feats = pad(torch.randn(B, F, D, generator=g) * 2 - 3)
+    off = torch.rand(B, F, D, generator=g)
+    if act == "ReLU":
+        off = (off - 0.3).clamp_min(0.0)
+    off, inp, tar = pad(off), pad(torch.randn(B, F, D, generator=g) ** 2), pad(torch.randn(B, F, D, generator=g) ** 2)
+    frames = torch.randint(1, F + 1, (B,), generator=g)
+    frames[0] = F
+    lens = (((frames - 1) * hop + torch.randint(0, max(hop, 1), (B,), generator=g)) if hop else frames).cuda()
+    frames = frames.cuda()
+    assert ops.linear_head_bwd_sisdr_supported(B, F, D, D, LD, LD, LD, LD)
+    sums = ops.feature_sums(feats, D) if cmvn else None
+    loss, loss_u, g_off, sums3 = ops.sisdr_mask_step(off, inp, tar, lens, hop, D)
+    gw0, gb0 = ops.linear_head_bwd_fused(feats, D, sums, 1e-6, off, g_off, D, act)
+    loss1, _, none, sums3b = ops.sisdr_mask_step(off, inp, tar, lens, hop, D, want_grad=False)
+    assert none is None and abs(loss.item() - loss1.item()) < 1e-6                  # (the sums are double-precision atomics: order-dependent last bits)
+    assert torch.allclose(sums3, sums3b, rtol=1e-12, atol=0)
+    gw1, gb1 = ops.linear_head_bwd_sisdr(feats, D, sums, 1e-6, off, inp, tar, lens, hop, sums3, D, act)
+    torch.cuda.synchronize()
+    assert torch.isfinite(gw1).all() and torch.isfinite(gb1).all()
+    # same TF32 operands up to the last bit of the re-derived gradient: far inside the TF32 rounding of either
+    sw, sb = gw0.abs().max().item(), gb0.abs().max().item()
+    assert (gw1 - gw0).abs().max().item() < 2e-4 * sw and (gb1 - gb0).abs().max().item() < 2e-4 * sb
+    if act == "ReLU":
+        return                                   # (autograd of sqrt(relu(0)) is 0 * inf = NaN; the kernels define that gradient as 0)
+    # and against float64 autograd of the reference formulas
+    o64, x64, t64 = (v[..., :D].double() for v in (off, inp, tar))
+    xh = feats[..., :D].double()
+    if cmvn:
+        xh = (xh - xh.mean(1, keepdim=True)) / (xh.std(1, keepdim=True) + 1e-6)
+    o64.requires_grad_(True)
+    m = (torch.arange(F, device="cuda")[None, :] < frames[:, None]).double()[..., None]
+    src, tgt = (o64 * x64).clamp_min(0).sqrt() * m, t64.clamp_min(0).sqrt() * m
+    al = (src * tgt).sum((1, 2)) / ((tgt ** 2).sum((1, 2)) + 1e-10)
+    num = ((al[:, None, None] * tgt) ** 2).sum((1, 2))
+    den = ((al[:, None, None] * tgt - src) ** 2).sum((1, 2)) + 1e-10
+    l64 = (-10 * torch.log10(num / den + 1e-10)).mean()
+    assert abs(l64.item() - loss.item()) < 1e-4
+    l64.backward()
+    dz = o64.grad
+    if act == "Sigmoid":
+        dz = dz * o64.detach() * (1 - o64.detach())
+    elif act == "ReLU":
+        dz = dz * (o64.detach() > 0).double()
+    gw_ref = torch.einsum("bfn,bfk->nk", dz, xh)
+    assert (gw1.double() - gw_ref).abs().max().item() < 3e-3 * gw_ref.abs().max().item()
+
+
 def test_tensor_core_head_trains_like_fp32_head(se):
     """End to end through autograd: a few Adam steps with the tensor-core forward + backward track the fp32 head's loss."""
     _, mine = make_pair(se, 512)
