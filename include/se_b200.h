@@ -277,6 +277,17 @@ int se_head_grad_embeddings(const float* x, int64_t ldx, const float* mean, cons
 int se_match_scores(const float* query, int64_t n_query, const float* key, int64_t n_key, int64_t P, float eps, double* ws_d,
                     float* ws_qbar, float* scores, void* stream);
 
+/* se_head_grad_embeddings_sisdr: se_head_grad_embeddings for objective.SISDR on predicted = offset * linear_inp with the objective's
+ * backward folded in (as se_linear_head_bwd_sisdr, upstream gradient 1 per utterance): row u of grads_out is the gradient of the loss
+ * of utterance u ALONE (sampler.py:95-108).  Workspace: se_head_grad_embeddings_workspace.  Aligned operands only (_supported). */
+int se_head_grad_embeddings_sisdr_supported(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int64_t ldx, int64_t ld_off,
+                                            int64_t ld_inp, int64_t ld_tar);
+int se_head_grad_embeddings_sisdr(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps, const float* offset,
+                                  int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar, int64_t ld_tar,
+                                  const int64_t* lengths, int64_t len_hop, const double* sums3, float loss_eps, int64_t n_utt,
+                                  int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws, int64_t ws_floats, float* grads_out,
+                                  void* stream);
+
 /* ---- gradient clipping + Adam on the head's parameters (runner.py:463-466: clip_grad_norm_ then optimizer.step) -------
  * params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors (<= 8) device pointers, numels their sizes.  Semantics of
  * torch.nn.utils.clip_grad_norm_(max_norm) (skipped if max_norm <= 0; the scaled gradient is written back) followed by

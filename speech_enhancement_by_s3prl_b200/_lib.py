@@ -43,6 +43,9 @@ _SIGNATURES = {
     "se_linear_head_bwd_sisdr_supported": [i64, i64, i64, i64, i64, i64, i64, i64],
     "se_linear_head_bwd_sisdr": [c_f, i64, c_f, i64, c_float, c_f, i64, c_f, i64, c_f, i64, c_f, i64, c_f, c_float, i64, i64, i64, i64, c_int,
                                  c_f, i64, c_f, c_f, c_f],
+    "se_head_grad_embeddings_sisdr_supported": [i64, i64, i64, i64, i64, i64, i64, i64],
+    "se_head_grad_embeddings_sisdr": [c_f, i64, c_f, i64, c_float, c_f, i64, c_f, i64, c_f, i64, c_f, i64, c_f, c_float, i64, i64, i64, i64,
+                                      c_int, c_f, i64, c_f, c_f],
     "se_head_grad_embeddings_workspace": [i64, i64, i64, i64],
     "se_head_grad_embeddings": [c_f, i64, c_f, c_f, c_f, i64, c_float, c_f, c_f, i64, i64, i64, i64, i64, c_int, c_f, i64, c_f, c_f],
     "se_match_scores": [c_f, i64, c_f, i64, i64, c_float, c_f, c_f, c_f, c_f],

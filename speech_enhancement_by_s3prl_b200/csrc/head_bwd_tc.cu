@@ -887,6 +887,26 @@ int se_linear_head_bwd_sisdr(const float* x, int64_t ldx, const double* stat_sum
                          ws_partials, ws_floats, grad_W, grad_b, stream, nullptr, &l);
 }
 
+int se_head_grad_embeddings_sisdr_supported(int64_t n_utt, int64_t n_frames, int64_t D_in, int64_t D_out, int64_t ldx, int64_t ld_off,
+                                            int64_t ld_inp, int64_t ld_tar) {
+    Geometry g;
+    if (!plan(n_utt * n_frames, n_frames, D_in, D_out, &g, true)) return 0;
+    return (g.simt_rows <= 1 && ldx % 4 == 0 && ld_off % 4 == 0 && ld_inp % 4 == 0 && ld_tar % 4 == 0 && n_utt * n_frames < 0x7fffffffLL) ? 1 : 0;
+}
+
+int se_head_grad_embeddings_sisdr(const float* x, int64_t ldx, const double* stat_sums, int64_t ld_stats, float cmvn_eps, const float* offset,
+                                  int64_t ld_off, const float* linear_inp, int64_t ld_inp, const float* linear_tar, int64_t ld_tar,
+                                  const int64_t* lengths, int64_t len_hop, const double* sums3, float loss_eps, int64_t n_utt,
+                                  int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws, int64_t ws_floats, float* grads_out,
+                                  void* stream) {
+    SE_REQUIRE(linear_inp && linear_tar && sums3 && grads_out, "null pointer");
+    SE_REQUIRE(ld_inp >= D_out && ld_tar >= D_out && len_hop >= 0 && len_hop < (1LL << 30), "bad stride / hop");
+    SE_REQUIRE(!stat_sums || n_frames >= 2, "CMVN statistics need at least two frames");
+    LossArgs l{linear_inp, ld_inp, linear_tar, ld_tar, sums3, lengths, len_hop, loss_eps, 1.0f, nullptr};   // row u: gradient of loss_u alone
+    return head_bwd_impl(x, ldx, nullptr, nullptr, stat_sums, ld_stats, cmvn_eps, offset, nullptr, ld_off, n_utt, n_frames, D_in, D_out, act,
+                         ws, ws_floats, nullptr, nullptr, stream, grads_out, &l);
+}
+
 static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const float* std, const double* stat_sums, int64_t ld_stats,
                          float cmvn_eps, const float* offset, const float* grad_offset, int64_t ld_off, int64_t n_utt,
                          int64_t n_frames, int64_t D_in, int64_t D_out, int act, float* ws_partials, int64_t ws_floats,

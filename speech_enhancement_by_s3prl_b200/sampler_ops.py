@@ -164,10 +164,65 @@ def scoring_loop(head, criterion, features, linear_inp, linear_tar, stft_lengths
     return torch.stack(grads, dim=0)
 
 
+def _fused_ok(preprocessor, head, criterion, B, T, feat_log):
+    """The whole scoring pass on the engine's row-padded tensors (register-resident STFT with fused log / CMVN sums, TMA head, the
+    objective's backward folded into the per-utterance weight-gradient kernel): LinearResidual on log-power + SISDR, tensor-core head."""
+    if type(head) is not model.LinearResidual or type(criterion) is not objective.SISDR or not feat_log or getattr(head, "precision", 0) != 1:
+        return False
+    n_fft, hop = preprocessor._win_args["n_fft"], preprocessor._win_args["hop_length"]
+    K, F = n_fft // 2 + 1, T // hop + 1
+    LD = ops.round4(K)
+    if tuple(head.linear.weight.shape) != (K, K):
+        return False
+    lib = _lib.load()
+    return bool(lib.se_linear_head_fused_supported(B, F, K, K, LD, LD, LD)) and \
+        bool(lib.se_head_grad_embeddings_sisdr_supported(B, F, K, K, LD, LD, LD, LD))
+
+
+@torch.no_grad()
+def scoring_fused(preprocessor, head, criterion, lengths, wavs, mean=False):
+    """sampler.py:59-110 in seven launches: K1 (noisy: power + log-power + CMVN sums), K1 (clean: power), TMA head, SISDR sums +
+    finish, per-utterance weight gradient with the objective's backward folded in, pack.  Rows as ``scoring_batched``."""
+    B, C, T = wavs.shape
+    dev = wavs.device
+    n_fft, hop = preprocessor._win_args["n_fft"], preprocessor._win_args["hop_length"]
+    K = n_fft // 2 + 1
+    LD = ops.round4(K)
+    window = preprocessor._frame_window
+    if window.device != dev:
+        preprocessor.to(dev)
+        window = preprocessor._frame_window
+    ch_i, ch_t = int(getattr(preprocessor, "channel_inp", 0)), int(getattr(preprocessor, "channel_tar", 1))
+    ws = torch.zeros(B * (2 * LD + 3), device=dev, dtype=torch.float64)
+    stat_sums, sums3 = ws[:B * 2 * LD].view(B, LD, 2), ws[B * 2 * LD:].view(B, 3)
+    linear_inp, logp, _ = ops.stft_features2(wavs, ch_i, n_fft, hop, window, want_power=True, want_logpower=True,
+                                             log_eps=preprocessor.eps, stat_sums=stat_sums)
+    linear_tar = ops.stft_padded(wavs, ch_t, n_fft, hop, window, logpower=False)
+    wpad = ops.round_tf32(ops.pad_weight(head.linear.weight.detach()))
+    stats = stat_sums if head.cmvn else None
+    offset = ops.linear_head_tma(logp, K, wpad, head.linear.bias, head.activation, stats, head.eps)
+    lens = lengths.to(device=dev, dtype=torch.int64).contiguous()
+    ops.sisdr_mask_step(offset, linear_inp, linear_tar, lens, hop, K, criterion.eps, sums3=sums3, sums_zeroed=True, want_grad=False)
+    F = logp.shape[1]
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws_floats = lib.se_head_grad_embeddings_workspace(B, F, K, K)
+        wsf = torch.empty(ws_floats, device=dev)
+        out = torch.empty(B, K * K + K, device=dev)
+        rc = lib.se_head_grad_embeddings_sisdr(logp.data_ptr(), LD, ops._p(stats), LD, float(head.eps), offset.data_ptr(), offset.shape[2],
+                                               linear_inp.data_ptr(), linear_inp.shape[2], linear_tar.data_ptr(), linear_tar.shape[2],
+                                               lens.data_ptr(), int(hop), sums3.data_ptr(), float(criterion.eps), B, F, K, K,
+                                               ops.ACT[head.activation], wsf.data_ptr(), ws_floats, out.data_ptr(), ops._stream())
+        _lib.check(rc, "se_head_grad_embeddings_sisdr")
+    return out.mean(dim=0, keepdim=True) if mean else out
+
+
 def scoring(preprocessor, head, criterion, lengths, wavs, mean=False, feat_log=True, projection_only=False):
     """sampler.py:59-110 for ``--from_rawfeature``: (B, 3, T) batch -> (B, n_params) gradient embeddings
     ((1, n_params) with mean=True).  projection_only: score with the gradients of the head's last (projection) layer only --
     for the recurrent ``LSTM`` head that is the part the library computes in one pass; all parameters go through the loop."""
+    if wavs.is_cuda and _fused_ok(preprocessor, head, criterion, wavs.shape[0], wavs.shape[2], feat_log):
+        return scoring_fused(preprocessor, head, criterion, lengths, wavs, mean=mean)
     c = preprocessor.get_feat_config
     ch_i, ch_t = int(getattr(preprocessor, "channel_inp", 0)), int(getattr(preprocessor, "channel_tar", 1))
     feats, linear_inp, linear_tar = preprocessor(wavs, [c("linear", ch_i, log=feat_log), c("linear", ch_i), c("linear", ch_t)])

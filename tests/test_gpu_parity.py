@@ -1565,6 +1565,41 @@ def test_scoring_batched_equals_per_utterance_loop(se, n_fft, cmvn, act):
         assert (s_fast - s_loop).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("n_fft,cmvn,act", [(400, True, "Sigmoid"), (512, True, "Sigmoid"), (256, False, "ReLU")])
+def test_scoring_fused_pass_equals_per_utterance_loop(se, n_fft, cmvn, act):
+    """se.scoring with the tensor-core head takes the engine's padded pipeline (K1 with fused log / CMVN sums, TMA head, the
+    objective's backward folded into the per-utterance weight-gradient kernel): rows against the reference's loop of backward
+    calls (sampler.py:77-110) on an fp32 copy of the head, ragged lengths."""
+    from speech_enhancement_by_s3prl_b200 import sampler_ops
+    _, mine = make_pair(se, n_fft)
+    hop = mine._win_args["hop_length"]
+    K = n_fft // 2 + 1
+    B, T = 5, 12000
+    lengths, wavs = synth(B, T, seed=n_fft + 1, lengths=torch.LongTensor([12000, 9000, 12000, 5000, 11111]))
+    lengths, wavs = lengths.cuda(), wavs.cuda()
+    torch.manual_seed(4)
+    head32 = se.LinearResidual(input_size=K, output_size=K, activation=act, cmvn=cmvn).cuda()
+    head = se.LinearResidual(input_size=K, output_size=K, activation=act, cmvn=cmvn, precision=1).cuda()
+    head.load_state_dict(head32.state_dict())
+    crit = se.SISDR()
+    assert sampler_ops._fused_ok(mine, head, crit, B, T, True) and not sampler_ops._fused_ok(mine, head32, crit, B, T, True)
+    fast = se.scoring(mine, head, crit, lengths, wavs)
+    c = mine.get_feat_config
+    feats, lin_i, lin_t = mine(wavs, [c("linear", 0, log=True), c("linear", 0), c("linear", 1)])
+    # ReLU: a unit within TF32 rounding of its threshold switches between the fp32 and the TF32 forward, and its whole gradient row
+    # with it -- compare that case against the loop on the TF32 head itself
+    loop = sampler_ops.scoring_loop(head if act == "ReLU" else head32, crit, feats, lin_i, lin_t, lengths // hop + 1)
+    assert fast.shape == loop.shape == (B, K * K + K) and torch.isfinite(fast).all()
+    for u in range(B):
+        scale = loop[u].abs().max().item()
+        assert (fast[u] - loop[u]).abs().max().item() < 3e-3 * scale          # TF32 operands in the head and in the gradient kernel
+        assert torch.nn.functional.cosine_similarity(fast[u], loop[u], dim=0).item() > 0.99999
+    fast_m = se.scoring(mine, head, crit, lengths, wavs, mean=True)
+    assert fast_m.shape == (1, K * K + K) and (fast_m[0] - fast.mean(0)).abs().max().item() <= 1e-6 * fast.abs().max().item()
+    s_fast, s_loop = se.matching(fast[:2], fast[2:]), se.matching(loop[:2], loop[2:])
+    assert (s_fast - s_loop).abs().max().item() < 3e-3
+
+
 # ------------------------------------------------------------------------------ pseudo-wave generation (runner.py:266-305)
 def test_scoring_matches_reference_sampler_golden(se, golden_dir):
     """sampler.py:59-116 pinned by the reference ITSELF: tests/golden/scoring_ref.npz holds what the unmodified
