@@ -434,7 +434,8 @@ constexpr int kTSmemBytes = kTOffCoef + kMaxUtt * 12;
 // LOSS variant (the SISDR objective's backward folded in): stages of inp | offset | tar | x = 12 + 9 boxes, two of them
 constexpr int kLStages = 2, kLOffT = 8 * kTBox, kLOffX = 12 * kTBox, kLStageBytes = (12 + kTMaxXBoxes) * kTBox;
 static_assert(kLStages * kLStageBytes <= kTStages * kTStageBytes && BM * kStageLd * 4 <= kLStages * kLStageBytes, "LOSS ring inside the plain ring");
-constexpr int kTWorkWarps = 8, kTWorkThreads = kTWorkWarps * 32, kTThreads = kTWorkThreads + 64;   // + MMA warp + TMA warp
+constexpr int kTWorkWarps = 16, kTWorkThreads = kTWorkWarps * 32, kTThreads = kTWorkThreads + 64;   // + MMA warp + TMA warp
+// (16 worker warps: the in-place rewrite of a stage -- shared-memory round trips and MUFU latency -- is the critical path of a block, not TMA)
 static_assert(kTSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(BM * kStageLd * 4 <= kTStages * kTStageBytes && 32 * kTStatLd * 4 <= kTStages * kTStageBytes, "staging tiles fit in the ring");
 
@@ -602,13 +603,14 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
         }
     } else {
         // ===================== workers: rewrite the landed tiles in place, then the epilogue =====================
-        const int t = threadIdx.x;
-        const int row = t >> 3, pc = t & 7, lc = pc ^ ((row & 3) << 1);    // this thread's row of every box, physical / logical 16-byte chunk
+        const int t = threadIdx.x, tl = t & 255, th = t >> 8;              // th: which half of the boxes this thread rewrites
+        const int row = tl >> 3, pc = tl & 7, lc = pc ^ ((row & 3) << 1);  // this thread's row of every box, physical / logical 16-byte chunk
         const bool do_left = a.simt_rows > 0 && blockIdx.y == 0;           // leftover output row n_left (at most one here)
         const int n_left = a.m_tiles * BM;
-        float4 acc_l[kTMaxXBoxes];
+        constexpr int kXPer = (kTMaxXBoxes + 1) / 2;                       // x boxes per thread: j = th, th + 2, ...
+        float4 acc_l[kXPer];
 #pragma unroll
-        for (int j = 0; j < kTMaxXBoxes; ++j) acc_l[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < kXPer; ++j) acc_l[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             const long long r0 = ra + (long long)kb * BK;
@@ -636,34 +638,36 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
             const float4* Tt = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + kLOffT);
             float4* X = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + OFF_X);
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {                                  // dZ = grad * act'(offset); rows past R / columns past D_out landed as 0
-                float4 g = G[t + 256 * m];
-                const float4 o = O[t + 256 * m];
+            for (int mi = 0; mi < 2; ++mi) {                               // dZ = grad * act'(offset); rows past R / columns past D_out landed as 0
+                const int ci = tl + 256 * (th + 2 * mi);
+                float4 g = G[ci];
+                const float4 o = O[ci];
                 if (LOSS) {                                                // G holds linear_inp: rebuild d loss / d offset first
-                    const float4 tt = Tt[t + 256 * m];
+                    const float4 tt = Tt[ci];
                     g = make_float4(sisdr_grad(o.x, g.x, tt.x, coef), sisdr_grad(o.y, g.y, tt.y, coef), sisdr_grad(o.z, g.z, tt.z, coef),
                                     sisdr_grad(o.w, g.w, tt.w, coef));
                 }
-                G[t + 256 * m] = make_float4(to_tf32(live * dact(g.x, o.x, a.act)), to_tf32(live * dact(g.y, o.y, a.act)),
-                                             to_tf32(live * dact(g.z, o.z, a.act)), to_tf32(live * dact(g.w, o.w, a.act)));
+                G[ci] = make_float4(to_tf32(live * dact(g.x, o.x, a.act)), to_tf32(live * dact(g.y, o.y, a.act)),
+                                    to_tf32(live * dact(g.z, o.z, a.act)), to_tf32(live * dact(g.w, o.w, a.act)));
             }
 #pragma unroll
-            for (int j = 0; j < kTMaxXBoxes; ++j) {
+            for (int ji = 0; ji < kXPer; ++ji) {
+                const int j = th + 2 * ji;
                 if (j < nbx) {
                     const float4 sc = *reinterpret_cast<const float4*>(s_scale + so + 32 * j);
                     const float4 sh = *reinterpret_cast<const float4*>(s_shift + so + 32 * j);
-                    float4 v = X[t + 256 * j];
+                    float4 v = X[tl + 256 * j];
                     v.x = to_tf32(fmaf(v.x, sc.x, sh.x));
                     v.y = to_tf32(fmaf(v.y, sc.y, sh.y));
                     v.z = to_tf32(fmaf(v.z, sc.z, sh.z));
                     v.w = to_tf32(fmaf(v.w, sc.w, sh.w));
                     if (r0 + row >= rb) v = make_float4(0.f, 0.f, 0.f, 0.f);   // (only the ones column matters: dZ of these rows is 0)
-                    X[t + 256 * j] = v;
+                    X[tl + 256 * j] = v;
                     if (do_left) {
-                        acc_l[j].x = fmaf(v.x, dzl, acc_l[j].x);
-                        acc_l[j].y = fmaf(v.y, dzl, acc_l[j].y);
-                        acc_l[j].z = fmaf(v.z, dzl, acc_l[j].z);
-                        acc_l[j].w = fmaf(v.w, dzl, acc_l[j].w);
+                        acc_l[ji].x = fmaf(v.x, dzl, acc_l[ji].x);
+                        acc_l[ji].y = fmaf(v.y, dzl, acc_l[ji].y);
+                        acc_l[ji].z = fmaf(v.z, dzl, acc_l[ji].z);
+                        acc_l[ji].w = fmaf(v.w, dzl, acc_l[ji].w);
                     }
                 }
             }
@@ -679,8 +683,8 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
         if (do_left) {
             // partial row n_left of this split: column sums over the 32 rows of the per-thread accumulators
 #pragma unroll
-            for (int j = 0; j < kTMaxXBoxes; ++j)
-                if (j < nbx) *reinterpret_cast<float4*>(stage + row * kTStatLd + 32 * j + 4 * lc) = acc_l[j];
+            for (int ji = 0; ji < kXPer; ++ji)
+                if (th + 2 * ji < nbx) *reinterpret_cast<float4*>(stage + row * kTStatLd + 32 * (th + 2 * ji) + 4 * lc) = acc_l[ji];
             asm volatile("bar.sync 1, %0;" ::"n"(kTWorkThreads) : "memory");
             float* dst = a.partials + ((long long)split * a.m_rows + n_left) * kMaxBRows;
             for (int k = t; k < a.b_rows; k += kTWorkThreads) {
@@ -692,10 +696,10 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
             asm volatile("bar.sync 1, %0;" ::"n"(kTWorkThreads) : "memory");
         }
         // ---- epilogue: the CTA's partial D -> workspace
-        const int quad = warp & 3, half = warp >> 2;
+        const int quad = warp & 3, part = warp >> 2;                        // TMEM lane quadrant, quarter of the columns
         const int trow = quad * 32 + lane;
         const int ncol16 = a.b_rows / 16;
-        const int c_lo = 16 * (half == 0 ? 0 : ncol16 / 2), c_hi = 16 * (half == 0 ? ncol16 / 2 : ncol16);
+        const int c_lo = 16 * (ncol16 * part / (kTWorkWarps / 4)), c_hi = 16 * (ncol16 * (part + 1) / (kTWorkWarps / 4));
         for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
             uint32_t acc[16];
             if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
