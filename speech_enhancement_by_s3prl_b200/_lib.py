@@ -33,6 +33,8 @@ _SIGNATURES = {
     "se_mask_istft_ex": [c_f, c_f, i64, c_f, i64, c_f, i64, i64, c_int, c_int, c_f, c_f, i64, i64, c_f, c_int, c_f],
     "se_stft_features": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_int, c_f, i64, c_f, i64, c_int, c_f],
     "se_stft_features2": [c_f, i64, i64, i64, c_int, c_int, c_f, c_float, c_f, c_f, i64, c_f, i64, c_int, c_f],
+    "se_stft_features_pair_supported": [c_int, c_int],
+    "se_stft_features_pair": [c_f, i64, i64, i64, i64, c_int, c_int, c_f, c_float, c_f, c_f, i64, c_f, i64, c_int, c_f],
     "se_linear_head_bwd_fused": [c_f, i64, c_f, i64, c_float, c_f, c_f, i64, i64, i64, i64, i64, c_int, c_f, i64, c_f, c_f, c_f],
     "se_adam_clip_step": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_int, c_float, c_float,
                           c_float, c_float, c_float, c_float, c_f, c_f, c_f],

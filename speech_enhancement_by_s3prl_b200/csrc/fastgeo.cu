@@ -357,12 +357,14 @@ __global__ void __launch_bounds__(K1Cfg<Geo>::WARPS * 32, K1Cfg<Geo>::MIN_BLOCKS
     for (int r = 0; r < V; ++r) x[r] = make_float2(0.0f, 0.0f);
     if (active) {
         run_range((int)(unit - (long long)u * plan.runs_per_utt), a.n_frames, plan.runs_per_utt, fa, len);
-        row = a.wav + (long long)u * a.utt_stride;
+        row = (a.n_real > 0 && u >= a.n_real) ? a.wav + (long long)(u - a.n_real) * a.utt_stride + a.chan_step
+                                               : a.wav + (long long)u * a.utt_stride;
         if (len > 0) load_frame<Geo>(x, row, a.T, fa * H - N / 2, core.tidx);       // first loads in flight before the tables
     }
+    const bool second = a.n_real > 0 && u >= a.n_real;                              // pair mode, second channel: power only
     for (int i = threadIdx.x; i < M; i += THREADS)
         s_win2[i] = make_float2(0.5f * a.tab.window[2 * i], 0.5f * a.tab.window[2 * i + 1]);
-    if (STATS && core.active && jg == 0) s_utt[gslot] = (active && len > 0) ? u : -1;
+    if (STATS && core.active && jg == 0) s_utt[gslot] = (active && len > 0 && !second) ? u : -1;
     float2 sacc[2 * NP + 1];
 #pragma unroll
     for (int i = 0; i < 2 * NP + 1; ++i) sacc[i] = make_float2(0.0f, 0.0f);
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(K1Cfg<Geo>::WARPS * 32, K1Cfg<Geo>::MIN_BLOCKS
     griddep_launch();
     const int n_iter = __reduce_max_sync(kFull, len);
     const int F = a.n_frames;
-    const bool want_pw = a.power != nullptr, want_lg = a.logp != nullptr;
+    const bool want_pw = a.power != nullptr, want_lg = a.logp != nullptr && !second;
 #pragma unroll 1
     for (int it = 0; it < n_iter; ++it) {
         const bool live = it < len;

@@ -274,6 +274,31 @@ int se_stft_features2(const float* wav, int64_t n_utt, int64_t utt_stride, int64
     return se_feature_sums(logpower ? logpower : power, spec_stride, n_utt, T / hop + 1, n_fft / 2 + 1, stat_sums, ld_stats, stream);
 }
 
+int se_stft_features_pair_supported(int n_fft, int hop) { return (sefast::geo_supported(n_fft, hop) && !g_force_generic) ? 1 : 0; }
+
+int se_stft_features_pair(const float* wav, int64_t n_utt, int64_t utt_stride, int64_t chan_step, int64_t T, int n_fft, int hop,
+                          const float* window, float log_eps, float* power2, float* logpower, int64_t spec_stride, double* stat_sums,
+                          int64_t ld_stats, int flags, void* stream) {
+    SE_REQUIRE(wav && window && power2 && stat_sums, "null pointer");
+    SE_REQUIRE(spec_stride >= n_fft / 2 + 1 && ld_stats >= n_fft / 2 + 1, "spec_stride / ld_stats smaller than K");
+    int rc = check_geometry(2 * n_utt, T, n_fft, hop);
+    if (rc != SE_OK) return rc;
+    if (!se_stft_features_pair_supported(n_fft, hop))
+        return fail(SE_ERR_UNSUPPORTED, "se_stft_features_pair: n_fft=%d hop=%d has no register-resident kernel (use two se_stft_features2 calls)", n_fft, hop);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(flags & SE_FLAG_SUMS_ZEROED)) SE_CUDA_CHECK(cudaMemsetAsync(stat_sums, 0, sizeof(double) * 2 * ld_stats * n_utt, st));
+    DeviceTables t;
+    if ((rc = get_tables(n_fft, &t)) != SE_OK) return rc;
+    StftArgs a{};
+    a.wav = wav; a.utt_stride = utt_stride; a.n_utt = (int)(2 * n_utt); a.n_real = (int)n_utt; a.chan_step = chan_step;
+    a.T = (int)T; a.hop = hop; a.n_frames = (int)(T / hop) + 1;
+    a.tab.window = window; a.tab.twM = t.twM; a.tab.twN = t.twN;
+    a.power = power2; a.logp = logpower; a.log_eps = log_eps; a.spec_stride = spec_stride;
+    a.stat_sums = stat_sums; a.ld_stats = ld_stats;
+    a.trace = secommon::trace_ptr();
+    return sefast::launch_stft_run(a, n_fft, st);
+}
+
 int se_istft(const float* power, const float* phase, int64_t n_utt, int64_t n_frames, int n_fft, int hop,
              const float* window, float* wav_out, int64_t out_stride, int64_t pad_to, void* stream) {
     SE_REQUIRE(power && phase && window && wav_out, "null pointer");

@@ -46,6 +46,10 @@ struct StftArgs {
     unsigned long long* trace; // CTA timeline buffer (se_set_trace) or null
     double* zero_ptr;          // SE_FLAG_WS_SELF_CLEAN: doubles this kernel zeroes for the step's next replay (or null)
     long long zero_count;
+    // pair mode (se_stft_features_pair; register-resident geo kernels only): n_utt counts BOTH channels' rows; row v >= n_real is
+    // row v - n_real of the second channel, chan_step floats further into the utterance; only `power` is written for it
+    int n_real;                // 0: plain mode
+    long long chan_step;
 };
 
 struct IstftArgs {

@@ -250,8 +250,13 @@ class EnhancementEngine:
                 ws = torch.zeros(B * (2 * LD + 3), device=dev, dtype=torch.float64)
                 stat_sums = ws[:B * 2 * LD].view(B, LD, 2)
                 sums3 = ws[B * 2 * LD:].view(B, 3)
-                linear_inp, logp, _ = ops.stft_features2(wavs, self.ch_inp, self.n_fft, self.hop, window, want_power=True,
-                                                         want_logpower=self.log_features, log_eps=self.pre.eps, stat_sums=stat_sums)
+                linear_tar = None
+                if self.log_features:        # one K1 launch for both channels where the register-resident kernel exists
+                    linear_inp, logp, linear_tar, _ = ops.stft_features_pair(wavs, self.ch_inp, self.ch_tar, self.n_fft, self.hop, window,
+                                                                             log_eps=self.pre.eps, stat_sums=stat_sums)
+                else:
+                    linear_inp, logp, _ = ops.stft_features2(wavs, self.ch_inp, self.n_fft, self.hop, window, want_power=True,
+                                                             want_logpower=False, log_eps=self.pre.eps, stat_sums=stat_sums)
                 feats, D = (logp if self.log_features else linear_inp), K
             else:
                 cfg = self.feat_cfg
@@ -261,7 +266,8 @@ class EnhancementEngine:
                                          order=int(cfg.get("delta", 0)), K=K)
                 D = feats.shape[2]
                 stat_sums = ops.feature_sums(feats, D) if head.cmvn else None
-            linear_tar = ops.stft_padded(wavs, self.ch_tar, self.n_fft, self.hop, window, logpower=False)
+            if self.feat_cfg is not None or linear_tar is None:
+                linear_tar = ops.stft_padded(wavs, self.ch_tar, self.n_fft, self.hop, window, logpower=False)
             wpad = self._padded_weight()            # current: refreshed in place after every update (_clip_and_step)
             stats = stat_sums if head.cmvn else None
             offset = ops.linear_head_tma(feats, D, wpad, head.linear.bias, head.activation, stats, head.eps)

@@ -155,6 +155,34 @@ def stft_features2(wavs, channel, n_fft, hop, window, want_power=True, want_logp
     return power, logp, stat_sums
 
 
+def stft_features_pair(wavs, ch_inp, ch_tar, n_fft, hop, window, log_eps=1e-10, stat_sums=None):
+    """Both K1 launches of a training / scoring step in one (register-resident geometries): power + log-power + CMVN sums of the
+    input channel and the power of the target channel.  Returns (linear_inp, logpower, linear_tar, stat_sums), each (B, F, LD);
+    falls back to two ``stft_features2`` / ``stft_padded`` launches where the one-launch kernel does not exist."""
+    wavs = _chk(wavs, "wavs")
+    B, C, T = wavs.shape
+    lib = _lib.load()
+    if not lib.se_stft_features_pair_supported(int(n_fft), int(hop)):
+        linear_inp, logp, stat_sums = stft_features2(wavs, ch_inp, n_fft, hop, window, True, True, log_eps, stat_sums)
+        return linear_inp, logp, stft_padded(wavs, ch_tar, n_fft, hop, window, logpower=False), stat_sums
+    F, K = T // hop + 1, n_fft // 2 + 1
+    LD = round4(K)
+    window = _c(window, "window")
+    with torch.cuda.device(wavs.device):
+        power2 = torch.empty(2, B, F, LD, device=wavs.device, dtype=torch.float32)
+        logp = torch.empty(B, F, LD, device=wavs.device, dtype=torch.float32)
+        flags = FLAG_SUMS_ZEROED
+        if stat_sums is None:
+            stat_sums = torch.empty(B, LD, 2, device=wavs.device, dtype=torch.float64)
+            flags = 0
+        assert stat_sums.shape == (B, LD, 2) and stat_sums.dtype == torch.float64 and stat_sums.is_contiguous()
+        rc = lib.se_stft_features_pair(wavs.data_ptr() + 4 * int(ch_inp) * T, B, C * T, (int(ch_tar) - int(ch_inp)) * T, T, n_fft, hop,
+                                       window.data_ptr(), float(log_eps), power2.data_ptr(), logp.data_ptr(), LD, stat_sums.data_ptr(),
+                                       LD, flags, _stream())
+        _lib.check(rc, "se_stft_features_pair")
+    return power2[0], logp, power2[1], stat_sums
+
+
 def linear_head_bwd_fused_supported(B, F, D_in, D_out):
     return _lib.load().se_linear_head_bwd_tc_workspace(B, F, D_in, D_out) > 0
 

@@ -195,9 +195,8 @@ def scoring_fused(preprocessor, head, criterion, lengths, wavs, mean=False):
     ch_i, ch_t = int(getattr(preprocessor, "channel_inp", 0)), int(getattr(preprocessor, "channel_tar", 1))
     ws = torch.zeros(B * (2 * LD + 3), device=dev, dtype=torch.float64)
     stat_sums, sums3 = ws[:B * 2 * LD].view(B, LD, 2), ws[B * 2 * LD:].view(B, 3)
-    linear_inp, logp, _ = ops.stft_features2(wavs, ch_i, n_fft, hop, window, want_power=True, want_logpower=True,
-                                             log_eps=preprocessor.eps, stat_sums=stat_sums)
-    linear_tar = ops.stft_padded(wavs, ch_t, n_fft, hop, window, logpower=False)
+    linear_inp, logp, linear_tar, _ = ops.stft_features_pair(wavs, ch_i, ch_t, n_fft, hop, window, log_eps=preprocessor.eps,
+                                                             stat_sums=stat_sums)
     wpad = ops.round_tf32(ops.pad_weight(head.linear.weight.detach()))
     stats = stat_sums if head.cmvn else None
     offset = ops.linear_head_tma(logp, K, wpad, head.linear.bias, head.activation, stats, head.eps)

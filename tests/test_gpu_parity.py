@@ -1127,6 +1127,27 @@ def test_train_step_graph_matches_eager_training(se):
     assert np.isfinite(l_g) and l_g < l_e + 0.5
 
 
+@pytest.mark.parametrize("n_fft,B,T,chans", [(400, 5, 16000, (0, 1)), (1024, 3, 20000, (0, 1)), (400, 4, 7777, (2, 0)), (512, 3, 9999, (0, 1))])
+def test_stft_features_pair_equals_two_launches(se, n_fft, B, T, chans):
+    """se_stft_features_pair (input-channel power + log-power + CMVN sums and target-channel power in ONE launch of the
+    register-resident kernels; two launches at n_fft 512) is bit-identical to se_stft_features2 + the target channel's own launch."""
+    from speech_enhancement_by_s3prl_b200 import ops
+    _, mine = make_pair(se, n_fft)
+    hop = mine._win_args["hop_length"]
+    lengths, wavs = synth(B, T, seed=n_fft + B)
+    wavs = wavs.cuda()
+    window = mine._frame_window
+    K, LD = n_fft // 2 + 1, ops.round4(n_fft // 2 + 1)
+    ci, ct = chans
+    p0, l0, s0 = ops.stft_features2(wavs, ci, n_fft, hop, window, True, True, 1e-10)
+    t0 = ops.stft_padded(wavs, ct, n_fft, hop, window, logpower=False)
+    p1, l1, t1, s1 = ops.stft_features_pair(wavs, ci, ct, n_fft, hop, window, 1e-10)
+    torch.cuda.synchronize()
+    assert p1.shape == t1.shape == l1.shape == (B, T // hop + 1, LD) and p1.is_contiguous() and t1.is_contiguous()
+    assert torch.equal(p1[..., :K], p0[..., :K]) and torch.equal(l1[..., :K], l0[..., :K]) and torch.equal(t1[..., :K], t0[..., :K])
+    assert torch.allclose(s1[:, :K], s0[:, :K], rtol=1e-12, atol=1e-9)           # double-precision atomics: order-dependent last bits
+
+
 # ------------------------------------------------------------------------------ tensor-core head backward (tcgen05 split-K)
 @pytest.mark.parametrize("B,F,Din,Dout,act,cmvn", [(3, 101, 257, 257, "Sigmoid", True), (64, 251, 257, 257, "Sigmoid", True),
                                                    (2, 300, 201, 201, "ReLU", False), (5, 64, 120, 201, "Identity", True),
