@@ -16,7 +16,6 @@
 // fp32 dot products accumulated by the B-operand producers of the first tile's CTAs (they hold xhat in registers anyway)
 // instead of a third tensor-core tile that would transpose the whole B operand again for one useful row.  A second kernel sums the partials over the splits into grad_W / grad_b.
 #include <cuda.h>
-#include <cstdlib>
 #include "se_common.cuh"
 
 using secommon::fail;
@@ -111,6 +110,7 @@ struct BwdArgs {
     const float* offset; const float* grad_offset; long long ld_off;
     long long R; int n_frames, Din, Dout, act;
     long long rows_per_split;      // multiple of 32
+    int sub;                       // per-utterance mode: splits per utterance (0: rows [split * rows_per_split, ...) of the whole batch)
     int b_rows;                    // round16(Din + 1) <= 272
     int n_main, n_tail;
     float* partials;               // (splits, m_rows, 272)
@@ -138,8 +138,14 @@ __global__ void __launch_bounds__(kThreads, 1) linear_head_bwd_tc_kernel(const B
     const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, n0 = blockIdx.y * BM;
-    const long long ra = (long long)split * a.rows_per_split;
-    const long long rb = ra + a.rows_per_split < a.R ? ra + a.rows_per_split : a.R;
+    long long ra = (long long)split * a.rows_per_split;
+    long long rb = ra + a.rows_per_split < a.R ? ra + a.rows_per_split : a.R;
+    if (a.sub > 0) {                                                   // per-utterance mode: split = (utterance, part of its frames)
+        const long long u = split / a.sub, ue = (u + 1) * a.n_frames;
+        ra = u * a.n_frames + (long long)(split - u * a.sub) * a.rows_per_split;
+        rb = ra + a.rows_per_split < ue ? ra + a.rows_per_split : ue;
+        if (ra > ue) ra = ue;
+    }
     const int nkb = rb > ra ? (int)((rb - ra + BK - 1) / BK) : 0;
 
     if (threadIdx.x == 0) {
@@ -503,8 +509,14 @@ __global__ void __launch_bounds__(kTThreads, 1) linear_head_bwd_tma_kernel(const
     int* s_valid = reinterpret_cast<int*>(smem + kTOffCoef + kMaxUtt * 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, n0 = blockIdx.y * BM;
-    const long long ra = (long long)split * a.rows_per_split;
-    const long long rb = ra + a.rows_per_split < a.R ? ra + a.rows_per_split : a.R;
+    long long ra = (long long)split * a.rows_per_split;
+    long long rb = ra + a.rows_per_split < a.R ? ra + a.rows_per_split : a.R;
+    if (a.sub > 0) {                                                   // per-utterance mode: split = (utterance, part of its frames)
+        const long long u = split / a.sub, ue = (u + 1) * a.n_frames;
+        ra = u * a.n_frames + (long long)(split - u * a.sub) * a.rows_per_split;
+        rb = ra + a.rows_per_split < ue ? ra + a.rows_per_split : ue;
+        if (ra > ue) ra = ue;
+    }
     const int nkb = rb > ra ? (int)((rb - ra + BK - 1) / BK) : 0;
     const int nbx = (a.b_rows + 31) / 32;                              // x boxes per block
 
@@ -774,21 +786,24 @@ __global__ void head_bwd_reduce_kernel(const float* __restrict__ partials, int s
 }
 
 // per-utterance partials (n_utt, m_rows, 272) -> embeddings (n_utt, Dout * Din + Dout) = [grad_W.view(-1), grad_b] (sampler.py:95-108)
-__global__ void head_grad_pack_kernel(const float* __restrict__ partials, int m_rows, int Din, int Dout, float* __restrict__ out) {
+__global__ void head_grad_pack_kernel(const float* __restrict__ partials, int m_rows, int Din, int Dout, int sub, float* __restrict__ out) {
     const long long P = (long long)Dout * Din + Dout;
-    const float* src = partials + (long long)blockIdx.y * m_rows * kMaxBRows;
+    const long long stride = (long long)m_rows * kMaxBRows;
+    const float* src = partials + (long long)blockIdx.y * sub * stride;      // `sub` partials per utterance, summed in a fixed order
     float* dst = out + (long long)blockIdx.y * P;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
         const long long wn = (long long)Dout * Din;
         const int n = i < wn ? (int)(i / Din) : (int)(i - wn);
         const int k = i < wn ? (int)(i - (long long)n * Din) : Din;
-        dst[i] = src[(long long)n * kMaxBRows + k];
+        float v = src[(long long)n * kMaxBRows + k];
+        for (int q = 1; q < sub; ++q) v += src[q * stride + (long long)n * kMaxBRows + k];
+        dst[i] = v;
     }
 }
 
 int num_sms() { return secommon::device_sms(); }
 
-struct Geometry { int m_tiles, simt_rows, m_rows, splits; long long rows_per_split; };
+struct Geometry { int m_tiles, simt_rows, m_rows, splits, sub; long long rows_per_split; };
 
 // per_utt: one split per utterance (its partial IS that utterance's gradient: per-sample gradients for sampler.py:59-110)
 bool plan(long long R, long long n_frames, long long Din, long long Dout, Geometry* g, bool per_utt = false) {
@@ -797,10 +812,18 @@ bool plan(long long R, long long n_frames, long long Din, long long Dout, Geomet
     g->simt_rows = (Dout > BM && rem > 0 && rem <= kMaxSimtRows) ? rem : 0;
     g->m_tiles = (int)((Dout - g->simt_rows + BM - 1) / BM);
     g->m_rows = g->m_tiles * BM + g->simt_rows;
+    g->sub = 0;
     if (per_utt) {
-        if (R / n_frames > 0x7fffffffLL) return false;
-        g->rows_per_split = n_frames;
-        g->splits = (int)(R / n_frames);
+        // one split per utterance, or up to 4 per utterance while the grid stays below one wave (few long utterances)
+        const long long n_utt = R / n_frames;
+        if (n_utt > 0x3fffffffLL) return false;
+        long long sub = num_sms() / (n_utt * g->m_tiles);
+        sub = sub < 1 ? 1 : (sub > 4 ? 4 : sub);
+        long long rows = ((n_frames + sub - 1) / sub + BK - 1) / BK * BK;
+        sub = (n_frames + rows - 1) / rows;
+        g->sub = (int)sub;
+        g->rows_per_split = rows;
+        g->splits = (int)(n_utt * sub);
         return true;
     }
     long long splits = num_sms() / g->m_tiles;
@@ -928,7 +951,7 @@ static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const f
     a.sums = stat_sums; a.inv_n = 1.0 / (double)n_frames; a.inv_nm1 = n_frames > 1 ? 1.0 / (double)(n_frames - 1) : 0.0;
     a.offset = offset; a.grad_offset = grad_offset; a.ld_off = ld_off;
     a.R = n_utt * n_frames; a.n_frames = (int)n_frames; a.Din = (int)D_in; a.Dout = (int)D_out; a.act = act;
-    a.rows_per_split = g.rows_per_split;
+    a.rows_per_split = g.rows_per_split; a.sub = g.sub;
     a.b_rows = (int)((D_in + 1 + 15) / 16 * 16);
     a.n_main = a.b_rows > 256 ? 256 : a.b_rows;
     a.n_tail = a.b_rows - a.n_main;
@@ -946,8 +969,6 @@ static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const f
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(offset) | reinterpret_cast<uintptr_t>(gsrc)) & 15) == 0;
     if (loss) aligned = aligned && loss->ld_tar % 4 == 0 && (reinterpret_cast<uintptr_t>(loss->tar) & 15) == 0;
     CUtensorMap tmG, tmO, tmX, tmT;
-    static int force_old = -1;
-    if (force_old < 0) { const char* e = getenv("SE_B200_BWD_OLD"); force_old = e && atoi(e) ? 1 : 0; }
     int rc;
     const bool tma_ok = aligned && g.simt_rows <= 1 && a.R < 0x7fffffffLL && make_map32(&tmG, gsrc, D_out, a.R, ld_g) &&
                         make_map32(&tmO, offset, D_out, a.R, ld_off) && make_map32(&tmX, x, D_in, a.R, ldx) &&
@@ -960,14 +981,14 @@ static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const f
         a.grad_uniform = loss->grad_uniform; a.grad_out = loss->grad_out;
     }
     static unsigned long long opted_t = 0;
-    if (tma_ok && !force_old && secommon::first_use_on_device(opted_t)) {
+    if (tma_ok && secommon::first_use_on_device(opted_t)) {
         SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes));
         SE_CUDA_CHECK(cudaFuncSetAttribute(linear_head_bwd_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes));
     }
     if (loss) {
         linear_head_bwd_tma_kernel<true><<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kTThreads, kTSmemBytes, st>>>(tmG, tmO, tmX, tmT, a);
         rc = secommon::check_launch("linear_head_bwd_tma_kernel<loss>");
-    } else if (!force_old && tma_ok) {
+    } else if (tma_ok) {
         linear_head_bwd_tma_kernel<false><<<dim3((unsigned)g.splits, (unsigned)g.m_tiles), kTThreads, kTSmemBytes, st>>>(tmG, tmO, tmX, tmX, a);
         rc = secommon::check_launch("linear_head_bwd_tma_kernel");
     } else {
@@ -978,7 +999,7 @@ static int head_bwd_impl(const float* x, int64_t ldx, const float* mean, const f
     const long long total = D_out * (D_in + 1);
     if (per_utt_out) {
         head_grad_pack_kernel<<<dim3((unsigned)((total + 1023) / 1024), (unsigned)n_utt), 256, 0, st>>>(ws_partials, a.m_rows, (int)D_in,
-                                                                                                      (int)D_out, per_utt_out);
+                                                                                                      (int)D_out, g.sub, per_utt_out);
         return secommon::check_launch("head_grad_pack_kernel");
     }
     head_bwd_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws_partials, g.splits, a.m_rows, (int)D_in, (int)D_out,
