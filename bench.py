@@ -493,7 +493,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU oracle timing for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
-    ap.add_argument("--streams", type=int, default=2, help="independent steps in flight (CUDA streams) in the device-resident run")
+    ap.add_argument("--streams", type=int, default=3, help="independent steps in flight (CUDA streams) in the device-resident run")
     ap.add_argument("--head-precision", type=int, default=1, help="0 = fp32 SIMT head, 1 = TF32 tcgen05 head")
     ap.add_argument("--long-utts", type=int, default=1024, help="utterances (60 s each) of the long-form configuration, in total")
     ap.add_argument("--skip-configs", action="store_true", help="headline only (no `configs` object)")
