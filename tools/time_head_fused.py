@@ -1,5 +1,5 @@
 """Time the fused TMA / tcgen05 head alone (se_linear_head_fused) over shapes and launch shapes:
-python tools/time_head_fused.py   (SE_B200_HEAD_MODE=1 forces one CTA per SM, =2 two CTAs per SM; unset = automatic)"""
+python tools/time_head_fused.py"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from speech_enhancement_by_s3prl_b200 import ops
