@@ -95,3 +95,36 @@ def test_shard_bounds_partition_the_batch():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_launch_planning_is_host_logic():
+    """The `_supported` / `_workspace` entry points are pure host planning (148 SMs assumed without a device): the shapes of the
+    BASELINE configs are inside the fast paths, the stated limits are enforced, and the workspaces have the documented sizes."""
+    from speech_enhancement_by_s3prl_b200 import _lib
+    lib = _lib.load()
+    # TMA / tcgen05 head: configs[1] (257), configs[2] (201, mel 120 -> 201), configs[3] (513); rows must be 16-byte multiples
+    for B, F, Din, Dout in [(64, 251, 257, 257), (48, 1001, 201, 201), (48, 1001, 120, 201), (128, 3751, 513, 513)]:
+        r4 = lambda v: (v + 3) // 4 * 4
+        assert lib.se_linear_head_fused_supported(B, F, Din, Dout, r4(Din), r4(Din), r4(Dout)) == 1
+    assert lib.se_linear_head_fused_supported(64, 251, 257, 257, 257, 260, 260) == 0          # ldx not a multiple of 4 floats
+    assert lib.se_linear_head_fused_supported(64, 251, 600, 257, 600, 600, 260) == 0          # more than 544 input features
+    assert lib.se_linear_head_fused_supported(64, 4, 257, 257, 260, 260, 260) == 0            # fewer than 8 frames
+    # split-K weight gradient: one wave of (row split, 128-row output tile) CTAs, partials (splits, m_rows, 272)
+    def splits(R, per_wave):                                                                   # rows per split: a multiple of 32
+        rows = -(-(-(-R // per_wave)) // 32) * 32
+        return -(-R // rows)
+    assert lib.se_linear_head_bwd_tc_workspace(64, 251, 257, 257) == splits(64 * 251, 74) * 257 * 272   # 2 tiles + 1 leftover row
+    assert lib.se_linear_head_bwd_tc_workspace(48, 1001, 201, 201) == splits(48 * 1001, 74) * 256 * 272
+    assert lib.se_linear_head_bwd_tc_workspace(1024, 251, 257, 257) > 0                        # large batches: more splits than one wave
+    assert lib.se_linear_head_bwd_tc_workspace(64, 16, 257, 257) == 0                          # utterances shorter than one 32-row block
+    assert lib.se_linear_head_bwd_tc_workspace(64, 251, 513, 513) == 0                         # D_in + 1 > 272 columns of tensor memory
+    # per-utterance gradients (sampler.py:95-108): one split per utterance, up to four while the grid stays below one wave
+    assert lib.se_head_grad_embeddings_workspace(44, 1001, 201, 201) == 44 * 256 * 272
+    assert lib.se_head_grad_embeddings_workspace(12, 1001, 201, 201) == 12 * 4 * 256 * 272
+    # the objective folded into the weight gradient needs TMA-able (16-byte) rows
+    assert lib.se_linear_head_bwd_sisdr_supported(48, 1001, 201, 201, 204, 204, 204, 204) == 1
+    assert lib.se_linear_head_bwd_sisdr_supported(48, 1001, 201, 201, 201, 204, 204, 204) == 0
+    assert lib.se_head_grad_embeddings_sisdr_supported(44, 1001, 201, 201, 204, 204, 204, 204) == 1
+    # one K1 launch for both channels exists for the register-resident geometries of fastgeo.cu only
+    assert lib.se_stft_features_pair_supported(400, 160) == 1 and lib.se_stft_features_pair_supported(1024, 256) == 1
+    assert lib.se_stft_features_pair_supported(512, 256) == 0 and lib.se_stft_features_pair_supported(400, 200) == 0
