@@ -4,7 +4,15 @@
 //     dZ = grad_offset * act'(offset)                   xhat = (x - mean) / (std + eps)   (the head's CMVN input)
 //
 // A split-K tcgen05 GEMM: CTA (split s, m-tile mt) owns rows [ra, rb) of the batch and output features
-// [128 mt, 128 mt + 128), and accumulates D[128 n][272 k] in tensor memory over its row blocks of 32.
+// [128 mt, 128 mt + 128), and accumulates D[128 n][272 k] in tensor memory over its row blocks of 32.  A second kernel sums the
+// partials over the splits (deterministic), or packs one partial per utterance (per-sample gradients, sampler.py:95-108).
+//
+// TWO kernels share the plan, the epilogue and the reduction:
+//   linear_head_bwd_tma_kernel<LOSS>  (further down; 16-byte aligned, row-padded operands -- the engine's tensors): TMA lands the
+//       operands as they lie in HBM, MN-major tcgen05 operands, in-place rewrite; LOSS also folds the SISDR objective's backward in
+//   linear_head_bwd_tc_kernel         (below; any strides -- the autograd custom op on un-padded tensors): transposing producers
+//
+// linear_head_bwd_tc_kernel:
 //   * warps 0-7  producers: both operands are row-major in r (the reduction index), so they are TRANSPOSED on the way
 //                into shared memory: thread -> one n (or k), four consecutive rows per 16-byte chunk, coalesced 128-byte
 //                loads across the warp, one conflict-free STS.128 into the K-major SWIZZLE_128B tile; dZ's activation
@@ -14,7 +22,7 @@
 //   * epilogue   tcgen05.ld -> staging tile -> coalesced stores of the CTA's partial into the workspace
 // Output rows that do not fill a 128-row tile are few when D_out = 257 (one row): up to kMaxSimtRows such rows go through a
 // fp32 dot products accumulated by the B-operand producers of the first tile's CTAs (they hold xhat in registers anyway)
-// instead of a third tensor-core tile that would transpose the whole B operand again for one useful row.  A second kernel sums the partials over the splits into grad_W / grad_b.
+// instead of a third tensor-core tile that would transpose the whole B operand again for one useful row.
 #include <cuda.h>
 #include "se_common.cuh"
 
