@@ -366,11 +366,21 @@ __global__ void __launch_bounds__(256) row_sumsq_kernel(const float* __restrict_
 }
 __global__ void __launch_bounds__(256) match_qbar_kernel(const float* __restrict__ q, int nq, long long P, float eps,
                                                          const double* __restrict__ q_sumsq, float* __restrict__ qbar) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
-        float s = 0.0f;
-        for (int r = 0; r < nq; ++r) s += q[(long long)r * P + i] / ((float)sqrt(q_sumsq[r]) + eps);
-        qbar[i] = s / (float)nq;
+    // the row norms once per CTA (256 rows at a time) instead of a double-precision sqrt and a divide per element
+    __shared__ float s_inv[256];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // grid covers P (se_match_scores)
+    float s = 0.0f;
+    for (int r0 = 0; r0 < nq; r0 += 256) {
+        __syncthreads();
+        if (r0 + (int)threadIdx.x < nq) s_inv[threadIdx.x] = 1.0f / ((float)sqrt(q_sumsq[r0 + threadIdx.x]) + eps);
+        __syncthreads();
+        const int n = min(256, nq - r0);
+        if (i < P) {
+#pragma unroll 8
+            for (int r = 0; r < n; ++r) s = fmaf(q[(long long)(r0 + r) * P + i], s_inv[r], s);
+        }
     }
+    if (i < P) qbar[i] = s / (float)nq;
 }
 __global__ void __launch_bounds__(256) match_dot_kernel(const float* __restrict__ k, long long P, int chunks,
                                                         const float* __restrict__ qbar, double* __restrict__ dots) {
@@ -1071,8 +1081,8 @@ int se_match_scores(const float* query, int64_t n_query, const float* key, int64
     const int cq = pick_chunks(n_query, P, 4096), ck = pick_chunks(n_key, P, 4096);
     row_sumsq_kernel<<<(unsigned)(n_query * cq), 256, 0, st>>>(query, P, cq, q_sumsq);
     row_sumsq_kernel<<<(unsigned)(n_key * ck), 256, 0, st>>>(key, P, ck, k_sumsq);
-    long long blocks = (P + 255) / 256;
-    if (blocks > 1184) blocks = 1184;
+    const long long blocks = (P + 255) / 256;
+    SE_REQUIRE(blocks < 0x7fffffffLL, "P=%lld too large", (long long)P);
     match_qbar_kernel<<<(unsigned)blocks, 256, 0, st>>>(query, (int)n_query, P, eps, q_sumsq, ws_qbar);
     match_dot_kernel<<<(unsigned)(n_key * ck), 256, 0, st>>>(key, P, ck, ws_qbar, dots);
     match_finish_kernel<<<(unsigned)((n_key + 127) / 128), 128, 0, st>>>(k_sumsq, dots, (int)n_key, eps, scores);
